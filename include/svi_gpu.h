@@ -1,0 +1,216 @@
+/* svi_gpu.h -- C-ABI of libsvi_gpu.so: svi_mapper's stereo front-end hot path on one B200.
+ *
+ * This boundary does not exist in the reference (it is a single C++ process calling OpenCV);
+ * it is what the reference's own seams would bind if the arithmetic moved to the GPU.  Each
+ * entry point cites the reference interface it replaces (paths relative to the svi_mapper tree).
+ *
+ *   - plain C, no C++ types, no exceptions across the boundary
+ *   - the caller owns every host buffer (inputs and pre-sized outputs); the library owns all
+ *     device memory inside svi_ctx; nothing returned outlives svi_destroy
+ *   - call-level failures are negative return codes + svi_last_error(); per-item outcomes
+ *     (the reference's CExceptionNoMatchFound control flow) are DATA: one svi_status per item
+ *   - one svi_ctx per (host thread, GPU); calls on one ctx are serialised by the caller;
+ *     every export is synchronous on return unless its name ends in _device
+ */
+#ifndef SVI_GPU_H
+#define SVI_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVI_DESCRIPTOR_BYTES 32 /* src/types/Types.h:73-75 DESCRIPTOR_SIZE_BYTES */
+
+typedef struct svi_ctx svi_ctx;
+
+/* call-level return codes */
+enum {
+    SVI_SUCCESS = 0,
+    SVI_ERR_INVALID = -1,    /* bad argument */
+    SVI_ERR_CUDA = -2,       /* CUDA runtime error, text in svi_last_error */
+    SVI_ERR_CAPACITY = -3,   /* a caller- or ctx-sized buffer was too small (never a silent drop) */
+    SVI_ERR_NO_DEVICE = -4,
+    SVI_ERR_UNSUPPORTED = -5
+};
+
+/* Per-item outcome: one value per distinct failure string the reference throws on this path
+ * (SURVEY.md Appendix C).  svi_status_text() returns the reference's what() text. */
+typedef enum svi_status {
+    SVI_OK = 0,
+    SVI_TRI_RANGE = 1,      /* src/core/CTriangulator.cpp:65,199,270  "insufficient search range"   */
+    SVI_TRI_NO_DESC = 2,    /* src/core/CTriangulator.cpp:88,222,293  "could not compute descriptors" */
+    SVI_TRI_NO_MATCH = 3,   /* src/core/CTriangulator.cpp:97,231,302  "no match found"               */
+    SVI_TRI_DISTANCE = 4,   /* src/core/CTriangulator.cpp:117,251,322 "matching distance"            */
+    SVI_TRI_ZERO_DISP = 5,  /* src/core/CTriangulator.cpp:332         "zero disparity"               */
+    SVI_TRI_BAD_ROI = 6,    /* search ROI leaves the image: the reference aborts in cv::Mat::operator() */
+    SVI_TRK_DEPTH = 7,      /* src/core/CFundamentalMatcher.cpp:1446,1508 "invalid depth"            */
+    SVI_TRK_STAGE1_DIST = 8,/* src/core/CFundamentalMatcher.cpp:1471,1533 "insufficient matching distance" */
+    SVI_TRK_TRI_DESC = 9,   /* src/core/CFundamentalMatcher.cpp:1452,1514 "triangulation descriptor mismatch" */
+    SVI_TRK_OUT_OF_FOV = 10 /* src/core/CFundamentalMatcher.cpp:1416 projection outside m_cFieldOfView */
+} svi_status;
+
+/* src/vision/CPinholeCamera.h:16-64: the members the hot path reads
+ * (m_uWidthPixel, m_uHeightPixel, m_matProjection row-major 3x4). */
+typedef struct svi_camera {
+    uint32_t width;
+    uint32_t height;
+    double P[12];
+} svi_camera;
+
+/* The reference's compile-time constants; svi_params_default() fills in
+ * exactly those values.  max_corners / search_range_px are parameters because the batch and
+ * stress configurations of BASELINE.json raise them. */
+typedef struct svi_params {
+    double quality_level;      /* 0.01  src/core/CFundamentalMatcher.cpp:18 (cv::GFTTDetector takes doubles) */
+    double min_distance;       /* 7.0   ibid. */
+    double harris_k;           /* 0.04  OpenCV default for GFTTDetector */
+    double min_disparity_px;   /* 0.01  src/core/CTriangulator.h:21 */
+    int32_t max_corners;       /* 1000  src/core/CFundamentalMatcher.cpp:18 */
+    float keypoint_size;       /* 7.0   cv::KeyPoint::size GFTT reports (= blockSize) */
+    float search_range_px;     /* 60.0  src/core/CTriangulator.h:20 */
+    float match_cutoff;        /* 100.0 src/core/CTriangulator.cpp:13 */
+    float cutoff_stage1;       /* 25.0  src/core/CFundamentalMatcher.cpp:23 */
+    float cutoff_stage2;       /* 50.0  :24 */
+    float cutoff_stage3;       /* 50.0  :25 */
+    float cutoff_original;     /* 100.0 :26 */
+    int32_t max_candidates;    /* per-frame capacity of the NMS candidate list (default 16384) */
+    int32_t chunk_frames;      /* frames per kernel wave; 0 = library default */
+    int32_t max_queries;       /* capacity of the per-query entry points (triangulate_*, describe, track) */
+} svi_params;
+
+int svi_params_default(svi_params* p);
+const char* svi_status_text(int status);
+
+/* Replaces the CTriangulator / CFundamentalMatcher constructors' OpenCV object creation
+ * (src/core/CTriangulator.cpp:8-21, src/core/CFundamentalMatcher.cpp:14-28). */
+int svi_create(const svi_camera* left, const svi_camera* right, const svi_params* params,
+               int device, svi_ctx** out);
+void svi_destroy(svi_ctx* ctx);
+const char* svi_last_error(const svi_ctx* ctx); /* ctx may be NULL: last create error */
+int svi_device_count(void);
+
+/* SoA result of the new-landmark path, caller-owned.  Slot (f, i) lives at index
+ * f*capacity_per_frame + i; slots i >= n_keypoints[f] are untouched. 113 bytes per key-point. */
+typedef struct svi_stereo_result {
+    int32_t capacity_per_frame; /* in: >= params.max_corners */
+    int32_t* n_keypoints;       /* [n_frames] corners that survived BRIEF's 28-px border filter */
+    int32_t* n_detected;        /* [n_frames] GFTT corners before that filter; may be NULL */
+    float* uv_left;             /* [.. * 2] */
+    float* uv_right;            /* [.. * 2] valid when status == SVI_OK */
+    double* xyz_left;           /* [.. * 3] valid when status == SVI_OK */
+    uint8_t* desc_left;         /* [.. * 32] */
+    uint8_t* desc_right;        /* [.. * 32] valid when status == SVI_OK */
+    int32_t* distance;          /* Hamming distance of the arg-min candidate, -1 if none evaluated */
+    int32_t* match_index;       /* pool index (cv::DMatch::trainIdx), -1 if none */
+    uint8_t* status;            /* svi_status */
+} svi_stereo_result;
+
+/* CFundamentalMatcher::addNewLandmarks (src/core/CFundamentalMatcher.cpp:83-193) minus landmark
+ * bookkeeping, for a batch of independent stereo pairs: GFTT/Harris detect on LEFT (optional
+ * u8 masks, 0 = blocked), BRIEF-32 on the kept corners, per corner the dense same-row search in
+ * RIGHT (CTriangulator::getPointTriangulatedInRIGHTFull, src/core/CTriangulator.cpp:51-119),
+ * Hamming arg-min, cut-off, closed-form triangulation.  Host buffers; images are n_frames
+ * planes of height x pitch bytes, frame_stride bytes apart. */
+int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                      size_t frame_stride, int n_frames, const uint8_t* masks_or_null,
+                      svi_stereo_result* out);
+
+/* Same, but every pointer (images, masks, and the arrays inside *out) is a DEVICE pointer on
+ * ctx's GPU and the work is enqueued after everything already queued on `cuda_stream`
+ * (a cudaStream_t; NULL = default stream); later work on that stream waits for it.
+ * Returns without synchronising. */
+int svi_stereo_frames_device(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                             size_t frame_stride, int n_frames, const uint8_t* masks_or_null,
+                             const svi_stereo_result* out, void* cuda_stream);
+
+/* cv::cornerHarris(img, 7, 3, k) as GFTTDetector runs it (response plane, fp32, W*H). */
+int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* response);
+
+/* cv::GFTTDetector::detect(img, kps, mask) (src/core/CFundamentalMatcher.cpp:101): integer corner
+ * coordinates as floats in OpenCV's order; xy holds n_frames * params.max_corners * 2 floats. */
+int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stride, int n_frames,
+               const uint8_t* masks_or_null, float* xy, int32_t* counts);
+
+/* cv::xfeatures2d::BriefDescriptorExtractor::compute(img, kps, desc) on a full image
+ * (src/core/CFundamentalMatcher.cpp:106): kept[i] = 0 where OpenCV erases the key-point
+ * (28-px border); desc32 rows are written for every i (zero where erased). */
+int svi_describe(svi_ctx* ctx, const uint8_t* img, size_t pitch, const float* xy, int n,
+                 uint8_t* desc32, uint8_t* kept);
+
+/* cv::BFMatcher(NORM_HAMMING)::match(query, train) (src/core/CTriangulator.cpp:93): per query the
+ * first arg-min train index and its distance; -1/-1 when n_train == 0. */
+int svi_match_hamming(svi_ctx* ctx, const uint8_t* query32, int n_query, const uint8_t* train32,
+                      int n_train, int32_t* index, int32_t* distance);
+
+/* Per-query results of the triangulating scan-line searches. */
+typedef struct svi_tri_result {
+    float* uv;          /* [n*2] matched point in the searched image */
+    double* xyz_left;   /* [n*3] */
+    uint8_t* desc;      /* [n*32] descriptor at the matched point */
+    int32_t* distance;  /* [n] */
+    int32_t* match_index; /* [n] */
+    uint8_t* status;    /* [n] */
+} svi_tri_result;
+
+/* CTriangulator::getPointTriangulatedInRIGHT / ...Full (src/core/CTriangulator.cpp:51-119,185-253)
+ * for n queries against one RIGHT image: top_left = (p_fUTopLeft, p_fVTopLeft) per query,
+ * uv_left = p_ptUVLEFT, desc_left = p_matReferenceDescriptorLEFT, size = p_fKeyPointSizePixels. */
+int svi_triangulate_right(svi_ctx* ctx, const uint8_t* img_right, size_t pitch, int n,
+                          const float* top_left, const float* uv_left, const uint8_t* desc_left,
+                          float keypoint_size, svi_tri_result* out);
+
+/* CTriangulator::getPointTriangulatedInLEFT, 7-argument overload (src/core/CTriangulator.cpp:255-324). */
+int svi_triangulate_left(svi_ctx* ctx, const uint8_t* img_left, size_t pitch, int n,
+                         const float* search_range, const float* top_left, const float* uv_right,
+                         const uint8_t* desc_right, float keypoint_size, svi_tri_result* out);
+
+/* CTriangulator::getPointInLEFT (src/core/CTriangulator.cpp:326-356) in bulk. */
+int svi_point_in_left(svi_ctx* ctx, int n, const float* uv_left, const float* uv_right,
+                      double* xyz_left, uint8_t* status);
+
+/* Landmark state the tracker hands over (fields of CLandmark the stage reads:
+ * src/types/CLandmark.h:35-59, src/core/CFundamentalMatcher.cpp:1404-1413). */
+typedef struct svi_landmarks {
+    const double* xyz_world;      /* [n*3] vecPointXYZOptimized */
+    const uint8_t* last_desc_left;  /* [n*32] getLastDescriptorLEFT() */
+    const uint8_t* last_desc_right; /* [n*32] getLastDescriptorRIGHT() */
+    const float* last_disparity;  /* [n] getLastDisparity() */
+    const float* keypoint_size;   /* [n] dKeyPointSize */
+} svi_landmarks;
+
+typedef struct svi_track_result {
+    uint8_t* status;     /* [n] svi_status of the LAST stage tried */
+    uint8_t* stage;      /* [n] 0 = not tracked, 1 = stage 1 LEFT, 2 = stage 1 RIGHT */
+    float* uv_left;      /* [n*2] */
+    float* uv_right;     /* [n*2] */
+    double* xyz_left;    /* [n*3] */
+    uint8_t* desc_left;  /* [n*32] */
+    uint8_t* desc_right; /* [n*32] */
+} svi_track_result;
+
+/* CFundamentalMatcher::trackManual, stage 1 LEFT then stage 1 RIGHT
+ * (src/core/CFundamentalMatcher.cpp:1404-1538): projection-window landmark tracking for n
+ * landmarks against one stereo pair.  T_world_to_left is the row-major 4x4 of
+ * p_matTransformationWORLDtoLEFT. Stages 2-3 stay with the caller this round. */
+int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* img_right,
+                        size_t pitch, const double* T_world_to_left, const svi_landmarks* lm, int n,
+                        double motion_scaling, svi_track_result* out);
+
+/* Stage profiling: when enabled, every kernel of the new-landmark path is bracketed by CUDA events
+ * on the stream it is launched on.  svi_set_profiling also clears the accumulators;
+ * svi_stage_timings waits for the ctx to go idle and returns, per stage, the summed launch
+ * duration in ms and the number of launches (arrays of length >= 5; returns the stage count). */
+int svi_set_profiling(svi_ctx* ctx, int enable);
+int svi_stage_timings(svi_ctx* ctx, const char** names, double* total_ms, int64_t* launches, int capacity);
+
+/* How this ctx was configured: frames per kernel wave, number of stream lanes, whether corner
+ * selection runs out of shared memory (1) or the global-memory variant for very large frames (0). */
+int svi_config(const svi_ctx* ctx, int32_t* chunk_frames, int32_t* n_lanes, int32_t* select_in_smem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVI_GPU_H */

@@ -1,0 +1,521 @@
+"""CPU oracle (numpy [+ cv2 where importable]) for svi_mapper's stereo front-end hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under svi_mapper_b200/ imports this module; only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+
+What it restates (all file:line relative to /root/reference):
+  * cv::GFTTDetector::create(1000, 0.01, 7.0, 7, true)        src/core/CFundamentalMatcher.cpp:18
+    -> harris_response(), gftt()            (OpenCV imgproc arithmetic)
+  * cv::xfeatures2d::BriefDescriptorExtractor::create(32)       src/core/CTriangulator.cpp:11
+    -> brief32()                            (OpenCV-contrib algorithm)
+  * cv::BFMatcher(NORM_HAMMING)::match                           src/core/CTriangulator.cpp:12,93
+    -> match_hamming()
+  * CTriangulator::getPointTriangulatedInRIGHT[Full]             src/core/CTriangulator.cpp:51-119,185-253
+  * CTriangulator::getPointTriangulatedInLEFT (7 args)           src/core/CTriangulator.cpp:255-324
+  * CTriangulator::getPointInLEFT                                src/core/CTriangulator.cpp:326-356
+  * CFundamentalMatcher::addNewLandmarks                         src/core/CFundamentalMatcher.cpp:83-193
+  * CFundamentalMatcher::getMaskActiveLandmarks                  src/core/CFundamentalMatcher.cpp:2043-2073
+  * CFundamentalMatcher::trackManual stage 1                     src/core/CFundamentalMatcher.cpp:1404-1538
+
+Pinning status: the reference ships no tests and no golden vectors.
+  detect        : pinned against cv2 4.13 (setUseOptimized(False), 1 thread) -- tests/test_oracle_cv2.py
+  Hamming/argmin: pinned against cv2.BFMatcher
+  mask stencil  : pinned against cv2.circle
+  triangulation : pinned against the closed form of src/runnable/triangulation_sampling.cpp:99-120
+  BRIEF         : PARITY UNPINNED -- opencv_contrib's generated_32.i pair table is not in this image;
+                  the algorithm is restated from the published BRIEF/OpenCV description and uses the
+                  stand-in table svi_mapper_b200/brief_pattern_32.txt.
+"""
+from __future__ import annotations
+
+import math
+import pathlib
+from dataclasses import dataclass, field
+
+import numpy as np
+
+F32 = np.float32
+
+# ----------------------------------------------------------------------------- status codes
+# One value per reference failure string.  Must match include/svi_gpu.h.
+ST_OK = 0
+ST_TRI_RANGE = 1      # "<CTriangulator>(getPointTriangulatedIn...) insufficient search range"
+ST_TRI_NO_DESC = 2    # "... could not compute descriptors"
+ST_TRI_NO_MATCH = 3   # "... no match found"
+ST_TRI_DISTANCE = 4   # "... matching distance"
+ST_TRI_ZERO_DISP = 5  # "<CTriangulator>(getPointInLEFT) zero disparity"
+ST_TRI_BAD_ROI = 6    # ROI leaves the image: the reference dies with cv::Exception here
+ST_TRK_DEPTH = 7      # "invalid depth"
+ST_TRK_STAGE1_DIST = 8  # "insufficient matching distance"
+ST_TRK_TRI_DESC = 9   # "triangulation descriptor mismatch"
+ST_TRK_OUT_OF_FOV = 10  # projection outside m_cFieldOfView -> ++uFailedSubsequentTrackings
+
+PATTERN_FILE = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "brief_pattern_32.txt"
+
+
+def load_pattern(path=PATTERN_FILE) -> np.ndarray:
+    rows = [list(map(int, l.split())) for l in open(path) if l.strip() and not l.startswith("#")]
+    pat = np.asarray(rows, dtype=np.int32)
+    assert pat.shape == (256, 4) and np.abs(pat).max() <= 24
+    return pat
+
+
+PATTERN = load_pattern()
+
+
+# ----------------------------------------------------------------------------- camera
+@dataclass
+class Camera:
+    """Subset of CPinholeCamera (src/vision/CPinholeCamera.h:16-64)."""
+    width: int
+    height: int
+    P: np.ndarray  # 3x4 float64 m_matProjection
+    label: str = ""
+
+
+@dataclass
+class StereoParams:
+    """Constants of the hot path; defaults == reference."""
+    max_corners: int = 1000
+    quality_level: float = 0.01
+    min_distance: float = 7.0
+    block_size: int = 7
+    harris_k: float = 0.04
+    search_range: float = 60.0          # CTriangulator.h:20
+    match_cutoff: float = 100.0         # CTriangulator.cpp:13
+    min_disparity: float = 0.01         # CTriangulator.h:21
+    cutoff_stage1: float = 25.0         # CFundamentalMatcher.cpp:23
+
+
+def _reflect101(i: np.ndarray, n: int) -> np.ndarray:
+    i = np.where(i < 0, -i, i)
+    return np.where(i >= n, 2 * n - 2 - i, i)
+
+
+# ----------------------------------------------------------------------------- Harris
+_SCALE = 1.0 / (4.0 * 7.0 * 255.0)  # cornerHarris: 1/((1<<(ksize-1))*blockSize) / 255 for CV_8U
+_F1 = F32(_SCALE)
+_F0 = F32(2.0 * _SCALE)
+
+
+def sobel_products(img: np.ndarray):
+    """Dx, Dy as cv::Sobel(CV_32F, ksize 3, scale) computes them, then the three products.
+
+    Row filter then column filter, every * and + rounded to fp32 separately (no FMA), in the
+    operand order validated against cv2 in SURVEY.md Appendix A.1.
+    """
+    h, w = img.shape
+    p = img.astype(F32)
+    xi = _reflect101(np.arange(-1, w + 1), w)
+    yi = _reflect101(np.arange(-1, h + 1), h)
+    pp = p[yi][:, xi]  # (h+2, w+2) padded, REFLECT_101
+    # dx=1,dy=0: row kernel [-1,0,1], column kernel [1,2,1]*s (symmetric column filter)
+    r = pp[:, 2:] - pp[:, :-2]                                  # exact in fp32
+    dx = (r[:-2] + r[2:]) * _F1 + r[1:-1] * _F0
+    # dx=0,dy=1: row kernel [1,2,1]*s (generic sequential row filter), column kernel [-1,0,1]
+    q = (pp[:, :-2] * _F1 + pp[:, 1:-1] * _F0) + pp[:, 2:] * _F1
+    dy = q[2:] - q[:-2]
+    assert dx.dtype == F32 and dy.dtype == F32
+    return dx * dx, dx * dy, dy * dy
+
+
+def box7_opencv_order(c: np.ndarray) -> np.ndarray:
+    """cv::boxFilter(cov, 7x7, normalize=false, REFLECT_101) on an fp32 plane, in OpenCV's own
+    operation order: RowSum<float,double> (running sum along x) then ColumnSum<double,float>
+    (running sum along y), both in fp64, one rounding to fp32 at the end."""
+    h, w = c.shape
+    xi = _reflect101(np.arange(-3, w + 3), w)
+    s = c[:, xi].astype(np.float64)  # (h, w+6)
+    hs = np.empty((h, w), np.float64)
+    acc = np.zeros(h, np.float64)
+    for i in range(7):
+        acc = acc + s[:, i]
+    hs[:, 0] = acc
+    for i in range(w - 1):
+        acc = acc + (s[:, i + 7] - s[:, i])
+        hs[:, i + 1] = acc
+    yi = _reflect101(np.arange(-3, h + 3), h)
+    hp = hs[yi]  # (h+6, w)
+    out = np.empty((h, w), F32)
+    acc = np.zeros(w, np.float64)
+    for i in range(6):
+        acc = acc + hp[i]
+    for y in range(h):
+        s0 = acc + hp[y + 6]
+        out[y] = s0.astype(F32)
+        acc = s0 - hp[y]
+    return out
+
+
+def box7_exact(c: np.ndarray) -> np.ndarray:
+    """Order-independent variant: plain fp64 sum of the 49 taps, rounded once.  Equal to
+    box7_opencv_order whenever no fp64 rounding happens (the common case)."""
+    h, w = c.shape
+    xi = _reflect101(np.arange(-3, w + 3), w)
+    yi = _reflect101(np.arange(-3, h + 3), h)
+    s = c[yi][:, xi].astype(np.float64)
+    hsum = np.zeros((h + 6, w), np.float64)
+    for i in range(7):
+        hsum += s[:, i:i + w]
+    out = np.zeros((h, w), np.float64)
+    for i in range(7):
+        out += hsum[i:i + h]
+    return out.astype(F32)
+
+
+def harris_response(img: np.ndarray, k: float = 0.04, box=box7_opencv_order) -> np.ndarray:
+    """cv::cornerHarris(img, blockSize 7, ksize 3, k) with optimisations off, fp32 bit-exact."""
+    xx, xy, yy = sobel_products(np.ascontiguousarray(img))
+    a, b, c = box(xx), box(xy), box(yy)
+    kf = F32(k)
+    return (a * c - b * b) - (kf * (a + c)) * (a + c)
+
+
+def gftt(img: np.ndarray, max_corners=1000, quality=0.01, min_distance=7.0, mask=None,
+         response: np.ndarray | None = None, k: float = 0.04) -> np.ndarray:
+    """cv::goodFeaturesToTrack(..., useHarrisDetector=true) -> (n,2) int32 (x,y), in cv2's order.
+
+    M = max over mask; threshold TOZERO at float(double(M)*quality); 3x3 dilate equality;
+    1-px image border excluded; sort by response desc, ties by larger linear address;
+    greedy accept unless an accepted corner lies at squared distance < minDistance^2.
+    """
+    R = harris_response(img, k) if response is None else response
+    h, w = R.shape
+    m = np.ones((h, w), bool) if mask is None else (mask != 0)
+    if not m.any():
+        return np.zeros((0, 2), np.int32)
+    M = float(R[m].max())
+    thr = F32(M * quality)
+    Rt = np.where(R > thr, R, F32(0))
+    pad = np.full((h + 2, w + 2), -np.inf, F32)
+    pad[1:-1, 1:-1] = Rt
+    D = Rt.copy()
+    for dy in range(3):
+        for dx in range(3):
+            D = np.maximum(D, pad[dy:dy + h, dx:dx + w])
+    cand = (Rt != 0) & (Rt == D) & m
+    cand[0, :] = cand[-1, :] = False
+    cand[:, 0] = cand[:, -1] = False
+    ys, xs = np.nonzero(cand)
+    vals = Rt[ys, xs]
+    addr = ys.astype(np.int64) * w + xs
+    order = np.lexsort((-addr, -vals.astype(np.float64)))
+    ys, xs = ys[order], xs[order]
+    md2 = float(min_distance) * float(min_distance)
+    if min_distance < 1:
+        pts = np.stack([xs, ys], 1)
+        return pts[:max_corners].astype(np.int32) if max_corners > 0 else pts.astype(np.int32)
+    cell = int(round(min_distance))
+    gw, gh = (w + cell - 1) // cell, (h + cell - 1) // cell
+    grid = [[] for _ in range(gw * gh)]
+    out = []
+    for x, y in zip(xs.tolist(), ys.tolist()):
+        cx, cy = x // cell, y // cell
+        good = True
+        for yy in range(max(0, cy - 1), min(gh - 1, cy + 1) + 1):
+            for xx in range(max(0, cx - 1), min(gw - 1, cx + 1) + 1):
+                for (px, py) in grid[yy * gw + xx]:
+                    if (x - px) * (x - px) + (y - py) * (y - py) < md2:
+                        good = False
+                        break
+                if not good:
+                    break
+            if not good:
+                break
+        if good:
+            grid[cy * gw + cx].append((x, y))
+            out.append((x, y))
+            if max_corners > 0 and len(out) == max_corners:
+                break
+    return np.asarray(out, np.int32).reshape(-1, 2)
+
+
+def detect_cv2(img, max_corners=1000, quality=0.01, min_distance=7.0, mask=None):
+    """The genuine OpenCV detector in the reference's runtime mode (CTrackerGT.cpp:48-49)."""
+    import cv2
+    cv2.setUseOptimized(False)
+    cv2.setNumThreads(1)
+    det = cv2.GFTTDetector_create(max_corners, quality, min_distance, 7, True)
+    kps = det.detect(img, mask)
+    return np.asarray([[int(kp.pt[0]), int(kp.pt[1])] for kp in kps], np.int32).reshape(-1, 2)
+
+
+# ----------------------------------------------------------------------------- BRIEF
+def integral(img: np.ndarray) -> np.ndarray:
+    """cv::integral(img, CV_32S): (h+1, w+1) int32."""
+    s = np.zeros((img.shape[0] + 1, img.shape[1] + 1), np.int64)
+    s[1:, 1:] = np.cumsum(np.cumsum(img.astype(np.int64), 0), 1)
+    return s.astype(np.int32)
+
+
+def cv_round(v: float) -> int:
+    """cvRound: round half to even (lrint)."""
+    return int(np.rint(np.float64(v)))
+
+
+def brief32(img: np.ndarray, pts, pattern: np.ndarray = PATTERN):
+    """BriefDescriptorExtractor(32)::compute on `img` (an ROI view is just a numpy slice).
+
+    Returns (kept_indices, desc[k,32] u8).  Key-points whose cvRound'ed position is outside
+    [28, w-28) x [28, h-28) are erased (KeyPointsFilter::runByImageBorder, PATCH 48 + KERNEL 9);
+    the 9x9 box sums are centred on ((int)(y+0.5)+dy, (int)(x+0.5)+dx); test 8j+i -> byte j bit 7-i.
+    """
+    h, w = img.shape
+    pts = np.asarray(pts, F32).reshape(-1, 2)
+    keep, cx, cy = [], [], []
+    for i, (x, y) in enumerate(pts):
+        rx, ry = cv_round(x), cv_round(y)
+        if 28 <= rx < w - 28 and 28 <= ry < h - 28:
+            keep.append(i)
+            cx.append(int(float(F32(x)) + 0.5))   # (int)(pt.x + 0.5), double arithmetic
+            cy.append(int(float(F32(y)) + 0.5))
+    if not keep:
+        return np.zeros(0, np.int64), np.zeros((0, 32), np.uint8)
+    S = integral(img).astype(np.int64)
+    cx = np.asarray(cx)[:, None]
+    cy = np.asarray(cy)[:, None]
+
+    def smoothed(dy, dx):
+        y = cy + dy[None, :]
+        x = cx + dx[None, :]
+        return S[y + 5, x + 5] - S[y + 5, x - 4] - S[y - 4, x + 5] + S[y - 4, x - 4]
+
+    bits = smoothed(pattern[:, 0], pattern[:, 1]) < smoothed(pattern[:, 2], pattern[:, 3])
+    desc = np.packbits(bits.astype(np.uint8), axis=1, bitorder="big")
+    return np.asarray(keep), desc
+
+
+def boxsum9(img: np.ndarray) -> np.ndarray:
+    """9x9 box sum centred at every pixel (valid where the box is inside the image), uint16."""
+    h, w = img.shape
+    S = integral(img).astype(np.int64)
+    out = np.zeros((h, w), np.uint16)
+    out[4:h - 4, 4:w - 4] = (S[9:, 9:] - S[9:, :-9] - S[:-9, 9:] + S[:-9, :-9]).astype(np.uint16)
+    return out
+
+
+# ----------------------------------------------------------------------------- matcher
+_POP8 = np.array([bin(i).count("1") for i in range(256)], np.int32)
+
+
+def hamming(a: np.ndarray, b: np.ndarray):
+    return _POP8[np.bitwise_xor(a, b)].sum(axis=-1)
+
+
+def match_hamming(q: np.ndarray, t: np.ndarray):
+    """BFMatcher(NORM_HAMMING).match(q 1x32, t Nx32): first arg-min, distance; (-1, -1) if empty."""
+    if len(t) == 0:
+        return -1, -1
+    d = hamming(q.reshape(1, 32), t)
+    i = int(np.argmin(d))  # numpy argmin returns the first minimum
+    return i, int(d[i])
+
+
+# ----------------------------------------------------------------------------- triangulator
+class Triangulator:
+    """CTriangulator (src/core/CTriangulator.cpp)."""
+
+    def __init__(self, cam_l: Camera, cam_r: Camera, params: StereoParams | None = None):
+        self.cl, self.cr = cam_l, cam_r
+        self.p = params or StereoParams()
+        self.f = float(cam_l.P[0, 0])           # :14
+        self.f_inv = 1.0 / self.f               # :15
+        self.pu = float(cam_l.P[0, 2])          # :16
+        self.pv = float(cam_l.P[1, 2])          # :17
+        self.du_r = float(cam_r.P[0, 3])        # :18
+        self.du_r_flipped = -self.du_r          # :19
+        self.depth_min = self.du_r_flipped / cam_l.width          # :20
+        self.depth_max = self.du_r_flipped / self.p.min_disparity  # :21
+
+    def point_in_left(self, uvl, uvr):
+        """getPointInLEFT :326-356 -> (status, xyz)."""
+        d = F32(uvl[0]) - F32(uvr[0])
+        if float(d) < self.p.min_disparity:
+            return ST_TRI_ZERO_DISP, None
+        z = self.du_r_flipped / float(d)
+        x = self.f_inv * z * (float(F32(uvl[0])) - self.pu)
+        y = self.f_inv * z * (float(F32(uvl[1])) - self.pv)
+        return ST_OK, np.array([x, y, z], np.float64)
+
+    def _search(self, img, u_tl, v_tl, size, n_pool, first_u, width_f):
+        """Shared body of :59-117 / :264-322: ROI, pool, BRIEF, match, cut-off."""
+        border = F32(4) * F32(size)
+        full_h = F32(8) * F32(size) + F32(1)
+        roi_w_f = min(F32(n_pool) + full_h, F32(width_f) - F32(u_tl))
+        rx, ry, rw, rh = int(F32(u_tl)), int(F32(v_tl)), int(roi_w_f), int(full_h)  # cv::Rect(float..) truncates
+        h, w = img.shape
+        if rx < 0 or ry < 0 or rw < 0 or rh < 0 or rx + rw > w or ry + rh > h:
+            return ST_TRI_BAD_ROI, None
+        pool = [(F32(border + F32(first_u) + F32(i)), border) for i in range(n_pool)]
+        keep, desc = brief32(img[ry:ry + rh, rx:rx + rw], pool)
+        if len(keep) == 0:
+            return ST_TRI_NO_DESC, None
+        return ST_OK, (pool, keep, desc)
+
+    def triangulate_right(self, img_r, u_tl, v_tl, size, uvl, desc_l):
+        """getPointTriangulatedInRIGHT[Full] :51-119/:185-253 -> dict(status, uv, xyz, desc, dist, idx)."""
+        u_tl, v_tl = F32(u_tl), F32(v_tl)
+        border = F32(4) * F32(size)
+        xl = F32(uvl[0])
+        if xl <= u_tl + border:
+            return dict(status=ST_TRI_RANGE)
+        n = int(math.ceil(float(F32(xl - u_tl) - border)))
+        st, res = self._search(img_r, u_tl, v_tl, size, n, 0, self.cr.width)
+        if st != ST_OK:
+            return dict(status=st)
+        pool, keep, desc = res
+        idx, dist = match_hamming(np.asarray(desc_l, np.uint8), desc)
+        if idx < 0:
+            return dict(status=ST_TRI_NO_MATCH)
+        if not (F32(self.p.match_cutoff) > F32(dist)):
+            return dict(status=ST_TRI_DISTANCE, dist=dist, idx=idx)
+        px, py = pool[keep[idx]]
+        uvr = (F32(px + u_tl), F32(py + v_tl))
+        st, xyz = self.point_in_left((xl, F32(uvl[1])), uvr)
+        if st != ST_OK:
+            return dict(status=st, dist=dist, idx=idx)
+        return dict(status=ST_OK, uv=uvr, xyz=xyz, desc=desc[idx].copy(), dist=dist, idx=idx)
+
+    def triangulate_left(self, img_l, search_range, u_tl, v_tl, size, uvr, desc_r):
+        """getPointTriangulatedInLEFT (7 args) :255-324."""
+        u_tl, v_tl = F32(u_tl), F32(v_tl)
+        if 0 >= F32(search_range):
+            return dict(status=ST_TRI_RANGE)
+        n = int(math.ceil(float(min(F32(search_range), F32(self.cl.width) - u_tl)))) + 1
+        st, res = self._search(img_l, u_tl, v_tl, size, n, 1, self.cl.width)
+        if st != ST_OK:
+            return dict(status=st)
+        pool, keep, desc = res
+        idx, dist = match_hamming(np.asarray(desc_r, np.uint8), desc)
+        if idx < 0:
+            return dict(status=ST_TRI_NO_MATCH)
+        if not (F32(self.p.match_cutoff) > F32(dist)):
+            return dict(status=ST_TRI_DISTANCE, dist=dist, idx=idx)
+        px, py = pool[keep[idx]]
+        uvl = (F32(px + u_tl), F32(py + v_tl))
+        st, xyz = self.point_in_left(uvl, (F32(uvr[0]), F32(uvr[1])))
+        if st != ST_OK:
+            return dict(status=st, dist=dist, idx=idx)
+        return dict(status=ST_OK, uv=uvl, xyz=xyz, desc=desc[idx].copy(), dist=dist, idx=idx)
+
+
+# ----------------------------------------------------------------------------- addNewLandmarks
+def mask_active_landmarks(width, height, centres) -> np.ndarray:
+    """getMaskActiveLandmarks :2043-2073: 255 everywhere, filled radius-7 zero discs (cv::circle
+    stencil pinned in SURVEY.md A.6: row widths 1,7,9,11,13,13,13,15,13,13,13,11,9,7,1)."""
+    half = [0, 3, 4, 5, 6, 6, 6, 7, 6, 6, 6, 5, 4, 3, 0]
+    m = np.full((height, width), 255, np.uint8)
+    for (cx, cy) in centres:
+        cx, cy = cv_round(cx), cv_round(cy)
+        for dy in range(-7, 8):
+            y = cy + dy
+            if 0 <= y < height:
+                hw = half[dy + 7]
+                x0, x1 = max(cx - hw, 0), min(cx + hw, width - 1)
+                if x0 <= x1:
+                    m[y, x0:x1 + 1] = 0
+    return m
+
+
+def add_new_landmarks(img_l, img_r, tri: Triangulator, mask=None, use_cv2=False, size=7.0):
+    """addNewLandmarks :83-193 minus landmark bookkeeping.  Returns a dict of per-key-point
+    arrays in the reference's iteration order (GFTT order after BRIEF's border filter)."""
+    p = tri.p
+    if use_cv2:
+        kps = detect_cv2(img_l, p.max_corners, p.quality_level, p.min_distance, mask)
+    else:
+        kps = gftt(img_l, p.max_corners, p.quality_level, p.min_distance, mask, k=p.harris_k)
+    keep, desc_l = brief32(img_l, kps.astype(F32))                      # :106
+    kps = kps[keep] if len(keep) else kps[:0]
+    n = len(kps)
+    out = dict(uv_l=kps.astype(F32), desc_l=desc_l,
+               uv_r=np.zeros((n, 2), F32), xyz=np.zeros((n, 3), np.float64),
+               desc_r=np.zeros((n, 32), np.uint8), dist=np.full(n, -1, np.int32),
+               idx=np.full(n, -1, np.int32), status=np.zeros(n, np.uint8))
+    for u in range(n):
+        x, y = F32(kps[u, 0]), F32(kps[u, 1])
+        u_tl = max(F32(0), F32(x - F32(p.search_range)) - F32(4) * F32(size))   # :120
+        v_tl = y - F32(4) * F32(size)                                            # :121
+        r = tri.triangulate_right(img_r, u_tl, v_tl, size, (x, y), desc_l[u])
+        out["status"][u] = r["status"]
+        out["dist"][u] = r.get("dist", -1)
+        out["idx"][u] = r.get("idx", -1)
+        if r["status"] == ST_OK:
+            out["uv_r"][u] = r["uv"]
+            out["xyz"][u] = r["xyz"]
+            out["desc_r"][u] = r["desc"]
+    return out
+
+
+# ----------------------------------------------------------------------------- projection helpers
+def round_half_away(v) -> F32:
+    v = F32(v)
+    return F32(math.floor(float(v) + 0.5)) if v >= 0 else F32(-math.floor(float(-v) + 0.5))
+
+
+def projection_rounded(P: np.ndarray, xyz) -> tuple:
+    """CPinholeCamera::getProjectionRounded CPinholeCamera.h:202-210 (std::round on float)."""
+    h = P @ np.array([xyz[0], xyz[1], xyz[2], 1.0])
+    return round_half_away(F32(h[0] / h[2])), round_half_away(F32(h[1] / h[2]))
+
+
+def fov_contains(cam: Camera, uv) -> bool:
+    """m_cFieldOfView(28,28,W-56,H-56).contains(Point2f) CPinholeCamera.h:61."""
+    return 28 <= uv[0] < cam.width - 28 and 28 <= uv[1] < cam.height - 28
+
+
+def track_stage1(img_l, img_r, tri: Triangulator, T_w2l: np.ndarray, landmarks, motion_scaling: float):
+    """trackManual stage 1 (LEFT then RIGHT) :1404-1538 for a list of landmark dicts with keys
+    xyz_w (3,), last_desc_l, last_desc_r (32,), last_disparity (float), size (float).
+    Returns per-landmark dicts(status, stage, uv_l, uv_r, xyz, desc_l, desc_r)."""
+    p = tri.p
+    tri_scale = F32(1.0 + motion_scaling)                                     # :1363
+    res = []
+    for lm in landmarks:
+        xyz_l = (T_w2l @ np.append(np.asarray(lm["xyz_w"], np.float64), 1.0))[:3]   # :1404
+        uvl = projection_rounded(tri.cl.P, xyz_l)
+        uvr = projection_rounded(tri.cr.P, xyz_l)
+        size = F32(lm["size"])
+        half = F32(4) * size
+        search = tri_scale * F32(lm["last_disparity"])                      # :1413
+        if not (fov_contains(tri.cl, uvl) and fov_contains(tri.cr, uvr)):
+            res.append(dict(status=ST_TRK_OUT_OF_FOV, stage=0))
+            continue
+        out = None
+        # STAGE 1 LEFT :1419-1476
+        roi = (F32(uvl[0] - half), F32(uvl[1] - half))
+        keep, d = brief32(img_l[int(roi[1]):int(roi[1]) + int(8 * size + 1), int(roi[0]):int(roi[0]) + int(8 * size + 1)], [(half, half)])
+        st = ST_TRK_STAGE1_DIST
+        if len(keep) == 1 and p.cutoff_stage1 > hamming(np.asarray(lm["last_desc_l"], np.uint8), d[0]):
+            r = tri.triangulate_right(img_r, max(F32(0), F32(roi[0] - search)), roi[1], size,
+                                      (F32(roi[0] + half), F32(roi[1] + half)), d[0])
+            st = r["status"]
+            if st == ST_OK:
+                z = r["xyz"][2]
+                if tri.depth_min > z or tri.depth_max < z:
+                    st = ST_TRK_DEPTH
+                elif p.cutoff_stage1 < hamming(np.asarray(lm["last_desc_r"], np.uint8), r["desc"]):
+                    st = ST_TRK_TRI_DESC
+                else:
+                    out = dict(status=ST_OK, stage=1, uv_l=(uvl[0], uvl[1]), uv_r=r["uv"], xyz=r["xyz"],
+                               desc_l=d[0].copy(), desc_r=r["desc"])
+        if out is None:
+            # STAGE 1 RIGHT :1480-1538
+            roi = (F32(uvr[0] - half), F32(uvr[1] - half))
+            keep, d = brief32(img_r[int(roi[1]):int(roi[1]) + int(8 * size + 1), int(roi[0]):int(roi[0]) + int(8 * size + 1)], [(half, half)])
+            st = ST_TRK_STAGE1_DIST
+            if len(keep) == 1 and p.cutoff_stage1 > hamming(np.asarray(lm["last_desc_r"], np.uint8), d[0]):
+                r = tri.triangulate_left(img_l, search, roi[0], roi[1], size,
+                                         (F32(roi[0] + half), F32(roi[1] + half)), d[0])
+                st = r["status"]
+                if st == ST_OK:
+                    z = r["xyz"][2]
+                    if tri.depth_min > z or tri.depth_max < z:
+                        st = ST_TRK_DEPTH
+                    elif p.cutoff_stage1 < hamming(np.asarray(lm["last_desc_l"], np.uint8), r["desc"]):
+                        st = ST_TRK_TRI_DESC
+                    else:
+                        out = dict(status=ST_OK, stage=2, uv_l=r["uv"], uv_r=(uvr[0], uvr[1]), xyz=r["xyz"],
+                                   desc_l=r["desc"], desc_r=d[0].copy())
+        res.append(out if out is not None else dict(status=st, stage=0))
+    return res

@@ -1,0 +1,105 @@
+"""ctypes binding of libsvi_gpu.so (include/svi_gpu.h).  Fails loudly when the library is
+missing or cannot be loaded -- there is no Python/CPU fallback for any entry point."""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+LIB_PATH = pathlib.Path(__file__).resolve().parent / "libsvi_gpu.so"
+
+SVI_SUCCESS = 0
+SVI_ERR_INVALID, SVI_ERR_CUDA, SVI_ERR_CAPACITY, SVI_ERR_NO_DEVICE, SVI_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+
+# svi_status
+(SVI_OK, SVI_TRI_RANGE, SVI_TRI_NO_DESC, SVI_TRI_NO_MATCH, SVI_TRI_DISTANCE, SVI_TRI_ZERO_DISP, SVI_TRI_BAD_ROI,
+ SVI_TRK_DEPTH, SVI_TRK_STAGE1_DIST, SVI_TRK_TRI_DESC, SVI_TRK_OUT_OF_FOV) = range(11)
+
+EXPORTS = (
+    "svi_params_default", "svi_status_text", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
+    "svi_stereo_frames", "svi_stereo_frames_device", "svi_harris_response", "svi_detect", "svi_describe",
+    "svi_match_hamming", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
+    "svi_track_landmarks", "svi_set_profiling", "svi_stage_timings", "svi_config",
+)
+
+u8p, i32p, f32p, f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("P", C.c_double * 12)]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("quality_level", C.c_double), ("min_distance", C.c_double), ("harris_k", C.c_double),
+        ("min_disparity_px", C.c_double),
+        ("max_corners", C.c_int32), ("keypoint_size", C.c_float), ("search_range_px", C.c_float),
+        ("match_cutoff", C.c_float), ("cutoff_stage1", C.c_float), ("cutoff_stage2", C.c_float),
+        ("cutoff_stage3", C.c_float), ("cutoff_original", C.c_float),
+        ("max_candidates", C.c_int32), ("chunk_frames", C.c_int32), ("max_queries", C.c_int32),
+    ]
+
+
+class StereoResult(C.Structure):
+    _fields_ = [
+        ("capacity_per_frame", C.c_int32), ("n_keypoints", C.c_void_p), ("n_detected", C.c_void_p),
+        ("uv_left", C.c_void_p), ("uv_right", C.c_void_p), ("xyz_left", C.c_void_p),
+        ("desc_left", C.c_void_p), ("desc_right", C.c_void_p), ("distance", C.c_void_p),
+        ("match_index", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+class TriResult(C.Structure):
+    _fields_ = [("uv", C.c_void_p), ("xyz_left", C.c_void_p), ("desc", C.c_void_p), ("distance", C.c_void_p),
+                ("match_index", C.c_void_p), ("status", C.c_void_p)]
+
+
+class Landmarks(C.Structure):
+    _fields_ = [("xyz_world", C.c_void_p), ("last_desc_left", C.c_void_p), ("last_desc_right", C.c_void_p),
+                ("last_disparity", C.c_void_p), ("keypoint_size", C.c_void_p)]
+
+
+class TrackResult(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("stage", C.c_void_p), ("uv_left", C.c_void_p), ("uv_right", C.c_void_p),
+                ("xyz_left", C.c_void_p), ("desc_left", C.c_void_p), ("desc_right", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load libsvi_gpu.so once; raise with a build hint if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m svi_mapper_b200.build` "
+            "(svi_mapper_b200 has no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+    lib.svi_params_default.argtypes = [C.POINTER(Params)]
+    lib.svi_status_text.argtypes = [ci]
+    lib.svi_status_text.restype = C.c_char_p
+    lib.svi_create.argtypes = [C.POINTER(Camera), C.POINTER(Camera), C.POINTER(Params), ci, C.POINTER(vp)]
+    lib.svi_destroy.argtypes = [vp]
+    lib.svi_destroy.restype = None
+    lib.svi_last_error.argtypes = [vp]
+    lib.svi_last_error.restype = C.c_char_p
+    lib.svi_device_count.argtypes = []
+    lib.svi_stereo_frames.argtypes = [vp, vp, vp, sz, sz, ci, vp, C.POINTER(StereoResult)]
+    lib.svi_stereo_frames_device.argtypes = [vp, vp, vp, sz, sz, ci, vp, C.POINTER(StereoResult), vp]
+    lib.svi_harris_response.argtypes = [vp, vp, sz, vp]
+    lib.svi_detect.argtypes = [vp, vp, sz, sz, ci, vp, vp, vp]
+    lib.svi_describe.argtypes = [vp, vp, sz, vp, ci, vp, vp]
+    lib.svi_match_hamming.argtypes = [vp, vp, ci, vp, ci, vp, vp]
+    lib.svi_triangulate_right.argtypes = [vp, vp, sz, ci, vp, vp, vp, C.c_float, C.POINTER(TriResult)]
+    lib.svi_triangulate_left.argtypes = [vp, vp, sz, ci, vp, vp, vp, vp, C.c_float, C.POINTER(TriResult)]
+    lib.svi_point_in_left.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.svi_track_landmarks.argtypes = [vp, vp, vp, sz, vp, C.POINTER(Landmarks), ci, C.c_double, C.POINTER(TrackResult)]
+    lib.svi_set_profiling.argtypes = [vp, ci]
+    lib.svi_stage_timings.argtypes = [vp, C.POINTER(C.c_char_p), f64p, C.POINTER(C.c_int64), ci]
+    lib.svi_config.argtypes = [vp, i32p, i32p, i32p]
+    for name in EXPORTS:
+        getattr(lib, name)  # AttributeError here = header/library mismatch
+    _lib = lib
+    return lib

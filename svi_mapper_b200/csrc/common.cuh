@@ -1,0 +1,58 @@
+// common.cuh -- shared device helpers for libsvi_gpu (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svi {
+
+constexpr int kBriefBorder = 28;  // PATCH_SIZE/2 + KERNEL_SIZE/2 of OpenCV BRIEF
+constexpr int kBriefReach = 24;   // max |offset| of a test point
+constexpr int kDescWords = 8;     // 256 bit
+
+// Geometry + constants every kernel needs; lives in kernel parameter space.
+struct FrameGeom {
+    int W, H;           // image size
+    int img_pitch;      // bytes per image row (caller's layout)
+    size_t img_stride;  // bytes per frame
+    int resp_pitch;     // floats per response row
+    int box_pitch;      // uint16 per box-sum row
+};
+
+// CTriangulator members (src/core/CTriangulator.cpp:13-21)
+struct TriConst {
+    double f_inv, pu, pv, du_r_flipped, min_disp, depth_min, depth_max;
+    float width_left, width_right;
+    float match_cutoff;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);
+}
+
+// order-preserving float <-> uint mapping (for atomicMax and for sort keys)
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __host__ __forceinline__ uint32_t ordered_to_float_bits(uint32_t e) {
+    return (e & 0x80000000u) ? (e ^ 0x80000000u) : ~e;
+}
+
+// u8 -> float without the slow I2F path: 0x4B000000 | v is 8388608 + v exactly.
+__device__ __forceinline__ float u8_to_float(uint32_t v) {
+    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+}
+
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+
+// cvRound (lrint, half to even) and OpenCV BRIEF's (int)(v + 0.5)
+__device__ __forceinline__ int cv_round_f(float v) { return __float2int_rn(v); }
+__device__ __forceinline__ int brief_centre(float v) { return (int)((double)v + 0.5); }
+
+// std::round(float): half away from zero
+__device__ __forceinline__ float round_half_away(float v) { return roundf(v); }
+
+}  // namespace svi

@@ -1,0 +1,279 @@
+// harris.cuh -- detection front half: Harris response (bit-exact to cv::cornerHarris with
+// optimisations off), 9x9 box-sum images for BRIEF, threshold + 3x3 NMS candidate extraction.
+//
+// Replaces, for cv::GFTTDetector::create(1000, 0.01, 7.0, 7, true)->detect
+// (reference src/core/CFundamentalMatcher.cpp:18,101), the OpenCV calls cornerHarris
+// (Sobel x2, covariance products, 7x7 boxFilter), minMaxLoc, threshold(TOZERO), dilate 3x3 and
+// the candidate collection loop of goodFeaturesToTrack; arithmetic order from SURVEY.md App. A.
+#pragma once
+#include "common.cuh"
+
+namespace svi {
+
+constexpr int HT_W = 64, HT_H = 32, HT_THREADS = 256;
+constexpr int U8_P = HT_W + 8;       // u8 tile: 4-px halo (1 Sobel + 3 box; also the 9x9 box sum)
+constexpr int U8_ROWS = HT_H + 8;
+constexpr int COV_W = HT_W + 6;      // covariance products: 3-px halo
+constexpr int COV_ROWS = HT_H + 6;
+constexpr int COV_P = 73;            // odd pitches: row-per-lane accesses are bank-conflict free
+constexpr int HS_P = 65;
+constexpr int COV_SEG_ROWS = 13;     // 38 rows = 3 segments for the sliding Sobel
+constexpr int HS_SEG = 16;           // horizontal box sums: 16 outputs per work item
+
+struct __align__(16) HarrisSmem {
+    double hs[3][COV_ROWS][HS_P];     // horizontal 7-sums, fp64
+    float cov[3][COV_ROWS][COV_P];    // Dx*Dx, Dx*Dy, Dy*Dy (fp32); reused as the 9-sum rows (u16)
+    uint8_t tile[U8_ROWS][U8_P];
+    uint32_t red[HT_THREADS / 32];
+};
+static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS * HT_W, "h9 alias");
+
+__device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_t* __restrict__ img,
+                                             int pitch, int W, int H, int x0, int y0) {
+    for (int idx = threadIdx.x; idx < U8_ROWS * U8_P; idx += HT_THREADS) {
+        int ly = idx / U8_P, lx = idx - ly * U8_P;
+        int gy = reflect101(y0 - 4 + ly, H), gx = reflect101(x0 - 4 + lx, W);
+        tile[ly][lx] = __ldg(img + (size_t)gy * pitch + gx);
+    }
+}
+
+// 9x9 box sums (u16, max 81*255 = 20655) of the 64x32 tile from its u8 tile with 4-px halo.
+// S(y,x) = sum over [y-4,y+4]x[x-4,x+4]; equals the 4-corner integral-image expression of
+// OpenCV BRIEF's smoothedSum.  Values within 4 px of the image border are never sampled.
+__device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint16_t (*h9)[HT_W],
+                                               uint16_t* __restrict__ box, int box_pitch, int W, int H,
+                                               int x0, int y0) {
+    for (int item = threadIdx.x; item < U8_ROWS * (HT_W / 16); item += HT_THREADS) {
+        int r = item % U8_ROWS, c0 = (item / U8_ROWS) * 16;
+        const uint8_t* row = tile[r] + c0;
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s += row[i];
+        h9[r][c0] = (uint16_t)s;
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+            s += (int)row[j + 8] - (int)row[j - 1];
+            h9[r][c0 + j] = (uint16_t)s;
+        }
+    }
+    __syncthreads();
+    {
+        int x = threadIdx.x % HT_W, oy0 = (threadIdx.x / HT_W) * 8;
+        int gx = x0 + x;
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s += h9[oy0 + i][x];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k > 0) s += (int)h9[oy0 + k + 8][x] - (int)h9[oy0 + k - 1][x];
+            int gy = y0 + oy0 + k;
+            if (gx < W && gy < H) box[(size_t)gy * box_pitch + gx] = (uint16_t)s;
+        }
+    }
+}
+
+// K2: box-sum image of one plane per blockIdx.z (used for the RIGHT image, and for both images
+// on the per-query entry points).
+__global__ void __launch_bounds__(HT_THREADS)
+boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box) {
+    __shared__ uint8_t tile[U8_ROWS][U8_P];
+    __shared__ uint16_t h9[U8_ROWS][HT_W];
+    const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
+    load_tile_u8(tile, img + (size_t)f * g.img_stride, g.img_pitch, g.W, g.H, x0, y0);
+    __syncthreads();
+    box9_from_tile(tile, h9, box + (size_t)f * g.H * g.box_pitch, g.box_pitch, g.W, g.H, x0, y0);
+}
+
+// K1: Harris response + per-frame masked maximum + LEFT box-sum image, one 64x32 tile per CTA.
+//   Sobel:  r = p[x+1]-p[x-1];  Dx = (r[y-1]+r[y+1])*f1 + r[y]*f0
+//                           q = (p[x-1]*f1 + p[x]*f0) + p[x+1]*f1;  Dy = q[y+1]-q[y-1]
+//   every op rounded to fp32 on its own (explicit _rn intrinsics, never an FMA).
+//   Box 7x7 (A.2): products accumulated in fp64, REFLECT_101 on the PRODUCT planes, one rounding
+//   to fp32.  Harris (A.3): R = (a*c - b*b) - (k*(a+c))*(a+c) in fp32.
+__global__ void __launch_bounds__(HT_THREADS, 2)
+harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
+                  float f1, float f0, float kf, float* __restrict__ resp, uint16_t* __restrict__ box,
+                  uint32_t* __restrict__ frame_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HarrisSmem& sm = *reinterpret_cast<HarrisSmem*>(smem_raw);
+    const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
+    const int W = g.W, H = g.H, tid = threadIdx.x;
+    const uint8_t* im = img + (size_t)f * g.img_stride;
+
+    load_tile_u8(sm.tile, im, g.img_pitch, W, H, x0, y0);
+    __syncthreads();
+
+    // ---- covariance products on the (HT_H+6) x (HT_W+6) region, sliding down columns
+    if (tid < COV_W * 3) {
+        const int c = tid % COV_W, seg = tid / COV_W;
+        const int ly0 = seg * COV_SEG_ROWS, ly1 = min(ly0 + COV_SEG_ROWS, COV_ROWS);
+        const int gx = x0 - 3 + c, tx = c + 1;
+        if (gx >= 0 && gx < W) {
+            float r_m, r_c, q_m, q_c;
+            {
+                const uint8_t* t = sm.tile[ly0];  // tile row of cov row ly0-1 (tile row = cov row + 1)
+                float a = u8_to_float(t[tx - 1]), b = u8_to_float(t[tx]), d = u8_to_float(t[tx + 1]);
+                r_m = __fsub_rn(d, a);
+                q_m = __fadd_rn(__fadd_rn(__fmul_rn(a, f1), __fmul_rn(b, f0)), __fmul_rn(d, f1));
+                t = sm.tile[ly0 + 1];
+                a = u8_to_float(t[tx - 1]); b = u8_to_float(t[tx]); d = u8_to_float(t[tx + 1]);
+                r_c = __fsub_rn(d, a);
+                q_c = __fadd_rn(__fadd_rn(__fmul_rn(a, f1), __fmul_rn(b, f0)), __fmul_rn(d, f1));
+            }
+            for (int ly = ly0; ly < ly1; ++ly) {
+                const uint8_t* t = sm.tile[ly + 2];
+                float a = u8_to_float(t[tx - 1]), b = u8_to_float(t[tx]), d = u8_to_float(t[tx + 1]);
+                float r_p = __fsub_rn(d, a);
+                float q_p = __fadd_rn(__fadd_rn(__fmul_rn(a, f1), __fmul_rn(b, f0)), __fmul_rn(d, f1));
+                int gy = y0 - 3 + ly;
+                if (gy >= 0 && gy < H) {
+                    float dx = __fadd_rn(__fmul_rn(__fadd_rn(r_m, r_p), f1), __fmul_rn(r_c, f0));
+                    float dy = __fsub_rn(q_p, q_m);
+                    sm.cov[0][ly][c] = __fmul_rn(dx, dx);
+                    sm.cov[1][ly][c] = __fmul_rn(dx, dy);
+                    sm.cov[2][ly][c] = __fmul_rn(dy, dy);
+                }
+                r_m = r_c; r_c = r_p; q_m = q_c; q_c = q_p;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- REFLECT_101 of the product planes for halo positions outside the image (border tiles only)
+    if (x0 < 3 || y0 < 3 || x0 + HT_W + 3 > W || y0 + HT_H + 3 > H) {
+        for (int idx = tid; idx < COV_ROWS * COV_W; idx += HT_THREADS) {
+            int ly = idx / COV_W, c = idx - ly * COV_W;
+            int gy = y0 - 3 + ly, gx = x0 - 3 + c;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) continue;
+            int sy = reflect101(gy, H) - (y0 - 3), sx = reflect101(gx, W) - (x0 - 3);
+            bool ok = (gy >= -3 && gy < H + 3 && gx >= -3 && gx < W + 3 && sy >= 0 && sy < COV_ROWS && sx >= 0 && sx < COV_W);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) sm.cov[p][ly][c] = ok ? sm.cov[p][sy][sx] : 0.f;
+        }
+        __syncthreads();
+    }
+    // ---- horizontal 7-sums in fp64: one work item = (plane, 16-output segment, row)
+    for (int item = tid; item < 3 * (HT_W / HS_SEG) * COV_ROWS; item += HT_THREADS) {
+        const int r = item % COV_ROWS, sgm = (item / COV_ROWS) % (HT_W / HS_SEG), p = item / (COV_ROWS * (HT_W / HS_SEG));
+        const float* src = &sm.cov[p][r][sgm * HS_SEG];
+        double v[HS_SEG + 6];
+#pragma unroll
+        for (int i = 0; i < HS_SEG + 6; ++i) v[i] = (double)src[i];
+        double s = v[0];
+#pragma unroll
+        for (int i = 1; i < 7; ++i) s = __dadd_rn(s, v[i]);
+        double* dst = &sm.hs[p][r][sgm * HS_SEG];
+        dst[0] = s;
+#pragma unroll
+        for (int j = 1; j < HS_SEG; ++j) {
+            s = __dadd_rn(s, __dsub_rn(v[j + 6], v[j - 1]));
+            dst[j] = s;
+        }
+    }
+    __syncthreads();
+    // ---- vertical 7-sums + Harris: thread = (column, 8-row segment)
+    uint32_t local_max = 0u;
+    {
+        const int x = tid % HT_W, oy0 = (tid / HT_W) * 8;
+        const int gx = x0 + x;
+        double sa = sm.hs[0][oy0][x], sb = sm.hs[1][oy0][x], sc = sm.hs[2][oy0][x];
+#pragma unroll
+        for (int i = 1; i < 7; ++i) {
+            sa = __dadd_rn(sa, sm.hs[0][oy0 + i][x]);
+            sb = __dadd_rn(sb, sm.hs[1][oy0 + i][x]);
+            sc = __dadd_rn(sc, sm.hs[2][oy0 + i][x]);
+        }
+        float* rrow = resp + ((size_t)f * H) * g.resp_pitch;
+        const uint8_t* mrow = mask ? mask + (size_t)f * g.img_stride : nullptr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k > 0) {
+                sa = __dadd_rn(sa, __dsub_rn(sm.hs[0][oy0 + k + 6][x], sm.hs[0][oy0 + k - 1][x]));
+                sb = __dadd_rn(sb, __dsub_rn(sm.hs[1][oy0 + k + 6][x], sm.hs[1][oy0 + k - 1][x]));
+                sc = __dadd_rn(sc, __dsub_rn(sm.hs[2][oy0 + k + 6][x], sm.hs[2][oy0 + k - 1][x]));
+            }
+            const int gy = y0 + oy0 + k;
+            if (gx < W && gy < H) {
+                float a = __double2float_rn(sa), b = __double2float_rn(sb), c = __double2float_rn(sc);
+                float det = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b));
+                float tr = __fadd_rn(a, c);
+                float R = __fsub_rn(det, __fmul_rn(__fmul_rn(kf, tr), tr));
+                rrow[(size_t)gy * g.resp_pitch + gx] = R;
+                if (!mrow || mrow[(size_t)gy * g.img_pitch + gx]) local_max = max(local_max, float_to_ordered(R));
+            }
+        }
+    }
+    local_max = warp_max_u32(local_max);
+    if ((tid & 31) == 0) sm.red[tid >> 5] = local_max;
+    __syncthreads();   // also: cov no longer read -> may be reused for the 9-sum rows
+    if (tid == 0) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < HT_THREADS / 32; ++i) m = max(m, sm.red[i]);
+        if (m) atomicMax(frame_max + f, m);
+    }
+    if (box) {
+        box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[HT_W]>(&sm.cov[0][0][0]),
+                       box + (size_t)f * H * g.box_pitch, g.box_pitch, W, H, x0, y0);
+    }
+}
+
+// Threshold as cv::goodFeaturesToTrack computes it: minMaxLoc gives a double, threshold()
+// converts (double)max * qualityLevel to float for the 32F image.
+__device__ __forceinline__ float gftt_threshold(uint32_t ordered_max, double quality) {
+    if (ordered_max == 0u) return 0.f;  // empty mask: minMaxLoc leaves maxVal = 0
+    return (float)((double)__uint_as_float(ordered_to_float_bits(ordered_max)) * quality);
+}
+
+// K3: threshold(TOZERO) + 3x3 dilate equality + mask + 1-px image border -> candidate keys.
+// key = ordered(R) << 32 | y << 16 | x ; descending key order == cv's greaterThanPtr order
+// (value desc, then larger address first).
+constexpr int NMS_TW = 32, NMS_TH = 8;
+__global__ void __launch_bounds__(NMS_TW * NMS_TH)
+nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict__ mask, FrameGeom g,
+                      double quality, const uint32_t* __restrict__ frame_max,
+                      unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
+    __shared__ float t[NMS_TH + 2][NMS_TW + 2];
+    const int f = blockIdx.z, x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
+    const int tid = threadIdx.y * NMS_TW + threadIdx.x;
+    const float thr = gftt_threshold(frame_max[f], quality);
+    const float* R = resp + (size_t)f * g.H * g.resp_pitch;
+    for (int idx = tid; idx < (NMS_TH + 2) * (NMS_TW + 2); idx += NMS_TW * NMS_TH) {
+        int ly = idx / (NMS_TW + 2), lx = idx - ly * (NMS_TW + 2);
+        int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+        float v = -INFINITY;  // dilate ignores pixels outside the image
+        if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) {
+            v = R[(size_t)gy * g.resp_pitch + gx];
+            v = (v > thr) ? v : 0.f;
+        }
+        t[ly][lx] = v;
+    }
+    __syncthreads();
+    const int gx = x0 + threadIdx.x, gy = y0 + threadIdx.y;
+    bool is_cand = false;
+    float v = 0.f;
+    if (gx >= 1 && gx < g.W - 1 && gy >= 1 && gy < g.H - 1) {
+        v = t[threadIdx.y + 1][threadIdx.x + 1];
+        if (v != 0.f) {
+            float m = v;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, t[threadIdx.y + dy][threadIdx.x + dx]);
+            is_cand = (v == m) && (!mask || mask[(size_t)f * g.img_stride + (size_t)gy * g.img_pitch + gx]);
+        }
+    }
+    unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_cand);
+    if (ballot) {
+        int lane = tid & 31, leader = __ffs(ballot) - 1, base = 0;
+        if (lane == leader) base = atomicAdd(cand_count + f, __popc(ballot));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (is_cand) {
+            int pos = base + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < cand_cap)
+                cand[(size_t)f * cand_cap + pos] =
+                    ((unsigned long long)float_to_ordered(v) << 32) | ((unsigned)gy << 16) | (unsigned)gx;
+        }
+    }
+}
+
+}  // namespace svi

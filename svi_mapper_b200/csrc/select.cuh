@@ -1,0 +1,211 @@
+// select.cuh -- corner selection of cv::goodFeaturesToTrack after candidate collection:
+// sort by (response desc, address desc), greedy minimum-distance filter, cut at maxCorners,
+// then BRIEF's 28-px image-border filter (KeyPointsFilter::runByImageBorder) that
+// BriefDescriptorExtractor::compute applies in place (reference
+// src/core/CFundamentalMatcher.cpp:101,106).  One CTA per frame.
+//
+// The sequential greedy loop is evaluated in its exact parallel form:
+// with candidates in priority order and hp(i) = higher-priority candidates closer than
+// minDistance, i is REJECTED once some member of hp(i) is ACCEPTED and ACCEPTED once all of
+// hp(i) are REJECTED; iterate to the fixed point.  Decisions are monotone, so reading a
+// neighbour's state while another thread updates it is benign.
+#pragma once
+#include "common.cuh"
+
+namespace svi {
+
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_SMEM_KEYS = 16384;   // keys that fit the shared-memory fast path
+constexpr int SEL_SMEM_CELLS = 8192;
+constexpr uint32_t SEL_NIL = 0xFFFFFFFFu;
+
+struct SelectParams {
+    int W, H;
+    int cand_cap;        // per-frame stride of `cand` (power of two)
+    int max_corners;
+    int cell;            // grid cell edge >= ceil(minDistance)
+    int gw, gh;          // grid size
+    double min_dist_sq;  // minDistance^2 (cv compares dx*dx+dy*dy < minDistance*minDistance)
+    int filter;          // 0 when minDistance < 1 (cv skips the distance filter)
+};
+
+__device__ __forceinline__ void key_xy(unsigned long long k, int& x, int& y) {
+    x = (int)(k & 0xFFFFu);
+    y = (int)((k >> 16) & 0xFFFFu);
+}
+
+// kSmem: keys/lists in shared memory (n <= SEL_SMEM_KEYS, cells <= SEL_SMEM_CELLS); otherwise
+// they live in the per-frame global scratch (stress-size frames).
+template <bool kSmem>
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
+                      SelectParams sp, uint32_t* __restrict__ g_head, uint32_t* __restrict__ g_next,
+                      uint8_t* __restrict__ g_state, ushort2* __restrict__ det_xy,
+                      int* __restrict__ n_detected, ushort2* __restrict__ kp_xy,
+                      int* __restrict__ n_keypoints, int* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    __shared__ unsigned long long wsum[SEL_THREADS / 32];
+    __shared__ uint32_t block_total;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    int n = cand_count[f];
+    if (n > sp.cand_cap) {
+        if (tid == 0) atomicExch(overflow, 1);
+        n = sp.cand_cap;
+    }
+    if (kSmem && n > SEL_SMEM_KEYS) {  // host picks the global variant when this can happen
+        if (tid == 0) atomicExch(overflow, 2);
+        n = SEL_SMEM_KEYS;
+    }
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    const int ncells = sp.gw * sp.gh;
+
+    // shared layout: keys[16384] u64 | next16[16384] u16 | state[16384] u8 | head[8192] u32
+    unsigned long long* gk = cand + (size_t)f * sp.cand_cap;
+    unsigned long long* keys = kSmem ? reinterpret_cast<unsigned long long*>(sel_smem) : gk;
+    uint16_t* next16 = reinterpret_cast<uint16_t*>(sel_smem + sizeof(unsigned long long) * SEL_SMEM_KEYS);
+    uint8_t* state = kSmem ? reinterpret_cast<uint8_t*>(next16 + SEL_SMEM_KEYS) : g_state + (size_t)f * sp.cand_cap;
+    uint32_t* head = kSmem ? reinterpret_cast<uint32_t*>(sel_smem + 11 * SEL_SMEM_KEYS)
+                           : g_head + (size_t)f * ncells;
+    uint32_t* next = kSmem ? nullptr : g_next + (size_t)f * sp.cand_cap;
+    if (kSmem) {
+        for (int i = tid; i < n_pad; i += SEL_THREADS) keys[i] = (i < n) ? gk[i] : 0ull;
+    } else {
+        for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
+    }
+    __syncthreads();
+
+    // ---- bitonic sort, descending
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (n_pad >> 1); t += SEL_THREADS) {
+                int i = 2 * t - (t & (j - 1));
+                int l = i + j;
+                unsigned long long a = keys[i], b = keys[l];
+                bool desc = ((i & k) == 0);
+                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- grid cell lists (linked through `next`)
+    for (int c = tid; c < ncells; c += SEL_THREADS) head[c] = SEL_NIL;
+    for (int i = tid; i < n; i += SEL_THREADS) state[i] = 0;
+    __syncthreads();
+    if (sp.filter) {
+        for (int i = tid; i < n; i += SEL_THREADS) {
+            int x, y;
+            key_xy(keys[i], x, y);
+            int c = (y / sp.cell) * sp.gw + (x / sp.cell);
+            uint32_t prev = atomicExch(&head[c], (uint32_t)i);
+            if (kSmem) next16[i] = (uint16_t)(prev == SEL_NIL ? 0xFFFFu : prev);
+            else next[i] = prev;
+        }
+        __syncthreads();
+        // ---- peel to the fixed point
+        for (;;) {
+            int changed = 0;
+            for (int i = tid; i < n; i += SEL_THREADS) {
+                if (state[i] != 0) continue;
+                int x, y;
+                key_xy(keys[i], x, y);
+                const int cx = x / sp.cell, cy = y / sp.cell;
+                bool any_acc = false, any_und = false;
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1); ++yy)
+                    for (int xx = max(cx - 1, 0); xx <= min(cx + 1, sp.gw - 1); ++xx) {
+                        uint32_t j = head[yy * sp.gw + xx];
+                        while (j != SEL_NIL) {
+                            if ((int)j < i) {
+                                int px, py;
+                                key_xy(keys[j], px, py);
+                                int dx = x - px, dy = y - py;
+                                if ((double)(dx * dx + dy * dy) < sp.min_dist_sq) {
+                                    uint8_t s = state[j];
+                                    any_acc |= (s == 1);
+                                    any_und |= (s == 0);
+                                }
+                            }
+                            if (kSmem) { uint16_t nx = next16[j]; j = (nx == 0xFFFFu) ? SEL_NIL : nx; }
+                            else j = next[j];
+                        }
+                    }
+                if (any_acc) { state[i] = 2; changed = 1; }
+                else if (!any_und) { state[i] = 1; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+    } else {
+        for (int i = tid; i < n; i += SEL_THREADS) state[i] = 1;
+        __syncthreads();
+    }
+
+    // ---- ranks among accepted corners and among those passing BRIEF's border filter
+    const int per = (n + SEL_THREADS - 1) / SEL_THREADS;
+    const int i0 = tid * per, i1 = min(i0 + per, n);
+    uint32_t acc_cnt = 0, kp_cnt = 0;
+    for (int i = i0; i < i1; ++i) {
+        if (state[i] == 1) {
+            int x, y;
+            key_xy(keys[i], x, y);
+            ++acc_cnt;
+            kp_cnt += (x >= kBriefBorder && x < sp.W - kBriefBorder && y >= kBriefBorder && y < sp.H - kBriefBorder);
+        }
+    }
+    // block exclusive scan of (acc_cnt, kp_cnt) packed as 2 x 32 bit
+    unsigned long long v = ((unsigned long long)kp_cnt << 32) | acc_cnt, incl = v;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        wsum[lane] = wi - w;  // exclusive
+        if (lane == 31) {
+            uint32_t tot_acc = (uint32_t)(wi & 0xFFFFFFFFu);
+            block_total = tot_acc;
+        }
+    }
+    __syncthreads();
+    unsigned long long excl = wsum[wid] + incl - v;
+    uint32_t acc_rank = (uint32_t)(excl & 0xFFFFFFFFu), kp_rank = (uint32_t)(excl >> 32);
+    ushort2* det = det_xy + (size_t)f * sp.max_corners;
+    ushort2* kp = kp_xy + (size_t)f * sp.max_corners;
+    for (int i = i0; i < i1; ++i) {
+        if (state[i] == 1) {
+            if ((int)acc_rank >= sp.max_corners) break;
+            int x, y;
+            key_xy(keys[i], x, y);
+            det[acc_rank] = make_ushort2((unsigned short)x, (unsigned short)y);
+            ++acc_rank;
+            if (x >= kBriefBorder && x < sp.W - kBriefBorder && y >= kBriefBorder && y < sp.H - kBriefBorder) {
+                kp[kp_rank] = make_ushort2((unsigned short)x, (unsigned short)y);
+                ++kp_rank;
+            }
+        }
+    }
+    // the key-point count is the kp_rank reached by the element with acc_rank == max_corners-1
+    // (or the last accepted one): the thread that writes the last detected corner publishes it.
+    {
+        uint32_t a0 = (uint32_t)(excl & 0xFFFFFFFFu);
+        uint32_t total = block_total;
+        uint32_t limit = min(total, (uint32_t)sp.max_corners);
+        if (limit == 0) {
+            if (tid == 0) { n_detected[f] = 0; n_keypoints[f] = 0; }
+        } else if (a0 < limit && a0 + acc_cnt >= limit && acc_cnt > 0) {
+            n_detected[f] = (int)limit;
+            n_keypoints[f] = (int)kp_rank;  // kp_rank after this thread's emission loop
+        }
+    }
+}
+
+}  // namespace svi

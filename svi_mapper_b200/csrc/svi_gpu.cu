@@ -1,0 +1,815 @@
+// svi_gpu.cu -- libsvi_gpu.so: context, scratch management, kernel pipeline and the C-ABI of
+// include/svi_gpu.h.  sm_100a only; there is no CPU fallback anywhere in this file.
+//
+// Execution model.  A batch of independent stereo pairs is cut into chunks of `chunk_frames`
+// frames; chunk c runs on lane c % n_lanes.  A lane is one CUDA stream plus the scratch of one
+// chunk (response plane, two box-sum planes, candidate lists), sized so that the scratch of all
+// lanes stays resident in the B200's 126 MB L2 between the producing and the consuming kernel;
+// different lanes overlap each other's copies, wide kernels (Harris, match) and the
+// one-CTA-per-frame selection kernel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/svi_gpu.h"
+#include "brief_match.cuh"
+#include "harris.cuh"
+#include "select.cuh"
+
+using namespace svi;
+
+namespace {
+
+constexpr int kMaxLanes = 4;
+constexpr int kStages = 5;
+const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "nms_candidates", "select_corners", "stereo_match"};
+
+std::string g_create_error;
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    float* resp = nullptr;
+    uint16_t* box_l = nullptr;
+    uint16_t* box_r = nullptr;
+    uint32_t* frame_max = nullptr;
+    int* cand_count = nullptr;
+    unsigned long long* cand = nullptr;
+    ushort2* det_xy = nullptr;
+    ushort2* kp_xy = nullptr;
+    int* n_det = nullptr;
+    int* n_kp = nullptr;
+    uint32_t* g_head = nullptr;
+    uint32_t* g_next = nullptr;
+    uint8_t* g_state = nullptr;
+    // staging for the host-buffer entry points
+    uint8_t* img_l = nullptr;
+    uint8_t* img_r = nullptr;
+    uint8_t* mask = nullptr;
+    StereoOutDev out{};
+    std::vector<cudaEvent_t> ev;  // stage boundary events (profiling)
+    size_t ev_used = 0;
+};
+
+}  // namespace
+
+struct svi_ctx {
+    int device = 0;
+    svi_camera cam_l{}, cam_r{};
+    svi_params p{};
+    int W = 0, H = 0;
+    int dev_pitch = 0;   // bytes per row of the staged images
+    int resp_pitch = 0, box_pitch = 0;
+    int chunk = 0, n_lanes = 0;
+    int cand_cap = 0;
+    bool select_smem = true;
+    SelectParams sel{};
+    TriConst tc{};
+    float f1 = 0, f0 = 0, kf = 0;
+    Lane lanes[kMaxLanes];
+    int* d_overflow = nullptr;
+    cudaEvent_t fork = nullptr;
+    // per-query arena
+    unsigned char* arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    bool profiling = false;
+    double stage_ms[kStages] = {0, 0, 0, 0, 0};
+    long stage_launches[kStages] = {0, 0, 0, 0, 0};
+    std::string err;
+};
+
+namespace {
+
+int fail(svi_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, SVI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+FrameGeom make_geom(const svi_ctx* c, int img_pitch, size_t img_stride) {
+    FrameGeom g;
+    g.W = c->W; g.H = c->H;
+    g.img_pitch = img_pitch;
+    g.img_stride = img_stride;
+    g.resp_pitch = c->resp_pitch;
+    g.box_pitch = c->box_pitch;
+    return g;
+}
+
+void* arena_alloc(svi_ctx* c, size_t bytes) {
+    size_t off = (c->arena_used + 255) & ~size_t(255);
+    if (off + bytes > c->arena_bytes) return nullptr;
+    c->arena_used = off + bytes;
+    return c->arena + off;
+}
+
+cudaEvent_t lane_event(Lane& l) {
+    if (l.ev_used == l.ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        l.ev.push_back(e);
+    }
+    return l.ev[l.ev_used++];
+}
+
+void mark(svi_ctx* c, Lane& l) {
+    if (c->profiling) cudaEventRecord(lane_event(l), l.stream);
+}
+
+// Fold the recorded stage events into per-stage totals (call after the lanes are idle).
+void collect_timings(svi_ctx* c) {
+    for (int li = 0; li < c->n_lanes; ++li) {
+        Lane& l = c->lanes[li];
+        for (size_t i = 0; i + kStages < l.ev_used; i += kStages + 1) {
+            for (int s = 0; s < kStages; ++s) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, l.ev[i + s], l.ev[i + s + 1]) == cudaSuccess) {
+                    c->stage_ms[s] += ms;
+                    c->stage_launches[s] += 1;
+                }
+            }
+        }
+        l.ev_used = 0;
+    }
+}
+
+// The five kernels of the new-landmark path for `nf` frames on one lane.
+int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_right, const uint8_t* d_mask,
+                 const FrameGeom& g, int nf, const StereoOutDev& out, int out_frame0, int* n_kp, int* n_det) {
+    cudaStream_t s = l.stream;
+    CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
+    CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
+    const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, nf);
+    mark(ctx, l);
+    harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf,
+                                                                    l.resp, l.box_l, l.frame_max);
+    mark(ctx, l);
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r);
+    mark(ctx, l);
+    const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_TH - 1) / NMS_TH, nf);
+    nms_candidates_kernel<<<ngrid, dim3(NMS_TW, NMS_TH), 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
+                                                                 l.cand, l.cand_count, ctx->cand_cap);
+    mark(ctx, l);
+    if (ctx->select_smem) {
+        select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(
+            l.cand, l.cand_count, ctx->sel, nullptr, nullptr, nullptr, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow);
+    } else {
+        select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(
+            l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow);
+    }
+    mark(ctx, l);
+    const dim3 mgrid((ctx->p.max_corners + MATCH_WARPS - 1) / MATCH_WARPS, nf);
+    stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, g, ctx->tc, ctx->p.keypoint_size,
+                                                                    ctx->p.search_range_px, l.kp_xy, n_kp,
+                                                                    ctx->p.max_corners, out, out_frame0);
+    mark(ctx, l);
+    CK(cudaGetLastError());
+    return SVI_SUCCESS;
+}
+
+int check_overflow(svi_ctx* ctx) {
+    int h = 0;
+    CK(cudaMemcpy(&h, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) {
+        CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
+        return fail(ctx, SVI_ERR_CAPACITY,
+                    "NMS candidate list overflow: raise svi_params.max_candidates (a frame produced more than " +
+                        std::to_string(ctx->cand_cap) + " candidates)");
+    }
+    return SVI_SUCCESS;
+}
+
+int sync_lanes(svi_ctx* ctx) {
+    for (int i = 0; i < ctx->n_lanes; ++i) CK(cudaStreamSynchronize(ctx->lanes[i].stream));
+    if (ctx->profiling) collect_timings(ctx);
+    return SVI_SUCCESS;
+}
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)); }
+
+}  // namespace
+
+// ---- per-query entry points: one image (or pair) staged in lane 0, queries in the arena ----
+namespace {
+int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, cudaStream_t s) {
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
+    CK(cudaMemcpy2DAsync(d_img, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
+    const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_img, g, d_box);
+    CK(cudaGetLastError());
+    return SVI_SUCCESS;
+}
+template <typename T>
+int upload(svi_ctx* ctx, T** d, const T* h, size_t count, cudaStream_t s) {
+    *d = static_cast<T*>(arena_alloc(ctx, count * sizeof(T)));
+    if (!*d) return fail(ctx, SVI_ERR_CAPACITY, "query arena exhausted: raise svi_params.max_queries");
+    if (h) CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return SVI_SUCCESS;
+}
+#define UP(d, h, count)                                        \
+    do {                                                       \
+        int rc_ = upload(ctx, &(d), (h), (count), s);          \
+        if (rc_ != SVI_SUCCESS) return rc_;                    \
+    } while (0)
+}  // namespace
+
+
+namespace {
+int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_t pitch, int n, const float* search_range,
+                       const float* top_left, const float* uv_ref, const uint8_t* desc_ref, float size, svi_tri_result* out) {
+    if (!img || !top_left || !uv_ref || !desc_ref || !out || n < 0 || (int)pitch < ctx->W || (left_search && !search_range))
+        return fail(ctx, SVI_ERR_INVALID, "svi_triangulate: bad argument");
+    if (!out->uv || !out->xyz_left || !out->desc || !out->distance || !out->match_index || !out->status)
+        return fail(ctx, SVI_ERR_INVALID, "svi_triangulate: null output array");
+    if (n > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_triangulate: n > max_queries");
+    if (n == 0) return SVI_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    cudaStream_t s = l.stream;
+    ctx->arena_used = 0;
+    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, s);
+    if (rc != SVI_SUCCESS) return rc;
+    float* d_range = nullptr; float* d_tl; float* d_uv; uint8_t* d_desc;
+    TriOutDev o;
+    if (left_search) UP(d_range, search_range, (size_t)n);
+    UP(d_tl, top_left, (size_t)n * 2);
+    UP(d_uv, uv_ref, (size_t)n * 2);
+    UP(d_desc, desc_ref, (size_t)n * 32);
+    UP(o.uv, (const float*)nullptr, (size_t)n * 2);
+    UP(o.xyz, (const double*)nullptr, (size_t)n * 3);
+    UP(o.desc, (const uint8_t*)nullptr, (size_t)n * 32);
+    UP(o.dist, (const int*)nullptr, (size_t)n);
+    UP(o.idx, (const int*)nullptr, (size_t)n);
+    UP(o.status, (const uint8_t*)nullptr, (size_t)n);
+    CK(cudaMemsetAsync(o.uv, 0, sizeof(float) * 2 * n, s));
+    CK(cudaMemsetAsync(o.xyz, 0, sizeof(double) * 3 * n, s));
+    CK(cudaMemsetAsync(o.desc, 0, (size_t)32 * n, s));
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
+    const int blocks = (n + MATCH_WARPS - 1) / MATCH_WARPS;
+    if (left_search)
+        triangulate_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, g, ctx->tc, n, d_range, d_tl, d_uv, d_desc, size, o);
+    else
+        triangulate_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, g, ctx->tc, n, nullptr, d_tl, d_uv, d_desc, size, o);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out->uv, o.uv, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->xyz_left, o.xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->desc, o.desc, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->distance, o.dist, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->match_index, o.idx, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+}  // namespace
+
+
+extern "C" {
+
+int svi_params_default(svi_params* p) {
+    if (!p) return SVI_ERR_INVALID;
+    std::memset(p, 0, sizeof(*p));
+    p->quality_level = 0.01;
+    p->min_distance = 7.0;
+    p->harris_k = 0.04;
+    p->min_disparity_px = 0.01;
+    p->max_corners = 1000;
+    p->keypoint_size = 7.0f;
+    p->search_range_px = 60.0f;
+    p->match_cutoff = 100.0f;
+    p->cutoff_stage1 = 25.0f;
+    p->cutoff_stage2 = 50.0f;
+    p->cutoff_stage3 = 50.0f;
+    p->cutoff_original = 100.0f;
+    p->max_candidates = 16384;
+    p->chunk_frames = 0;
+    p->max_queries = 16384;
+    return SVI_SUCCESS;
+}
+
+const char* svi_status_text(int status) {
+    switch (status) {
+        case SVI_OK: return "ok";
+        case SVI_TRI_RANGE: return "<CTriangulator>(getPointTriangulatedInRIGHT) insufficient search range";
+        case SVI_TRI_NO_DESC: return "<CTriangulator>(getPointTriangulatedInRIGHT) could not compute descriptors";
+        case SVI_TRI_NO_MATCH: return "<CTriangulator>(getPointTriangulatedInRIGHT) no match found";
+        case SVI_TRI_DISTANCE: return "<CTriangulator>(getPointTriangulatedInRIGHT) matching distance";
+        case SVI_TRI_ZERO_DISP: return "<CTriangulator>(getPointInLEFT) zero disparity";
+        case SVI_TRI_BAD_ROI: return "search region outside image";
+        case SVI_TRK_DEPTH: return "invalid depth";
+        case SVI_TRK_STAGE1_DIST: return "insufficient matching distance";
+        case SVI_TRK_TRI_DESC: return "triangulation descriptor mismatch";
+        case SVI_TRK_OUT_OF_FOV: return "out of tracking range";
+        default: return "unknown status";
+    }
+}
+
+int svi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* svi_last_error(const svi_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void svi_destroy(svi_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < kMaxLanes; ++i) {
+        Lane& l = ctx->lanes[i];
+        if (l.stream) cudaStreamSynchronize(l.stream);
+        void* ptrs[] = {l.resp, l.box_l, l.box_r, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
+                        l.g_head, l.g_next, l.g_state, l.img_l, l.img_r, l.mask, l.out.uv_l, l.out.uv_r, l.out.xyz,
+                        l.out.desc_l, l.out.desc_r, l.out.dist, l.out.idx, l.out.status};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        for (cudaEvent_t e : l.ev) cudaEventDestroy(e);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    if (ctx->d_overflow) cudaFree(ctx->d_overflow);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
+    delete ctx;
+}
+
+int svi_create(const svi_camera* left, const svi_camera* right, const svi_params* params, int device, svi_ctx** out) {
+    svi_ctx* ctx = nullptr;
+    if (!left || !right || !out) return fail(nullptr, SVI_ERR_INVALID, "svi_create: null argument");
+    *out = nullptr;
+    int ndev = svi_device_count();
+    if (ndev <= 0) return fail(nullptr, SVI_ERR_NO_DEVICE, "svi_create: no CUDA device (libsvi_gpu has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, SVI_ERR_INVALID, "svi_create: bad device index");
+    if (left->width != right->width || left->height != right->height)
+        return fail(nullptr, SVI_ERR_INVALID, "svi_create: left/right image sizes differ");
+    if (left->width < 64 || left->height < 64 || left->width > 65535 || left->height > 65535)
+        return fail(nullptr, SVI_ERR_INVALID, "svi_create: image size must be within [64, 65535]");
+    svi_params p;
+    if (params) p = *params; else svi_params_default(&p);
+    if (p.max_corners <= 0 || p.max_corners > 65535) return fail(nullptr, SVI_ERR_INVALID, "svi_create: max_corners must be in [1, 65535]");
+    if (p.max_candidates < 1024) p.max_candidates = 1024;
+    if (p.max_queries < 1) p.max_queries = 1;
+    {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) return fail(nullptr, SVI_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    }
+    ctx = new svi_ctx();
+#undef CK
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            svi_destroy(ctx);                                                                    \
+            return fail(nullptr, SVI_ERR_CUDA, m_);                                              \
+        }                                                                                        \
+    } while (0)
+    ctx->device = device;
+    ctx->cam_l = *left;
+    ctx->cam_r = *right;
+    ctx->p = p;
+    ctx->W = (int)left->width;
+    ctx->H = (int)left->height;
+    ctx->dev_pitch = align_up(ctx->W, 16);
+    ctx->resp_pitch = align_up(ctx->W, 32);
+    ctx->box_pitch = align_up(ctx->W, 64);
+    const char* env_chunk = std::getenv("SVI_CHUNK_FRAMES");
+    const char* env_lanes = std::getenv("SVI_LANES");
+    ctx->chunk = p.chunk_frames > 0 ? p.chunk_frames : (env_chunk ? std::atoi(env_chunk) : 16);
+    ctx->chunk = std::max(1, std::min(ctx->chunk, 4096));
+    ctx->n_lanes = env_lanes ? std::max(1, std::min(std::atoi(env_lanes), kMaxLanes)) : 3;
+    ctx->profiling = std::getenv("SVI_PROFILE") != nullptr;
+    int cap = 1024;
+    while (cap < p.max_candidates) cap <<= 1;
+    ctx->cand_cap = cap;
+
+    // cornerHarris scale: 1 / ((1 << (ksize-1)) * blockSize) / 255 for 8-bit input (ksize 3, block 7)
+    const double scale = 1.0 / (4.0 * 7.0 * 255.0);
+    ctx->f1 = (float)scale;
+    ctx->f0 = (float)(2.0 * scale);
+    ctx->kf = (float)p.harris_k;
+
+    // goodFeaturesToTrack's bucket grid; cell >= minDistance keeps the 3x3 neighbourhood sufficient
+    SelectParams& sp = ctx->sel;
+    sp.W = ctx->W; sp.H = ctx->H;
+    sp.cand_cap = cap;
+    sp.max_corners = p.max_corners;
+    sp.filter = p.min_distance >= 1.0 ? 1 : 0;
+    sp.min_dist_sq = p.min_distance * p.min_distance;
+    int cell = std::max(1, (int)std::ceil(p.min_distance));
+    while (((ctx->W + cell - 1) / cell) * ((ctx->H + cell - 1) / cell) > SEL_SMEM_CELLS && cap <= SEL_SMEM_KEYS && cell < 64) ++cell;
+    sp.cell = cell;
+    sp.gw = (ctx->W + cell - 1) / cell;
+    sp.gh = (ctx->H + cell - 1) / cell;
+    ctx->select_smem = (cap <= SEL_SMEM_KEYS) && (sp.gw * sp.gh <= SEL_SMEM_CELLS);
+
+    // CTriangulator constants (src/core/CTriangulator.cpp:13-21)
+    TriConst& tc = ctx->tc;
+    const double f = left->P[0];
+    tc.f_inv = 1.0 / f;
+    tc.pu = left->P[2];
+    tc.pv = left->P[6];
+    tc.du_r_flipped = -right->P[3];
+    tc.min_disp = p.min_disparity_px;
+    tc.depth_min = tc.du_r_flipped / (double)left->width;
+    tc.depth_max = tc.du_r_flipped / p.min_disparity_px;
+    tc.width_left = (float)left->width;
+    tc.width_right = (float)right->width;
+    tc.match_cutoff = p.match_cutoff;
+
+    CK(cudaFuncSetAttribute(harris_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HarrisSmem)));
+    CK(cudaFuncSetAttribute(select_corners_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * SEL_SMEM_KEYS));
+    CK(cudaFuncSetAttribute(stereo_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(triangulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(triangulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(track_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+
+    const size_t C = (size_t)ctx->chunk, HH = (size_t)ctx->H, MC = (size_t)p.max_corners;
+    for (int i = 0; i < ctx->n_lanes; ++i) {
+        Lane& l = ctx->lanes[i];
+        CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        CK(dmalloc(&l.resp, C * HH * ctx->resp_pitch));
+        CK(dmalloc(&l.box_l, C * HH * ctx->box_pitch));
+        CK(dmalloc(&l.box_r, C * HH * ctx->box_pitch));
+        CK(dmalloc(&l.frame_max, C));
+        CK(dmalloc(&l.cand_count, C));
+        CK(dmalloc(&l.cand, C * cap));
+        CK(dmalloc(&l.det_xy, C * MC));
+        CK(dmalloc(&l.kp_xy, C * MC));
+        CK(dmalloc(&l.n_det, C));
+        CK(dmalloc(&l.n_kp, C));
+        if (!ctx->select_smem) {
+            CK(dmalloc(&l.g_head, C * sp.gw * sp.gh));
+            CK(dmalloc(&l.g_next, C * cap));
+            CK(dmalloc(&l.g_state, C * cap));
+        }
+        CK(dmalloc(&l.img_l, C * HH * ctx->dev_pitch));
+        CK(dmalloc(&l.img_r, C * HH * ctx->dev_pitch));
+        CK(dmalloc(&l.mask, C * HH * ctx->dev_pitch));
+        l.out.cap = p.max_corners;
+        CK(dmalloc(&l.out.uv_l, C * MC * 2));
+        CK(dmalloc(&l.out.uv_r, C * MC * 2));
+        CK(dmalloc(&l.out.xyz, C * MC * 3));
+        CK(dmalloc(&l.out.desc_l, C * MC * 32));
+        CK(dmalloc(&l.out.desc_r, C * MC * 32));
+        CK(dmalloc(&l.out.dist, C * MC));
+        CK(dmalloc(&l.out.idx, C * MC));
+        CK(dmalloc(&l.out.status, C * MC));
+    }
+    CK(dmalloc(&ctx->d_overflow, 1));
+    CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
+    CK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    ctx->arena_bytes = (size_t)p.max_queries * 512 + (size_t)p.max_corners * 64 + 3 * HH * ctx->dev_pitch + (1 << 20);
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), ctx->arena_bytes));
+    *out = ctx;
+    return SVI_SUCCESS;
+#undef CK
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, SVI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+}
+
+int svi_stereo_frames_device(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch, size_t frame_stride,
+                             int n_frames, const uint8_t* masks, const svi_stereo_result* out, void* cuda_stream) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!left || !right || !out || n_frames < 0 || (int)pitch < ctx->W || frame_stride < pitch * (size_t)ctx->H)
+        return fail(ctx, SVI_ERR_INVALID, "svi_stereo_frames_device: bad argument");
+    if (out->capacity_per_frame < ctx->p.max_corners) return fail(ctx, SVI_ERR_CAPACITY, "svi_stereo_frames_device: capacity_per_frame < max_corners");
+    if (!out->n_keypoints || !out->uv_left || !out->uv_right || !out->xyz_left || !out->desc_left || !out->desc_right ||
+        !out->distance || !out->match_index || !out->status)
+        return fail(ctx, SVI_ERR_INVALID, "svi_stereo_frames_device: null output array");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(cuda_stream);
+    CK(cudaEventRecord(ctx->fork, user));
+    for (int i = 0; i < ctx->n_lanes; ++i) CK(cudaStreamWaitEvent(ctx->lanes[i].stream, ctx->fork, 0));
+    const FrameGeom g = make_geom(ctx, (int)pitch, frame_stride);
+    StereoOutDev o;
+    o.cap = out->capacity_per_frame;
+    o.uv_l = out->uv_left; o.uv_r = out->uv_right; o.xyz = out->xyz_left;
+    o.desc_l = out->desc_left; o.desc_r = out->desc_right;
+    o.dist = out->distance; o.idx = out->match_index; o.status = out->status;
+    int chunk_id = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk, ++chunk_id) {
+        Lane& l = ctx->lanes[chunk_id % ctx->n_lanes];
+        const int nf = std::min(ctx->chunk, n_frames - f0);
+        int* n_det = out->n_detected ? out->n_detected + f0 : l.n_det;
+        int rc = run_pipeline(ctx, l, left + (size_t)f0 * frame_stride, right + (size_t)f0 * frame_stride,
+                              masks ? masks + (size_t)f0 * frame_stride : nullptr, g, nf, o, f0, out->n_keypoints + f0, n_det);
+        if (rc != SVI_SUCCESS) return rc;
+    }
+    for (int i = 0; i < ctx->n_lanes; ++i) {
+        CK(cudaEventRecord(ctx->lanes[i].done, ctx->lanes[i].stream));
+        CK(cudaStreamWaitEvent(user, ctx->lanes[i].done, 0));
+    }
+    return SVI_SUCCESS;
+}
+
+int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch, size_t frame_stride,
+                      int n_frames, const uint8_t* masks, svi_stereo_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!left || !right || !out || n_frames < 0 || (int)pitch < ctx->W || (n_frames > 1 && frame_stride < pitch * (size_t)ctx->H))
+        return fail(ctx, SVI_ERR_INVALID, "svi_stereo_frames: bad argument");
+    if (out->capacity_per_frame < ctx->p.max_corners) return fail(ctx, SVI_ERR_CAPACITY, "svi_stereo_frames: capacity_per_frame < max_corners");
+    if (!out->n_keypoints || !out->uv_left || !out->uv_right || !out->xyz_left || !out->desc_left || !out->desc_right ||
+        !out->distance || !out->match_index || !out->status)
+        return fail(ctx, SVI_ERR_INVALID, "svi_stereo_frames: null output array");
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->W, H = ctx->H, MC = ctx->p.max_corners, cap = out->capacity_per_frame;
+    const size_t dstride = (size_t)H * ctx->dev_pitch;
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, dstride);
+    const bool dense = (frame_stride == pitch * (size_t)H);
+    int chunk_id = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk, ++chunk_id) {
+        Lane& l = ctx->lanes[chunk_id % ctx->n_lanes];
+        cudaStream_t s = l.stream;
+        const int nf = std::min(ctx->chunk, n_frames - f0);
+        const uint8_t* srcs[3] = {left, right, masks};
+        uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
+        for (int k = 0; k < 3; ++k) {
+            if (!srcs[k]) continue;
+            if (dense) {
+                CK(cudaMemcpy2DAsync(dsts[k], ctx->dev_pitch, srcs[k] + (size_t)f0 * frame_stride, pitch, W, (size_t)H * nf,
+                                     cudaMemcpyHostToDevice, s));
+            } else {
+                for (int f = 0; f < nf; ++f)
+                    CK(cudaMemcpy2DAsync(dsts[k] + f * dstride, ctx->dev_pitch, srcs[k] + (size_t)(f0 + f) * frame_stride,
+                                         pitch, W, H, cudaMemcpyHostToDevice, s));
+            }
+        }
+        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, masks ? l.mask : nullptr, g, nf, l.out, 0, l.n_kp, l.n_det);
+        if (rc != SVI_SUCCESS) return rc;
+        const size_t o0 = (size_t)f0 * cap;
+#define D2H(dst, src, elem)                                                                                         \
+    CK(cudaMemcpy2DAsync((dst) + o0 * (elem), (size_t)cap * (elem) * sizeof(*(dst)), (src), (size_t)MC * (elem) * sizeof(*(dst)), \
+                         (size_t)MC * (elem) * sizeof(*(dst)), nf, cudaMemcpyDeviceToHost, s))
+        D2H(out->uv_left, l.out.uv_l, 2);
+        D2H(out->uv_right, l.out.uv_r, 2);
+        D2H(out->xyz_left, l.out.xyz, 3);
+        D2H(out->desc_left, l.out.desc_l, 32);
+        D2H(out->desc_right, l.out.desc_r, 32);
+        D2H(out->distance, l.out.dist, 1);
+        D2H(out->match_index, l.out.idx, 1);
+        D2H(out->status, l.out.status, 1);
+#undef D2H
+        CK(cudaMemcpyAsync(out->n_keypoints + f0, l.n_kp, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        if (out->n_detected) CK(cudaMemcpyAsync(out->n_detected + f0, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+    }
+    int rc = sync_lanes(ctx);
+    if (rc != SVI_SUCCESS) return rc;
+    return check_overflow(ctx);
+}
+
+int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* response) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!img || !response || (int)pitch < ctx->W) return fail(ctx, SVI_ERR_INVALID, "svi_harris_response: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    cudaStream_t s = l.stream;
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
+    CK(cudaMemcpy2DAsync(l.img_l, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t), s));
+    const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
+    harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
+                                                                    nullptr, l.frame_max);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, l.resp, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
+                         ctx->H, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
+int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stride, int n_frames, const uint8_t* masks,
+               float* xy, int32_t* counts) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!img || !xy || !counts || n_frames < 0 || (int)pitch < ctx->W) return fail(ctx, SVI_ERR_INVALID, "svi_detect: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    cudaStream_t s = l.stream;
+    const int W = ctx->W, H = ctx->H, MC = ctx->p.max_corners;
+    const size_t dstride = (size_t)H * ctx->dev_pitch;
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, dstride);
+    std::vector<ushort2> h_xy((size_t)ctx->chunk * MC);
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk) {
+        const int nf = std::min(ctx->chunk, n_frames - f0);
+        for (int f = 0; f < nf; ++f) {
+            CK(cudaMemcpy2DAsync(l.img_l + f * dstride, ctx->dev_pitch, img + (size_t)(f0 + f) * frame_stride, pitch, W, H,
+                                 cudaMemcpyHostToDevice, s));
+            if (masks)
+                CK(cudaMemcpy2DAsync(l.mask + f * dstride, ctx->dev_pitch, masks + (size_t)(f0 + f) * frame_stride, pitch, W, H,
+                                     cudaMemcpyHostToDevice, s));
+        }
+        const uint8_t* d_mask = masks ? l.mask : nullptr;
+        CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
+        CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
+        const dim3 tiles((W + HT_W - 1) / HT_W, (H + HT_H - 1) / HT_H, nf);
+        harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
+                                                                        nullptr, l.frame_max);
+        const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_TH - 1) / NMS_TH, nf);
+        nms_candidates_kernel<<<ngrid, dim3(NMS_TW, NMS_TH), 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
+                                                                     l.cand_count, ctx->cand_cap);
+        if (ctx->select_smem)
+            select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(l.cand, l.cand_count, ctx->sel, nullptr, nullptr,
+                                                                                  nullptr, l.det_xy, l.n_det, l.kp_xy, l.n_kp,
+                                                                                  ctx->d_overflow);
+        else
+            select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state,
+                                                                   l.det_xy, l.n_det, l.kp_xy, l.n_kp, ctx->d_overflow);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_xy.data(), l.det_xy, sizeof(ushort2) * (size_t)nf * MC, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(counts + f0, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int f = 0; f < nf; ++f)
+            for (int i = 0; i < counts[f0 + f]; ++i) {
+                xy[((size_t)(f0 + f) * MC + i) * 2] = (float)h_xy[(size_t)f * MC + i].x;
+                xy[((size_t)(f0 + f) * MC + i) * 2 + 1] = (float)h_xy[(size_t)f * MC + i].y;
+            }
+    }
+    return check_overflow(ctx);
+}
+
+int svi_describe(svi_ctx* ctx, const uint8_t* img, size_t pitch, const float* xy, int n, uint8_t* desc32, uint8_t* kept) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!img || !xy || !desc32 || !kept || n < 0 || (int)pitch < ctx->W) return fail(ctx, SVI_ERR_INVALID, "svi_describe: bad argument");
+    if (n > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_describe: n > max_queries");
+    if (n == 0) return SVI_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    cudaStream_t s = l.stream;
+    ctx->arena_used = 0;
+    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, s);
+    if (rc != SVI_SUCCESS) return rc;
+    float* d_xy; uint8_t* d_desc; uint8_t* d_kept;
+    UP(d_xy, xy, (size_t)n * 2);
+    UP(d_desc, (const uint8_t*)nullptr, (size_t)n * 32);
+    UP(d_kept, (const uint8_t*)nullptr, (size_t)n);
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
+    describe_kernel<<<(n + 3) / 4, 128, 0, s>>>(l.box_l, g, d_xy, n, d_desc, d_kept);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(desc32, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
+int svi_match_hamming(svi_ctx* ctx, const uint8_t* query32, int n_query, const uint8_t* train32, int n_train, int32_t* index,
+                      int32_t* distance) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!query32 || !index || !distance || n_query < 0 || n_train < 0 || (n_train > 0 && !train32))
+        return fail(ctx, SVI_ERR_INVALID, "svi_match_hamming: bad argument");
+    if ((size_t)(n_query + n_train) * 40 > ctx->arena_bytes) return fail(ctx, SVI_ERR_CAPACITY, "svi_match_hamming: raise max_queries");
+    if (n_query == 0) return SVI_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->lanes[0].stream;
+    ctx->arena_used = 0;
+    uint8_t* d_q; uint8_t* d_t; int* d_i; int* d_d;
+    UP(d_q, query32, (size_t)n_query * 32);
+    UP(d_t, n_train > 0 ? train32 : (const uint8_t*)nullptr, (size_t)std::max(n_train, 1) * 32);
+    UP(d_i, (const int*)nullptr, (size_t)n_query);
+    UP(d_d, (const int*)nullptr, (size_t)n_query);
+    hamming_match_kernel<<<(n_query + 3) / 4, 128, 0, s>>>(d_q, n_query, d_t, n_train, d_i, d_d);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(index, d_i, sizeof(int) * n_query, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(distance, d_d, sizeof(int) * n_query, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
+int svi_triangulate_right(svi_ctx* ctx, const uint8_t* img_right, size_t pitch, int n, const float* top_left,
+                          const float* uv_left, const uint8_t* desc_left, float keypoint_size, svi_tri_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    return triangulate_common(ctx, false, img_right, pitch, n, nullptr, top_left, uv_left, desc_left, keypoint_size, out);
+}
+
+int svi_triangulate_left(svi_ctx* ctx, const uint8_t* img_left, size_t pitch, int n, const float* search_range,
+                         const float* top_left, const float* uv_right, const uint8_t* desc_right, float keypoint_size,
+                         svi_tri_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    return triangulate_common(ctx, true, img_left, pitch, n, search_range, top_left, uv_right, desc_right, keypoint_size, out);
+}
+
+int svi_point_in_left(svi_ctx* ctx, int n, const float* uv_left, const float* uv_right, double* xyz_left, uint8_t* status) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!uv_left || !uv_right || !xyz_left || !status || n < 0) return fail(ctx, SVI_ERR_INVALID, "svi_point_in_left: bad argument");
+    if (n > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_point_in_left: n > max_queries");
+    if (n == 0) return SVI_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->lanes[0].stream;
+    ctx->arena_used = 0;
+    float* d_l; float* d_r; double* d_xyz; uint8_t* d_st;
+    UP(d_l, uv_left, (size_t)n * 2);
+    UP(d_r, uv_right, (size_t)n * 2);
+    UP(d_xyz, (const double*)nullptr, (size_t)n * 3);
+    UP(d_st, (const uint8_t*)nullptr, (size_t)n);
+    point_in_left_kernel<<<(n + 127) / 128, 128, 0, s>>>(ctx->tc, n, d_l, d_r, d_xyz, d_st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xyz_left, d_xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, d_st, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
+int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* img_right, size_t pitch,
+                        const double* T_world_to_left, const svi_landmarks* lm, int n, double motion_scaling,
+                        svi_track_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!img_left || !img_right || !T_world_to_left || !lm || !out || n < 0 || (int)pitch < ctx->W)
+        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: bad argument");
+    if (!lm->xyz_world || !lm->last_desc_left || !lm->last_desc_right || !lm->last_disparity || !lm->keypoint_size ||
+        !out->status || !out->stage || !out->uv_left || !out->uv_right || !out->xyz_left || !out->desc_left || !out->desc_right)
+        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: null array");
+    if (n > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_track_landmarks: n > max_queries");
+    if (n == 0) return SVI_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    cudaStream_t s = l.stream;
+    ctx->arena_used = 0;
+    int rc = stage_box(ctx, img_left, pitch, l.img_l, l.box_l, s);
+    if (rc != SVI_SUCCESS) return rc;
+    rc = stage_box(ctx, img_right, pitch, l.img_r, l.box_r, s);
+    if (rc != SVI_SUCCESS) return rc;
+    double* d_xyzw; uint8_t* d_dl; uint8_t* d_dr; float* d_disp; float* d_size;
+    UP(d_xyzw, lm->xyz_world, (size_t)n * 3);
+    UP(d_dl, lm->last_desc_left, (size_t)n * 32);
+    UP(d_dr, lm->last_desc_right, (size_t)n * 32);
+    UP(d_disp, lm->last_disparity, (size_t)n);
+    UP(d_size, lm->keypoint_size, (size_t)n);
+    TrackOutDev o;
+    UP(o.status, (const uint8_t*)nullptr, (size_t)n);
+    UP(o.stage, (const uint8_t*)nullptr, (size_t)n);
+    UP(o.uv_l, (const float*)nullptr, (size_t)n * 2);
+    UP(o.uv_r, (const float*)nullptr, (size_t)n * 2);
+    UP(o.xyz, (const double*)nullptr, (size_t)n * 3);
+    UP(o.desc_l, (const uint8_t*)nullptr, (size_t)n * 32);
+    UP(o.desc_r, (const uint8_t*)nullptr, (size_t)n * 32);
+    CK(cudaMemsetAsync(o.uv_l, 0, sizeof(float) * 2 * n, s));
+    CK(cudaMemsetAsync(o.uv_r, 0, sizeof(float) * 2 * n, s));
+    CK(cudaMemsetAsync(o.xyz, 0, sizeof(double) * 3 * n, s));
+    CK(cudaMemsetAsync(o.desc_l, 0, (size_t)32 * n, s));
+    CK(cudaMemsetAsync(o.desc_r, 0, (size_t)32 * n, s));
+    TrackConst k;
+    for (int i = 0; i < 12; ++i) { k.T[i] = T_world_to_left[i]; k.PL[i] = ctx->cam_l.P[i]; k.PR[i] = ctx->cam_r.P[i]; }
+    k.tri_scale = (float)(1.0 + motion_scaling);
+    k.cutoff1 = ctx->p.cutoff_stage1;
+    LandmarksDev ld{d_xyzw, d_dl, d_dr, d_disp, d_size};
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
+    track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, g, ctx->tc, k, ld, n, o);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->uv_left, o.uv_l, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->uv_right, o.uv_r, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->xyz_left, o.xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->desc_left, o.desc_l, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->desc_right, o.desc_r, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
+int svi_set_profiling(svi_ctx* ctx, int enable) {
+    if (!ctx) return SVI_ERR_INVALID;
+    for (int i = 0; i < ctx->n_lanes; ++i) cudaStreamSynchronize(ctx->lanes[i].stream);
+    collect_timings(ctx);
+    for (int s = 0; s < kStages; ++s) { ctx->stage_ms[s] = 0.0; ctx->stage_launches[s] = 0; }
+    ctx->profiling = enable != 0;
+    return SVI_SUCCESS;
+}
+
+int svi_stage_timings(svi_ctx* ctx, const char** names, double* total_ms, int64_t* launches, int capacity) {
+    if (!ctx || !names || !total_ms || !launches) return SVI_ERR_INVALID;
+    for (int i = 0; i < ctx->n_lanes; ++i) cudaStreamSynchronize(ctx->lanes[i].stream);
+    collect_timings(ctx);
+    int n = std::min(capacity, kStages);
+    for (int i = 0; i < n; ++i) {
+        names[i] = kStageNames[i];
+        total_ms[i] = ctx->stage_ms[i];
+        launches[i] = ctx->stage_launches[i];
+    }
+    return n;
+}
+
+int svi_config(const svi_ctx* ctx, int32_t* chunk_frames, int32_t* n_lanes, int32_t* select_in_smem) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (chunk_frames) *chunk_frames = ctx->chunk;
+    if (n_lanes) *n_lanes = ctx->n_lanes;
+    if (select_in_smem) *select_in_smem = ctx->select_smem ? 1 : 0;
+    return SVI_SUCCESS;
+}
+
+}  // extern "C"

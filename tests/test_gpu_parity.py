@@ -1,0 +1,239 @@
+"""GPU parity tests proper: libsvi_gpu (through the C-ABI / ctypes) against the CPU oracle on the
+same seeded inputs.  Integer / byte / index outputs must be bit-exact; xyz within 1e-5 relative
+(north_star), and in practice bit-equal because the fp64 path has no fused operations."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import frontend_np as o
+from svi_mapper_b200 import StereoFrontend, _lib
+from svi_mapper_b200.synth import stereo_pair
+
+
+def _tri(cams, **kw):
+    cl, cr = cams
+    return o.Triangulator(o.Camera(cl.width, cl.height, cl.P), o.Camera(cr.width, cr.height, cr.P), o.StereoParams(**kw))
+
+
+def _compare_frame(got: dict, ref: dict):
+    n = len(ref["uv_l"])
+    assert len(got["uv_l"]) == n
+    np.testing.assert_array_equal(got["uv_l"], ref["uv_l"])
+    np.testing.assert_array_equal(got["desc_l"], ref["desc_l"])
+    np.testing.assert_array_equal(got["status"], ref["status"])
+    np.testing.assert_array_equal(got["dist"], ref["dist"])
+    np.testing.assert_array_equal(got["idx"], ref["idx"])
+    ok = ref["status"] == 0
+    np.testing.assert_array_equal(got["uv_r"][ok], ref["uv_r"][ok])
+    np.testing.assert_array_equal(got["desc_r"][ok], ref["desc_r"][ok])
+    if ok.any():
+        rel = np.linalg.norm(got["xyz"][ok] - ref["xyz"][ok], axis=1) / np.linalg.norm(ref["xyz"][ok], axis=1)
+        assert rel.max() <= 1e-5          # north_star tolerance
+        np.testing.assert_array_equal(got["xyz"][ok], ref["xyz"][ok])   # and in fact bit-equal
+
+
+@pytest.mark.parametrize("cams_name,seed", [("kitti_cams", 0), ("vi_cams", 4000), ("kitti1112_cams", 2000)])
+def test_harris_response_bit_exact(request, cams_name, seed):
+    cams = request.getfixturevalue(cams_name)
+    L, _ = stereo_pair(cams[0].width, cams[0].height, seed)
+    with StereoFrontend(*cams) as fe:
+        got = fe.harris_response(L)
+    ref = o.harris_response(L)
+    bad = got.view(np.uint32) != ref.view(np.uint32)
+    assert bad.sum() == 0, f"{bad.sum()} response pixels differ, first at {np.argwhere(bad)[:5]}"
+
+
+@pytest.mark.parametrize("max_corners", [1000, 2000])
+def test_detect_matches_gftt(kitti_cams, max_corners):
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    imgs = np.stack([stereo_pair(W, H, s)[0] for s in (0, 1, 2)])
+    rng = np.random.default_rng(5)
+    centres = np.stack([rng.uniform(0, W, 300), rng.uniform(0, H, 300)], 1)
+    masks = np.stack([np.full((H, W), 255, np.uint8), o.mask_active_landmarks(W, H, centres), o.mask_active_landmarks(W, H, centres[:50])])
+    with StereoFrontend(*kitti_cams, max_corners=max_corners) as fe:
+        got = fe.detect(imgs, masks)
+        got_nomask = fe.detect(imgs[:1])
+    for f in range(3):
+        ref = o.gftt(imgs[f], max_corners, mask=masks[f])
+        np.testing.assert_array_equal(got[f].astype(np.int32), ref)
+    np.testing.assert_array_equal(got_nomask[0].astype(np.int32), o.gftt(imgs[0], max_corners))
+
+
+def test_describe_and_hamming(kitti_cams):
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, R = stereo_pair(W, H, 7)
+    rng = np.random.default_rng(1)
+    pts = np.stack([rng.integers(0, W, 500), rng.integers(0, H, 500)], 1).astype(np.float32)
+    pts[:8] = [[28, 28], [27, 28], [W - 29, H - 29], [W - 28, 40], [40, H - 28], [28.4, 30.5], [27.5, 28.5], [100.5, 99.5]]
+    with StereoFrontend(*kitti_cams) as fe:
+        desc, kept = fe.describe(L, pts)
+        keep_ref, desc_ref = o.brief32(L, pts)
+        assert np.array_equal(np.nonzero(kept)[0], keep_ref)
+        np.testing.assert_array_equal(desc[kept], desc_ref)
+        _, desc_r = o.brief32(R, pts)
+        idx, dist = fe.match_hamming(desc_ref[:64], desc_r)
+        for q in range(64):
+            i, d = o.match_hamming(desc_ref[q], desc_r)
+            assert (idx[q], dist[q]) == (i, d)
+        # constructed ties: the first minimum wins
+        t = np.repeat(desc_ref[:1], 5, 0)
+        idx, dist = fe.match_hamming(desc_ref[:1], t)
+        assert idx[0] == 0 and dist[0] == 0
+        idx, dist = fe.match_hamming(desc_ref[:3], np.zeros((0, 32), np.uint8))
+        assert (idx == -1).all() and (dist == -1).all()
+
+
+@pytest.mark.parametrize("cams_name,seed,kw", [
+    ("kitti_cams", 0, {}),                       # C1
+    ("kitti_cams", 1000, {"max_corners": 2000}), # C2-shaped frame
+    ("kitti1112_cams", 2000, {}),                # C4-shaped frame
+    ("vi_cams", 4000, {}),
+])
+def test_stereo_frame_parity(request, cams_name, seed, kw):
+    cams = request.getfixturevalue(cams_name)
+    L, R = stereo_pair(cams[0].width, cams[0].height, seed)
+    with StereoFrontend(*cams, **kw) as fe:
+        got = fe.add_new_landmarks(L, R)
+    ref = o.add_new_landmarks(L, R, _tri(cams, **kw))
+    assert (ref["status"] == 0).sum() > 100      # the synthetic pair really has matches
+    _compare_frame(got, ref)
+
+
+def test_stereo_batch_chunks_and_masks(kitti_cams):
+    """Several chunks over several lanes, with per-frame masks; every frame equals the oracle."""
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    pairs = [stereo_pair(W, H, 1000 + i) for i in range(7)]
+    Ls, Rs = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    rng = np.random.default_rng(3)
+    masks = np.stack([o.mask_active_landmarks(W, H, np.stack([rng.uniform(0, W, 100 * i), rng.uniform(0, H, 100 * i)], 1)) for i in range(7)])
+    tri = _tri(kitti_cams)
+    with StereoFrontend(*kitti_cams, chunk_frames=2) as fe:
+        res = fe.stereo_frames(Ls, Rs, masks)
+        res2 = fe.stereo_frames(Ls, Rs, masks)    # idempotent: scratch reuse leaves no residue
+    for f in range(7):
+        ref = o.add_new_landmarks(Ls[f], Rs[f], tri, mask=masks[f])
+        _compare_frame(res.frame(f), ref)
+        _compare_frame(res2.frame(f), ref)
+        assert res.n_detected[f] == len(o.gftt(Ls[f], 1000, mask=masks[f]))
+
+
+def test_triangulate_right_left_queries(kitti_cams):
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, R = stereo_pair(W, H, 11)
+    tri = _tri(kitti_cams)
+    rng = np.random.default_rng(2)
+    n = 300
+    xl = rng.integers(28, W - 28, n).astype(np.float32)
+    yl = rng.integers(28, H - 28, n).astype(np.float32)
+    _, dl = o.brief32(L, np.stack([xl, yl], 1))
+    _, dr = o.brief32(R, np.stack([xl, yl], 1))
+    rng_f = rng.uniform(0.5, 90.0, n).astype(np.float32)          # fractional search ranges (tracking)
+    u_tl = np.maximum(np.float32(0), (xl - np.float32(28)) - rng_f).astype(np.float32)
+    v_tl = (yl - np.float32(28)).astype(np.float32)
+    u_tl[:5] = xl[:5]                                               # insufficient search range
+    with StereoFrontend(*kitti_cams) as fe:
+        got = fe.triangulate_right(R, np.stack([u_tl, v_tl], 1), np.stack([xl, yl], 1), dl)
+        for i in range(n):
+            r = tri.triangulate_right(R, u_tl[i], v_tl[i], 7.0, (xl[i], yl[i]), dl[i])
+            assert got["status"][i] == r["status"], i
+            assert got["dist"][i] == r.get("dist", -1) and got["idx"][i] == r.get("idx", -1), i
+            if r["status"] == 0:
+                assert tuple(got["uv"][i]) == tuple(np.float32(v) for v in r["uv"])
+                np.testing.assert_array_equal(got["xyz"][i], r["xyz"])
+                np.testing.assert_array_equal(got["desc"][i], r["desc"])
+        # search in LEFT for right-image points
+        tl = np.stack([xl - np.float32(28), v_tl], 1).astype(np.float32)
+        sr = rng_f.copy()
+        sr[:3] = [0.0, -1.0, 1e-3]
+        got = fe.triangulate_left(L, sr, tl, np.stack([xl, yl], 1), dr)
+        for i in range(n):
+            r = tri.triangulate_left(L, sr[i], tl[i, 0], tl[i, 1], 7.0, (xl[i], yl[i]), dr[i])
+            assert got["status"][i] == r["status"], i
+            assert got["dist"][i] == r.get("dist", -1) and got["idx"][i] == r.get("idx", -1), i
+            if r["status"] == 0:
+                assert tuple(got["uv"][i]) == tuple(np.float32(v) for v in r["uv"])
+                np.testing.assert_array_equal(got["xyz"][i], r["xyz"])
+                np.testing.assert_array_equal(got["desc"][i], r["desc"])
+
+
+def test_point_in_left_closed_form(kitti_cams):
+    """Known-answer check from src/runnable/triangulation_sampling.cpp:99-120: uR = uL + Du_R/Z."""
+    tri = _tri(kitti_cams)
+    z = np.array([0.5, 1.0, 5.0, 20.0, 80.0])
+    ul = np.full(5, 700.0, np.float32)
+    ur = (ul + np.float32(1) * (tri.du_r / z)).astype(np.float32)
+    uvl = np.stack([ul, np.full(5, 150.0, np.float32)], 1)
+    uvr = np.stack([ur, np.full(5, 150.0, np.float32)], 1)
+    with StereoFrontend(*kitti_cams) as fe:
+        xyz, st = fe.point_in_left(uvl, uvr)
+        xyz0, st0 = fe.point_in_left([[100.0, 50.0]], [[100.0, 50.0]])
+    assert (st == 0).all() and st0[0] == _lib.SVI_TRI_ZERO_DISP
+    np.testing.assert_allclose(xyz[:, 2], z, rtol=1e-4)
+    for i in range(5):
+        s, ref = tri.point_in_left(uvl[i], uvr[i])
+        np.testing.assert_array_equal(xyz[i], ref)
+        # compiled-out reference assert (CTriangulator.cpp:351): X == (Z*xR - Z*cx - DuR)/f
+        assert abs(xyz[i, 0] - tri.f_inv * (xyz[i, 2] * float(ur[i]) - xyz[i, 2] * tri.pu - tri.du_r)) < 1e-9
+
+
+def test_track_stage1(vi_cams):
+    """Projection-window tracking: landmarks from frame 0's stereo result re-found in a shifted pair."""
+    W, H = vi_cams[0].width, vi_cams[0].height
+    L, R = stereo_pair(W, H, 4000)
+    tri = _tri(vi_cams)
+    ref0 = o.add_new_landmarks(L, R, tri)
+    ok = np.nonzero(ref0["status"] == 0)[0][:400]
+    xyz_w = ref0["xyz"][ok]                      # identity pose: world == left camera
+    T = np.eye(4)
+    T[0, 3] = 0.01                               # small translation so projections move by < 1 px .. few px
+    disp = (ref0["uv_l"][ok, 0] - ref0["uv_r"][ok, 0]).astype(np.float32)
+    lms = [dict(xyz_w=xyz_w[i], last_desc_l=ref0["desc_l"][ok[i]], last_desc_r=ref0["desc_r"][ok[i]],
+                last_disparity=disp[i], size=7.0) for i in range(len(ok))]
+    for scaling in (1.0, 2.5):
+        ref = o.track_stage1(L, R, tri, T, lms, scaling)
+        with StereoFrontend(*vi_cams) as fe:
+            got = fe.track_landmarks(L, R, T, xyz_w, ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, scaling)
+        stages = [r["stage"] for r in ref]
+        assert sum(s > 0 for s in stages) > 50
+        for i, r in enumerate(ref):
+            assert got["stage"][i] == r["stage"], i
+            assert got["status"][i] == r["status"], i
+            if r["stage"]:
+                assert tuple(got["uv_l"][i]) == tuple(np.float32(v) for v in r["uv_l"])
+                assert tuple(got["uv_r"][i]) == tuple(np.float32(v) for v in r["uv_r"])
+                np.testing.assert_array_equal(got["xyz"][i], r["xyz"])
+                np.testing.assert_array_equal(got["desc_l"][i], r["desc_l"])
+                np.testing.assert_array_equal(got["desc_r"][i], r["desc_r"])
+
+
+def test_device_resident_entry(kitti_cams):
+    """svi_stereo_frames_device on torch-owned device memory == the host-buffer entry point."""
+    import torch
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    pairs = [stereo_pair(W, H, 1000 + i) for i in range(5)]
+    Ls, Rs = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    n, cap = 5, 1000
+    dev = torch.device("cuda:0")
+    dL, dR = torch.from_numpy(Ls).to(dev), torch.from_numpy(Rs).to(dev)
+    t = dict(n_kp=torch.zeros(n, dtype=torch.int32, device=dev), n_det=torch.zeros(n, dtype=torch.int32, device=dev),
+             uv_l=torch.zeros(n, cap, 2, device=dev), uv_r=torch.zeros(n, cap, 2, device=dev),
+             xyz=torch.zeros(n, cap, 3, dtype=torch.float64, device=dev),
+             dl=torch.zeros(n, cap, 32, dtype=torch.uint8, device=dev), dr=torch.zeros(n, cap, 32, dtype=torch.uint8, device=dev),
+             dist=torch.zeros(n, cap, dtype=torch.int32, device=dev), idx=torch.zeros(n, cap, dtype=torch.int32, device=dev),
+             st=torch.zeros(n, cap, dtype=torch.uint8, device=dev))
+    res = _lib.StereoResult(cap, t["n_kp"].data_ptr(), t["n_det"].data_ptr(), t["uv_l"].data_ptr(), t["uv_r"].data_ptr(),
+                            t["xyz"].data_ptr(), t["dl"].data_ptr(), t["dr"].data_ptr(), t["dist"].data_ptr(),
+                            t["idx"].data_ptr(), t["st"].data_ptr())
+    with StereoFrontend(*kitti_cams, chunk_frames=2) as fe:
+        fe.stereo_frames_device(dL.data_ptr(), dR.data_ptr(), W, W * H, n, res, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        host = fe.stereo_frames(Ls, Rs)
+    np.testing.assert_array_equal(t["n_kp"].cpu().numpy(), host.n_keypoints)
+    for f in range(n):
+        k = host.n_keypoints[f]
+        np.testing.assert_array_equal(t["uv_l"][f, :k].cpu().numpy(), host.uv_left[f, :k])
+        np.testing.assert_array_equal(t["st"][f, :k].cpu().numpy(), host.status[f, :k])
+        ok = host.status[f, :k] == 0
+        np.testing.assert_array_equal(t["xyz"][f, :k].cpu().numpy()[ok], host.xyz_left[f, :k][ok])
+        np.testing.assert_array_equal(t["dr"][f, :k].cpu().numpy()[ok], host.desc_right[f, :k][ok])
