@@ -17,6 +17,7 @@
 // comparisons of a pair are one 32-bit subtract (values <= 20655 < 2^15 leave the half-word sign
 // bits free): d = b + 0x7FFF7FFF - a has bit 15 / bit 31 set iff a < b in the low / high half.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <utility>
 #include "brief_pattern_32.h"
 #include "common.cuh"
@@ -27,13 +28,74 @@ constexpr signed char kPat[SVI_BRIEF_NTESTS][4] = SVI_BRIEF_PATTERN_INIT;
 __device__ const signed char d_pat[SVI_BRIEF_NTESTS][4] = SVI_BRIEF_PATTERN_INIT;
 
 constexpr int PATCH_ROWS = 2 * kBriefReach + 1;        // 49
-constexpr int PATCH_CHUNK = 64;                        // candidates per pass
-constexpr int PATCH_W = PATCH_CHUNK + 2 * kBriefReach; // 112 u16 per row
-constexpr int PATCH_WORDS = PATCH_W / 2;               // 56
-constexpr int PATCH_COPY_WORDS = PATCH_ROWS * PATCH_WORDS;
-constexpr int MATCH_WARPS = 4;
-constexpr int MATCH_SMEM_PER_WARP = 2 * PATCH_COPY_WORDS * 4;  // even- and odd-aligned copies
-constexpr int MATCH_SMEM = MATCH_WARPS * MATCH_SMEM_PER_WARP;
+constexpr int PATCH_SLOTS = 64;                        // 2 candidate slots per lane and pass
+constexpr int PATCH_CHUNK = PATCH_SLOTS - 2;           // candidates per pass (slot 0 is idle when the window parity is odd)
+constexpr int PATCH_W = PATCH_SLOTS + 2 * kBriefReach + 8; // 120 u16 per row: window start rounded down to 8 elements
+constexpr int PATCH_WORDS = PATCH_W / 2;               // 60
+constexpr int PATCH_COPY_BYTES = PATCH_ROWS * PATCH_W * 2;          // 10976: one TMA box
+constexpr int PATCH_COPY_STRIDE = (PATCH_COPY_BYTES + 127) / 128 * 128; // TMA destinations are 128-B aligned
+constexpr int PATCH_COPY_WORDS = PATCH_COPY_STRIDE / 4;
+constexpr int MATCH_WARPS = 3;                                      // 3 CTAs/SM -> 9 warps, 207 KB of windows
+constexpr int MATCH_SMEM_PER_WARP = 2 * PATCH_COPY_STRIDE;          // even- and odd-aligned copies
+constexpr int MATCH_SMEM = MATCH_WARPS * MATCH_SMEM_PER_WARP + MATCH_WARPS * 8;  // + one mbarrier per warp
+
+// ------------------------------------------------------------------ TMA / mbarrier (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
+// Per-warp staging state: two shared copies of the box-sum window + the warp's mbarrier.
+// TMA tile loads must start on a 16-byte boundary of the inner dimension (measured on B200: any
+// other start faults with "illegal instruction"), so a window starts at a multiple of 8 columns and
+// the copy that is one element further right comes from the plane stored shifted by one element.
+struct PatchStage {
+    const CUtensorMap* map;    // 2-D u16 tensor over S(y,x):   (W, frames*H), row pitch box_pitch
+    const CUtensorMap* map_s;  // same geometry over the shifted plane S(y,x+1)
+    int row_base;              // first tensor row of this query's frame
+    uint32_t smem_a;          // shared address of copy A (copy B follows at +PATCH_COPY_STRIDE)
+    const uint32_t* words;    // generic pointer to copy A
+    uint32_t bar;             // shared address of the mbarrier
+    uint32_t phase;           // parity of the next completion
+};
+
+// One elected lane arms the barrier and issues both box copies (col0 is a multiple of 8):
+// A[r][k] = S[row0+r][col0+k], B[r][k] = S[row0+r][col0+1+k]; out-of-range elements are zero-filled.
+__device__ __forceinline__ void patch_issue(const PatchStage& ps, int row0, int col0, int lane) {
+    if (lane == 0) {
+        fence_proxy_async();   // earlier generic-proxy reads of the buffers are ordered before the async writes
+        mbar_expect_tx(ps.bar, 2 * PATCH_COPY_BYTES);
+        tma_load_2d(ps.smem_a, ps.map, col0, ps.row_base + row0, ps.bar);
+        tma_load_2d(ps.smem_a + PATCH_COPY_STRIDE, ps.map_s, col0, ps.row_base + row0, ps.bar);
+    }
+}
+__device__ __forceinline__ void patch_wait(PatchStage& ps) {
+    mbar_wait(ps.bar, ps.phase);
+    ps.phase ^= 1u;
+}
 
 // ------------------------------------------------------------------ descriptor at one point
 // Lanes = tests (8 rounds of 32).  Word format used throughout the kernels: word j holds tests
@@ -105,35 +167,25 @@ struct SearchResult {
     uint32_t w[kDescWords];
 };
 
-// Stage the (49 x 112) u16 window of `box` whose top-left is (row0, col0) into the warp's two
-// shared copies: A[r][k] = box[row0+r][col0+k], B[r][k] = A[r][k+1].
-__device__ __forceinline__ void load_patch(const uint16_t* __restrict__ box, int box_pitch, int W, int H,
-                                           int row0, int col0, uint16_t* __restrict__ A, uint16_t* __restrict__ B,
-                                           int lane) {
-    for (int idx = lane; idx < PATCH_ROWS * PATCH_W; idx += 32) {
-        int r = idx / PATCH_W, k = idx - r * PATCH_W;
-        int gy = row0 + r, gx = col0 + k;
-        uint16_t v = 0;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(box + (size_t)gy * box_pitch + gx);
-        A[idx] = v;
-        if (k > 0) B[idx - 1] = v;
-    }
-}
+// Geometry of one scan-line search, shared body of CTriangulator.cpp:59-117 (RIGHT, first = 0) and
+// :264-322 (LEFT, first = 1): ROI by truncation, pool key-points (border + first + i, border),
+// BRIEF's border filter inside the ROI.  Warp-uniform.
+struct SearchPlan {
+    int status;        // SVI_OK when there is at least one candidate to evaluate
+    int n_valid, i_lo; // surviving pool key-points [i_lo, i_lo + n_valid)
+    int gx_lo, gy;     // image column of candidate i_lo, image row of all candidates
+    int first;
+    float border, u_tl, v_tl;
+};
 
-// Shared body of CTriangulator.cpp:59-117 (RIGHT, first = 0) and :264-322 (LEFT, first = 1):
-// ROI by truncation, pool key-points (border + first + i, border), BRIEF's border filter inside
-// the ROI, descriptors of the survivors, first arg-min, cut-off.  Warp-uniform arguments.
-__device__ __forceinline__ void scanline_search(const uint16_t* __restrict__ box, int box_pitch, int W, int H,
-                                                float img_width_f, float u_tl, float v_tl, float size,
-                                                int first, int n_pool, const uint32_t (&ref)[kDescWords],
-                                                float cutoff, uint32_t* __restrict__ smem, int lane,
-                                                SearchResult& out) {
+__device__ __forceinline__ void search_plan(int W, int H, float img_width_f, float u_tl, float v_tl, float size,
+                                            int first, int n_pool, int lane, SearchPlan& p) {
     const float border = 4.f * size, full_h = 8.f * size + 1.f;
     const float roi_w_f = fminf((float)n_pool + full_h, img_width_f - u_tl);
     const int rx = (int)u_tl, ry = (int)v_tl, rw = (int)roi_w_f, rh = (int)full_h;  // cv::Rect(float...) truncates
-    out.dist = -1;
-    out.idx = -1;
-    if (rx < 0 || ry < 0 || rw < 0 || rh < 0 || rx + rw > W || ry + rh > H) { out.status = SVI_TRI_BAD_ROI; return; }
+    p.border = border; p.u_tl = u_tl; p.v_tl = v_tl; p.first = first;
+    p.n_valid = 0; p.i_lo = 0; p.gx_lo = 0; p.gy = 0;
+    if (rx < 0 || ry < 0 || rw < 0 || rh < 0 || rx + rw > W || ry + rh > H) { p.status = SVI_TRI_BAD_ROI; return; }
     // KeyPointsFilter::runByImageBorder inside the ROI: keep 28 <= cvRound(pt) < size - 28
     const int ky_r = cv_round_f(border);
     int i_lo = 0, i_hi = 0;
@@ -146,25 +198,51 @@ __device__ __forceinline__ void scanline_search(const uint16_t* __restrict__ box
             i_hi += __popc(__ballot_sync(0xFFFFFFFFu, in && kr < rw - kBriefBorder));
         }
     }
-    const int n_valid = i_hi - i_lo;
-    if (n_valid <= 0) { out.status = SVI_TRI_NO_DESC; return; }
+    p.n_valid = i_hi - i_lo;
+    p.i_lo = i_lo;
+    if (p.n_valid <= 0) { p.status = SVI_TRI_NO_DESC; return; }
     const float kx_lo = (border + (float)i_lo) + (float)first;
-    const int gx_lo = rx + brief_centre(kx_lo), gy = ry + brief_centre(border);
+    p.gx_lo = rx + brief_centre(kx_lo);
+    p.gy = ry + brief_centre(border);
+    p.status = SVI_OK;
+}
 
-    uint16_t* A = reinterpret_cast<uint16_t*>(smem);
-    uint16_t* B = A + PATCH_ROWS * PATCH_W;
-    const uint32_t* Al = smem + lane;
-    const uint32_t* Bl = smem + PATCH_COPY_WORDS + lane;
+// Window of the pass that starts at candidate `cb`: its left image column, rounded down to the TMA
+// alignment.  The remainder splits into an even word offset and a parity that shifts the slots.
+__device__ __forceinline__ int window_col(const SearchPlan& p, int cb) { return p.gx_lo + cb - kBriefReach; }
+__device__ __forceinline__ int window_col_aligned(int col) { return (col >> 3) << 3; }
+
+// Start staging the first window of a planned search.
+__device__ __forceinline__ void search_prefetch(const SearchPlan& p, const PatchStage& ps, int lane) {
+    if (p.status == SVI_OK) patch_issue(ps, p.gy - kBriefReach, window_col_aligned(window_col(p, 0)), lane);
+}
+
+// Descriptors of the surviving candidates, first arg-min against `ref`, cut-off (the first window must
+// already be in flight: search_prefetch).
+__device__ __forceinline__ void search_run(const SearchPlan& p, PatchStage& ps, const uint32_t (&ref)[kDescWords],
+                                           float cutoff, int lane, SearchResult& out) {
+    out.dist = -1;
+    out.idx = -1;
+    out.status = p.status;
+    if (p.status != SVI_OK) return;
     uint32_t best_key = 0xFFFFFFFFu;
-    for (int cb = 0; cb < n_valid; cb += PATCH_CHUNK) {
-        __syncwarp();
-        load_patch(box, box_pitch, W, H, gy - kBriefReach, gx_lo + cb - kBriefReach, A, B, lane);
-        __syncwarp();
+    for (int cb = 0; cb < p.n_valid; cb += PATCH_CHUNK) {
+        const int col = window_col(p, cb), col_a = window_col_aligned(col);
+        const int par = (col - col_a) & 1;             // slot s evaluates candidate cb + s - par
+        const int woff = (col - col_a) >> 1;           // even part of the remainder, in 32-bit words
+        if (cb > 0) {
+            __syncwarp();
+            patch_issue(ps, p.gy - kBriefReach, col_a, lane);
+        }
+        patch_wait(ps);
+        const uint32_t* Al = ps.words + woff + lane;
+        const uint32_t* Bl = ps.words + PATCH_COPY_WORDS + woff + lane;
         uint32_t wlo[kDescWords], whi[kDescWords];
         brief_pair_all(Al, Bl, wlo, whi, std::make_integer_sequence<int, kDescWords>{});
-        const int c_lo = cb + 2 * lane, c_hi = c_lo + 1;
-        uint32_t k_lo = (c_lo < n_valid) ? (((uint32_t)hamming_words(wlo, ref) << 16) | (uint32_t)(c_lo & 0xFFFF)) : 0xFFFFFFFFu;
-        uint32_t k_hi = (c_hi < n_valid) ? (((uint32_t)hamming_words(whi, ref) << 16) | (uint32_t)(c_hi & 0xFFFF)) : 0xFFFFFFFFu;
+        const int l_lo = 2 * lane - par, l_hi = l_lo + 1;   // candidate index within this pass
+        const int c_lo = cb + l_lo, c_hi = cb + l_hi;
+        uint32_t k_lo = (l_lo >= 0 && l_lo < PATCH_CHUNK && c_lo < p.n_valid) ? (((uint32_t)hamming_words(wlo, ref) << 16) | (uint32_t)(c_lo & 0xFFFF)) : 0xFFFFFFFFu;
+        uint32_t k_hi = (l_hi < PATCH_CHUNK && c_hi < p.n_valid) ? (((uint32_t)hamming_words(whi, ref) << 16) | (uint32_t)(c_hi & 0xFFFF)) : 0xFFFFFFFFu;
         const uint32_t k_mine = min(k_lo, k_hi);
         const uint32_t k_min = warp_min_u32(k_mine);
         if (k_min < best_key) {  // strict: earlier chunks win ties (BFMatcher keeps the first minimum)
@@ -179,9 +257,9 @@ __device__ __forceinline__ void scanline_search(const uint16_t* __restrict__ box
     out.dist = (int)(best_key >> 16);
     out.idx = (int)(best_key & 0xFFFFu);
     if (!(cutoff > (float)out.dist)) { out.status = SVI_TRI_DISTANCE; return; }
-    const float px = (border + (float)(i_lo + out.idx)) + (float)first;
-    out.u = px + u_tl;
-    out.v = border + v_tl;
+    const float px = (p.border + (float)(p.i_lo + out.idx)) + (float)p.first;
+    out.u = px + p.u_tl;
+    out.v = p.border + p.v_tl;
     out.status = SVI_OK;
 }
 
@@ -197,32 +275,62 @@ __device__ __forceinline__ int point_in_left(const TriConst& tc, float xl, float
     return SVI_OK;
 }
 
-// getPointTriangulatedInRIGHT: range check + pool size (:63-67), then the shared body.
-__device__ __forceinline__ void triangulate_right_dev(const uint16_t* __restrict__ box_r, const FrameGeom& g,
-                                                      const TriConst& tc, float u_tl, float v_tl, float size,
-                                                      float xl, float yl, const uint32_t (&ref)[kDescWords],
-                                                      uint32_t* smem, int lane, SearchResult& r, double* xyz) {
+// getPointTriangulatedInRIGHT: range check + pool size (:63-67), then the shared plan.
+__device__ __forceinline__ void plan_right(const FrameGeom& g, const TriConst& tc, float u_tl, float v_tl, float size,
+                                           float xl, int lane, SearchPlan& p) {
     const float border = 4.f * size;
-    r.dist = -1; r.idx = -1;
-    if (xl <= u_tl + border) { r.status = SVI_TRI_RANGE; return; }
+    if (xl <= u_tl + border) { p.status = SVI_TRI_RANGE; p.n_valid = 0; return; }
     const int n_pool = (int)ceilf((xl - u_tl) - border);
-    scanline_search(box_r, g.box_pitch, g.W, g.H, tc.width_right, u_tl, v_tl, size, 0, n_pool, ref,
-                    tc.match_cutoff, smem, lane, r);
+    search_plan(g.W, g.H, tc.width_right, u_tl, v_tl, size, 0, n_pool, lane, p);
+}
+
+// getPointTriangulatedInLEFT (7 args): :268-272, then the shared plan.
+__device__ __forceinline__ void plan_left(const FrameGeom& g, const TriConst& tc, float search_range, float u_tl,
+                                          float v_tl, float size, int lane, SearchPlan& p) {
+    if (0.f >= search_range) { p.status = SVI_TRI_RANGE; p.n_valid = 0; return; }
+    const int n_pool = (int)ceilf(fminf(search_range, tc.width_left - u_tl)) + 1;
+    search_plan(g.W, g.H, tc.width_left, u_tl, v_tl, size, 1, n_pool, lane, p);
+}
+
+// Whole searches (plan, stage, evaluate, triangulate) for the callers that have nothing to overlap.
+__device__ __forceinline__ void triangulate_right_dev(const FrameGeom& g, const TriConst& tc, PatchStage& ps, float u_tl,
+                                                      float v_tl, float size, float xl, float yl,
+                                                      const uint32_t (&ref)[kDescWords], int lane, SearchResult& r,
+                                                      double* xyz) {
+    SearchPlan p;
+    plan_right(g, tc, u_tl, v_tl, size, xl, lane, p);
+    search_prefetch(p, ps, lane);
+    search_run(p, ps, ref, tc.match_cutoff, lane, r);
     if (r.status == SVI_OK) r.status = point_in_left(tc, xl, yl, r.u, xyz);
 }
 
-// getPointTriangulatedInLEFT (7 args): :268-272 then the shared body; the LEFT point is the match.
-__device__ __forceinline__ void triangulate_left_dev(const uint16_t* __restrict__ box_l, const FrameGeom& g,
-                                                     const TriConst& tc, float search_range, float u_tl, float v_tl,
-                                                     float size, float xr, float yr, const uint32_t (&ref)[kDescWords],
-                                                     uint32_t* smem, int lane, SearchResult& r, double* xyz) {
-    r.dist = -1; r.idx = -1;
-    if (0.f >= search_range) { r.status = SVI_TRI_RANGE; return; }
-    const int n_pool = (int)ceilf(fminf(search_range, tc.width_left - u_tl)) + 1;
-    scanline_search(box_l, g.box_pitch, g.W, g.H, tc.width_left, u_tl, v_tl, size, 1, n_pool, ref,
-                    tc.match_cutoff, smem, lane, r);
+__device__ __forceinline__ void triangulate_left_dev(const FrameGeom& g, const TriConst& tc, PatchStage& ps,
+                                                     float search_range, float u_tl, float v_tl, float size, float xr,
+                                                     const uint32_t (&ref)[kDescWords], int lane, SearchResult& r,
+                                                     double* xyz) {
+    SearchPlan p;
+    plan_left(g, tc, search_range, u_tl, v_tl, size, lane, p);
+    search_prefetch(p, ps, lane);
+    search_run(p, ps, ref, tc.match_cutoff, lane, r);
     if (r.status == SVI_OK) r.status = point_in_left(tc, r.u, r.v, xr, xyz);
-    (void)yr;
+}
+
+// Carve the warp's staging buffers and barrier out of the CTA's dynamic shared memory.
+__device__ __forceinline__ void patch_stage_init(PatchStage& ps, unsigned char* smem, const CUtensorMap* map,
+                                                 const CUtensorMap* map_s, int row_base, int warp, int lane) {
+    unsigned char* mine = smem + (size_t)warp * MATCH_SMEM_PER_WARP;
+    ps.map = map;
+    ps.map_s = map_s;
+    ps.row_base = row_base;
+    ps.smem_a = smem_u32(mine);
+    ps.words = reinterpret_cast<const uint32_t*>(mine);
+    ps.bar = smem_u32(smem + (size_t)MATCH_WARPS * MATCH_SMEM_PER_WARP + warp * 8);
+    ps.phase = 0u;
+    if (lane == 0) {
+        mbar_init(ps.bar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
 }
 
 struct StereoOutDev {
@@ -233,28 +341,33 @@ struct StereoOutDev {
 
 // K5: per key-point of addNewLandmarks (:109-175): LEFT descriptor, scan-line search in RIGHT
 // with uTL = max(0, x - range - 4*size), vTL = y - 4*size (:120-121), triangulation, outputs.
-__global__ void __launch_bounds__(MATCH_WARPS * 32)
-stereo_match_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restrict__ box_r, FrameGeom g,
-                    TriConst tc, float size, float range, const ushort2* __restrict__ kp_xy,
+// The RIGHT window is put in flight by TMA first; the LEFT descriptor gathers run under it.
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
+                    const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float size, float range, const ushort2* __restrict__ kp_xy,
                     const int* __restrict__ n_kp, int max_corners, StereoOutDev out, int out_frame0) {
-    extern __shared__ __align__(16) uint32_t match_smem[];
+    extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y, slot = blockIdx.x * MATCH_WARPS + warp;
     if (slot >= n_kp[f]) return;
-    uint32_t* smem = match_smem + warp * (MATCH_SMEM_PER_WARP / 4);
+    PatchStage ps;
+    patch_stage_init(ps, match_smem, &map_r, &map_rs, f * g.H, warp, lane);
     const ushort2 kp = kp_xy[(size_t)f * max_corners + slot];
     const uint16_t* bl = box_l + (size_t)f * g.H * g.box_pitch;
-    const uint16_t* br = box_r + (size_t)f * g.H * g.box_pitch;
     const float x = (float)kp.x, y = (float)kp.y;
+    const float u_tl = fmaxf(0.f, (x - range) - 4.f * size);
+    const float v_tl = y - 4.f * size;
+    SearchPlan plan;
+    plan_right(g, tc, u_tl, v_tl, size, x, lane, plan);
+    search_prefetch(plan, ps, lane);
 
     uint32_t ref[kDescWords];
     brief_at_point(bl, g.box_pitch, kp.x, kp.y, lane, ref);
 
-    const float u_tl = fmaxf(0.f, (x - range) - 4.f * size);
-    const float v_tl = y - 4.f * size;
     SearchResult r;
     double xyz[3] = {0.0, 0.0, 0.0};
-    triangulate_right_dev(br, g, tc, u_tl, v_tl, size, x, y, ref, smem, lane, r, xyz);
+    search_run(plan, ps, ref, tc.match_cutoff, lane, r);
+    if (r.status == SVI_OK) r.status = point_in_left(tc, x, y, r.u, xyz);
 
     const size_t o = (size_t)(out_frame0 + f) * out.cap + slot;
     store_desc(out.desc_l + o * 32, ref, lane);
@@ -313,22 +426,24 @@ struct TriOutDev {
 
 // svi_triangulate_right / svi_triangulate_left: one warp per query against one image.
 template <bool kLeft>
-__global__ void __launch_bounds__(MATCH_WARPS * 32)
-triangulate_kernel(const uint16_t* __restrict__ box, FrameGeom g, TriConst tc, int n, const float* __restrict__ search_range,
-                   const float* __restrict__ top_left, const float* __restrict__ uv_ref,
-                   const uint8_t* __restrict__ desc_ref, float size, TriOutDev out) {
-    extern __shared__ __align__(16) uint32_t match_smem[];
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+triangulate_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_s, FrameGeom g,
+                   TriConst tc, int n,
+                   const float* __restrict__ search_range, const float* __restrict__ top_left,
+                   const float* __restrict__ uv_ref, const uint8_t* __restrict__ desc_ref, float size, TriOutDev out) {
+    extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * MATCH_WARPS + warp;
     if (q >= n) return;
-    uint32_t* smem = match_smem + warp * (MATCH_SMEM_PER_WARP / 4);
+    PatchStage ps;
+    patch_stage_init(ps, match_smem, &map, &map_s, 0, warp, lane);
     uint32_t ref[kDescWords];
     load_desc(desc_ref + (size_t)q * 32, ref);
     SearchResult r;
     double xyz[3] = {0.0, 0.0, 0.0};
     const float u_tl = top_left[2 * q], v_tl = top_left[2 * q + 1], xq = uv_ref[2 * q], yq = uv_ref[2 * q + 1];
-    if (kLeft) triangulate_left_dev(box, g, tc, search_range[q], u_tl, v_tl, size, xq, yq, ref, smem, lane, r, xyz);
-    else triangulate_right_dev(box, g, tc, u_tl, v_tl, size, xq, yq, ref, smem, lane, r, xyz);
+    if (kLeft) triangulate_left_dev(g, tc, ps, search_range[q], u_tl, v_tl, size, xq, ref, lane, r, xyz);
+    else triangulate_right_dev(g, tc, ps, u_tl, v_tl, size, xq, yq, ref, lane, r, xyz);
     if (r.status == SVI_OK) store_desc(out.desc + (size_t)q * 32, r.w, lane);
     if (lane == 0) {
         out.status[q] = (uint8_t)r.status;
@@ -374,14 +489,17 @@ __device__ __forceinline__ void projection_rounded(const double* P, const double
     v = round_half_away((float)__ddiv_rn(h1, h2));
 }
 
-__global__ void __launch_bounds__(MATCH_WARPS * 32)
-track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restrict__ box_r, FrameGeom g, TriConst tc,
-                    TrackConst k, LandmarksDev lm, int n, TrackOutDev out) {
-    extern __shared__ __align__(16) uint32_t match_smem[];
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restrict__ box_r,
+                    const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_ls,
+                    const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_rs, FrameGeom g,
+                    TriConst tc, TrackConst k, LandmarksDev lm, int n, TrackOutDev out) {
+    extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * MATCH_WARPS + warp;
     if (q >= n) return;
-    uint32_t* smem = match_smem + warp * (MATCH_SMEM_PER_WARP / 4);
+    PatchStage ps;
+    patch_stage_init(ps, match_smem, &map_r, &map_rs, 0, warp, lane);
     const double wx = lm.xyz_w[3 * q], wy = lm.xyz_w[3 * q + 1], wz = lm.xyz_w[3 * q + 2];
     double p[3];
 #pragma unroll
@@ -413,8 +531,9 @@ track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restri
                 brief_at_point(box_l, g.box_pitch, (int)roi_x + brief_centre(half), (int)roi_y + brief_centre(half), lane, mine);
             status = roi_ok ? SVI_TRK_STAGE1_DIST : SVI_TRI_BAD_ROI;
             if (kp_ok && roi_ok && k.cutoff1 > (float)hamming_words(last_l, mine)) {
-                triangulate_right_dev(box_r, g, tc, fmaxf(0.f, roi_x - search), roi_y, size, roi_x + half, roi_y + half,
-                                      mine, smem, lane, r, xyz);
+                ps.map = &map_r; ps.map_s = &map_rs;
+                triangulate_right_dev(g, tc, ps, fmaxf(0.f, roi_x - search), roi_y, size, roi_x + half, roi_y + half, mine,
+                                      lane, r, xyz);
                 status = r.status;
                 if (status == SVI_OK) {
                     if (tc.depth_min > xyz[2] || tc.depth_max < xyz[2]) status = SVI_TRK_DEPTH;
@@ -431,8 +550,8 @@ track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restri
                 brief_at_point(box_r, g.box_pitch, (int)roi_x + brief_centre(half), (int)roi_y + brief_centre(half), lane, mine);
             status = roi_ok ? SVI_TRK_STAGE1_DIST : SVI_TRI_BAD_ROI;
             if (kp_ok && roi_ok && k.cutoff1 > (float)hamming_words(last_r, mine)) {
-                triangulate_left_dev(box_l, g, tc, search, roi_x, roi_y, size, roi_x + half, roi_y + half, mine, smem,
-                                     lane, r, xyz);
+                ps.map = &map_l; ps.map_s = &map_ls;
+                triangulate_left_dev(g, tc, ps, search, roi_x, roi_y, size, roi_x + half, mine, lane, r, xyz);
                 status = r.status;
                 if (status == SVI_OK) {
                     if (tc.depth_min > xyz[2] || tc.depth_max < xyz[2]) status = SVI_TRK_DEPTH;

@@ -40,9 +40,12 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
 // 9x9 box sums (u16, max 81*255 = 20655) of the 64x32 tile from its u8 tile with 4-px halo.
 // S(y,x) = sum over [y-4,y+4]x[x-4,x+4]; equals the 4-corner integral-image expression of
 // OpenCV BRIEF's smoothedSum.  Values within 4 px of the image border are never sampled.
+// `box_shift` (optional) receives the same plane stored one element to the left,
+// box_shift[y][x] = S(y, x+1): TMA tile loads must start on a 16-byte boundary, so the match
+// kernels fetch their odd-aligned copy of a window from this plane at the same aligned address.
 __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint16_t (*h9)[HT_W],
-                                               uint16_t* __restrict__ box, int box_pitch, int W, int H,
-                                               int x0, int y0) {
+                                               uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift,
+                                               int box_pitch, int W, int H, int x0, int y0) {
     for (int item = threadIdx.x; item < U8_ROWS * (HT_W / 16); item += HT_THREADS) {
         int r = item % U8_ROWS, c0 = (item / U8_ROWS) * 16;
         const uint8_t* row = tile[r] + c0;
@@ -67,7 +70,10 @@ __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint
         for (int k = 0; k < 8; ++k) {
             if (k > 0) s += (int)h9[oy0 + k + 8][x] - (int)h9[oy0 + k - 1][x];
             int gy = y0 + oy0 + k;
-            if (gx < W && gy < H) box[(size_t)gy * box_pitch + gx] = (uint16_t)s;
+            if (gx < W && gy < H) {
+                box[(size_t)gy * box_pitch + gx] = (uint16_t)s;
+                if (box_shift && gx > 0) box_shift[(size_t)gy * box_pitch + gx - 1] = (uint16_t)s;
+            }
         }
     }
 }
@@ -75,13 +81,14 @@ __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint
 // K2: box-sum image of one plane per blockIdx.z (used for the RIGHT image, and for both images
 // on the per-query entry points).
 __global__ void __launch_bounds__(HT_THREADS)
-boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box) {
+boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift) {
     __shared__ uint8_t tile[U8_ROWS][U8_P];
     __shared__ uint16_t h9[U8_ROWS][HT_W];
     const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
     load_tile_u8(tile, img + (size_t)f * g.img_stride, g.img_pitch, g.W, g.H, x0, y0);
     __syncthreads();
-    box9_from_tile(tile, h9, box + (size_t)f * g.H * g.box_pitch, g.box_pitch, g.W, g.H, x0, y0);
+    const size_t fo = (size_t)f * g.H * g.box_pitch;
+    box9_from_tile(tile, h9, box + fo, box_shift ? box_shift + fo : nullptr, g.box_pitch, g.W, g.H, x0, y0);
 }
 
 // K1: Harris response + per-frame masked maximum + LEFT box-sum image, one 64x32 tile per CTA.
@@ -93,7 +100,7 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
 __global__ void __launch_bounds__(HT_THREADS, 2)
 harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
                   float f1, float f0, float kf, float* __restrict__ resp, uint16_t* __restrict__ box,
-                  uint32_t* __restrict__ frame_max) {
+                  uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarrisSmem& sm = *reinterpret_cast<HarrisSmem*>(smem_raw);
     const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
@@ -212,8 +219,9 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
         if (m) atomicMax(frame_max + f, m);
     }
     if (box) {
-        box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[HT_W]>(&sm.cov[0][0][0]),
-                       box + (size_t)f * H * g.box_pitch, g.box_pitch, W, H, x0, y0);
+        const size_t fo = (size_t)f * H * g.box_pitch;
+        box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[HT_W]>(&sm.cov[0][0][0]), box + fo,
+                       box_shift ? box_shift + fo : nullptr, g.box_pitch, W, H, x0, y0);
     }
 }
 

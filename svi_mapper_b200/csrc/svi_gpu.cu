@@ -7,6 +7,7 @@
 // lanes stays resident in the B200's 126 MB L2 between the producing and the consuming kernel;
 // different lanes overlap each other's copies, wide kernels (Harris, match) and the
 // one-CTA-per-frame selection kernel.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -36,8 +37,10 @@ struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     float* resp = nullptr;
-    uint16_t* box_l = nullptr;
-    uint16_t* box_r = nullptr;
+    uint16_t* box_l = nullptr;   // S(y,x) of LEFT
+    uint16_t* box_r = nullptr;   // S(y,x) of RIGHT
+    uint16_t* box_ls = nullptr;  // planes stored shifted by one element, S(y,x+1): the odd-aligned TMA copies
+    uint16_t* box_rs = nullptr;
     uint32_t* frame_max = nullptr;
     int* cand_count = nullptr;
     unsigned long long* cand = nullptr;
@@ -52,6 +55,7 @@ struct Lane {
     uint8_t* img_l = nullptr;
     uint8_t* img_r = nullptr;
     uint8_t* mask = nullptr;
+    CUtensorMap map_l{}, map_r{}, map_ls{}, map_rs{};  // TMA views of the four planes: (W, chunk*H) u16, row pitch box_pitch
     StereoOutDev out{};
     std::vector<cudaEvent_t> ev;  // stage boundary events (profiling)
     size_t ev_used = 0;
@@ -117,6 +121,36 @@ void* arena_alloc(svi_ctx* c, size_t bytes) {
     return c->arena + off;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no libcuda link needed).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch, std::string* err) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p ||
+            q != cudaDriverEntryPointSuccess) {
+            *err = "cuTensorMapEncodeTiled is not available from this driver";
+            return false;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)box_pitch * sizeof(uint16_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)PATCH_W, (cuuint32_t)PATCH_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
 cudaEvent_t lane_event(Lane& l) {
     if (l.ev_used == l.ev.size()) {
         cudaEvent_t e;
@@ -156,9 +190,9 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, nf);
     mark(ctx, l);
     harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf,
-                                                                    l.resp, l.box_l, l.frame_max);
+                                                                    l.resp, l.box_l, nullptr, l.frame_max);
     mark(ctx, l);
-    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r);
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
     const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_TH - 1) / NMS_TH, nf);
     nms_candidates_kernel<<<ngrid, dim3(NMS_TW, NMS_TH), 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
@@ -173,7 +207,7 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     }
     mark(ctx, l);
     const dim3 mgrid((ctx->p.max_corners + MATCH_WARPS - 1) / MATCH_WARPS, nf);
-    stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, g, ctx->tc, ctx->p.keypoint_size,
+    stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size,
                                                                     ctx->p.search_range_px, l.kp_xy, n_kp,
                                                                     ctx->p.max_corners, out, out_frame0);
     mark(ctx, l);
@@ -206,11 +240,12 @@ cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<vo
 
 // ---- per-query entry points: one image (or pair) staged in lane 0, queries in the arena ----
 namespace {
-int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, cudaStream_t s) {
+int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, uint16_t* d_box_shift,
+              cudaStream_t s) {
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
     CK(cudaMemcpy2DAsync(d_img, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
-    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_img, g, d_box);
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_img, g, d_box, d_box_shift);
     CK(cudaGetLastError());
     return SVI_SUCCESS;
 }
@@ -242,7 +277,7 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0;
-    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, s);
+    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     float* d_range = nullptr; float* d_tl; float* d_uv; uint8_t* d_desc;
     TriOutDev o;
@@ -262,9 +297,9 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
     const int blocks = (n + MATCH_WARPS - 1) / MATCH_WARPS;
     if (left_search)
-        triangulate_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, g, ctx->tc, n, d_range, d_tl, d_uv, d_desc, size, o);
+        triangulate_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.map_l, l.map_ls, g, ctx->tc, n, d_range, d_tl, d_uv, d_desc, size, o);
     else
-        triangulate_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, g, ctx->tc, n, nullptr, d_tl, d_uv, d_desc, size, o);
+        triangulate_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.map_l, l.map_ls, g, ctx->tc, n, nullptr, d_tl, d_uv, d_desc, size, o);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out->uv, o.uv, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->xyz_left, o.xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
@@ -332,7 +367,7 @@ void svi_destroy(svi_ctx* ctx) {
     for (int i = 0; i < kMaxLanes; ++i) {
         Lane& l = ctx->lanes[i];
         if (l.stream) cudaStreamSynchronize(l.stream);
-        void* ptrs[] = {l.resp, l.box_l, l.box_r, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
+        void* ptrs[] = {l.resp, l.box_l, l.box_r, l.box_ls, l.box_rs, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
                         l.g_head, l.g_next, l.g_state, l.img_l, l.img_r, l.mask, l.out.uv_l, l.out.uv_r, l.out.xyz,
                         l.out.desc_l, l.out.desc_r, l.out.dist, l.out.idx, l.out.status};
         for (void* p : ptrs) if (p) cudaFree(p);
@@ -383,7 +418,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     ctx->p = p;
     ctx->W = (int)left->width;
     ctx->H = (int)left->height;
-    ctx->dev_pitch = align_up(ctx->W, 16);
+    ctx->dev_pitch = ctx->W;  // dense rows: staging copies are 1-D DMA transfers at full PCIe rate
     ctx->resp_pitch = align_up(ctx->W, 32);
     ctx->box_pitch = align_up(ctx->W, 64);
     const char* env_chunk = std::getenv("SVI_CHUNK_FRAMES");
@@ -436,6 +471,17 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(cudaFuncSetAttribute(triangulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(triangulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(track_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    // one shared-memory carve-out for every kernel of the pipeline: back-to-back kernels with different
+    // carve-outs make the SMs drain and reconfigure between launches
+    {
+        const void* kernels[] = {(const void*)harris_box_kernel, (const void*)boxsum9_kernel, (const void*)nms_candidates_kernel,
+                                 (const void*)select_corners_kernel<true>, (const void*)select_corners_kernel<false>,
+                                 (const void*)stereo_match_kernel, (const void*)triangulate_kernel<true>,
+                                 (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
+                                 (const void*)describe_kernel, (const void*)hamming_match_kernel};
+        for (const void* k : kernels)
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
 
     const size_t C = (size_t)ctx->chunk, HH = (size_t)ctx->H, MC = (size_t)p.max_corners;
     for (int i = 0; i < ctx->n_lanes; ++i) {
@@ -445,6 +491,20 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         CK(dmalloc(&l.resp, C * HH * ctx->resp_pitch));
         CK(dmalloc(&l.box_l, C * HH * ctx->box_pitch));
         CK(dmalloc(&l.box_r, C * HH * ctx->box_pitch));
+        CK(dmalloc(&l.box_ls, C * HH * ctx->box_pitch));
+        CK(dmalloc(&l.box_rs, C * HH * ctx->box_pitch));
+        CK(cudaMemset(l.box_ls, 0, sizeof(uint16_t) * C * HH * ctx->box_pitch));
+        CK(cudaMemset(l.box_rs, 0, sizeof(uint16_t) * C * HH * ctx->box_pitch));
+        {
+            std::string merr;
+            if (!make_box_map(&l.map_l, l.box_l, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
+                !make_box_map(&l.map_ls, l.box_ls, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
+                !make_box_map(&l.map_rs, l.box_rs, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
+                !make_box_map(&l.map_r, l.box_r, ctx->W, (int)(C * HH), ctx->box_pitch, &merr)) {
+                svi_destroy(ctx);
+                return fail(nullptr, SVI_ERR_CUDA, merr);
+            }
+        }
         CK(dmalloc(&l.frame_max, C));
         CK(dmalloc(&l.cand_count, C));
         CK(dmalloc(&l.cand, C * cap));
@@ -544,7 +604,9 @@ int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, s
         uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
         for (int k = 0; k < 3; ++k) {
             if (!srcs[k]) continue;
-            if (dense) {
+            if (dense && (int)pitch == ctx->dev_pitch) {
+                CK(cudaMemcpyAsync(dsts[k], srcs[k] + (size_t)f0 * frame_stride, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, s));
+            } else if (dense) {
                 CK(cudaMemcpy2DAsync(dsts[k], ctx->dev_pitch, srcs[k] + (size_t)f0 * frame_stride, pitch, W, (size_t)H * nf,
                                      cudaMemcpyHostToDevice, s));
             } else {
@@ -556,9 +618,16 @@ int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, s
         int rc = run_pipeline(ctx, l, l.img_l, l.img_r, masks ? l.mask : nullptr, g, nf, l.out, 0, l.n_kp, l.n_det);
         if (rc != SVI_SUCCESS) return rc;
         const size_t o0 = (size_t)f0 * cap;
-#define D2H(dst, src, elem)                                                                                         \
-    CK(cudaMemcpy2DAsync((dst) + o0 * (elem), (size_t)cap * (elem) * sizeof(*(dst)), (src), (size_t)MC * (elem) * sizeof(*(dst)), \
-                         (size_t)MC * (elem) * sizeof(*(dst)), nf, cudaMemcpyDeviceToHost, s))
+#define D2H(dst, src, elem)                                                                                             \
+    do {                                                                                                                \
+        if (cap == MC)                                                                                                  \
+            CK(cudaMemcpyAsync((dst) + o0 * (elem), (src), (size_t)nf * MC * (elem) * sizeof(*(dst)),                   \
+                               cudaMemcpyDeviceToHost, s));                                                             \
+        else                                                                                                            \
+            CK(cudaMemcpy2DAsync((dst) + o0 * (elem), (size_t)cap * (elem) * sizeof(*(dst)), (src),                     \
+                                 (size_t)MC * (elem) * sizeof(*(dst)), (size_t)MC * (elem) * sizeof(*(dst)), nf,        \
+                                 cudaMemcpyDeviceToHost, s));                                                           \
+    } while (0)
         D2H(out->uv_left, l.out.uv_l, 2);
         D2H(out->uv_right, l.out.uv_r, 2);
         D2H(out->xyz_left, l.out.xyz, 3);
@@ -587,7 +656,7 @@ int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* r
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t), s));
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
     harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                    nullptr, l.frame_max);
+                                                                    nullptr, nullptr, l.frame_max);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, l.resp, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
                          ctx->H, cudaMemcpyDeviceToHost, s));
@@ -620,7 +689,7 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
         const dim3 tiles((W + HT_W - 1) / HT_W, (H + HT_H - 1) / HT_H, nf);
         harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                        nullptr, l.frame_max);
+                                                                        nullptr, nullptr, l.frame_max);
         const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_TH - 1) / NMS_TH, nf);
         nms_candidates_kernel<<<ngrid, dim3(NMS_TW, NMS_TH), 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
                                                                      l.cand_count, ctx->cand_cap);
@@ -653,7 +722,7 @@ int svi_describe(svi_ctx* ctx, const uint8_t* img, size_t pitch, const float* xy
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0;
-    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, s);
+    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     float* d_xy; uint8_t* d_desc; uint8_t* d_kept;
     UP(d_xy, xy, (size_t)n * 2);
@@ -740,9 +809,9 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0;
-    int rc = stage_box(ctx, img_left, pitch, l.img_l, l.box_l, s);
+    int rc = stage_box(ctx, img_left, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
-    rc = stage_box(ctx, img_right, pitch, l.img_r, l.box_r, s);
+    rc = stage_box(ctx, img_right, pitch, l.img_r, l.box_r, l.box_rs, s);
     if (rc != SVI_SUCCESS) return rc;
     double* d_xyzw; uint8_t* d_dl; uint8_t* d_dr; float* d_disp; float* d_size;
     UP(d_xyzw, lm->xyz_world, (size_t)n * 3);
@@ -769,7 +838,8 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
     k.cutoff1 = ctx->p.cutoff_stage1;
     LandmarksDev ld{d_xyzw, d_dl, d_dr, d_disp, d_size};
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
-    track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, g, ctx->tc, k, ld, n, o);
+    track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
+                                                                                                  ctx->tc, k, ld, n, o);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
