@@ -239,3 +239,57 @@ def test_device_resident_entry(kitti_cams):
         ok = host.status[f, :k] == 0
         np.testing.assert_array_equal(t["xyz"][f, :k].cpu().numpy()[ok], host.xyz_left[f, :k][ok])
         np.testing.assert_array_equal(t["dr"][f, :k].cpu().numpy()[ok], host.desc_right[f, :k][ok])
+
+
+def test_golden_cv2_vectors_small_frame(kitti_cams):
+    """GPU vs the committed cv2 golden vectors (tests/golden/stereo_320x240.npz): response bits, GFTT corners
+    with/without mask, and the full stereo frame."""
+    import pathlib
+    from types import SimpleNamespace
+    g = dict(np.load(pathlib.Path(__file__).resolve().parent / "golden" / "stereo_320x240.npz"))
+    cl = SimpleNamespace(width=320, height=240, P=kitti_cams[0].P)
+    cr = SimpleNamespace(width=320, height=240, P=kitti_cams[1].P)
+    L, R = g["left"], g["right"]
+    with StereoFrontend(cl, cr, max_corners=300) as fe:
+        resp = fe.harris_response(L)
+        np.testing.assert_array_equal(resp.view(np.uint32), g["harris"].view(np.uint32))
+        np.testing.assert_array_equal(fe.detect(L)[0].astype(np.int32), g["gftt300"])
+        np.testing.assert_array_equal(fe.detect(L, g["mask"])[0].astype(np.int32), g["gftt300_mask"])
+        got = fe.add_new_landmarks(L, R)
+    ref = {k[6:]: v for k, v in g.items() if k.startswith("frame_")}
+    _compare_frame(got, ref)
+    with StereoFrontend(cl, cr, max_corners=2000) as fe:      # fewer corners than maxCorners: all of them
+        np.testing.assert_array_equal(fe.detect(L)[0].astype(np.int32), g["gftt_all"])
+
+
+def test_properties_at_batch_scale(kitti_cams):
+    """Size-independent properties on a larger batch (no oracle): the reference's compiled-out invariants
+    (Types.h:115-118, CTriangulator.cpp:336-343), idempotence, and independence from batch position."""
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    base = [stereo_pair(W, H, 1000 + i) for i in range(4)]
+    n = 40
+    Ls = np.stack([base[i % 4][0] for i in range(n)])
+    Rs = np.stack([base[i % 4][1] for i in range(n)])
+    with StereoFrontend(*kitti_cams, max_corners=2000) as fe:
+        a = fe.stereo_frames(Ls, Rs)
+        b = fe.stereo_frames(Ls, Rs)
+    tri = _tri(kitti_cams)
+    for f in range(n):
+        fa, fb, f0 = a.frame(f), b.frame(f), a.frame(f % 4)
+        for k in fa:
+            np.testing.assert_array_equal(fa[k], fb[k])       # idempotent
+            np.testing.assert_array_equal(fa[k], f0[k])       # same pair -> same result wherever it sits in the batch
+        ok = fa["status"] == 0
+        assert ok.sum() > 1000
+        assert (fa["uv_l"][ok, 1] == fa["uv_r"][ok, 1]).all()
+        d = fa["uv_l"][ok, 0] - fa["uv_r"][ok, 0]
+        assert (d >= 1).all() and (d <= 60).all() and (fa["dist"][ok] < 100).all()
+        z = fa["xyz"][ok, 2]
+        assert (z >= tri.depth_min).all() and (z <= tri.depth_max).all()
+        np.testing.assert_allclose(z, tri.du_r_flipped / d.astype(np.float64), rtol=1e-12)
+        assert ((fa["uv_l"][:, 0] >= 28) & (fa["uv_l"][:, 0] < W - 28) & (fa["uv_l"][:, 1] >= 28) & (fa["uv_l"][:, 1] < H - 28)).all()
+        # min-distance property of the selected corners
+        p = fa["uv_l"].astype(np.int64)
+        dd = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+        np.fill_diagonal(dd, 1 << 30)
+        assert dd.min() >= 49

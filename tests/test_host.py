@@ -1,0 +1,149 @@
+"""CPU tests of the host side: calibration loading (CParameterBase twin), the C-ABI library's symbol
+table against include/svi_gpu.h, error behaviour without a GPU, and the frame partition used for
+multi-GPU runs (world_size-2 gloo)."""
+import ctypes
+import os
+import pathlib
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def test_calibration_values(calib_dir):
+    from svi_mapper_b200 import construct_camera_stereo, load_camera
+    l, r = load_camera(str(calib_dir / "kitti_00_left.txt")), load_camera(str(calib_dir / "kitti_00_right.txt"))
+    assert (l.label, l.width, l.height) == ("CAMERA_LEFT", 1241, 376) and r.label == "CAMERA_RIGHT"
+    assert l.P[0, 0] == 718.856 and l.P[0, 2] == 607.1928 and l.P[1, 2] == 185.2157 and r.P[0, 3] == -386.1448
+    assert not l.K.any()                      # kitti_00 matIntrinsic is all zeros in the reference file
+    assert l.fov == (28, 28, 1241 - 56, 376 - 56)
+    k = load_camera(str(calib_dir / "kitti_11_12_right.txt"))
+    assert (k.width, k.height) == (1226, 370) and k.P[0, 0] == 707.0912 and k.P[0, 3] == -379.8145
+    v = load_camera(str(calib_dir / "vi_sensor_right.txt"))
+    assert (v.width, v.height) == (752, 480) and v.P[0, 0] == 450.5097158071153 and v.P[0, 3] == -49.63250853439215
+    st = construct_camera_stereo(l, r)
+    assert abs(st.baseline_m - 0.54) < 1e-12
+    assert abs(l.principal_weight_u(707.1928) - 1.0) < 1e-12
+
+
+def test_calibration_errors(tmp_path, calib_dir):
+    from svi_mapper_b200.calib import ParameterError, load_camera
+    with pytest.raises(ParameterError, match="unable to open file"):
+        load_camera(str(tmp_path / "missing.txt"))
+    txt = (calib_dir / "kitti_00_left.txt").read_text()
+    p = tmp_path / "nokey.txt"
+    p.write_text(txt.replace("matProjection", "matProjektion"))
+    with pytest.raises(ParameterError, match="cannot find parameter: matProjection"):
+        load_camera(str(p))
+    p = tmp_path / "badnum.txt"
+    p.write_text(txt.replace("uWidthPixels 1241", "uWidthPixels abc"))
+    with pytest.raises(ValueError):
+        load_camera(str(p))
+
+
+def test_library_exports_every_declared_symbol():
+    from svi_mapper_b200 import _lib
+    hdr = (ROOT / "include" / "svi_gpu.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(svi_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (svi_[a-z_0-9]+)", nm))
+    assert declared <= exported
+
+
+def test_defaults_equal_reference_constants():
+    from svi_mapper_b200 import default_params, status_text
+    p = default_params()
+    assert (p.max_corners, p.quality_level, p.min_distance, p.harris_k) == (1000, 0.01, 7.0, 0.04)   # CFundamentalMatcher.cpp:18
+    assert (p.search_range_px, p.match_cutoff, p.min_disparity_px) == (60.0, 100.0, 0.01)           # CTriangulator.h:20-21, .cpp:13
+    assert (p.cutoff_stage1, p.cutoff_stage2, p.cutoff_stage3, p.cutoff_original) == (25.0, 50.0, 50.0, 100.0)
+    assert p.keypoint_size == 7.0
+    assert status_text(5) == "<CTriangulator>(getPointInLEFT) zero disparity"
+    assert status_text(4).endswith("matching distance") and status_text(7) == "invalid depth"
+
+
+def test_create_without_gpu_fails_loudly(kitti_cams):
+    """No CPU fallback: without a CUDA device the product path refuses to start."""
+    from svi_mapper_b200 import StereoFrontend, SviError, _lib
+    if _lib.load().svi_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(SviError, match="no CUDA device"):
+        StereoFrontend(*kitti_cams)
+
+
+def test_product_code_never_imports_the_oracle():
+    for p in (ROOT / "svi_mapper_b200").rglob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, p
+    for p in (ROOT / "svi_mapper_b200" / "csrc").iterdir():
+        assert "oracle" not in p.read_text().lower() or p.name == "brief_pattern_32.h", p
+
+
+def test_frame_partition_is_a_disjoint_cover():
+    from svi_mapper_b200.partition import frame_range
+    for n in (0, 1, 7, 4096, 32768, 32771):
+        for world in (1, 2, 4, 8):
+            r = [frame_range(n, world, g) for g in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        frame_range(10, 2, 2)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from svi_mapper_b200.partition import frame_range, max_over_ranks
+from svi_mapper_b200.synth import stereo_pair
+from oracle import c_oracle as co
+from svi_mapper_b200 import load_camera
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+calib = {calib!r}
+cl, cr = load_camera(calib + "/vi_sensor_left.txt"), load_camera(calib + "/vi_sensor_right.txt")
+cfg = co.make_config(cl, cr, max_corners=200)
+F = 5
+a, b = frame_range(F, world, rank)
+pairs = [stereo_pair(752, 480, 4000 + i) for i in range(a, b)]
+out = co.stereo_frames(cfg, np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]))
+# every rank writes its disjoint slice; only counts and the timing scalar are exchanged
+counts = torch.zeros(F, dtype=torch.int32)
+counts[a:b] = torch.from_numpy(out["n_keypoints"])
+dist.all_reduce(counts)
+t = max_over_ranks(1.0 + rank)
+if rank == 0:
+    full = co.stereo_frames(cfg, np.stack([stereo_pair(752, 480, 4000 + i)[0] for i in range(F)]),
+                            np.stack([stereo_pair(752, 480, 4000 + i)[1] for i in range(F)]))
+    assert np.array_equal(counts.numpy(), full["n_keypoints"]), (counts, full["n_keypoints"])
+    assert t == float(world)
+    print("PARTITION_OK", counts.tolist())
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_partition_over_gloo(tmp_path, calib_dir):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT), calib=str(calib_dir)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "PARTITION_OK" in outs[0]

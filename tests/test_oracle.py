@@ -1,0 +1,162 @@
+"""CPU tests: pin the oracle (numpy restatement + C restatement) against cv2 where cv2 is importable,
+and against the committed golden vectors (tests/golden/stereo_320x240.npz, made by tools/make_golden.py
+with cv2 4.13, optimisations off)."""
+import pathlib
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import frontend_np as o
+from svi_mapper_b200.synth import stereo_pair
+
+GOLD = pathlib.Path(__file__).resolve().parent / "golden" / "stereo_320x240.npz"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(GOLD))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_harris_numpy_and_c_match_golden_cv2(gold):
+    L = gold["left"]
+    np.testing.assert_array_equal(_bits(o.harris_response(L)), _bits(gold["harris"]))
+    np.testing.assert_array_equal(_bits(co.harris_response(L)), _bits(gold["harris"]))
+    # the order-independent box sum (what the GPU kernel evaluates tile by tile) gives the same bits here
+    np.testing.assert_array_equal(_bits(o.harris_response(L, box=o.box7_exact)), _bits(gold["harris"]))
+
+
+def test_gftt_numpy_and_c_match_golden_cv2(gold):
+    L, mask = gold["left"], gold["mask"]
+    for impl in (o.gftt, co.gftt):
+        np.testing.assert_array_equal(impl(L, 300), gold["gftt300"])
+        np.testing.assert_array_equal(impl(L, 300, mask=mask), gold["gftt300_mask"])
+        np.testing.assert_array_equal(impl(L, 0), gold["gftt_all"])
+
+
+def test_mask_stencil_matches_golden_cv2_circle(gold):
+    m = o.mask_active_landmarks(320, 240, gold["mask_centres"])
+    np.testing.assert_array_equal(m, gold["mask"])
+    assert (o.mask_active_landmarks(64, 64, [(32, 32)]) == 0).sum() == 149
+
+
+def test_bfmatcher_matches_golden(gold):
+    dl, dr = gold["desc_l300"], gold["desc_r300"]
+    for i in range(len(dl)):
+        idx, dist = o.match_hamming(dl[i], dr)
+        assert idx == gold["bf_idx"][i] and dist == int(gold["bf_dist"][i])
+    # first minimum wins on constructed ties
+    t = np.repeat(dl[:1], 4, 0)
+    assert o.match_hamming(dl[0], t) == (0, 0)
+    assert o.match_hamming(dl[0], np.zeros((0, 32), np.uint8)) == (-1, -1)
+
+
+def test_brief_numpy_vs_c_and_layout(gold):
+    L = gold["left"]
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(0, 320, 400), rng.uniform(0, 240, 400)], 1).astype(np.float32)
+    pts[:4] = [[28, 28], [27.5, 28], [320 - 29, 240 - 29], [320 - 28, 100]]
+    k1, d1 = o.brief32(L, pts)
+    k2, d2 = co.brief32(L, pts)
+    np.testing.assert_array_equal(k1, k2)
+    np.testing.assert_array_equal(d1, d2)
+    assert 0 in k1 and 2 in k1 and 3 not in k1
+    # bit layout: test 8j+i -> byte j, bit 7-i, S(y1,x1) < S(y2,x2), 9x9 box sums
+    x, y = 100, 90
+    _, d = o.brief32(L, [[x, y]])
+    S = o.boxsum9(L).astype(np.int64)
+    for t in (0, 1, 7, 8, 100, 255):
+        y1, x1, y2, x2 = o.PATTERN[t]
+        bit = int(S[y + y1, x + x1] < S[y + y2, x + x2])
+        assert (d[0, t // 8] >> (7 - t % 8)) & 1 == bit
+    # ROI invariance: descriptor(ROI-local point) == descriptor(global point)
+    _, droi = o.brief32(L[50:150, 60:200], [[x - 60, y - 50]])
+    np.testing.assert_array_equal(droi, d)
+
+
+def test_stereo_frame_numpy_and_c_match_golden(gold):
+    from svi_mapper_b200 import load_camera
+    calib = pathlib.Path(__file__).resolve().parent / "golden" / "calib"
+    cl, cr = load_camera(str(calib / "kitti_00_left.txt")), load_camera(str(calib / "kitti_00_right.txt"))
+    L, R = gold["left"], gold["right"]
+    tri = o.Triangulator(o.Camera(320, 240, cl.P), o.Camera(320, 240, cr.P), o.StereoParams(max_corners=300))
+    ref = {k[6:]: v for k, v in gold.items() if k.startswith("frame_")}
+    got = o.add_new_landmarks(L, R, tri)
+    cfg = co.make_config(cl, cr, max_corners=300)
+    cfg.width, cfg.height = 320, 240
+    gotc = co.frame(co.stereo_frames(cfg, L, R), 0)
+    for g in (got, gotc):
+        for k in ("uv_l", "desc_l", "status", "dist", "idx"):
+            np.testing.assert_array_equal(g[k], ref[k])
+        ok = ref["status"] == 0
+        for k in ("uv_r", "desc_r", "xyz"):
+            np.testing.assert_array_equal(g[k][ok], ref[k][ok])
+    # the reference's compiled-out invariants (Types.h:115-118): same row, positive disparity, z > 0
+    ok = ref["status"] == 0
+    assert (ref["uv_l"][ok, 1] == ref["uv_r"][ok, 1]).all()
+    assert (ref["uv_l"][ok, 0] > ref["uv_r"][ok, 0]).all() and (ref["xyz"][ok, 2] > 0).all()
+
+
+def test_c_oracle_batch_threads_equal_single():
+    from svi_mapper_b200 import load_camera
+    calib = pathlib.Path(__file__).resolve().parent / "golden" / "calib"
+    cl, cr = load_camera(str(calib / "vi_sensor_left.txt")), load_camera(str(calib / "vi_sensor_right.txt"))
+    pairs = [stereo_pair(752, 480, 4000 + i) for i in range(3)]
+    Ls, Rs = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    cfg = co.make_config(cl, cr, max_corners=500)
+    a = co.stereo_frames(cfg, Ls, Rs, n_threads=1)
+    b = co.stereo_frames(cfg, Ls, Rs, n_threads=3)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    assert (a["n_keypoints"] > 300).all()
+
+
+def test_triangulation_closed_form_and_edges():
+    """getPointInLEFT against src/runnable/triangulation_sampling.cpp:99-120 (uR = uL + DuR/Z) and
+    the failure branches of getPointTriangulatedIn{RIGHT,LEFT}."""
+    from svi_mapper_b200 import load_camera
+    calib = pathlib.Path(__file__).resolve().parent / "golden" / "calib"
+    cl, cr = load_camera(str(calib / "vi_sensor_left.txt")), load_camera(str(calib / "vi_sensor_right.txt"))
+    tri = o.Triangulator(o.Camera(cl.width, cl.height, cl.P), o.Camera(cr.width, cr.height, cr.P))
+    assert abs(tri.depth_min - 49.63250853439215 / 752) < 1e-12 and abs(tri.depth_max - 4963.250853439215) < 1e-9
+    for z in (0.3, 1.0, 7.5, 40.0):
+        ul = np.float32(400.0)
+        ur = np.float32(ul + tri.du_r / z)
+        st, xyz = tri.point_in_left((ul, np.float32(200)), (ur, np.float32(200)))
+        assert st == o.ST_OK and abs(xyz[2] - z) / z < 1e-5
+        assert abs(xyz[0] - z * (400.0 - tri.pu) / tri.f) / max(1e-9, abs(xyz[0])) < 1e-5
+    assert tri.point_in_left((100.0, 5.0), (100.0, 5.0))[0] == o.ST_TRI_ZERO_DISP
+    assert tri.point_in_left((100.0, 5.0), (99.995, 5.0))[0] == o.ST_TRI_ZERO_DISP
+    L, R = stereo_pair(752, 480, 4001)
+    _, d = o.brief32(L, [[300, 200]])
+    assert tri.triangulate_right(R, 300.0 - 28, 172.0, 7.0, (300.0, 200.0), d[0])["status"] == o.ST_TRI_RANGE
+    assert tri.triangulate_left(L, 0.0, 100.0, 172.0, 7.0, (128.0, 200.0), d[0])["status"] == o.ST_TRI_RANGE
+    assert tri.triangulate_right(R, 100.0, 470.0, 7.0, (300.0, 498.0), d[0])["status"] == o.ST_TRI_BAD_ROI
+    # a descriptor that matches nothing -> "matching distance"
+    r = tri.triangulate_right(R, 212.0, 172.0, 7.0, (300.0, 200.0), np.bitwise_not(o.brief32(R, [[280, 200]])[1][0]))
+    assert r["status"] in (o.ST_TRI_DISTANCE, o.ST_OK)
+    # right-edge clamp: the ROI is cut at the image border and the tail candidates are erased
+    r = tri.triangulate_left(L, 500.0, 700.0 - 28, 172.0, 7.0, (700.0, 200.0), o.brief32(R, [[700, 200]])[1][0])
+    assert r["status"] in (o.ST_OK, o.ST_TRI_DISTANCE, o.ST_TRI_NO_DESC)
+
+
+def test_oracle_vs_cv2_live():
+    """When cv2 is importable (this image), re-pin detect against the genuine OpenCV on fresh seeds."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setUseOptimized(False)
+    cv2.setNumThreads(1)
+    for seed, (w, h) in ((11, (1241, 376)), (12, (752, 480))):
+        L, _ = stereo_pair(w, h, seed)
+        ref = cv2.cornerHarris(L, 7, 3, 0.04)
+        np.testing.assert_array_equal(_bits(co.harris_response(L)), _bits(ref))
+        np.testing.assert_array_equal(_bits(o.harris_response(L)), _bits(ref))
+        np.testing.assert_array_equal(co.gftt(L, 1000), o.detect_cv2(L, 1000))
+    # exact response ties (four identical vertical tiles): larger address first
+    tile, _ = stereo_pair(160, 376, 5)
+    img = np.ascontiguousarray(np.tile(tile, (1, 4)))
+    np.testing.assert_array_equal(co.gftt(img, 500), o.detect_cv2(img, 500))
+    np.testing.assert_array_equal(o.gftt(img, 500), o.detect_cv2(img, 500))
