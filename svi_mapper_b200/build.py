@@ -59,5 +59,18 @@ def build_library(force: bool = False, verbose: bool = False) -> pathlib.Path:
     return LIB
 
 
+def build_host_demo() -> pathlib.Path:
+    """g++ build of the C++ host facade's demo driver (links libsvi_gpu.so through an $ORIGIN rpath)."""
+    host = PKG / "host"
+    exe = host / "facade_demo"
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", str(exe), str(host / "facade_demo.cpp"),
+           "-L" + str(PKG), "-lsvi_gpu", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return exe
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host_demo())

@@ -1,0 +1,243 @@
+// CFundamentalMatcher -- image-space half of the reference's src/core/CFundamentalMatcher.{h,cpp}
+// (addNewLandmarks :83-193, trackManual stage 1 :1404-1538, getMaskActiveLandmarks :2043-2073,
+// visibility bookkeeping :244-263, :2005-2009) with the per-key-point / per-landmark image work done by
+// ONE batched GPU call per frame instead of one OpenCV call per item.  CLandmark keeps the fields the
+// optimisation side reads (src/types/CLandmark.h:35-59); CLandmark::optimize / g2o stay with the caller.
+#ifndef SVI_HOST_CFUNDAMENTALMATCHER_H
+#define SVI_HOST_CFUNDAMENTALMATCHER_H
+
+#include <cmath>
+
+#include "CTriangulator.h"
+
+class CLandmark {
+public:
+    CLandmark(const UIDLandmark& p_uID, const CDescriptor& p_matDescriptorLEFT, const CDescriptor& p_matDescriptorRIGHT, const double& p_dKeyPointSize,
+              const Point2f& p_ptUVLEFT, const Point2f& p_ptUVRIGHT, const CPoint3DCAMERA& p_vecPointXYZLEFT,
+              const Isometry3d& p_matTransformationLEFTtoWORLD, const Isometry3d& p_matTransformationWORLDtoLEFT,
+              const MatrixProjection& p_matProjectionWORLDtoLEFT, const MatrixProjection& p_matProjectionWORLDtoRIGHT, const UIDFrame& p_uIDFrame)
+        : uID(p_uID), matDescriptorReferenceLEFT(p_matDescriptorLEFT), matDescriptorReferenceRIGHT(p_matDescriptorRIGHT), dKeyPointSize(p_dKeyPointSize),
+          uIDFrameAtCreation(p_uIDFrame), vecPointXYZInitial(p_matTransformationLEFTtoWORLD * p_vecPointXYZLEFT), vecPointXYZOptimized(vecPointXYZInitial) {
+        addMeasurement(p_uIDFrame, p_ptUVLEFT, p_ptUVRIGHT, p_matDescriptorLEFT, p_matDescriptorRIGHT, p_vecPointXYZLEFT, p_matTransformationLEFTtoWORLD,
+                       p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT, p_matProjectionWORLDtoRIGHT);
+    }
+    ~CLandmark() { for (const CMeasurementLandmark* p : m_vecMeasurements) delete p; }
+    CLandmark(const CLandmark&) = delete;
+
+    const UIDLandmark uID;
+    const CDescriptor matDescriptorReferenceLEFT, matDescriptorReferenceRIGHT;
+    const double dKeyPointSize;
+    const UIDFrame uIDFrameAtCreation;
+    const CPoint3DWORLD vecPointXYZInitial;
+    CPoint3DWORLD vecPointXYZOptimized;
+    uint8_t uFailedSubsequentTrackings = 0;
+    uint32_t uOptimizationsSuccessful = 0, uOptimizationsFailed = 0;
+    bool bIsOptimal = false, bIsCurrentlyVisible = false;
+    uint32_t uNumberOfKeyFramePresences = 0;
+    std::vector<CDescriptor> vecDescriptorsLEFT, vecDescriptorsRIGHT;
+
+    // src/types/CLandmark.cpp:80-279 without the per-bit statistics (loop-closure data, out of scope)
+    void addMeasurement(const UIDFrame&, const Point2f& p_ptUVLEFT, const Point2f& p_ptUVRIGHT, const CDescriptor& p_matDescriptorLEFT,
+                        const CDescriptor& p_matDescriptorRIGHT, const CPoint3DCAMERA& p_vecXYZLEFT, const Isometry3d& p_matTransformationLEFTtoWORLD,
+                        const Isometry3d& p_matTransformationWORLDtoLEFT, const MatrixProjection& p_matProjectionWORLDtoLEFT,
+                        const MatrixProjection& p_matProjectionWORLDtoRIGHT) {
+        vecDescriptorsLEFT.push_back(p_matDescriptorLEFT);
+        vecDescriptorsRIGHT.push_back(p_matDescriptorRIGHT);
+        m_vecMeasurements.push_back(new CMeasurementLandmark(uID, p_ptUVLEFT, p_ptUVRIGHT, p_vecXYZLEFT, p_matTransformationLEFTtoWORLD * p_vecXYZLEFT,
+                                                             vecPointXYZOptimized, p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT,
+                                                             p_matProjectionWORLDtoRIGHT, uOptimizationsSuccessful));
+    }
+    const Point2f getLastDetectionLEFT() const { return m_vecMeasurements.back()->ptUVLEFT; }
+    const Point2f getLastDetectionRIGHT() const { return m_vecMeasurements.back()->ptUVRIGHT; }
+    const CDescriptor getLastDescriptorLEFT() const { return vecDescriptorsLEFT.back(); }
+    const CDescriptor getLastDescriptorRIGHT() const { return vecDescriptorsRIGHT.back(); }
+    float getLastDisparity() const { return m_vecMeasurements.back()->fDisparity; }
+    const CMeasurementLandmark* getLastMeasurement() const { return m_vecMeasurements.back(); }
+    std::vector<CMeasurementLandmark*>::size_type getNumberOfMeasurements() const { return m_vecMeasurements.size(); }
+
+private:
+    std::vector<CMeasurementLandmark*> m_vecMeasurements;
+};
+
+class CFundamentalMatcher {
+    struct CDetectionPoint {
+        UIDDetectionPoint uID;
+        Isometry3d matTransformationLEFTtoWORLD;
+        std::shared_ptr<std::vector<CLandmark*>> vecLandmarks;
+    };
+
+public:
+    CFundamentalMatcher(const std::shared_ptr<CStereoCamera> p_pCameraSTEREO, const std::shared_ptr<CGpuContext> p_pGpu)
+        : m_pGpu(p_pGpu), m_pTriangulator(std::make_shared<CTriangulator>(p_pCameraSTEREO, p_pGpu)), m_pCameraLEFT(p_pCameraSTEREO->m_pCameraLEFT),
+          m_pCameraRIGHT(p_pCameraSTEREO->m_pCameraRIGHT), m_pCameraSTEREO(p_pCameraSTEREO), m_dMinimumDepthMeters(m_pTriangulator->dDepthMinimumMeters),
+          m_dMaximumDepthMeters(m_pTriangulator->dDepthMaximumMeters) {}
+    ~CFundamentalMatcher() { for (CLandmark* p : m_vecLandmarksWINDOW) delete p; }
+
+    const std::shared_ptr<CTriangulator> getTriangulator() const { return m_pTriangulator; }
+    std::vector<CLandmark*>::size_type getNumberOfVisibleLandmarks() const { return m_vecVisibleLandmarks.size(); }
+    UIDLandmark getNumberOfLandmarksTotal() const { return m_uAvailableLandmarkID; }
+    UIDLandmark getNumberOfTracksStage1() const { return m_uNumberOfTracksStage1; }
+    const std::vector<CLandmark*>& getLandmarksWINDOW() const { return m_vecLandmarksWINDOW; }
+
+    // :244-254
+    void resetVisibilityActiveLandmarks() {
+        for (CLandmark* pLandmark : m_vecVisibleLandmarks) pLandmark->bIsCurrentlyVisible = false;
+        m_vecVisibleLandmarks.clear();
+    }
+    // :321-335
+    const std::vector<const CMeasurementLandmark*> getMeasurementsForVisibleLandmarks() {
+        m_vecMeasurementsVisible.clear();
+        for (CLandmark* pLandmark : m_vecVisibleLandmarks) m_vecMeasurementsVisible.push_back(pLandmark->getLastMeasurement());
+        return m_vecMeasurementsVisible;
+    }
+
+    // getMaskActiveLandmarks :2043-2073: 255 everywhere, filled radius-7 zero discs (cv::circle stencil)
+    std::vector<uint8_t> getMaskActiveLandmarks(const Isometry3d& p_matTransformationWORLDtoLEFT) const {
+        const int W = m_pCameraSTEREO->m_uPixelWidth, H = m_pCameraSTEREO->m_uPixelHeight;
+        std::vector<uint8_t> matMaskDetection((size_t)W * H, 255);
+        static const int arrHalfWidth[15] = {0, 3, 4, 5, 6, 6, 6, 7, 6, 6, 6, 5, 4, 3, 0};
+        for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
+            for (const CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
+                Point2f ptCenter;
+                if (pLandmark->bIsCurrentlyVisible) ptCenter = pLandmark->getLastDetectionLEFT();
+                else {
+                    const CPoint3DCAMERA p(p_matTransformationWORLDtoLEFT * pLandmark->vecPointXYZOptimized);
+                    const MatrixProjection& P = m_pCameraLEFT->m_matProjection;
+                    const double w = P(2, 0) * p.x() + P(2, 1) * p.y() + P(2, 2) * p.z() + P(2, 3);
+                    ptCenter = Point2f((float)((P(0, 0) * p.x() + P(0, 1) * p.y() + P(0, 2) * p.z() + P(0, 3)) / w),
+                                       (float)((P(1, 0) * p.x() + P(1, 1) * p.y() + P(1, 2) * p.z() + P(1, 3)) / w));
+                }
+                const long cx = std::lrint(ptCenter.x), cy = std::lrint(ptCenter.y);
+                for (int dy = -7; dy <= 7; ++dy) {
+                    const long y = cy + dy;
+                    if (y < 0 || y >= H) continue;
+                    const long x0 = std::max(cx - arrHalfWidth[dy + 7], 0L), x1 = std::min(cx + arrHalfWidth[dy + 7], (long)W - 1);
+                    for (long x = x0; x <= x1; ++x) matMaskDetection[(size_t)y * W + x] = 0;
+                }
+            }
+        return matMaskDetection;
+    }
+
+    // addNewLandmarks :83-193: mask -> detect -> describe -> per-key-point scan-line triangulation, one GPU call
+    std::vector<CLandmark*>::size_type addNewLandmarks(const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT,
+                                                       const Isometry3d& p_matTransformationWORLDtoLEFT,
+                                                       const Isometry3d& p_matTransformationLEFTtoWORLD, const UIDFrame& p_uIDFrame) {
+        const MatrixProjection matProjectionWORLDtoLEFT(m_pCameraLEFT->m_matProjection * p_matTransformationWORLDtoLEFT);
+        const MatrixProjection matProjectionWORLDtoRIGHT(m_pCameraRIGHT->m_matProjection * p_matTransformationWORLDtoLEFT);
+        const std::vector<uint8_t> matMask(getMaskActiveLandmarks(p_matTransformationWORLDtoLEFT));
+        const int W = m_pCameraSTEREO->m_uPixelWidth, H = m_pCameraSTEREO->m_uPixelHeight, cap = m_pGpu->params.max_corners;
+        // the mask shares the images' pitch: repack if the caller's rows are padded
+        std::vector<uint8_t> matMaskPitched;
+        const uint8_t* pMask = matMask.data();
+        if (p_matImageLEFT.pitch != (size_t)W) {
+            matMaskPitched.assign(p_matImageLEFT.pitch * H, 255);
+            for (int y = 0; y < H; ++y) std::memcpy(&matMaskPitched[y * p_matImageLEFT.pitch], &matMask[(size_t)y * W], W);
+            pMask = matMaskPitched.data();
+        }
+        int32_t nKeyPoints = 0, nDetected = 0;
+        std::vector<float> uvL(2 * cap), uvR(2 * cap);
+        std::vector<double> xyz(3 * cap);
+        std::vector<uint8_t> dL(32 * cap), dR(32 * cap), st(cap);
+        std::vector<int32_t> dist(cap), idx(cap);
+        svi_stereo_result r{cap, &nKeyPoints, &nDetected, uvL.data(), uvR.data(), xyz.data(), dL.data(), dR.data(), dist.data(), idx.data(), st.data()};
+        m_pGpu->check(svi_stereo_frames(m_pGpu->ctx, p_matImageLEFT.data, p_matImageRIGHT.data, p_matImageLEFT.pitch, p_matImageLEFT.pitch * H, 1, pMask, &r));
+
+        std::shared_ptr<std::vector<CLandmark*>> vecLandmarksNEW(std::make_shared<std::vector<CLandmark*>>());
+        for (int32_t u = 0; u < nKeyPoints; ++u) {
+            if (SVI_OK != st[u]) continue;   // catch( CExceptionNoMatchFound ) { continue; }  :170-174
+            CDescriptor matDescriptorLEFT, matDescriptorRIGHT;
+            std::memcpy(matDescriptorLEFT.data(), &dL[32 * u], 32);
+            std::memcpy(matDescriptorRIGHT.data(), &dR[32 * u], 32);
+            CLandmark* pLandmarkNEW = new CLandmark(m_uAvailableLandmarkID, matDescriptorLEFT, matDescriptorRIGHT, m_pGpu->params.keypoint_size,
+                                                    Point2f(uvL[2 * u], uvL[2 * u + 1]), Point2f(uvR[2 * u], uvR[2 * u + 1]),
+                                                    CPoint3DCAMERA(xyz[3 * u], xyz[3 * u + 1], xyz[3 * u + 2]), p_matTransformationLEFTtoWORLD,
+                                                    p_matTransformationWORLDtoLEFT, matProjectionWORLDtoLEFT, matProjectionWORLDtoRIGHT, p_uIDFrame);
+            pLandmarkNEW->bIsOptimal = true;   // :147
+            vecLandmarksNEW->push_back(pLandmarkNEW);
+            ++m_uAvailableLandmarkID;
+        }
+        if (vecLandmarksNEW->empty()) return 0;
+        m_vecDetectionPointsActive.push_back(CDetectionPoint{m_uAvailableDetectionPointID++, p_matTransformationLEFTtoWORLD, vecLandmarksNEW});
+        m_vecLandmarksWINDOW.insert(m_vecLandmarksWINDOW.end(), vecLandmarksNEW->begin(), vecLandmarksNEW->end());
+        return vecLandmarksNEW->size();
+    }
+
+    // trackManual :1334-2027, stage 1 on the GPU for ALL active landmarks in one call; landmarks stage 1 cannot
+    // place are returned in p_vecForStage2 for the caller's stage 2-3, and the
+    // failed-tracking bookkeeping of :1980-2009 is applied to them only once the caller reports them lost.
+    void trackManual(const UIDFrame p_uFrame, const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT,
+                     const Isometry3d& p_matTransformationWORLDtoLEFT, const Isometry3d& p_matTransformationLEFTtoWORLD,
+                     const double& p_dMotionScaling, std::vector<CLandmark*>* p_vecForStage2 = nullptr) {
+        m_uNumberOfTracksStage1 = 0;
+        const MatrixProjection matProjectionWORLDtoLEFT(m_pCameraLEFT->m_matProjection * p_matTransformationWORLDtoLEFT);
+        const MatrixProjection matProjectionWORLDtoRIGHT(m_pCameraRIGHT->m_matProjection * p_matTransformationWORLDtoLEFT);
+        std::vector<CLandmark*> vecCandidates;
+        for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
+            for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
+                if (0 < pLandmark->uOptimizationsFailed) { pLandmark->bIsCurrentlyVisible = false; pLandmark->bIsOptimal = false; }   // :1375-1384
+                else if (0 < pLandmark->uOptimizationsSuccessful && !pLandmark->bIsOptimal) pLandmark->bIsCurrentlyVisible = false;      // :1387-1395
+                else vecCandidates.push_back(pLandmark);
+            }
+        const int n = (int)vecCandidates.size();
+        if (0 < n) {
+            std::vector<double> xyzW(3 * n), xyz(3 * n);
+            std::vector<uint8_t> dL(32 * n), dR(32 * n), oL(32 * n), oR(32 * n), st(n), stage(n);
+            std::vector<float> disp(n), size(n), uvL(2 * n), uvR(2 * n);
+            for (int i = 0; i < n; ++i) {
+                const CLandmark* p = vecCandidates[i];
+                for (int k = 0; k < 3; ++k) xyzW[3 * i + k] = p->vecPointXYZOptimized.v[k];
+                std::memcpy(&dL[32 * i], p->getLastDescriptorLEFT().data(), 32);
+                std::memcpy(&dR[32 * i], p->getLastDescriptorRIGHT().data(), 32);
+                disp[i] = p->getLastDisparity();
+                size[i] = (float)p->dKeyPointSize;
+            }
+            svi_landmarks lm{xyzW.data(), dL.data(), dR.data(), disp.data(), size.data()};
+            svi_track_result r{st.data(), stage.data(), uvL.data(), uvR.data(), xyz.data(), oL.data(), oR.data()};
+            m_pGpu->check(svi_track_landmarks(m_pGpu->ctx, p_matImageLEFT.data, p_matImageRIGHT.data, p_matImageLEFT.pitch,
+                                              p_matTransformationWORLDtoLEFT.m, &lm, n, p_dMotionScaling, &r));
+            for (int i = 0; i < n; ++i) {
+                CLandmark* pLandmark = vecCandidates[i];
+                if (0 < stage[i]) {   // _addMeasurementToLandmarkSTEREO :2487-2524
+                    CDescriptor a, b;
+                    std::memcpy(a.data(), &oL[32 * i], 32);
+                    std::memcpy(b.data(), &oR[32 * i], 32);
+                    pLandmark->bIsCurrentlyVisible = true;
+                    pLandmark->uFailedSubsequentTrackings = 0;
+                    pLandmark->addMeasurement(p_uFrame, Point2f(uvL[2 * i], uvL[2 * i + 1]), Point2f(uvR[2 * i], uvR[2 * i + 1]), a, b,
+                                              CPoint3DCAMERA(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), p_matTransformationLEFTtoWORLD,
+                                              p_matTransformationWORLDtoLEFT, matProjectionWORLDtoLEFT, matProjectionWORLDtoRIGHT);
+                    m_vecVisibleLandmarks.push_back(pLandmark);
+                    ++m_uNumberOfTracksStage1;
+                } else if (SVI_TRK_OUT_OF_FOV == st[i] || !p_vecForStage2) {
+                    ++pLandmark->uFailedSubsequentTrackings;   // :1996-2001
+                    pLandmark->bIsCurrentlyVisible = false;
+                } else {
+                    p_vecForStage2->push_back(pLandmark);
+                }
+            }
+        }
+        // keep landmarks while failed trackings stay below the limit :2005-2009
+        for (CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive) {
+            std::vector<CLandmark*>& v = *cDetectionPoint.vecLandmarks;
+            v.erase(std::remove_if(v.begin(), v.end(), [this](CLandmark* p) { return p->uFailedSubsequentTrackings >= m_uMaximumFailedSubsequentTrackingsPerLandmark; }), v.end());
+        }
+        m_vecDetectionPointsActive.erase(std::remove_if(m_vecDetectionPointsActive.begin(), m_vecDetectionPointsActive.end(),
+                                                        [](const CDetectionPoint& d) { return d.vecLandmarks->empty(); }),
+                                         m_vecDetectionPointsActive.end());
+    }
+
+private:
+    const std::shared_ptr<CGpuContext> m_pGpu;
+    std::shared_ptr<CTriangulator> m_pTriangulator;
+    const std::shared_ptr<CPinholeCamera> m_pCameraLEFT, m_pCameraRIGHT;
+    const std::shared_ptr<CStereoCamera> m_pCameraSTEREO;
+    const double m_dMinimumDepthMeters, m_dMaximumDepthMeters;
+    const uint8_t m_uMaximumFailedSubsequentTrackingsPerLandmark = 5;   // CFundamentalMatcher.h:83
+    UIDDetectionPoint m_uAvailableDetectionPointID = 0;
+    std::vector<CDetectionPoint> m_vecDetectionPointsActive;
+    std::vector<CLandmark*> m_vecVisibleLandmarks, m_vecLandmarksWINDOW;
+    std::vector<const CMeasurementLandmark*> m_vecMeasurementsVisible;
+    UIDLandmark m_uAvailableLandmarkID = 0, m_uNumberOfTracksStage1 = 0;
+};
+
+#endif

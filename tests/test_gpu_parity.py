@@ -293,3 +293,46 @@ def test_properties_at_batch_scale(kitti_cams):
         dd = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
         np.fill_diagonal(dd, 1 << 30)
         assert dd.min() >= 49
+
+
+def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
+    """The C++ facade (svi_mapper_b200/host: CParameterBase -> CStereoCamera -> CFundamentalMatcher) driven like
+    CTrackerGT drives the reference: addNewLandmarks on frame 0, trackManual on frame 1; compared with the oracle."""
+    import pathlib
+    import subprocess
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    assert exe.exists(), "build it with `python -m svi_mapper_b200.build`"
+    W, H = vi_cams[0].width, vi_cams[0].height
+    L, R = stereo_pair(W, H, 4000)
+    for name, img in (("L0", L), ("R0", R)):
+        img.tofile(tmp_path / f"{name}.raw")
+    out = tmp_path / "out.txt"
+    r = subprocess.run([str(exe), str(calib_dir / "vi_sensor_left.txt"), str(calib_dir / "vi_sensor_right.txt"), str(W), str(H),
+                        str(tmp_path / "L0.raw"), str(tmp_path / "R0.raw"), str(tmp_path / "L0.raw"), str(tmp_path / "R0.raw"), str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = out.read_text().splitlines()
+    tri = _tri(vi_cams)
+    ref = o.add_new_landmarks(L, R, tri)
+    ok = np.nonzero(ref["status"] == 0)[0]
+    assert lines[0] == f"NEW {len(ok)}"
+    lm = [l.split() for l in lines if l.startswith("L ")]
+    assert len(lm) == len(ok)
+    for row, i in zip(lm, ok):
+        assert [float(v) for v in row[2:6]] == [ref["uv_l"][i, 0], ref["uv_l"][i, 1], ref["uv_r"][i, 0], ref["uv_r"][i, 1]]
+        assert [float(v) for v in row[6:9]] == list(ref["xyz"][i])
+    lms = [dict(xyz_w=ref["xyz"][i], last_desc_l=ref["desc_l"][i], last_desc_r=ref["desc_r"][i],
+                last_disparity=np.float32(ref["uv_l"][i, 0] - ref["uv_r"][i, 0]), size=7.0) for i in ok]
+    trk = o.track_stage1(L, R, tri, np.eye(4), lms, 1.0)
+    n_trk = sum(1 for t in trk if t["stage"] > 0)
+    n_fov = sum(1 for t in trk if t["status"] == o.ST_TRK_OUT_OF_FOV)
+    head = [l for l in lines if l.startswith("TRACKED")][0].split()
+    assert int(head[1]) == n_trk and int(head[3]) == len(ok) - n_trk - n_fov and int(head[5]) == n_trk
+    assert n_trk > 0.9 * len(ok)          # static camera: nearly everything is re-found in stage 1
+    t_lines = [l.split() for l in lines if l.startswith("T ")]
+    tracked = [(k, t) for k, t in enumerate(trk) if t["stage"] > 0]
+    for row, (k, t) in zip(t_lines, tracked):
+        assert int(row[1]) == k
+        assert [float(v) for v in row[2:6]] == [float(t["uv_l"][0]), float(t["uv_l"][1]), float(t["uv_r"][0]), float(t["uv_r"][1])]
+        assert float(row[6]) == t["xyz"][2]
+    assert lines[-1] == "EXC <CTriangulator>(getPointInLEFT) zero disparity"
