@@ -11,7 +11,9 @@
 namespace svi {
 
 constexpr int HT_W = 64, HT_H = 32, HT_THREADS = 256;
-constexpr int U8_P = HT_W + 8;       // u8 tile: 4-px halo (1 Sobel + 3 box; also the 9x9 box sum)
+constexpr int U8_W = HT_W + 8;       // u8 tile: 4-px halo (1 Sobel + 3 box; also the 9x9 box sum)
+constexpr int U8_P = U8_W + 4;       // 19 words per row: row-per-lane walks are bank-conflict free
+constexpr int H9_P = HT_W + 2;       // 33 words per row, same reason
 constexpr int U8_ROWS = HT_H + 8;
 constexpr int COV_W = HT_W + 6;      // covariance products: 3-px halo
 constexpr int COV_ROWS = HT_H + 6;
@@ -26,14 +28,27 @@ struct __align__(16) HarrisSmem {
     uint8_t tile[U8_ROWS][U8_P];
     uint32_t red[HT_THREADS / 32];
 };
-static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS * HT_W, "h9 alias");
+static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS * H9_P, "h9 alias");
 
+// Stage the (HT_H+8) x (HT_W+8) u8 tile with REFLECT_101 at the image border.  One thread copies a
+// 12-byte run of one row: the row address and the border test are computed once per run.
 __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_t* __restrict__ img,
                                              int pitch, int W, int H, int x0, int y0) {
-    for (int idx = threadIdx.x; idx < U8_ROWS * U8_P; idx += HT_THREADS) {
-        int ly = idx / U8_P, lx = idx - ly * U8_P;
-        int gy = reflect101(y0 - 4 + ly, H), gx = reflect101(x0 - 4 + lx, W);
-        tile[ly][lx] = __ldg(img + (size_t)gy * pitch + gx);
+    constexpr int RUN = 12, RUNS = U8_W / RUN;   // 72 = 6 x 12
+    static_assert(U8_W % RUN == 0 && U8_ROWS * RUNS <= HT_THREADS, "tile load mapping");
+    const int t = threadIdx.x;
+    if (t < U8_ROWS * RUNS) {
+        const int ly = t / RUNS, lx0 = (t - ly * RUNS) * RUN;
+        const int gy = reflect101(y0 - 4 + ly, H), gx0 = x0 - 4 + lx0;
+        const uint8_t* row = img + (size_t)gy * pitch;
+        uint8_t* dst = &tile[ly][lx0];
+        if (gx0 >= 0 && gx0 + RUN <= W) {
+#pragma unroll
+            for (int i = 0; i < RUN; ++i) dst[i] = __ldg(row + gx0 + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < RUN; ++i) dst[i] = __ldg(row + reflect101(gx0 + i, W));
+        }
     }
 }
 
@@ -43,7 +58,7 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
 // `box_shift` (optional) receives the same plane stored one element to the left,
 // box_shift[y][x] = S(y, x+1): TMA tile loads must start on a 16-byte boundary, so the match
 // kernels fetch their odd-aligned copy of a window from this plane at the same aligned address.
-__device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint16_t (*h9)[HT_W],
+__device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint16_t (*h9)[H9_P],
                                                uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift,
                                                int box_pitch, int W, int H, int x0, int y0) {
     for (int item = threadIdx.x; item < U8_ROWS * (HT_W / 16); item += HT_THREADS) {
@@ -83,7 +98,7 @@ __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint
 __global__ void __launch_bounds__(HT_THREADS)
 boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift) {
     __shared__ uint8_t tile[U8_ROWS][U8_P];
-    __shared__ uint16_t h9[U8_ROWS][HT_W];
+    __shared__ uint16_t h9[U8_ROWS][H9_P];
     const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
     load_tile_u8(tile, img + (size_t)f * g.img_stride, g.img_pitch, g.W, g.H, x0, y0);
     __syncthreads();
@@ -220,7 +235,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
     }
     if (box) {
         const size_t fo = (size_t)f * H * g.box_pitch;
-        box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[HT_W]>(&sm.cov[0][0][0]), box + fo,
+        box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[H9_P]>(&sm.cov[0][0][0]), box + fo,
                        box_shift ? box_shift + fo : nullptr, g.box_pitch, W, H, x0, y0);
     }
 }
@@ -235,53 +250,71 @@ __device__ __forceinline__ float gftt_threshold(uint32_t ordered_max, double qua
 // K3: threshold(TOZERO) + 3x3 dilate equality + mask + 1-px image border -> candidate keys.
 // key = ordered(R) << 32 | y << 16 | x ; descending key order == cv's greaterThanPtr order
 // (value desc, then larger address first).
-constexpr int NMS_TW = 32, NMS_TH = 8;
-__global__ void __launch_bounds__(NMS_TW * NMS_TH)
+// One thread owns a column of NMS_ROWS pixels: it issues all 3 x (NMS_ROWS+2) response loads up front
+// (coalesced across the warp, neighbours hit L1), reduces each row to its 3-wide maximum once and
+// reuses it for the three output rows it touches.  No shared memory, no barriers.
+constexpr int NMS_TW = 256, NMS_ROWS = 8;
+__global__ void __launch_bounds__(NMS_TW)
 nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict__ mask, FrameGeom g,
                       double quality, const uint32_t* __restrict__ frame_max,
                       unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
-    __shared__ float t[NMS_TH + 2][NMS_TW + 2];
-    const int f = blockIdx.z, x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
-    const int tid = threadIdx.y * NMS_TW + threadIdx.x;
+    // 3x3 NMS leaves at most one candidate per 2x2 block (ties aside); the list is sized for any outcome
+    __shared__ unsigned long long s_keys[NMS_TW * NMS_ROWS];
+    __shared__ int s_count, s_base;
+    const int f = blockIdx.z, gx = blockIdx.x * NMS_TW + threadIdx.x, y0 = blockIdx.y * NMS_ROWS;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_count = 0;
     const float thr = gftt_threshold(frame_max[f], quality);
     const float* R = resp + (size_t)f * g.H * g.resp_pitch;
-    for (int idx = tid; idx < (NMS_TH + 2) * (NMS_TW + 2); idx += NMS_TW * NMS_TH) {
-        int ly = idx / (NMS_TW + 2), lx = idx - ly * (NMS_TW + 2);
-        int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
-        float v = -INFINITY;  // dilate ignores pixels outside the image
-        if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) {
-            v = R[(size_t)gy * g.resp_pitch + gx];
-            v = (v > thr) ? v : 0.f;
+    float centre[NMS_ROWS + 2], rowmax[NMS_ROWS + 2];
+    const bool xin = gx < g.W, xl = xin && gx > 0, xr = gx + 1 < g.W;
+#pragma unroll
+    for (int i = 0; i < NMS_ROWS + 2; ++i) {
+        const int gy = y0 - 1 + i;
+        float a = -INFINITY, b = -INFINITY, c = -INFINITY;   // dilate ignores pixels outside the image
+        if (gy >= 0 && gy < g.H) {
+            const float* row = R + (size_t)gy * g.resp_pitch;
+            if (xl) a = row[gx - 1];
+            if (xin) b = row[gx];
+            if (xr) c = row[gx + 1];
         }
-        t[ly][lx] = v;
+        a = (a > thr) ? a : ((a == -INFINITY) ? a : 0.f);
+        b = (b > thr) ? b : ((b == -INFINITY) ? b : 0.f);
+        c = (c > thr) ? c : ((c == -INFINITY) ? c : 0.f);
+        centre[i] = b;
+        rowmax[i] = fmaxf(fmaxf(a, b), c);
     }
     __syncthreads();
-    const int gx = x0 + threadIdx.x, gy = y0 + threadIdx.y;
-    bool is_cand = false;
-    float v = 0.f;
-    if (gx >= 1 && gx < g.W - 1 && gy >= 1 && gy < g.H - 1) {
-        v = t[threadIdx.y + 1][threadIdx.x + 1];
-        if (v != 0.f) {
-            float m = v;
+    // same-address global atomics serialise in L2: aggregate per warp (ballot), then per CTA (shared
+    // counter), and claim the CTA's slice of the frame's list with ONE global atomic
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, t[threadIdx.y + dy][threadIdx.x + dx]);
+    for (int k = 0; k < NMS_ROWS; ++k) {
+        const int gy = y0 + k;
+        const float v = centre[k + 1];
+        bool is_cand = false;
+        if (gx >= 1 && gx < g.W - 1 && gy >= 1 && gy < g.H - 1 && v != 0.f) {
+            const float m = fmaxf(fmaxf(rowmax[k], rowmax[k + 1]), rowmax[k + 2]);
             is_cand = (v == m) && (!mask || mask[(size_t)f * g.img_stride + (size_t)gy * g.img_pitch + gx]);
         }
-    }
-    unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_cand);
-    if (ballot) {
-        int lane = tid & 31, leader = __ffs(ballot) - 1, base = 0;
-        if (lane == leader) base = atomicAdd(cand_count + f, __popc(ballot));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (is_cand) {
-            int pos = base + __popc(ballot & ((1u << lane) - 1u));
-            if (pos < cand_cap)
-                cand[(size_t)f * cand_cap + pos] =
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_cand);
+        if (ballot) {
+            const int leader = __ffs(ballot) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&s_count, __popc(ballot));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (is_cand)
+                s_keys[base + __popc(ballot & ((1u << lane) - 1u))] =
                     ((unsigned long long)float_to_ordered(v) << 32) | ((unsigned)gy << 16) | (unsigned)gx;
         }
     }
+    __syncthreads();
+    const int n = s_count;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(cand_count + f, n);
+    __syncthreads();
+    const int base = s_base;
+    for (int i = threadIdx.x; i < n; i += NMS_TW)
+        if (base + i < cand_cap) cand[(size_t)f * cand_cap + base + i] = s_keys[i];
 }
 
 }  // namespace svi

@@ -194,8 +194,8 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     mark(ctx, l);
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
-    const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_TH - 1) / NMS_TH, nf);
-    nms_candidates_kernel<<<ngrid, dim3(NMS_TW, NMS_TH), 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
+    const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
+    nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
                                                                  l.cand, l.cand_count, ctx->cand_cap);
     mark(ctx, l);
     if (ctx->select_smem) {
@@ -690,8 +690,8 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         const dim3 tiles((W + HT_W - 1) / HT_W, (H + HT_H - 1) / HT_H, nf);
         harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
                                                                         nullptr, nullptr, l.frame_max);
-        const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_TH - 1) / NMS_TH, nf);
-        nms_candidates_kernel<<<ngrid, dim3(NMS_TW, NMS_TH), 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
+        const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
+        nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
                                                                      l.cand_count, ctx->cand_cap);
         if (ctx->select_smem)
             select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(l.cand, l.cand_count, ctx->sel, nullptr, nullptr,
