@@ -27,7 +27,7 @@ using namespace svi;
 
 namespace {
 
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 8;
 constexpr int kStages = 5;
 const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "nms_candidates", "select_corners", "stereo_match"};
 
@@ -423,9 +423,9 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     ctx->box_pitch = align_up(ctx->W, 64);
     const char* env_chunk = std::getenv("SVI_CHUNK_FRAMES");
     const char* env_lanes = std::getenv("SVI_LANES");
-    ctx->chunk = p.chunk_frames > 0 ? p.chunk_frames : (env_chunk ? std::atoi(env_chunk) : 16);
+    ctx->chunk = p.chunk_frames > 0 ? p.chunk_frames : (env_chunk ? std::atoi(env_chunk) : 32);
     ctx->chunk = std::max(1, std::min(ctx->chunk, 4096));
-    ctx->n_lanes = env_lanes ? std::max(1, std::min(std::atoi(env_lanes), kMaxLanes)) : 3;
+    ctx->n_lanes = env_lanes ? std::max(1, std::min(std::atoi(env_lanes), kMaxLanes)) : 6;
     ctx->profiling = std::getenv("SVI_PROFILE") != nullptr;
     int cap = 1024;
     while (cap < p.max_candidates) cap <<= 1;
