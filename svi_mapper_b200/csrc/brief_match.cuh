@@ -339,47 +339,98 @@ struct StereoOutDev {
     int* dist; int* idx; uint8_t* status;
 };
 
+// Raw box-sum gathers of one descriptor (lanes = tests): issued early, turned into bits later, so the
+// global-memory round trip hides under other work.
+struct BriefGather {
+    uint16_t s1[kDescWords], s2[kDescWords];
+};
+__device__ __forceinline__ void brief_gather_issue(const uint16_t* __restrict__ box, int box_pitch, int cx, int cy,
+                                                   int lane, BriefGather& gth) {
+#pragma unroll
+    for (int j = 0; j < kDescWords; ++j) {
+        const signed char* p = d_pat[32 * j + lane];
+        gth.s1[j] = __ldg(box + (size_t)(cy + p[0]) * box_pitch + cx + p[1]);
+        gth.s2[j] = __ldg(box + (size_t)(cy + p[2]) * box_pitch + cx + p[3]);
+    }
+}
+__device__ __forceinline__ void brief_gather_finish(const BriefGather& gth, uint32_t (&w)[kDescWords]) {
+#pragma unroll
+    for (int j = 0; j < kDescWords; ++j) w[j] = __brev(__ballot_sync(0xFFFFFFFFu, gth.s1[j] < gth.s2[j]));
+}
+
 // K5: per key-point of addNewLandmarks (:109-175): LEFT descriptor, scan-line search in RIGHT
 // with uTL = max(0, x - range - 4*size), vTL = y - 4*size (:120-121), triangulation, outputs.
-// The RIGHT window is put in flight by TMA first; the LEFT descriptor gathers run under it.
+// A warp walks MATCH_KP_PER_WARP consecutive key-points as a three-stage software pipeline:
+//   stage A  key-point coordinates of slot i+2                      (one 4-byte load)
+//   stage B  search plan, LEFT descriptor gathers of slot i+1       (16 loads per lane in flight)
+//   stage C  tests / arg-min / triangulation of slot i from the shared window; the TMA for slot i+1
+//            is issued as soon as the last lane has finished reading the window
+// so every global round trip overlaps the ~1500 shared-memory/ALU instructions of stage C.
+constexpr int MATCH_KP_PER_WARP = 8;
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
 stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
-                    const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float size, float range, const ushort2* __restrict__ kp_xy,
-                    const int* __restrict__ n_kp, int max_corners, StereoOutDev out, int out_frame0) {
+                    const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float size, float range,
+                    const ushort2* __restrict__ kp_xy, const int* __restrict__ n_kp, int max_corners, StereoOutDev out,
+                    int out_frame0) {
     extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.y, slot = blockIdx.x * MATCH_WARPS + warp;
-    if (slot >= n_kp[f]) return;
+    const int f = blockIdx.y, slot0 = (blockIdx.x * MATCH_WARPS + warp) * MATCH_KP_PER_WARP;
+    const int n = n_kp[f];
+    if (slot0 >= n) return;
+    const int slot_end = min(slot0 + MATCH_KP_PER_WARP, n);
     PatchStage ps;
     patch_stage_init(ps, match_smem, &map_r, &map_rs, f * g.H, warp, lane);
-    const ushort2 kp = kp_xy[(size_t)f * max_corners + slot];
+    const ushort2* kps = kp_xy + (size_t)f * max_corners;
     const uint16_t* bl = box_l + (size_t)f * g.H * g.box_pitch;
-    const float x = (float)kp.x, y = (float)kp.y;
-    const float u_tl = fmaxf(0.f, (x - range) - 4.f * size);
-    const float v_tl = y - 4.f * size;
-    SearchPlan plan;
-    plan_right(g, tc, u_tl, v_tl, size, x, lane, plan);
-    search_prefetch(plan, ps, lane);
 
-    uint32_t ref[kDescWords];
-    brief_at_point(bl, g.box_pitch, kp.x, kp.y, lane, ref);
-
-    SearchResult r;
-    double xyz[3] = {0.0, 0.0, 0.0};
-    search_run(plan, ps, ref, tc.match_cutoff, lane, r);
-    if (r.status == SVI_OK) r.status = point_in_left(tc, x, y, r.u, xyz);
-
-    const size_t o = (size_t)(out_frame0 + f) * out.cap + slot;
-    store_desc(out.desc_l + o * 32, ref, lane);
-    if (r.status == SVI_OK) store_desc(out.desc_r + o * 32, r.w, lane);
-    if (lane == 0) {
-        out.uv_l[o * 2] = x; out.uv_l[o * 2 + 1] = y;
-        out.status[o] = (uint8_t)r.status;
-        out.dist[o] = r.dist;
-        out.idx[o] = r.idx;
-        if (r.status == SVI_OK) {
-            out.uv_r[o * 2] = r.u; out.uv_r[o * 2 + 1] = r.v;
-            out.xyz[o * 3] = xyz[0]; out.xyz[o * 3 + 1] = xyz[1]; out.xyz[o * 3 + 2] = xyz[2];
+    // prologue: slot0 through stages A and B, slot0+1 through stage A
+    ushort2 kp_b = kps[slot0];
+    ushort2 kp_a = (slot0 + 1 < slot_end) ? kps[slot0 + 1] : kp_b;
+    SearchPlan plan_b;
+    BriefGather gth_b;
+    {
+        const float x = (float)kp_b.x, y = (float)kp_b.y;
+        plan_right(g, tc, fmaxf(0.f, (x - range) - 4.f * size), y - 4.f * size, size, x, lane, plan_b);
+        search_prefetch(plan_b, ps, lane);
+        brief_gather_issue(bl, g.box_pitch, kp_b.x, kp_b.y, lane, gth_b);
+    }
+    for (int slot = slot0; slot < slot_end; ++slot) {
+        // ---- this slot enters stage C
+        const ushort2 kp = kp_b;
+        const SearchPlan plan = plan_b;
+        uint32_t ref[kDescWords];
+        brief_gather_finish(gth_b, ref);
+        // ---- next slot enters stage B, the one after it stage A
+        const bool has_next = slot + 1 < slot_end;
+        if (has_next) {
+            kp_b = kp_a;
+            const float xn = (float)kp_b.x, yn = (float)kp_b.y;
+            plan_right(g, tc, fmaxf(0.f, (xn - range) - 4.f * size), yn - 4.f * size, size, xn, lane, plan_b);
+            brief_gather_issue(bl, g.box_pitch, kp_b.x, kp_b.y, lane, gth_b);
+            if (slot + 2 < slot_end) kp_a = kps[slot + 2];
+        }
+        // ---- stage C
+        const float x = (float)kp.x, y = (float)kp.y;
+        SearchResult r;
+        double xyz[3] = {0.0, 0.0, 0.0};
+        search_run(plan, ps, ref, tc.match_cutoff, lane, r);
+        if (has_next) {
+            __syncwarp();                          // every lane is done reading this slot's window
+            search_prefetch(plan_b, ps, lane);     // next window in flight under the epilogue below
+        }
+        if (r.status == SVI_OK) r.status = point_in_left(tc, x, y, r.u, xyz);
+        const size_t o = (size_t)(out_frame0 + f) * out.cap + slot;
+        store_desc(out.desc_l + o * 32, ref, lane);
+        if (r.status == SVI_OK) store_desc(out.desc_r + o * 32, r.w, lane);
+        if (lane == 0) {
+            out.uv_l[o * 2] = x; out.uv_l[o * 2 + 1] = y;
+            out.status[o] = (uint8_t)r.status;
+            out.dist[o] = r.dist;
+            out.idx[o] = r.idx;
+            if (r.status == SVI_OK) {
+                out.uv_r[o * 2] = r.u; out.uv_r[o * 2 + 1] = r.v;
+                out.xyz[o * 3] = xyz[0]; out.xyz[o * 3 + 1] = xyz[1]; out.xyz[o * 3 + 2] = xyz[2];
+            }
         }
     }
 }

@@ -206,7 +206,8 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
             l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow);
     }
     mark(ctx, l);
-    const dim3 mgrid((ctx->p.max_corners + MATCH_WARPS - 1) / MATCH_WARPS, nf);
+    const int kp_per_cta = MATCH_WARPS * MATCH_KP_PER_WARP;
+    const dim3 mgrid((ctx->p.max_corners + kp_per_cta - 1) / kp_per_cta, nf);
     stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size,
                                                                     ctx->p.search_range_px, l.kp_xy, n_kp,
                                                                     ctx->p.max_corners, out, out_frame0);
