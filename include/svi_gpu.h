@@ -49,7 +49,11 @@ typedef enum svi_status {
     SVI_TRK_DEPTH = 7,      /* src/core/CFundamentalMatcher.cpp:1446,1508 "invalid depth"            */
     SVI_TRK_STAGE1_DIST = 8,/* src/core/CFundamentalMatcher.cpp:1471,1533 "insufficient matching distance" */
     SVI_TRK_TRI_DESC = 9,   /* src/core/CFundamentalMatcher.cpp:1452,1514 "triangulation descriptor mismatch" */
-    SVI_TRK_OUT_OF_FOV = 10 /* src/core/CFundamentalMatcher.cpp:1416 projection outside m_cFieldOfView */
+    SVI_TRK_OUT_OF_FOV = 10, /* src/core/CFundamentalMatcher.cpp:1416 projection outside m_cFieldOfView */
+    SVI_TRK_NO_FEATURES = 11, /* src/core/CFundamentalMatcher.cpp:1660,1780 "no features detected"  */
+    SVI_TRK_NO_MATCHES = 12,  /* src/core/CFundamentalMatcher.cpp:1654,1775 "no matches found"      */
+    SVI_TRK_DESC = 13,        /* src/core/CFundamentalMatcher.cpp:1648,1770 "descriptor mismatch"   */
+    SVI_TRK_RANGE = 14        /* src/core/CFundamentalMatcher.cpp:1642,1765 "out of tracking range" */
 } svi_status;
 
 /* src/vision/CPinholeCamera.h:16-64: the members the hot path reads
@@ -183,7 +187,7 @@ typedef struct svi_landmarks {
 
 typedef struct svi_track_result {
     uint8_t* status;     /* [n] svi_status of the LAST stage tried */
-    uint8_t* stage;      /* [n] 0 = not tracked, 1 = stage 1 LEFT, 2 = stage 1 RIGHT */
+    uint8_t* stage;      /* [n] 0 = not tracked, 1 / 2 = stage 1 LEFT / RIGHT, 3 / 4 = stage 2 LEFT / RIGHT */
     float* uv_left;      /* [n*2] */
     float* uv_right;     /* [n*2] */
     double* xyz_left;    /* [n*3] */
@@ -191,10 +195,14 @@ typedef struct svi_track_result {
     uint8_t* desc_right; /* [n*32] */
 } svi_track_result;
 
-/* CFundamentalMatcher::trackManual, stage 1 LEFT then stage 1 RIGHT
- * (src/core/CFundamentalMatcher.cpp:1404-1538): projection-window landmark tracking for n
- * landmarks against one stereo pair.  T_world_to_left is the row-major 4x4 of
- * p_matTransformationWORLDtoLEFT. Stages 2-3 stay with the caller this round. */
+/* CFundamentalMatcher::trackManual, stages 1 and 2 as the reference's first-success cascade
+ * (src/core/CFundamentalMatcher.cpp:1404-1785): stage 1 LEFT / RIGHT (descriptor exactly at the rounded
+ * projection), then stage 2 LEFT / RIGHT (GFTT inside the projection window of half size
+ * round(round(w + scaling) * 15), BRIEF on the window grown by 28 px, 1 x K match, cut-off 50) for the
+ * landmarks stage 1 could not place, each followed by the scan-line triangulation in the other image.
+ * T_world_to_left is the row-major 4x4 of p_matTransformationWORLDtoLEFT.  Landmarks left with stage 0
+ * and a status other than SVI_TRK_OUT_OF_FOV are the ones the reference hands to stage 3 (epipolar
+ * search, :1786-1993), which stays with the caller. */
 int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* img_right,
                         size_t pitch, const double* T_world_to_left, const svi_landmarks* lm, int n,
                         double motion_scaling, svi_track_result* out);

@@ -49,6 +49,10 @@ ST_TRK_DEPTH = 7      # "invalid depth"
 ST_TRK_STAGE1_DIST = 8  # "insufficient matching distance"
 ST_TRK_TRI_DESC = 9   # "triangulation descriptor mismatch"
 ST_TRK_OUT_OF_FOV = 10  # projection outside m_cFieldOfView -> ++uFailedSubsequentTrackings
+ST_TRK_NO_FEATURES = 11  # "no features detected"   (stage 2: GFTT found nothing in the window)
+ST_TRK_NO_MATCHES = 12   # "no matches found"       (stage 2: every corner was erased by BRIEF's border filter)
+ST_TRK_DESC = 13         # "descriptor mismatch"    (stage 2: best corner >= cut-off)
+ST_TRK_RANGE = 14        # "out of tracking range"  (stage 2: v - 28 < 0)
 
 PATTERN_FILE = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "brief_pattern_32.txt"
 
@@ -85,6 +89,8 @@ class StereoParams:
     match_cutoff: float = 100.0         # CTriangulator.cpp:13
     min_disparity: float = 0.01         # CTriangulator.h:21
     cutoff_stage1: float = 25.0         # CFundamentalMatcher.cpp:23
+    cutoff_stage2: float = 50.0         # CFundamentalMatcher.cpp:24
+    block_size_stage2: int = 15         # CFundamentalMatcher.h:95 m_uSearchBlockSizePoseOptimization
 
 
 def _reflect101(i: np.ndarray, n: int) -> np.ndarray:
@@ -167,6 +173,18 @@ def harris_response(img: np.ndarray, k: float = 0.04, box=box7_opencv_order) -> 
     """cv::cornerHarris(img, blockSize 7, ksize 3, k) with optimisations off, fp32 bit-exact."""
     xx, xy, yy = sobel_products(np.ascontiguousarray(img))
     a, b, c = box(xx), box(xy), box(yy)
+    kf = F32(k)
+    return (a * c - b * b) - (kf * (a + c)) * (a + c)
+
+
+def harris_response_roi(img: np.ndarray, roi, k: float = 0.04, box=box7_opencv_order) -> np.ndarray:
+    """cv::cornerHarris on the ROI view img(roi) of a larger image, as GFTTDetector::detect(img(roi)) runs
+    it (CFundamentalMatcher.cpp:1566): the Sobel filters read the parent image's real pixels outside the
+    ROI (no BORDER_ISOLATED), the box filter runs on the freshly allocated product planes and therefore
+    reflects at the ROI edge.  roi = (x, y, w, h)."""
+    x, y, w, h = roi
+    xx, xy, yy = sobel_products(np.ascontiguousarray(img))
+    a, b, c = (box(np.ascontiguousarray(p[y:y + h, x:x + w])) for p in (xx, xy, yy))
     kf = F32(k)
     return (a * c - b * b) - (kf * (a + c)) * (a + c)
 
@@ -519,3 +537,98 @@ def track_stage1(img_l, img_r, tri: Triangulator, T_w2l: np.ndarray, landmarks, 
                                    desc_l=r["desc"], desc_r=d[0].copy())
         res.append(out if out is not None else dict(status=st, stage=0))
     return res
+
+
+# ----------------------------------------------------------------------------- trackManual stage 2
+def round_half_away_d(v: float) -> float:
+    """std::round(double)."""
+    return math.floor(v + 0.5) if v >= 0 else -math.floor(-v + 0.5)
+
+
+def rect_from_points(p1, p2):
+    """cv::Rect(cv::Point2f, cv::Point2f): both corners through saturate_cast<int> (cvRound)."""
+    x1, y1, x2, y2 = cv_round(p1[0]), cv_round(p1[1]), cv_round(p2[0]), cv_round(p2[1])
+    x, y = min(x1, x2), min(y1, y2)
+    return x, y, max(x1, x2) - x, max(y1, y2) - y
+
+
+def stage2_window(cam: Camera, uv, motion_scaling: float, block: int = 15):
+    """Search window of stage 2 (:1548-1558): half sizes round(round(w + scaling) * 15) with
+    w = sqrt|u - cx| / 10 (CPinholeCamera.h:220-227), corners clamped to the image, as Point2f."""
+    wu = math.sqrt(abs(float(uv[0]) - float(cam.P[0, 2]))) / 10.0
+    wv = math.sqrt(abs(float(uv[1]) - float(cam.P[1, 2]))) / 10.0
+    hw = round_half_away_d(round_half_away_d(wu + motion_scaling) * block)
+    hh = round_half_away_d(round_half_away_d(wv + motion_scaling) * block)
+    ul = (F32(max(float(uv[0]) - hw, 0.0)), F32(max(float(uv[1]) - hh, 0.0)))
+    lr = (F32(min(float(uv[0]) + hw, float(cam.width))), F32(min(float(uv[1]) + hh, float(cam.height))))
+    return ul, lr
+
+
+def track_stage2_side(img_this, img_other, tri: Triangulator, cam_this: Camera, uv_est, last_desc_this, last_desc_other,
+                      search, size, motion_scaling: float, left: bool):
+    """One side of stage 2 (LEFT :1545-1665, RIGHT :1669-1785) -> dict(status[, uv_this, uv_other, xyz, desc_this, desc_other])."""
+    p = tri.p
+    size = F32(size)
+    half = F32(4) * size
+    ul, lr = stage2_window(cam_this, uv_est, motion_scaling, p.block_size_stage2)
+    rx, ry, rw, rh = rect_from_points(ul, lr)
+    if rw <= 0 or rh <= 0:
+        return dict(status=ST_TRK_NO_FEATURES)
+    R = harris_response_roi(img_this, (rx, ry, rw, rh), p.harris_k)
+    kps = gftt(None, p.max_corners, p.quality_level, p.min_distance, response=R, k=p.harris_k)     # :1566
+    if len(kps) == 0:
+        return dict(status=ST_TRK_NO_FEATURES)
+    wf, hf = F32(cam_this.width), F32(cam_this.height)
+    g_ul = (max(F32(ul[0] - half), F32(0)), max(F32(ul[1] - half), F32(0)))                         # :1572-1575
+    g_lr = (min(F32(lr[0] + half), wf), min(F32(lr[1] + half), hf))
+    gx, gy, gw, gh = rect_from_points(g_ul, g_lr)
+    pts = kps.astype(F32) + half                                                                     # :1579
+    keep, desc = brief32(img_this[gy:gy + gh, gx:gx + gw], pts)                                      # :1580
+    idx, dist = match_hamming(np.asarray(last_desc_this, np.uint8), desc)                            # :1584
+    if idx < 0:
+        return dict(status=ST_TRK_NO_MATCHES)
+    if not (p.cutoff_stage2 > dist):
+        return dict(status=ST_TRK_DESC)
+    best = pts[keep[idx]]
+    in_cam = (F32(F32(ul[0] + best[0]) - half), F32(F32(ul[1] + best[1]) - half))                    # :1592
+    d_this = desc[idx]
+    v_ref = F32(in_cam[1] - half)
+    if not (0.0 <= v_ref):
+        return dict(status=ST_TRK_RANGE)
+    if left:
+        r = tri.triangulate_right(img_other, max(F32(0), F32(F32(in_cam[0] - F32(search)) - half)), v_ref, size, in_cam, d_this)
+    else:
+        r = tri.triangulate_left(img_other, search, max(F32(0), F32(in_cam[0] - half)), v_ref, size, in_cam, d_this)
+    if r["status"] != ST_OK:
+        return dict(status=r["status"])
+    z = r["xyz"][2]
+    if tri.depth_min > z or tri.depth_max < z:
+        return dict(status=ST_TRK_DEPTH)
+    if not (p.cutoff_stage2 > hamming(np.asarray(last_desc_other, np.uint8), r["desc"])):
+        return dict(status=ST_TRK_TRI_DESC)
+    return dict(status=ST_OK, uv_this=in_cam, uv_other=r["uv"], xyz=r["xyz"], desc_this=d_this.copy(), desc_other=r["desc"])
+
+
+def track_manual(img_l, img_r, tri: Triangulator, T_w2l: np.ndarray, landmarks, motion_scaling: float):
+    """trackManual stages 1 and 2 (:1404-1785) as a first-success cascade; stage codes
+    1 = stage 1 LEFT, 2 = stage 1 RIGHT, 3 = stage 2 LEFT, 4 = stage 2 RIGHT, 0 = not tracked (stage 3 is the caller's)."""
+    s1 = track_stage1(img_l, img_r, tri, T_w2l, landmarks, motion_scaling)
+    tri_scale = F32(1.0 + motion_scaling)
+    out = []
+    for lm, r1 in zip(landmarks, s1):
+        if r1["stage"] or r1["status"] == ST_TRK_OUT_OF_FOV:
+            out.append(r1)
+            continue
+        xyz_l = (T_w2l @ np.append(np.asarray(lm["xyz_w"], np.float64), 1.0))[:3]
+        uvl, uvr = projection_rounded(tri.cl.P, xyz_l), projection_rounded(tri.cr.P, xyz_l)
+        search = tri_scale * F32(lm["last_disparity"])
+        r = track_stage2_side(img_l, img_r, tri, tri.cl, uvl, lm["last_desc_l"], lm["last_desc_r"], search, lm["size"], motion_scaling, True)
+        if r["status"] == ST_OK:
+            out.append(dict(status=ST_OK, stage=3, uv_l=r["uv_this"], uv_r=r["uv_other"], xyz=r["xyz"], desc_l=r["desc_this"], desc_r=r["desc_other"]))
+            continue
+        r = track_stage2_side(img_r, img_l, tri, tri.cr, uvr, lm["last_desc_r"], lm["last_desc_l"], search, lm["size"], motion_scaling, False)
+        if r["status"] == ST_OK:
+            out.append(dict(status=ST_OK, stage=4, uv_l=r["uv_other"], uv_r=r["uv_this"], xyz=r["xyz"], desc_l=r["desc_other"], desc_r=r["desc_this"]))
+        else:
+            out.append(dict(status=r["status"], stage=0))
+    return out

@@ -625,4 +625,114 @@ track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restri
     }
 }
 
+// ------------------------------------------------------------------ tracking, stage 2
+// One work item = one landmark on one side (CFundamentalMatcher.cpp:1545-1665 LEFT, :1669-1785 RIGHT).
+struct Stage2Item {
+    int q;                 // landmark index (output slot)
+    int gx, gy, gw, gh;    // window grown by 28 px and clamped (:1572-1575), as cv::Rect(Point2f, Point2f)
+    float ul_x, ul_y;      // ptUpperLeft of the search window (Point2f)
+    float search;          // fTriangulationScale * lastDisparity
+    float size;            // dKeyPointSize
+};
+
+// After GFTT has run inside every item's window (harris/nms/select kernels in window mode): shift the
+// corners by (+28,+28) (:1579), BRIEF on the grown window with its own border filter (:1580), 1 x K
+// Hamming arg-min against the landmark's last descriptor (:1584), cut-off 50, then the scan-line
+// triangulation in the other image, depth window and the other-side descriptor check (:1586-1637).
+// One warp per item; lanes = corners for the K descriptors (box-sum gathers from global memory).
+template <bool kLeft>
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant__ CUtensorMap map_other,
+                    const __grid_constant__ CUtensorMap map_other_s, FrameGeom g, TriConst tc, float cutoff2,
+                    const Stage2Item* __restrict__ items, int n_items, const ushort2* __restrict__ det_xy,
+                    const int* __restrict__ n_det, int max_corners, LandmarksDev lm, TrackOutDev out) {
+    extern __shared__ __align__(128) unsigned char match_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * MATCH_WARPS + warp;
+    if (i >= n_items) return;
+    const Stage2Item it = items[i];
+    const int q = it.q;
+    PatchStage ps;
+    patch_stage_init(ps, match_smem, &map_other, &map_other_s, 0, warp, lane);
+    const float half = 4.f * it.size;
+    uint32_t last_this[kDescWords], last_other[kDescWords];
+    load_desc((kLeft ? lm.desc_l : lm.desc_r) + (size_t)q * 32, last_this);
+    load_desc((kLeft ? lm.desc_r : lm.desc_l) + (size_t)q * 32, last_other);
+
+    int status = SVI_TRK_NO_FEATURES;
+    const int nd = n_det[i];
+    uint32_t best = 0xFFFFFFFFu;
+    if (nd > 0) {
+        status = SVI_TRK_NO_MATCHES;
+        const ushort2* corners = det_xy + (size_t)i * max_corners;
+        for (int k0 = 0; k0 < nd; k0 += 32) {
+            const int k = k0 + lane;
+            bool keep = false;
+            int sx = 0, sy = 0;
+            if (k < nd) {
+                const ushort2 c = corners[k];
+                const float px = (float)c.x + half, py = (float)c.y + half;
+                const int rx = cv_round_f(px), ry = cv_round_f(py);
+                keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder;
+                sx = it.gx + brief_centre(px);
+                sy = it.gy + brief_centre(py);
+            }
+            uint32_t dist = 0;
+            if (keep) {
+#pragma unroll 4
+                for (int t = 0; t < SVI_BRIEF_NTESTS; ++t) {
+                    const signed char* p = d_pat[t];
+                    const uint32_t s1 = __ldg(box_this + (size_t)(sy + p[0]) * g.box_pitch + sx + p[1]);
+                    const uint32_t s2 = __ldg(box_this + (size_t)(sy + p[2]) * g.box_pitch + sx + p[3]);
+                    const uint32_t bit = s1 < s2 ? 1u : 0u;
+                    dist += bit ^ ((last_this[t >> 5] >> (31 - (t & 31))) & 1u);
+                }
+            }
+            const uint32_t key = keep ? ((dist << 16) | (uint32_t)k) : 0xFFFFFFFFu;
+            best = min(best, warp_min_u32(key));   // smaller k wins ties: BFMatcher's first minimum in pool order
+        }
+    }
+    SearchResult r;
+    double xyz[3] = {0.0, 0.0, 0.0};
+    uint32_t mine[kDescWords];
+    float in_x = 0.f, in_y = 0.f;
+    if (best != 0xFFFFFFFFu) {
+        const int dist = (int)(best >> 16), k = (int)(best & 0xFFFFu);
+        status = SVI_TRK_DESC;
+        if (cutoff2 > (float)dist) {
+            const ushort2 c = det_xy[(size_t)i * max_corners + k];
+            const float px = (float)c.x + half, py = (float)c.y + half;
+            in_x = (it.ul_x + px) - half;       // ptUpperLeft + ptBestMatch - ptOffsetKeyPointHalf (:1592)
+            in_y = (it.ul_y + py) - half;
+            brief_at_point(box_this, g.box_pitch, it.gx + brief_centre(px), it.gy + brief_centre(py), lane, mine);
+            const float v_ref = in_y - half;
+            status = SVI_TRK_RANGE;
+            if (0.0f <= v_ref) {
+                if (kLeft) triangulate_right_dev(g, tc, ps, fmaxf(0.f, (in_x - it.search) - half), v_ref, it.size, in_x, in_y, mine, lane, r, xyz);
+                else triangulate_left_dev(g, tc, ps, it.search, fmaxf(0.f, in_x - half), v_ref, it.size, in_x, mine, lane, r, xyz);
+                status = r.status;
+                if (status == SVI_OK) {
+                    if (tc.depth_min > xyz[2] || tc.depth_max < xyz[2]) status = SVI_TRK_DEPTH;
+                    else if (!(cutoff2 > (float)hamming_words(last_other, r.w))) status = SVI_TRK_TRI_DESC;
+                }
+            }
+        }
+    }
+    if (status == SVI_OK) {
+        store_desc((kLeft ? out.desc_l : out.desc_r) + (size_t)q * 32, mine, lane);
+        store_desc((kLeft ? out.desc_r : out.desc_l) + (size_t)q * 32, r.w, lane);
+    }
+    if (lane == 0) {
+        out.status[q] = (uint8_t)status;
+        if (status == SVI_OK) {
+            out.stage[q] = kLeft ? 3 : 4;
+            float* uv_this = kLeft ? out.uv_l : out.uv_r;
+            float* uv_other = kLeft ? out.uv_r : out.uv_l;
+            uv_this[2 * q] = in_x; uv_this[2 * q + 1] = in_y;
+            uv_other[2 * q] = r.u; uv_other[2 * q + 1] = r.v;
+            out.xyz[3 * q] = xyz[0]; out.xyz[3 * q + 1] = xyz[1]; out.xyz[3 * q + 2] = xyz[2];
+        }
+    }
+}
+
 }  // namespace svi

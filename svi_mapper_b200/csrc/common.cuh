@@ -18,6 +18,13 @@ struct FrameGeom {
     int box_pitch;      // uint16 per box-sum row
 };
 
+// One detection work item when the detector runs on windows of an image instead of whole frames
+// (trackManual stage 2: GFTTDetector::detect(img(cSearchROI)), CFundamentalMatcher.cpp:1566,1690).
+// plane selects the image of the staged pair (0 = LEFT, 1 = RIGHT); the rectangle is in image pixels.
+struct RoiItem {
+    int plane, rx, ry, rw, rh;
+};
+
 // CTriangulator members (src/core/CTriangulator.cpp:13-21)
 struct TriConst {
     double f_inv, pu, pv, du_r_flipped, min_disp, depth_min, depth_max;

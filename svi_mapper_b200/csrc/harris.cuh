@@ -112,17 +112,30 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
 //   every op rounded to fp32 on its own (explicit _rn intrinsics, never an FMA).
 //   Box 7x7 (A.2): products accumulated in fp64, REFLECT_101 on the PRODUCT planes, one rounding
 //   to fp32.  Harris (A.3): R = (a*c - b*b) - (k*(a+c))*(a+c) in fp32.
+// With `rois` the z-th CTA layer works on the window rois[z] of image plane rois[z].plane instead of
+// frame z: the Sobel filters still read the real pixels around the window (OpenCV ROI semantics without
+// BORDER_ISOLATED), while the product planes reflect at the WINDOW edge and the maximum is window-local
+// -- exactly what cv::cornerHarris / goodFeaturesToTrack do on img(roi).  Output plane z has `out_rows` rows.
 __global__ void __launch_bounds__(HT_THREADS, 2)
 harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
                   float f1, float f0, float kf, float* __restrict__ resp, uint16_t* __restrict__ box,
-                  uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max) {
+                  uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max,
+                  const RoiItem* __restrict__ rois, int out_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarrisSmem& sm = *reinterpret_cast<HarrisSmem*>(smem_raw);
     const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
-    const int W = g.W, H = g.H, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    // W x H is the rectangle the detector sees (frame or window), (ox, oy) its origin in the image
+    int W = g.W, H = g.H, ox = 0, oy = 0;
     const uint8_t* im = img + (size_t)f * g.img_stride;
+    if (rois) {
+        const RoiItem it = rois[f];
+        W = it.rw; H = it.rh; ox = it.rx; oy = it.ry;
+        im = img + (size_t)it.plane * g.img_stride;
+        if (x0 >= W || y0 >= H) return;
+    }
 
-    load_tile_u8(sm.tile, im, g.img_pitch, W, H, x0, y0);
+    load_tile_u8(sm.tile, im, g.img_pitch, g.W, g.H, ox + x0, oy + y0);
     __syncthreads();
 
     // ---- covariance products on the (HT_H+6) x (HT_W+6) region, sliding down columns
@@ -204,7 +217,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
             sb = __dadd_rn(sb, sm.hs[1][oy0 + i][x]);
             sc = __dadd_rn(sc, sm.hs[2][oy0 + i][x]);
         }
-        float* rrow = resp + ((size_t)f * H) * g.resp_pitch;
+        float* rrow = resp + ((size_t)f * out_rows) * g.resp_pitch;
         const uint8_t* mrow = mask ? mask + (size_t)f * g.img_stride : nullptr;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -233,7 +246,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
         for (int i = 0; i < HT_THREADS / 32; ++i) m = max(m, sm.red[i]);
         if (m) atomicMax(frame_max + f, m);
     }
-    if (box) {
+    if (box) {   // whole-frame mode only
         const size_t fo = (size_t)f * H * g.box_pitch;
         box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[H9_P]>(&sm.cov[0][0][0]), box + fo,
                        box_shift ? box_shift + fo : nullptr, g.box_pitch, W, H, x0, y0);
@@ -257,22 +270,24 @@ constexpr int NMS_TW = 256, NMS_ROWS = 8;
 __global__ void __launch_bounds__(NMS_TW)
 nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict__ mask, FrameGeom g,
                       double quality, const uint32_t* __restrict__ frame_max,
-                      unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
+                      unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap,
+                      const RoiItem* __restrict__ rois, int in_rows) {
     // 3x3 NMS leaves at most one candidate per 2x2 block (ties aside); the list is sized for any outcome
     __shared__ unsigned long long s_keys[NMS_TW * NMS_ROWS];
     __shared__ int s_count, s_base;
     const int f = blockIdx.z, gx = blockIdx.x * NMS_TW + threadIdx.x, y0 = blockIdx.y * NMS_ROWS;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_count = 0;
+    const int W = rois ? rois[f].rw : g.W, H = rois ? rois[f].rh : g.H;   // block-uniform
     const float thr = gftt_threshold(frame_max[f], quality);
-    const float* R = resp + (size_t)f * g.H * g.resp_pitch;
+    const float* R = resp + (size_t)f * in_rows * g.resp_pitch;
     float centre[NMS_ROWS + 2], rowmax[NMS_ROWS + 2];
-    const bool xin = gx < g.W, xl = xin && gx > 0, xr = gx + 1 < g.W;
+    const bool xin = gx < W, xl = xin && gx > 0, xr = gx + 1 < W;
 #pragma unroll
     for (int i = 0; i < NMS_ROWS + 2; ++i) {
         const int gy = y0 - 1 + i;
         float a = -INFINITY, b = -INFINITY, c = -INFINITY;   // dilate ignores pixels outside the image
-        if (gy >= 0 && gy < g.H) {
+        if (gy >= 0 && gy < H) {
             const float* row = R + (size_t)gy * g.resp_pitch;
             if (xl) a = row[gx - 1];
             if (xin) b = row[gx];
@@ -292,7 +307,7 @@ nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict_
         const int gy = y0 + k;
         const float v = centre[k + 1];
         bool is_cand = false;
-        if (gx >= 1 && gx < g.W - 1 && gy >= 1 && gy < g.H - 1 && v != 0.f) {
+        if (gx >= 1 && gx < W - 1 && gy >= 1 && gy < H - 1 && v != 0.f) {
             const float m = fmaxf(fmaxf(rowmax[k], rowmax[k + 1]), rowmax[k + 2]);
             is_cand = (v == m) && (!mask || mask[(size_t)f * g.img_stride + (size_t)gy * g.img_pitch + gx]);
         }

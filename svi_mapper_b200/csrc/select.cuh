@@ -42,11 +42,18 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                       SelectParams sp, uint32_t* __restrict__ g_head, uint32_t* __restrict__ g_next,
                       uint8_t* __restrict__ g_state, ushort2* __restrict__ det_xy,
                       int* __restrict__ n_detected, ushort2* __restrict__ kp_xy,
-                      int* __restrict__ n_keypoints, int* __restrict__ overflow) {
+                      int* __restrict__ n_keypoints, int* __restrict__ overflow,
+                      const RoiItem* __restrict__ rois) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
     __shared__ uint32_t block_total;
     const int f = blockIdx.x, tid = threadIdx.x;
+    if (rois) {   // window mode: the bucket grid and the border filter follow the item's rectangle
+        sp.W = rois[f].rw;
+        sp.H = rois[f].rh;
+        sp.gw = (sp.W + sp.cell - 1) / sp.cell;
+        sp.gh = (sp.H + sp.cell - 1) / sp.cell;
+    }
     int n = cand_count[f];
     if (n > sp.cand_cap) {
         if (tid == 0) atomicExch(overflow, 1);

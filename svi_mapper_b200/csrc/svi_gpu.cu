@@ -79,6 +79,22 @@ struct svi_ctx {
     Lane lanes[kMaxLanes];
     int* d_overflow = nullptr;
     cudaEvent_t fork = nullptr;
+    // tracking: both images of the current pair as two planes of one buffer, and the scratch of the
+    // window-mode detector of stage 2 (grown on demand)
+    uint8_t* trk_img = nullptr;
+    struct RoiScratch {
+        int items = 0, rows = 0, pitch = 0;
+        float* resp = nullptr;
+        uint32_t* max = nullptr;
+        int* cand_count = nullptr;
+        unsigned long long* cand = nullptr;
+        ushort2* det = nullptr;
+        ushort2* kp = nullptr;
+        int* n_det = nullptr;
+        int* n_kp = nullptr;
+        RoiItem* rois = nullptr;
+        Stage2Item* s2 = nullptr;
+    } roi;
     // per-query arena
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
@@ -190,20 +206,20 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, nf);
     mark(ctx, l);
     harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf,
-                                                                    l.resp, l.box_l, nullptr, l.frame_max);
+                                                                    l.resp, l.box_l, nullptr, l.frame_max, nullptr, g.H);
     mark(ctx, l);
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
     const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
     nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
-                                                                 l.cand, l.cand_count, ctx->cand_cap);
+                                                                 l.cand, l.cand_count, ctx->cand_cap, nullptr, g.H);
     mark(ctx, l);
     if (ctx->select_smem) {
         select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(
-            l.cand, l.cand_count, ctx->sel, nullptr, nullptr, nullptr, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow);
+            l.cand, l.cand_count, ctx->sel, nullptr, nullptr, nullptr, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     } else {
         select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(
-            l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow);
+            l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     }
     mark(ctx, l);
     const int kp_per_cta = MATCH_WARPS * MATCH_KP_PER_WARP;
@@ -314,6 +330,146 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
 }  // namespace
 
 
+
+namespace {
+
+// std::round / cvRound helpers for the host-side window arithmetic of stage 2 (plain IEEE double/float ops)
+inline float host_projection(const double* P, int row, const double* p) {
+    const double h = ((P[4 * row] * p[0] + P[4 * row + 1] * p[1]) + P[4 * row + 2] * p[2]) + P[4 * row + 3];
+    const double w = ((P[8] * p[0] + P[9] * p[1]) + P[10] * p[2]) + P[11];
+    return std::round(static_cast<float>(h / w));
+}
+
+int ensure_roi_scratch(svi_ctx* ctx, int items, int rows, int pitch) {
+    svi_ctx::RoiScratch& r = ctx->roi;
+    if (items <= r.items && rows <= r.rows && pitch <= r.pitch) return SVI_SUCCESS;
+    void* rp[] = {r.resp, r.max, r.cand_count, r.cand, r.det, r.kp, r.n_det, r.n_kp, r.rois, r.s2};
+    for (void* q : rp) if (q) cudaFree(q);
+    r = svi_ctx::RoiScratch();
+    items = std::max(items, 64);
+    const size_t MC = (size_t)ctx->p.max_corners;
+    CK(dmalloc(&r.resp, (size_t)items * rows * pitch));
+    CK(dmalloc(&r.max, (size_t)items));
+    CK(dmalloc(&r.cand_count, (size_t)items));
+    CK(dmalloc(&r.cand, (size_t)items * ctx->cand_cap));
+    CK(dmalloc(&r.det, (size_t)items * MC));
+    CK(dmalloc(&r.kp, (size_t)items * MC));
+    CK(dmalloc(&r.n_det, (size_t)items));
+    CK(dmalloc(&r.n_kp, (size_t)items));
+    CK(dmalloc(&r.rois, (size_t)items));
+    CK(dmalloc(&r.s2, (size_t)items));
+    r.items = items; r.rows = rows; r.pitch = pitch;
+    return SVI_SUCCESS;
+}
+
+// One side of trackManual stage 2 for every landmark that is still untracked (host_out->stage == 0 and not
+// out of the field of view).  The window arithmetic of :1548-1575 runs here on the host; detection inside the
+// windows, description, matching and triangulation run on the GPU; statuses come back into host_out.
+int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landmarks* lm, int n, const double* T,
+                      double motion_scaling, bool left, const LandmarksDev& ld, const TrackOutDev& o, svi_track_result* host_out) {
+    cudaStream_t s = l.stream;
+    const svi_camera& cam = left ? ctx->cam_l : ctx->cam_r;
+    const double cx = cam.P[2], cy = cam.P[6];
+    const int W = ctx->W, H = ctx->H;
+    const float tri_scale = (float)(1.0 + motion_scaling);
+    std::vector<RoiItem> rois;
+    std::vector<Stage2Item> items;
+    std::vector<int> no_window;   // landmarks whose window is empty: GFTT on an empty image finds nothing
+    int max_w = 0, max_h = 0;
+    for (int q = 0; q < n; ++q) {
+        if (host_out->stage[q] != 0 || host_out->status[q] == SVI_TRK_OUT_OF_FOV) continue;
+        const double* pw = lm->xyz_world + 3 * q;
+        double p[3];
+        for (int r = 0; r < 3; ++r) p[r] = ((T[4 * r] * pw[0] + T[4 * r + 1] * pw[1]) + T[4 * r + 2] * pw[2]) + T[4 * r + 3];
+        const float u = host_projection(cam.P, 0, p), v = host_projection(cam.P, 1, p);
+        const float size = lm->keypoint_size[q], half = 4.f * size;
+        // :1548-1558 half sizes round(round(w + scaling) * 15), corners clamped, cv::Rect(Point2f, Point2f)
+        const double su = std::round(std::sqrt(std::fabs((double)u - cx)) / 10.0 + motion_scaling);
+        const double sv = std::round(std::sqrt(std::fabs((double)v - cy)) / 10.0 + motion_scaling);
+        const double hw = std::round(su * 15.0), hh = std::round(sv * 15.0);
+        const float ul_x = (float)std::max((double)u - hw, 0.0), ul_y = (float)std::max((double)v - hh, 0.0);
+        const float lr_x = (float)std::min((double)u + hw, (double)W), lr_y = (float)std::min((double)v + hh, (double)H);
+        const int rx = (int)std::lrintf(ul_x), ry = (int)std::lrintf(ul_y);
+        const int rw = (int)std::lrintf(lr_x) - rx, rh = (int)std::lrintf(lr_y) - ry;
+        if (rw <= 0 || rh <= 0 || rx < 0 || ry < 0 || rx + rw > W || ry + rh > H) {
+            host_out->status[q] = SVI_TRK_NO_FEATURES;
+            no_window.push_back(q);
+            continue;
+        }
+        // :1572-1575 window grown by 4*size and clamped
+        const float g_ulx = std::max(ul_x - half, 0.0f), g_uly = std::max(ul_y - half, 0.0f);
+        const float g_lrx = std::min(lr_x + half, (float)W), g_lry = std::min(lr_y + half, (float)H);
+        Stage2Item it;
+        it.q = q;
+        it.gx = (int)std::lrintf(g_ulx); it.gy = (int)std::lrintf(g_uly);
+        it.gw = (int)std::lrintf(g_lrx) - it.gx; it.gh = (int)std::lrintf(g_lry) - it.gy;
+        it.ul_x = ul_x; it.ul_y = ul_y;
+        it.search = tri_scale * lm->last_disparity[q];
+        it.size = size;
+        items.push_back(it);
+        rois.push_back(RoiItem{left ? 0 : 1, rx, ry, rw, rh});
+        max_w = std::max(max_w, rw);
+        max_h = std::max(max_h, rh);
+    }
+    const int total = (int)items.size();
+    if (total == 0) {
+        for (int q : no_window) {
+            const uint8_t st = SVI_TRK_NO_FEATURES;
+            CK(cudaMemcpyAsync(o.status + q, &st, 1, cudaMemcpyHostToDevice, s));
+        }
+        CK(cudaStreamSynchronize(s));
+        return SVI_SUCCESS;
+    }
+    const int pitch = align_up(max_w, 32), rows = max_h;
+    // bound the response scratch to ~256 MB per batch
+    const size_t plane_bytes = (size_t)rows * pitch * sizeof(float);
+    const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)total, (256u << 20) / plane_bytes));
+    int rc = ensure_roi_scratch(ctx, batch, rows, pitch);
+    if (rc != SVI_SUCCESS) return rc;
+    svi_ctx::RoiScratch& r = ctx->roi;
+    FrameGeom gr = g;
+    gr.resp_pitch = r.pitch;
+    SelectParams sp = ctx->sel;
+    sp.cell = std::max(1, (int)std::ceil(ctx->p.min_distance));
+    if (!ctx->select_smem) return fail(ctx, SVI_ERR_UNSUPPORTED, "svi_track_landmarks: stage 2 needs max_candidates <= 16384");
+    for (int b0 = 0; b0 < total; b0 += batch) {
+        const int nb = std::min(batch, total - b0);
+        CK(cudaMemcpyAsync(r.rois, rois.data() + b0, sizeof(RoiItem) * nb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(r.s2, items.data() + b0, sizeof(Stage2Item) * nb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(r.max, 0, sizeof(uint32_t) * nb, s));
+        CK(cudaMemsetAsync(r.cand_count, 0, sizeof(int) * nb, s));
+        const dim3 tiles((max_w + HT_W - 1) / HT_W, (max_h + HT_H - 1) / HT_H, nb);
+        harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(ctx->trk_img, nullptr, gr, ctx->f1, ctx->f0, ctx->kf, r.resp,
+                                                                        nullptr, nullptr, r.max, r.rois, r.rows);
+        const dim3 ngrid((max_w + NMS_TW - 1) / NMS_TW, (max_h + NMS_ROWS - 1) / NMS_ROWS, nb);
+        nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(r.resp, nullptr, gr, ctx->p.quality_level, r.max, r.cand, r.cand_count,
+                                                       ctx->cand_cap, r.rois, r.rows);
+        select_corners_kernel<true><<<nb, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(r.cand, r.cand_count, sp, nullptr, nullptr, nullptr, r.det,
+                                                                              r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois);
+        const int blocks = (nb + MATCH_WARPS - 1) / MATCH_WARPS;
+        if (left)
+            track_stage2_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage2,
+                                                                                  r.s2, nb, r.det, r.n_det, ctx->p.max_corners, ld, o);
+        else
+            track_stage2_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_r, l.map_l, l.map_ls, g, ctx->tc, ctx->p.cutoff_stage2,
+                                                                                   r.s2, nb, r.det, r.n_det, ctx->p.max_corners, ld, o);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s));   // the batch's item arrays are reused by the next batch
+    }
+    CK(cudaMemcpyAsync(host_out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(host_out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int q : no_window) {   // keep the host-side verdicts in both copies of the status array
+        host_out->status[q] = SVI_TRK_NO_FEATURES;
+        const uint8_t st = SVI_TRK_NO_FEATURES;
+        CK(cudaMemcpyAsync(o.status + q, &st, 1, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
+}  // namespace
+
 extern "C" {
 
 int svi_params_default(svi_params* p) {
@@ -349,7 +505,11 @@ const char* svi_status_text(int status) {
         case SVI_TRK_DEPTH: return "invalid depth";
         case SVI_TRK_STAGE1_DIST: return "insufficient matching distance";
         case SVI_TRK_TRI_DESC: return "triangulation descriptor mismatch";
-        case SVI_TRK_OUT_OF_FOV: return "out of tracking range";
+        case SVI_TRK_OUT_OF_FOV: return "projection outside the field of view";
+        case SVI_TRK_NO_FEATURES: return "no features detected";
+        case SVI_TRK_NO_MATCHES: return "no matches found";
+        case SVI_TRK_DESC: return "descriptor mismatch";
+        case SVI_TRK_RANGE: return "out of tracking range";
         default: return "unknown status";
     }
 }
@@ -378,6 +538,12 @@ void svi_destroy(svi_ctx* ctx) {
     }
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->trk_img) cudaFree(ctx->trk_img);
+    {
+        void* rp[] = {ctx->roi.resp, ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
+                      ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2};
+        for (void* q : rp) if (q) cudaFree(q);
+    }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
     delete ctx;
 }
@@ -472,6 +638,8 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(cudaFuncSetAttribute(triangulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(triangulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(track_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(track_stage2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(track_stage2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     // one shared-memory carve-out for every kernel of the pipeline: back-to-back kernels with different
     // carve-outs make the SMs drain and reconfigure between launches
     {
@@ -479,6 +647,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
                                  (const void*)select_corners_kernel<true>, (const void*)select_corners_kernel<false>,
                                  (const void*)stereo_match_kernel, (const void*)triangulate_kernel<true>,
                                  (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
+                                 (const void*)track_stage2_kernel<true>, (const void*)track_stage2_kernel<false>,
                                  (const void*)describe_kernel, (const void*)hamming_match_kernel};
         for (const void* k : kernels)
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -534,6 +703,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(dmalloc(&ctx->d_overflow, 1));
     CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
     CK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    CK(dmalloc(&ctx->trk_img, 2 * HH * ctx->dev_pitch));
     ctx->arena_bytes = (size_t)p.max_queries * 512 + (size_t)p.max_corners * 64 + 3 * HH * ctx->dev_pitch + (1 << 20);
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), ctx->arena_bytes));
     *out = ctx;
@@ -657,7 +827,7 @@ int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* r
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t), s));
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
     harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                    nullptr, nullptr, l.frame_max);
+                                                                    nullptr, nullptr, l.frame_max, nullptr, g.H);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, l.resp, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
                          ctx->H, cudaMemcpyDeviceToHost, s));
@@ -690,17 +860,17 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
         const dim3 tiles((W + HT_W - 1) / HT_W, (H + HT_H - 1) / HT_H, nf);
         harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                        nullptr, nullptr, l.frame_max);
+                                                                        nullptr, nullptr, l.frame_max, nullptr, g.H);
         const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
         nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
-                                                                     l.cand_count, ctx->cand_cap);
+                                                                     l.cand_count, ctx->cand_cap, nullptr, g.H);
         if (ctx->select_smem)
             select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(l.cand, l.cand_count, ctx->sel, nullptr, nullptr,
                                                                                   nullptr, l.det_xy, l.n_det, l.kp_xy, l.n_kp,
-                                                                                  ctx->d_overflow);
+                                                                                  ctx->d_overflow, nullptr);
         else
             select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state,
-                                                                   l.det_xy, l.n_det, l.kp_xy, l.n_kp, ctx->d_overflow);
+                                                                   l.det_xy, l.n_det, l.kp_xy, l.n_kp, ctx->d_overflow, nullptr);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_xy.data(), l.det_xy, sizeof(ushort2) * (size_t)nf * MC, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(counts + f0, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
@@ -810,9 +980,11 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0;
-    int rc = stage_box(ctx, img_left, pitch, l.img_l, l.box_l, l.box_ls, s);
+    const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
+    // both images as planes 0 / 1 of one buffer (the window-mode detector indexes them by plane)
+    int rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
-    rc = stage_box(ctx, img_right, pitch, l.img_r, l.box_r, l.box_rs, s);
+    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s);
     if (rc != SVI_SUCCESS) return rc;
     double* d_xyzw; uint8_t* d_dl; uint8_t* d_dr; float* d_disp; float* d_size;
     UP(d_xyzw, lm->xyz_world, (size_t)n * 3);
@@ -838,19 +1010,26 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
     k.tri_scale = (float)(1.0 + motion_scaling);
     k.cutoff1 = ctx->p.cutoff_stage1;
     LandmarksDev ld{d_xyzw, d_dl, d_dr, d_disp, d_size};
-    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, plane);
+    // ---- stage 1 LEFT / RIGHT for every landmark
     track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
                                                                                                   ctx->tc, k, ld, n, o);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    // ---- stage 2 LEFT, then stage 2 RIGHT, for what is still untracked
+    for (int side = 0; side < 2; ++side) {
+        rc = track_stage2_side(ctx, l, g, lm, n, T_world_to_left, motion_scaling, side == 0, ld, o, out);
+        if (rc != SVI_SUCCESS) return rc;
+    }
     CK(cudaMemcpyAsync(out->uv_left, o.uv_l, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->uv_right, o.uv_r, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->xyz_left, o.xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->desc_left, o.desc_l, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->desc_right, o.desc_r, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    return SVI_SUCCESS;
+    return check_overflow(ctx);
 }
 
 int svi_set_profiling(svi_ctx* ctx, int enable) {

@@ -179,34 +179,65 @@ def test_point_in_left_closed_form(kitti_cams):
         assert abs(xyz[i, 0] - alt) <= 1e-6 * max(1.0, abs(alt))
 
 
-def test_track_stage1(vi_cams):
-    """Projection-window tracking: landmarks from frame 0's stereo result re-found in a shifted pair."""
+def _landmarks_from_frame(ref0, ok):
+    disp = (ref0["uv_l"][ok, 0] - ref0["uv_r"][ok, 0]).astype(np.float32)
+    lms = [dict(xyz_w=ref0["xyz"][i], last_desc_l=ref0["desc_l"][i], last_desc_r=ref0["desc_r"][i],
+                last_disparity=disp[k], size=7.0) for k, i in enumerate(ok)]
+    return disp, lms
+
+
+def _compare_tracks(got, ref):
+    for i, r in enumerate(ref):
+        assert got["stage"][i] == r["stage"], (i, got["stage"][i], r)
+        assert got["status"][i] == r["status"], (i, got["status"][i], r)
+        if r["stage"]:
+            assert tuple(got["uv_l"][i]) == tuple(np.float32(v) for v in r["uv_l"]), i
+            assert tuple(got["uv_r"][i]) == tuple(np.float32(v) for v in r["uv_r"]), i
+            np.testing.assert_array_equal(got["xyz"][i], r["xyz"])
+            np.testing.assert_array_equal(got["desc_l"][i], r["desc_l"])
+            np.testing.assert_array_equal(got["desc_r"][i], r["desc_r"])
+
+
+def test_track_manual_stage1(vi_cams):
+    """Projection-exact tracking (stage 1 LEFT/RIGHT): landmarks of frame 0 re-found under a small camera translation."""
     W, H = vi_cams[0].width, vi_cams[0].height
     L, R = stereo_pair(W, H, 4000)
     tri = _tri(vi_cams)
     ref0 = o.add_new_landmarks(L, R, tri)
-    ok = np.nonzero(ref0["status"] == 0)[0][:400]
-    xyz_w = ref0["xyz"][ok]                      # identity pose: world == left camera
+    ok = np.nonzero(ref0["status"] == 0)[0][:300]
+    disp, lms = _landmarks_from_frame(ref0, ok)
     T = np.eye(4)
-    T[0, 3] = 0.01                               # small translation so projections move by < 1 px .. few px
-    disp = (ref0["uv_l"][ok, 0] - ref0["uv_r"][ok, 0]).astype(np.float32)
-    lms = [dict(xyz_w=xyz_w[i], last_desc_l=ref0["desc_l"][ok[i]], last_desc_r=ref0["desc_r"][ok[i]],
-                last_disparity=disp[i], size=7.0) for i in range(len(ok))]
+    T[0, 3] = 0.01
     for scaling in (1.0, 2.5):
-        ref = o.track_stage1(L, R, tri, T, lms, scaling)
+        ref = o.track_manual(L, R, tri, T, lms, scaling)
         with StereoFrontend(*vi_cams) as fe:
-            got = fe.track_landmarks(L, R, T, xyz_w, ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, scaling)
-        stages = [r["stage"] for r in ref]
-        assert sum(s > 0 for s in stages) > 50
-        for i, r in enumerate(ref):
-            assert got["stage"][i] == r["stage"], i
-            assert got["status"][i] == r["status"], i
-            if r["stage"]:
-                assert tuple(got["uv_l"][i]) == tuple(np.float32(v) for v in r["uv_l"])
-                assert tuple(got["uv_r"][i]) == tuple(np.float32(v) for v in r["uv_r"])
-                np.testing.assert_array_equal(got["xyz"][i], r["xyz"])
-                np.testing.assert_array_equal(got["desc_l"][i], r["desc_l"])
-                np.testing.assert_array_equal(got["desc_r"][i], r["desc_r"])
+            got = fe.track_landmarks(L, R, T, ref0["xyz"][ok], ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, scaling)
+        stages = np.bincount([r["stage"] for r in ref], minlength=5)
+        assert stages[1] > 50
+        _compare_tracks(got, ref)
+
+
+def test_track_manual_stage2_window_search(vi_cams):
+    """Stage 2 (GFTT inside the projection window): the next frame is the same scene moved by (3, 2) px, so the
+    exact projections miss and the window search has to re-find the corners; then the LEFT image is damaged
+    in a band so that stage 2 LEFT fails there and stage 2 RIGHT takes over."""
+    W, H = vi_cams[0].width, vi_cams[0].height
+    L, R = stereo_pair(W, H, 4000)
+    tri = _tri(vi_cams)
+    ref0 = o.add_new_landmarks(L, R, tri)
+    ok = np.nonzero(ref0["status"] == 0)[0][:160]
+    disp, lms = _landmarks_from_frame(ref0, ok)
+    L1, R1 = np.roll(L, (2, 3), axis=(0, 1)), np.roll(R, (2, 3), axis=(0, 1))
+    L2 = L1.copy()
+    rng = np.random.default_rng(0)
+    L2[:, 150:420] = rng.integers(0, 256, size=(H, 270), dtype=np.uint8)      # LEFT unusable in this band
+    for (a, b), want in (((L1, R1), 3), ((L2, R1), 4)):
+        ref = o.track_manual(a, b, tri, np.eye(4), lms, 1.0)
+        stages = np.bincount([r["stage"] for r in ref], minlength=5)
+        assert stages[want] >= 5, stages
+        with StereoFrontend(*vi_cams) as fe:
+            got = fe.track_landmarks(a, b, np.eye(4), ref0["xyz"][ok], ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, 1.0)
+        _compare_tracks(got, ref)
 
 
 def test_device_resident_entry(kitti_cams):
@@ -323,7 +354,7 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
         assert [float(v) for v in row[6:9]] == list(ref["xyz"][i])
     lms = [dict(xyz_w=ref["xyz"][i], last_desc_l=ref["desc_l"][i], last_desc_r=ref["desc_r"][i],
                 last_disparity=np.float32(ref["uv_l"][i, 0] - ref["uv_r"][i, 0]), size=7.0) for i in ok]
-    trk = o.track_stage1(L, R, tri, np.eye(4), lms, 1.0)
+    trk = o.track_manual(L, R, tri, np.eye(4), lms, 1.0)
     n_trk = sum(1 for t in trk if t["stage"] > 0)
     n_fov = sum(1 for t in trk if t["status"] == o.ST_TRK_OUT_OF_FOV)
     head = [l for l in lines if l.startswith("TRACKED")][0].split()
