@@ -367,3 +367,27 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
         assert [float(v) for v in row[2:6]] == [float(t["uv_l"][0]), float(t["uv_l"][1]), float(t["uv_r"][0]), float(t["uv_r"][1])]
         assert float(row[6]) == t["xyz"][2]
     assert lines[-1] == "EXC <CTriangulator>(getPointInLEFT) zero disparity"
+
+
+def test_stress_frame_global_select_and_long_scanlines(kitti_cams):
+    """C5-shaped case: 3840x1080 frame, far more than 16384 NMS candidates (global-memory selection variant),
+    3000 corners, 400 px scan-line range (several 62-candidate windows per key-point).  Checker: the C oracle."""
+    from types import SimpleNamespace
+    from oracle import c_oracle as co
+    W, H = 3840, 1080
+    L, R = stereo_pair(W, H, 3000, d_max=350)
+    cl = SimpleNamespace(width=W, height=H, P=kitti_cams[0].P)
+    cr = SimpleNamespace(width=W, height=H, P=kitti_cams[1].P)
+    cfg = co.make_config(cl, cr, max_corners=3000, search_range=400.0)
+    ref = co.frame(co.stereo_frames(cfg, L, R, n_threads=co.host_threads()), 0)
+    with StereoFrontend(cl, cr, max_corners=3000, search_range_px=400.0, max_candidates=131072, chunk_frames=1) as fe:
+        assert not fe.config()["select_in_smem"]
+        got = fe.add_new_landmarks(L, R)
+    from svi_mapper_b200 import SviError
+    with StereoFrontend(cl, cr, max_corners=3000, max_candidates=16384, chunk_frames=1) as small:
+        with pytest.raises(SviError, match="candidate list overflow"):   # never a silent drop
+            small.add_new_landmarks(L, R)
+    assert len(ref["status"]) > 2500 and (ref["status"] == 0).sum() > 2000
+    d = ref["uv_l"][ref["status"] == 0, 0] - ref["uv_r"][ref["status"] == 0, 0]
+    assert d.max() > 124          # matches beyond the second window really occur
+    _compare_frame(got, ref)
