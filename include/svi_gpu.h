@@ -53,7 +53,17 @@ typedef enum svi_status {
     SVI_TRK_NO_FEATURES = 11, /* src/core/CFundamentalMatcher.cpp:1660,1780 "no features detected"  */
     SVI_TRK_NO_MATCHES = 12,  /* src/core/CFundamentalMatcher.cpp:1654,1775 "no matches found"      */
     SVI_TRK_DESC = 13,        /* src/core/CFundamentalMatcher.cpp:1648,1770 "descriptor mismatch"   */
-    SVI_TRK_RANGE = 14        /* src/core/CFundamentalMatcher.cpp:1642,1765 "out of tracking range" */
+    SVI_TRK_RANGE = 14,       /* src/core/CFundamentalMatcher.cpp:1642,1765 "out of tracking range" */
+    SVI_EPI_OUT_OF_SIGHT = 15, /* CExceptionEpipolarLine :1814 "projection out of sight"                      */
+    SVI_EPI_VERTICAL = 16,     /* :1845 "vertical out of sight"                                               */
+    SVI_EPI_NEG_SLOPE = 17,    /* :1871 "caught bad projection negative slope"                                */
+    SVI_EPI_POS_SLOPE = 18,    /* :1900 "caught bad projection positive slope"                                */
+    SVI_EPI_ZERO_LEN = 19,     /* :1939 "zero line length"                                                    */
+    SVI_EPI_POOL_EMPTY = 20,   /* :2351 "could not find a matching descriptor (empty key point pool)"         */
+    SVI_EPI_NO_MATCHES = 21,   /* :2361 "could not find any matches (empty matches pool)"                     */
+    SVI_EPI_DIST = 22,         /* :2395 "could not find a matching descriptor"                                */
+    SVI_EPI_ORIG_DIST = 23,    /* :2390 "... (ORIGINAL matching distance too big)"                            */
+    SVI_EPI_NO_TRANSLATION = 24 /* :1804 detection pose == current pose: stage 3 is skipped for this landmark */
 } svi_status;
 
 /* src/vision/CPinholeCamera.h:16-64: the members the hot path reads
@@ -183,11 +193,16 @@ typedef struct svi_landmarks {
     const uint8_t* last_desc_right; /* [n*32] getLastDescriptorRIGHT() */
     const float* last_disparity;  /* [n] getLastDisparity() */
     const float* keypoint_size;   /* [n] dKeyPointSize */
+    /* stage 3 only; all three NULL = stop after stage 2 */
+    const double* uv_reference_left;      /* [n*2] vecUVReferenceLEFT (first LEFT detection) */
+    const uint8_t* desc_reference_left;   /* [n*32] matDescriptorReferenceLEFT */
+    const double* T_left_to_world_at_detection; /* [n*16] row-major matTransformationLEFTtoWORLD of the landmark's
+                                                   detection point (CFundamentalMatcher.h:27) */
 } svi_landmarks;
 
 typedef struct svi_track_result {
     uint8_t* status;     /* [n] svi_status of the LAST stage tried */
-    uint8_t* stage;      /* [n] 0 = not tracked, 1 / 2 = stage 1 LEFT / RIGHT, 3 / 4 = stage 2 LEFT / RIGHT */
+    uint8_t* stage;      /* [n] 0 = not tracked, 1 / 2 = stage 1 LEFT / RIGHT, 3 / 4 = stage 2 LEFT / RIGHT, 5 = stage 3 */
     float* uv_left;      /* [n*2] */
     float* uv_right;     /* [n*2] */
     double* xyz_left;    /* [n*3] */
@@ -195,14 +210,14 @@ typedef struct svi_track_result {
     uint8_t* desc_right; /* [n*32] */
 } svi_track_result;
 
-/* CFundamentalMatcher::trackManual, stages 1 and 2 as the reference's first-success cascade
- * (src/core/CFundamentalMatcher.cpp:1404-1785): stage 1 LEFT / RIGHT (descriptor exactly at the rounded
- * projection), then stage 2 LEFT / RIGHT (GFTT inside the projection window of half size
- * round(round(w + scaling) * 15), BRIEF on the window grown by 28 px, 1 x K match, cut-off 50) for the
- * landmarks stage 1 could not place, each followed by the scan-line triangulation in the other image.
- * T_world_to_left is the row-major 4x4 of p_matTransformationWORLDtoLEFT.  Landmarks left with stage 0
- * and a status other than SVI_TRK_OUT_OF_FOV are the ones the reference hands to stage 3 (epipolar
- * search, :1786-1993), which stays with the caller. */
+/* CFundamentalMatcher::trackManual, the reference's first-success cascade
+ * (src/core/CFundamentalMatcher.cpp:1404-1993): stage 1 LEFT / RIGHT (descriptor exactly at the rounded
+ * projection), stage 2 LEFT / RIGHT (GFTT inside the projection window of half size
+ * round(round(w + scaling) * 15), BRIEF on the window grown by 28 px, 1 x K match, cut-off 50) and stage 3
+ * (one key-point per pixel along the epipolar line F * uvReference in LEFT, clipped to the box around the
+ * projection, BRIEF, 1 x N match, cut-offs 50 / 100, one retry 2 px off the line; :1786-1993, :2142-2397),
+ * each followed by the scan-line triangulation in the other image.
+ * T_world_to_left is the row-major 4x4 of p_matTransformationWORLDtoLEFT. */
 int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* img_right,
                         size_t pitch, const double* T_world_to_left, const svi_landmarks* lm, int n,
                         double motion_scaling, svi_track_result* out);

@@ -53,6 +53,16 @@ ST_TRK_NO_FEATURES = 11  # "no features detected"   (stage 2: GFTT found nothing
 ST_TRK_NO_MATCHES = 12   # "no matches found"       (stage 2: every corner was erased by BRIEF's border filter)
 ST_TRK_DESC = 13         # "descriptor mismatch"    (stage 2: best corner >= cut-off)
 ST_TRK_RANGE = 14        # "out of tracking range"  (stage 2: v - 28 < 0)
+ST_EPI_OUT_OF_SIGHT = 15   # CExceptionEpipolarLine "projection out of sight"            :1814
+ST_EPI_VERTICAL = 16       # "vertical out of sight"                                      :1845
+ST_EPI_NEG_SLOPE = 17      # "caught bad projection negative slope"                       :1871
+ST_EPI_POS_SLOPE = 18      # "caught bad projection positive slope"                       :1900
+ST_EPI_ZERO_LEN = 19       # "zero line length"                                           :1939
+ST_EPI_POOL_EMPTY = 20     # "could not find a matching descriptor (empty key point pool)" :2351
+ST_EPI_NO_MATCHES = 21     # "could not find any matches (empty matches pool)"            :2361
+ST_EPI_DIST = 22           # "could not find a matching descriptor"                       :2395
+ST_EPI_ORIG_DIST = 23      # "... (ORIGINAL matching distance too big)"                   :2390
+ST_EPI_NO_TRANSLATION = 24 # detection pose == current pose: the essential matrix is undefined, stage 3 is skipped (:1804)
 
 PATTERN_FILE = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "brief_pattern_32.txt"
 
@@ -90,6 +100,9 @@ class StereoParams:
     min_disparity: float = 0.01         # CTriangulator.h:21
     cutoff_stage1: float = 25.0         # CFundamentalMatcher.cpp:23
     cutoff_stage2: float = 50.0         # CFundamentalMatcher.cpp:24
+    cutoff_stage3: float = 50.0         # CFundamentalMatcher.cpp:25
+    cutoff_original: float = 100.0      # CFundamentalMatcher.cpp:26
+    epipolar_base_length: float = 15.0  # CFundamentalMatcher.h:92
     block_size_stage2: int = 15         # CFundamentalMatcher.h:95 m_uSearchBlockSizePoseOptimization
 
 
@@ -283,10 +296,13 @@ def brief32(img: np.ndarray, pts, pattern: np.ndarray = PATTERN):
     keep, cx, cy = [], [], []
     for i, (x, y) in enumerate(pts):
         rx, ry = cv_round(x), cv_round(y)
-        if 28 <= rx < w - 28 and 28 <= ry < h - 28:
+        sx, sy = int(float(F32(x)) + 0.5), int(float(F32(y)) + 0.5)   # (int)(pt + 0.5), double arithmetic
+        # For x.5 coordinates cvRound (half to even) and the sampling centre can differ by one; at the border the
+        # reference then reads one column outside its integral image (undefined).  Defined here: erase the point.
+        if 28 <= rx < w - 28 and 28 <= ry < h - 28 and 28 <= sx < w - 28 and 28 <= sy < h - 28:
             keep.append(i)
-            cx.append(int(float(F32(x)) + 0.5))   # (int)(pt.x + 0.5), double arithmetic
-            cy.append(int(float(F32(y)) + 0.5))
+            cx.append(sx)
+            cy.append(sy)
     if not keep:
         return np.zeros(0, np.int64), np.zeros((0, 32), np.uint8)
     S = integral(img).astype(np.int64)
@@ -631,4 +647,193 @@ def track_manual(img_l, img_r, tri: Triangulator, T_w2l: np.ndarray, landmarks, 
             out.append(dict(status=ST_OK, stage=4, uv_l=r["uv_other"], uv_r=r["uv_this"], xyz=r["xyz"], desc_l=r["desc_other"], desc_r=r["desc_this"]))
         else:
             out.append(dict(status=r["status"], stage=0))
+    return out
+
+
+# ----------------------------------------------------------------------------- trackManual stage 3
+def _mul3(A, B):
+    """3x3 product, every element ((a0*b0 + a1*b1) + a2*b2) -- the order the host C++ uses."""
+    return [[(A[i][0] * B[0][j] + A[i][1] * B[1][j]) + A[i][2] * B[2][j] for j in range(3)] for i in range(3)]
+
+
+def _inv3(m):
+    """3x3 inverse by cofactors (adjugate / determinant), the closed form Eigen uses for fixed 3x3."""
+    def cof(i, j):
+        i1, i2, j1, j2 = (i + 1) % 3, (i + 2) % 3, (j + 1) % 3, (j + 2) % 3
+        return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1]
+    c0 = [cof(0, 0), cof(1, 0), cof(2, 0)]
+    det = (c0[0] * m[0][0] + c0[1] * m[1][0]) + c0[2] * m[2][0]
+    inv_det = 1.0 / det
+    return [[cof(j, i) * inv_det for j in range(3)] for i in range(3)]
+
+
+def _ieee_div(a: float, b: float) -> float:
+    """a / b with C semantics (inf / nan instead of ZeroDivisionError)."""
+    if b != 0.0:
+        return a / b
+    if a != a or a == 0.0:
+        return float("nan")
+    return math.copysign(float("inf"), a) * math.copysign(1.0, b)
+
+
+def epipolar_plan(tri: Triangulator, T_w2l, T_det_l2w, uv_ref, xyz_w, motion_scaling: float):
+    """Geometry of stage 3 up to the sampling request (:1795-1947) in plain double arithmetic.
+    Returns dict(status) or dict(status=ST_OK, along_u, start, count, coeff)."""
+    p = tri.p
+    Tw = [[float(T_w2l[i][j]) for j in range(4)] for i in range(4)]
+    Td = [[float(T_det_l2w[i][j]) for j in range(4)] for i in range(4)]
+    R = [[(Tw[i][0] * Td[0][j] + Tw[i][1] * Td[1][j]) + Tw[i][2] * Td[2][j] for j in range(3)] for i in range(3)]
+    t = [((Tw[i][0] * Td[0][3] + Tw[i][1] * Td[1][3]) + Tw[i][2] * Td[2][3]) + Tw[i][3] for i in range(3)]
+    if not (0.0 < (t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]):
+        return dict(status=ST_EPI_NO_TRANSLATION)
+    S = [[0.0, -t[2], t[1]], [t[2], 0.0, -t[0]], [-t[1], t[0], 0.0]]          # CMiniVisionToolbox::getSkew
+    E = _mul3(R, S)                                                           # :1800
+    P = tri.cl.P
+    K = [[float(P[i, j]) for j in range(3)] for i in range(3)]                # m_matIntrinsicP
+    Ki = _inv3(K)
+    KiT = [[Ki[j][i] for j in range(3)] for i in range(3)]
+    F = _mul3(_mul3(KiT, E), Ki)                                              # :1801
+    u0, v0 = float(uv_ref[0]), float(uv_ref[1])
+    c = [(F[i][0] * u0 + F[i][1] * v0) + F[i][2] * 1.0 for i in range(3)]      # :1818
+    xyz_l = [((Tw[i][0] * float(xyz_w[0]) + Tw[i][1] * float(xyz_w[1])) + Tw[i][2] * float(xyz_w[2])) + Tw[i][3] for i in range(3)]
+    proj = projection_rounded(tri.cl.P, xyz_l)                                # :1807
+    if not fov_contains(tri.cl, proj):
+        return dict(status=ST_EPI_OUT_OF_SIGHT)
+    W, H = float(tri.cl.width), float(tri.cl.height)
+    half = 10.0 * motion_scaling                                              # :1362
+    wu = math.sqrt(abs(float(proj[0]) - float(P[0, 2]))) / 10.0
+    wv = math.sqrt(abs(float(proj[1]) - float(P[1, 2]))) / 10.0
+    hl_u = p.epipolar_base_length + wu * half                                 # :1821-1822
+    hl_v = p.epipolar_base_length + wv * half
+
+    def curve_v(u):
+        return _ieee_div(-(c[0] * u + c[2]), c[1])
+
+    def curve_u(v):
+        return _ieee_div(-(c[1] * v + c[2]), c[0])
+
+    u_min_raw = max(float(proj[0]) - hl_u, 0.0)
+    u_max_raw = min(float(proj[0]) + hl_u, W)
+    v_min_raw, v_max_raw = curve_v(u_min_raw), curve_v(u_max_raw)
+    if (0.0 > v_min_raw and 0.0 > v_max_raw) or (H < v_min_raw and H < v_max_raw):
+        return dict(status=ST_EPI_VERTICAL)
+    v_lim_min = max(float(proj[1]) - hl_v, 0.0)
+    v_lim_max = min(float(proj[1]) + hl_v, H)
+    u_min, u_max = u_min_raw, u_max_raw
+    if v_min_raw < v_max_raw:
+        if v_lim_min > v_max_raw or v_lim_max < v_min_raw:
+            return dict(status=ST_EPI_NEG_SLOPE)
+        if v_lim_min > v_min_raw:
+            v_for_min = v_lim_min
+            u_min = curve_u(v_for_min)
+        else:
+            v_for_min = v_min_raw
+        if v_lim_max < v_max_raw:
+            v_for_max = v_lim_max
+            u_max = curve_u(v_for_max)
+        else:
+            v_for_max = v_max_raw
+    else:
+        if v_lim_min > v_min_raw or v_lim_max < v_max_raw:
+            return dict(status=ST_EPI_POS_SLOPE)
+        if v_lim_min > v_max_raw:
+            v_for_min = v_lim_min
+            u_max = curve_u(v_for_min)
+        else:
+            v_for_min = v_max_raw
+        if v_lim_max < v_min_raw:
+            v_for_max = v_lim_max
+            u_min = curve_u(v_for_max)
+        else:
+            v_for_max = v_min_raw
+    du, dv = u_max - u_min, v_for_max - v_for_min
+    if not (math.isfinite(du) and math.isfinite(dv)) or du < 0.0 or dv < 0.0 or du >= 65536.0 or dv >= 65536.0:
+        return dict(status=ST_EPI_ZERO_LEN)   # the reference's uint32 conversion is undefined here
+    delta_u, delta_v = int(du), int(dv)                                       # uint32_t truncation :1933-1934
+    if delta_u == 0 and delta_v == 0:
+        return dict(status=ST_EPI_ZERO_LEN)
+    if delta_v < delta_u:
+        return dict(status=ST_OK, along_u=True, start=u_min, count=delta_u, coeff=c)
+    return dict(status=ST_OK, along_u=False, start=v_for_min, count=delta_v, coeff=c)
+
+
+def epipolar_match(img, tri: Triangulator, plan, size, last_desc, orig_desc):
+    """_getMatchSampleRecursiveU/V + _getMatch (:2142-2397): one key-point per pixel along the line, BRIEF in the
+    bounding ROI, 1 x N match, cut-offs 50 (last) / 100 (original); one retry with the samples moved by +2 px."""
+    p = tri.p
+    c = plan["coeff"]
+    n = plan["count"]
+    size = F32(size)
+    wf, hf = F32(tri.cl.width), F32(tri.cl.height)
+    h, w = img.shape
+    status = ST_EPI_POOL_EMPTY
+    for off in (0, 2):                                                        # recursion depth 0, then 2 (limit 2, step 2)
+        pool = []
+        for i in range(n):
+            if plan["along_u"]:
+                du = plan["start"] + i
+                dv = _ieee_div(-(c[0] * du + c[2]), c[1]) + off
+            else:
+                dv = plan["start"] + i
+                du = _ieee_div(-(c[1] * dv + c[2]), c[0]) + off
+            pool.append((F32(du), F32(dv)))
+        centre = pool[n // 2]
+        f_du = F32(abs(F32(pool[0][0] - pool[-1][0]))) + F32(16) * size
+        f_dv = F32(abs(F32(pool[0][1] - pool[-1][1]))) + F32(16) * size
+        u_tl = max(F32(centre[0] - f_du / F32(2)), F32(0))
+        v_tl = max(F32(centre[1] - f_dv / F32(2)), F32(0))
+        width = min(f_du, F32(wf - u_tl))
+        height = min(f_dv, F32(hf - v_tl))
+        if not all(math.isfinite(float(x)) for x in (u_tl, v_tl, width, height)):
+            status = ST_EPI_POOL_EMPTY
+            continue
+        rx, ry, rw, rh = int(u_tl), int(v_tl), int(width), int(height)         # cv::Rect(float...) truncates
+        if rw <= 0 or rh <= 0 or rx + rw > w or ry + rh > h:
+            status = ST_EPI_POOL_EMPTY
+            continue
+        local = [(F32(a - u_tl), F32(b - v_tl)) for a, b in pool]
+        keep, desc = brief32(img[ry:ry + rh, rx:rx + rw], local)
+        if len(keep) == 0:
+            status = ST_EPI_POOL_EMPTY
+            continue
+        idx, dist = match_hamming(np.asarray(last_desc, np.uint8), desc)
+        if not (p.cutoff_stage3 > dist):
+            status = ST_EPI_DIST
+            continue
+        if not (p.cutoff_original > hamming(np.asarray(orig_desc, np.uint8), desc[idx])):
+            status = ST_EPI_ORIG_DIST
+            continue
+        k = local[keep[idx]]
+        return dict(status=ST_OK, uv=(F32(k[0] + u_tl), F32(k[1] + v_tl)), desc=desc[idx].copy())
+    return dict(status=status)
+
+
+def track_stage3(img_l, img_r, tri: Triangulator, T_w2l, lm, motion_scaling: float):
+    """Stage 3 for one landmark dict with the extra keys uv_ref (first LEFT detection), ref_desc_l
+    (matDescriptorReferenceLEFT) and T_det_l2w (pose of its detection point)."""
+    plan = epipolar_plan(tri, T_w2l, lm["T_det_l2w"], lm["uv_ref"], lm["xyz_w"], motion_scaling)
+    if plan["status"] != ST_OK:
+        return dict(status=plan["status"], stage=0)
+    m = epipolar_match(img_l, tri, plan, lm["size"], lm["last_desc_l"], lm["ref_desc_l"])
+    if m["status"] != ST_OK:
+        return dict(status=m["status"], stage=0)
+    size = F32(lm["size"])
+    search = F32((1.0 + motion_scaling) * float(F32(lm["last_disparity"])))    # :2415 double product, then float
+    x, y = m["uv"]
+    r = tri.triangulate_right(img_r, max(F32(0), F32(F32(x - search) - F32(4) * size)), F32(y - F32(4) * size), size, (x, y), m["desc"])
+    if r["status"] != ST_OK:
+        return dict(status=r["status"], stage=0)
+    z = r["xyz"][2]
+    if tri.depth_min > z or tri.depth_max < z:
+        return dict(status=ST_TRK_DEPTH, stage=0)
+    return dict(status=ST_OK, stage=5, uv_l=(x, y), uv_r=r["uv"], xyz=r["xyz"], desc_l=m["desc"], desc_r=r["desc"])
+
+
+def track_manual_full(img_l, img_r, tri: Triangulator, T_w2l, landmarks, motion_scaling: float):
+    """The whole cascade: stages 1, 2 (track_manual) and 3; stage code 5 = stage 3."""
+    out = track_manual(img_l, img_r, tri, T_w2l, landmarks, motion_scaling)
+    for i, (lm, r) in enumerate(zip(landmarks, out)):
+        if r["stage"] or r["status"] == ST_TRK_OUT_OF_FOV or "T_det_l2w" not in lm:
+            continue
+        out[i] = track_stage3(img_l, img_r, tri, T_w2l, lm, motion_scaling)
     return out

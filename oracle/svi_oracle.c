@@ -236,7 +236,10 @@ int svo_brief32(const uint8_t* img, int w, int h, int pitch, const float* pts, i
     if (w <= 56 || h <= 56) return 0;
     for (int i = 0; i < n; ++i) {
         long rx = lrint_half_even(pts[2 * i]), ry = lrint_half_even(pts[2 * i + 1]);
-        if (rx >= 28 && rx < w - 28 && ry >= 28 && ry < h - 28) kept[nk++] = i;
+        /* x.5 coordinates: cvRound and the sampling centre (int)(pt+0.5) can differ by one and the reference then
+         * reads outside its integral image (undefined); defined here: such a key-point is erased */
+        const int sx = (int)(pts[2 * i] + 0.5), sy = (int)(pts[2 * i + 1] + 0.5);
+        if (rx >= 28 && rx < w - 28 && ry >= 28 && ry < h - 28 && sx >= 28 && sx < w - 28 && sy >= 28 && sy < h - 28) kept[nk++] = i;
     }
     if (!nk) return 0;
     const int sw = w + 1;

@@ -13,7 +13,8 @@ SVI_ERR_INVALID, SVI_ERR_CUDA, SVI_ERR_CAPACITY, SVI_ERR_NO_DEVICE, SVI_ERR_UNSU
 # svi_status
 (SVI_OK, SVI_TRI_RANGE, SVI_TRI_NO_DESC, SVI_TRI_NO_MATCH, SVI_TRI_DISTANCE, SVI_TRI_ZERO_DISP, SVI_TRI_BAD_ROI,
  SVI_TRK_DEPTH, SVI_TRK_STAGE1_DIST, SVI_TRK_TRI_DESC, SVI_TRK_OUT_OF_FOV, SVI_TRK_NO_FEATURES, SVI_TRK_NO_MATCHES,
- SVI_TRK_DESC, SVI_TRK_RANGE) = range(15)
+ SVI_TRK_DESC, SVI_TRK_RANGE, SVI_EPI_OUT_OF_SIGHT, SVI_EPI_VERTICAL, SVI_EPI_NEG_SLOPE, SVI_EPI_POS_SLOPE, SVI_EPI_ZERO_LEN,
+ SVI_EPI_POOL_EMPTY, SVI_EPI_NO_MATCHES, SVI_EPI_DIST, SVI_EPI_ORIG_DIST, SVI_EPI_NO_TRANSLATION) = range(25)
 
 EXPORTS = (
     "svi_params_default", "svi_status_text", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
@@ -56,7 +57,8 @@ class TriResult(C.Structure):
 
 class Landmarks(C.Structure):
     _fields_ = [("xyz_world", C.c_void_p), ("last_desc_left", C.c_void_p), ("last_desc_right", C.c_void_p),
-                ("last_disparity", C.c_void_p), ("keypoint_size", C.c_void_p)]
+                ("last_disparity", C.c_void_p), ("keypoint_size", C.c_void_p), ("uv_reference_left", C.c_void_p),
+                ("desc_reference_left", C.c_void_p), ("T_left_to_world_at_detection", C.c_void_p)]
 
 
 class TrackResult(C.Structure):

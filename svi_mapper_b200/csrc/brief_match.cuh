@@ -187,15 +187,18 @@ __device__ __forceinline__ void search_plan(int W, int H, float img_width_f, flo
     p.n_valid = 0; p.i_lo = 0; p.gx_lo = 0; p.gy = 0;
     if (rx < 0 || ry < 0 || rw < 0 || rh < 0 || rx + rw > W || ry + rh > H) { p.status = SVI_TRI_BAD_ROI; return; }
     // KeyPointsFilter::runByImageBorder inside the ROI: keep 28 <= cvRound(pt) < size - 28
-    const int ky_r = cv_round_f(border);
+    // (a key-point whose sampling centre (int)(pt+0.5) falls outside the same range is erased too: for x.5
+    //  coordinates the two roundings differ and the reference would read outside its integral image)
+    const int ky_r = cv_round_f(border), ky_c = brief_centre(border);
     int i_lo = 0, i_hi = 0;
-    if (ky_r >= kBriefBorder && ky_r < rh - kBriefBorder) {
+    if (ky_r >= kBriefBorder && ky_r < rh - kBriefBorder && ky_c >= kBriefBorder && ky_c < rh - kBriefBorder) {
         for (int i0 = 0; i0 < n_pool; i0 += 32) {
             int i = i0 + lane;
-            int kr = cv_round_f((border + (float)i) + (float)first);
+            const float kx = (border + (float)i) + (float)first;
+            const int kr = cv_round_f(kx), kc = brief_centre(kx);
             bool in = i < n_pool;
-            i_lo += __popc(__ballot_sync(0xFFFFFFFFu, in && kr < kBriefBorder));
-            i_hi += __popc(__ballot_sync(0xFFFFFFFFu, in && kr < rw - kBriefBorder));
+            i_lo += __popc(__ballot_sync(0xFFFFFFFFu, in && (kr < kBriefBorder || kc < kBriefBorder)));
+            i_hi += __popc(__ballot_sync(0xFFFFFFFFu, in && kr < rw - kBriefBorder && kc < rw - kBriefBorder));
         }
     }
     p.n_valid = i_hi - i_lo;
@@ -441,8 +444,9 @@ __global__ void describe_kernel(const uint16_t* __restrict__ box, FrameGeom g, c
     const int lane = threadIdx.x & 31, q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= n) return;
     const float x = xy[2 * q], y = xy[2 * q + 1];
-    const int rx = cv_round_f(x), ry = cv_round_f(y);
-    const bool ok = rx >= kBriefBorder && rx < g.W - kBriefBorder && ry >= kBriefBorder && ry < g.H - kBriefBorder;
+    const int rx = cv_round_f(x), ry = cv_round_f(y), sx = brief_centre(x), sy = brief_centre(y);
+    const bool ok = rx >= kBriefBorder && rx < g.W - kBriefBorder && ry >= kBriefBorder && ry < g.H - kBriefBorder &&
+                    sx >= kBriefBorder && sx < g.W - kBriefBorder && sy >= kBriefBorder && sy < g.H - kBriefBorder;
     uint32_t w[kDescWords] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (ok) brief_at_point(box, g.box_pitch, brief_centre(x), brief_centre(y), lane, w);
     store_desc(desc + (size_t)q * 32, w, lane);
@@ -672,10 +676,11 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
             if (k < nd) {
                 const ushort2 c = corners[k];
                 const float px = (float)c.x + half, py = (float)c.y + half;
-                const int rx = cv_round_f(px), ry = cv_round_f(py);
-                keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder;
-                sx = it.gx + brief_centre(px);
-                sy = it.gy + brief_centre(py);
+                const int rx = cv_round_f(px), ry = cv_round_f(py), cx = brief_centre(px), cy = brief_centre(py);
+                keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder &&
+                       cx >= kBriefBorder && cx < it.gw - kBriefBorder && cy >= kBriefBorder && cy < it.gh - kBriefBorder;
+                sx = it.gx + cx;
+                sy = it.gy + cy;
             }
             uint32_t dist = 0;
             if (keep) {
@@ -730,6 +735,126 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
             float* uv_other = kLeft ? out.uv_r : out.uv_l;
             uv_this[2 * q] = in_x; uv_this[2 * q + 1] = in_y;
             uv_other[2 * q] = r.u; uv_other[2 * q + 1] = r.v;
+            out.xyz[3 * q] = xyz[0]; out.xyz[3 * q + 1] = xyz[1]; out.xyz[3 * q + 2] = xyz[2];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ tracking, stage 3 (epipolar line)
+struct Stage3Item {
+    int q;             // landmark index
+    int along_u;       // 1: one sample per u, v from the line (:2142-2238); 0: one per v, u from the line (:2240-2334)
+    int count;         // uDeltaU / uDeltaV
+    float size, search;   // dKeyPointSize, (float)((1 + scaling) * lastDisparity)  (:2415)
+    double start;      // dUMinimum / dVForUMinimum
+    double c0, c1, c2; // line coefficients F * uvReference (:1818)
+};
+
+__device__ __forceinline__ void epipolar_sample(const Stage3Item& it, int i, double off, float& fx, float& fy) {
+    if (it.along_u) {
+        const double du = __dadd_rn(it.start, (double)i);
+        const double dv = __dadd_rn(__ddiv_rn(-__dadd_rn(__dmul_rn(it.c0, du), it.c2), it.c1), off);   // _getCurveV + offset
+        fx = (float)du; fy = (float)dv;
+    } else {
+        const double dv = __dadd_rn(it.start, (double)i);
+        const double du = __dadd_rn(__ddiv_rn(-__dadd_rn(__dmul_rn(it.c1, dv), it.c2), it.c0), off);   // _getCurveU + offset
+        fx = (float)du; fy = (float)dv;
+    }
+}
+
+// _getMatchSampleRecursiveU/V + _getMatch (:2142-2397) and _addMeasurementToLandmarkLEFT (:2399-2453):
+// the line geometry (coefficients, clipped range, sampling direction) comes from the host; one warp per item.
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
+                    const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float cutoff3, float cutoff_orig,
+                    const Stage3Item* __restrict__ items, int n_items, const uint8_t* __restrict__ desc_orig,
+                    LandmarksDev lm, TrackOutDev out) {
+    extern __shared__ __align__(128) unsigned char match_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * MATCH_WARPS + warp;
+    if (idx >= n_items) return;
+    const Stage3Item it = items[idx];
+    const int q = it.q, n = it.count;
+    PatchStage ps;
+    patch_stage_init(ps, match_smem, &map_r, &map_rs, 0, warp, lane);
+    uint32_t last_l[kDescWords], orig_l[kDescWords], mine[kDescWords];
+    load_desc(lm.desc_l + (size_t)q * 32, last_l);
+    load_desc(desc_orig + (size_t)q * 32, orig_l);
+    const float wf = (float)g.W, hf = (float)g.H;
+    int status = SVI_EPI_POOL_EMPTY;
+    float res_x = 0.f, res_y = 0.f;
+    bool found = false;
+    for (int attempt = 0; attempt < 2 && !found; ++attempt) {
+        const double off = attempt ? 2.0 : 0.0;    // recursion depth 0, then 2 (limit 2, step 2)
+        float ax, ay, bx, by, cx, cy;
+        epipolar_sample(it, 0, off, ax, ay);
+        epipolar_sample(it, n - 1, off, bx, by);
+        epipolar_sample(it, n / 2, off, cx, cy);
+        const float f_du = fabsf(ax - bx) + 16.f * it.size, f_dv = fabsf(ay - by) + 16.f * it.size;
+        const float u_tl = fmaxf(cx - f_du / 2.f, 0.f), v_tl = fmaxf(cy - f_dv / 2.f, 0.f);
+        const float width = fminf(f_du, wf - u_tl), height = fminf(f_dv, hf - v_tl);
+        status = SVI_EPI_POOL_EMPTY;
+        if (!(isfinite(u_tl) && isfinite(v_tl) && isfinite(width) && isfinite(height))) continue;
+        const int rx = (int)u_tl, ry = (int)v_tl, rw = (int)width, rh = (int)height;   // cv::Rect(float...) truncates
+        if (rw <= 0 || rh <= 0 || rx + rw > g.W || ry + rh > g.H) continue;
+        uint32_t best = 0xFFFFFFFFu;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            bool keep = false;
+            int sx = 0, sy = 0;
+            if (i < n) {
+                float fx, fy;
+                epipolar_sample(it, i, off, fx, fy);
+                const float kx = fx - u_tl, ky = fy - v_tl;
+                const int rnx = cv_round_f(kx), rny = cv_round_f(ky), ccx = brief_centre(kx), ccy = brief_centre(ky);
+                keep = rnx >= kBriefBorder && rnx < rw - kBriefBorder && rny >= kBriefBorder && rny < rh - kBriefBorder &&
+                       ccx >= kBriefBorder && ccx < rw - kBriefBorder && ccy >= kBriefBorder && ccy < rh - kBriefBorder;
+                sx = rx + ccx;
+                sy = ry + ccy;
+            }
+            uint32_t dist = 0;
+            if (keep) {
+#pragma unroll 4
+                for (int t = 0; t < SVI_BRIEF_NTESTS; ++t) {
+                    const signed char* p = d_pat[t];
+                    const uint32_t s1 = __ldg(box_l + (size_t)(sy + p[0]) * g.box_pitch + sx + p[1]);
+                    const uint32_t s2 = __ldg(box_l + (size_t)(sy + p[2]) * g.box_pitch + sx + p[3]);
+                    dist += (s1 < s2 ? 1u : 0u) ^ ((last_l[t >> 5] >> (31 - (t & 31))) & 1u);
+                }
+            }
+            best = min(best, warp_min_u32(keep ? ((dist << 16) | (uint32_t)i) : 0xFFFFFFFFu));
+        }
+        if (best == 0xFFFFFFFFu) continue;                       // "empty key point pool"
+        status = SVI_EPI_DIST;
+        if (!(cutoff3 > (float)(best >> 16))) continue;
+        float fx, fy;
+        epipolar_sample(it, (int)(best & 0xFFFFu), off, fx, fy);
+        const float kx = fx - u_tl, ky = fy - v_tl;
+        brief_at_point(box_l, g.box_pitch, rx + brief_centre(kx), ry + brief_centre(ky), lane, mine);
+        status = SVI_EPI_ORIG_DIST;
+        if (!(cutoff_orig > (float)hamming_words(orig_l, mine))) continue;
+        res_x = kx + u_tl;                                        // cKeyPointShifted.pt += p_ptOffsetROI
+        res_y = ky + v_tl;
+        found = true;
+    }
+    SearchResult r;
+    double xyz[3] = {0.0, 0.0, 0.0};
+    if (found) {
+        triangulate_right_dev(g, tc, ps, fmaxf(0.f, (res_x - it.search) - 4.f * it.size), res_y - 4.f * it.size, it.size, res_x,
+                              res_y, mine, lane, r, xyz);
+        status = r.status;
+        if (status == SVI_OK && (tc.depth_min > xyz[2] || tc.depth_max < xyz[2])) status = SVI_TRK_DEPTH;
+    }
+    if (status == SVI_OK) {
+        store_desc(out.desc_l + (size_t)q * 32, mine, lane);
+        store_desc(out.desc_r + (size_t)q * 32, r.w, lane);
+    }
+    if (lane == 0) {
+        out.status[q] = (uint8_t)status;
+        if (status == SVI_OK) {
+            out.stage[q] = 5;
+            out.uv_l[2 * q] = res_x; out.uv_l[2 * q + 1] = res_y;
+            out.uv_r[2 * q] = r.u; out.uv_r[2 * q + 1] = r.v;
             out.xyz[3 * q] = xyz[0]; out.xyz[3 * q + 1] = xyz[1]; out.xyz[3 * q + 2] = xyz[2];
         }
     }

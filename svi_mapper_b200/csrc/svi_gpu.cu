@@ -95,6 +95,8 @@ struct svi_ctx {
         RoiItem* rois = nullptr;
         Stage2Item* s2 = nullptr;
     } roi;
+    Stage3Item* s3_items = nullptr;
+    int s3_capacity = 0;
     // per-query arena
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
@@ -468,6 +470,125 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
     return SVI_SUCCESS;
 }
 
+
+// ---- stage 3 geometry on the host (CFundamentalMatcher.cpp:1795-1947), plain IEEE double operations in the same
+// order as oracle/frontend_np.py::epipolar_plan
+inline void mul3(const double A[3][3], const double B[3][3], double C[3][3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[i][j] = (A[i][0] * B[0][j] + A[i][1] * B[1][j]) + A[i][2] * B[2][j];
+}
+
+inline void inv3(const double m[3][3], double out[3][3]) {   // adjugate / determinant (Eigen's fixed 3x3 closed form)
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+    };
+    const double c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const double det = (c0 * m[0][0] + c1 * m[1][0]) + c2 * m[2][0];
+    const double inv_det = 1.0 / det;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out[i][j] = cof(j, i) * inv_det;
+}
+
+// Returns SVI_OK and fills `it`, or the svi_status of the failing check.
+int epipolar_plan(const svi_ctx* ctx, const double* Tw, const double* Td, const double* uv_ref, const double* pw,
+                  double motion_scaling, Stage3Item& it) {
+    double R[3][3], t[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i][j] = (Tw[4 * i] * Td[j] + Tw[4 * i + 1] * Td[4 + j]) + Tw[4 * i + 2] * Td[8 + j];
+        t[i] = ((Tw[4 * i] * Td[3] + Tw[4 * i + 1] * Td[7]) + Tw[4 * i + 2] * Td[11]) + Tw[4 * i + 3];
+    }
+    if (!(0.0 < (t[0] * t[0] + t[1] * t[1]) + t[2] * t[2])) return SVI_EPI_NO_TRANSLATION;
+    const double S[3][3] = {{0.0, -t[2], t[1]}, {t[2], 0.0, -t[0]}, {-t[1], t[0], 0.0}};
+    double E[3][3], K[3][3], Ki[3][3], KiT[3][3], A[3][3], F[3][3];
+    mul3(R, S, E);
+    const double* P = ctx->cam_l.P;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) K[i][j] = P[4 * i + j];
+    inv3(K, Ki);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) KiT[i][j] = Ki[j][i];
+    mul3(KiT, E, A);
+    mul3(A, Ki, F);
+    double c[3];
+    for (int i = 0; i < 3; ++i) c[i] = (F[i][0] * uv_ref[0] + F[i][1] * uv_ref[1]) + F[i][2] * 1.0;
+    double p[3];
+    for (int r = 0; r < 3; ++r) p[r] = ((Tw[4 * r] * pw[0] + Tw[4 * r + 1] * pw[1]) + Tw[4 * r + 2] * pw[2]) + Tw[4 * r + 3];
+    const float pu = host_projection(P, 0, p), pv = host_projection(P, 1, p);
+    const int Wi = ctx->W, Hi = ctx->H;
+    if (!(pu >= 28.f && pu < (float)(Wi - 28) && pv >= 28.f && pv < (float)(Hi - 28))) return SVI_EPI_OUT_OF_SIGHT;
+    const double W = (double)Wi, H = (double)Hi;
+    const double half = 10.0 * motion_scaling;
+    const double wu = std::sqrt(std::fabs((double)pu - P[2])) / 10.0, wv = std::sqrt(std::fabs((double)pv - P[6])) / 10.0;
+    const double hl_u = 15.0 + wu * half, hl_v = 15.0 + wv * half;   // m_dEpipolarLineBaseLength = 15 (CFundamentalMatcher.h:92)
+    auto curve_v = [&](double u) { return -(c[0] * u + c[2]) / c[1]; };
+    auto curve_u = [&](double v) { return -(c[1] * v + c[2]) / c[0]; };
+    const double u_min_raw = std::max((double)pu - hl_u, 0.0), u_max_raw = std::min((double)pu + hl_u, W);
+    const double v_min_raw = curve_v(u_min_raw), v_max_raw = curve_v(u_max_raw);
+    if ((0.0 > v_min_raw && 0.0 > v_max_raw) || (H < v_min_raw && H < v_max_raw)) return SVI_EPI_VERTICAL;
+    const double v_lim_min = std::max((double)pv - hl_v, 0.0), v_lim_max = std::min((double)pv + hl_v, H);
+    double u_min = u_min_raw, u_max = u_max_raw, v_for_min, v_for_max;
+    if (v_min_raw < v_max_raw) {
+        if (v_lim_min > v_max_raw || v_lim_max < v_min_raw) return SVI_EPI_NEG_SLOPE;
+        if (v_lim_min > v_min_raw) { v_for_min = v_lim_min; u_min = curve_u(v_for_min); } else v_for_min = v_min_raw;
+        if (v_lim_max < v_max_raw) { v_for_max = v_lim_max; u_max = curve_u(v_for_max); } else v_for_max = v_max_raw;
+    } else {
+        if (v_lim_min > v_min_raw || v_lim_max < v_max_raw) return SVI_EPI_POS_SLOPE;
+        if (v_lim_min > v_max_raw) { v_for_min = v_lim_min; u_max = curve_u(v_for_min); } else v_for_min = v_max_raw;
+        if (v_lim_max < v_min_raw) { v_for_max = v_lim_max; u_min = curve_u(v_for_max); } else v_for_max = v_min_raw;
+    }
+    const double du = u_max - u_min, dv = v_for_max - v_for_min;
+    // the reference converts these to uint32_t; negative / non-finite values are undefined there
+    if (!(std::isfinite(du) && std::isfinite(dv)) || du < 0.0 || dv < 0.0 || du >= 65536.0 || dv >= 65536.0) return SVI_EPI_ZERO_LEN;
+    const int delta_u = (int)du, delta_v = (int)dv;
+    if (delta_u == 0 && delta_v == 0) return SVI_EPI_ZERO_LEN;
+    it.along_u = delta_v < delta_u ? 1 : 0;
+    it.count = it.along_u ? delta_u : delta_v;
+    it.start = it.along_u ? u_min : v_for_min;
+    it.c0 = c[0]; it.c1 = c[1]; it.c2 = c[2];
+    return SVI_OK;
+}
+
+int track_stage3_all(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landmarks* lm, int n, const double* T,
+                     double motion_scaling, const LandmarksDev& ld, const TrackOutDev& o, svi_track_result* host_out) {
+    cudaStream_t s = l.stream;
+    std::vector<Stage3Item> items;
+    std::vector<std::pair<int, uint8_t>> verdicts;   // landmarks decided by the host-side geometry checks
+    for (int q = 0; q < n; ++q) {
+        if (host_out->stage[q] != 0 || host_out->status[q] == SVI_TRK_OUT_OF_FOV) continue;
+        Stage3Item it;
+        it.q = q;
+        it.size = lm->keypoint_size[q];
+        it.search = (float)((1.0 + motion_scaling) * (double)lm->last_disparity[q]);   // :2415
+        const int st = epipolar_plan(ctx, T, lm->T_left_to_world_at_detection + 16 * (size_t)q, lm->uv_reference_left + 2 * (size_t)q,
+                                     lm->xyz_world + 3 * (size_t)q, motion_scaling, it);
+        if (st == SVI_OK) items.push_back(it);
+        else verdicts.emplace_back(q, (uint8_t)st);
+    }
+    const int total = (int)items.size();
+    if (total > 0) {
+        if (total > ctx->s3_capacity) {
+            if (ctx->s3_items) cudaFree(ctx->s3_items);
+            ctx->s3_items = nullptr;
+            ctx->s3_capacity = 0;
+            CK(dmalloc(&ctx->s3_items, (size_t)total));
+            ctx->s3_capacity = total;
+        }
+        uint8_t* d_orig = static_cast<uint8_t*>(arena_alloc(ctx, (size_t)n * 32));
+        if (!d_orig) return fail(ctx, SVI_ERR_CAPACITY, "query arena exhausted: raise svi_params.max_queries");
+        CK(cudaMemcpyAsync(d_orig, lm->desc_reference_left, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->s3_items, items.data(), sizeof(Stage3Item) * total, cudaMemcpyHostToDevice, s));
+        track_stage3_kernel<<<(total + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(
+            l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage3, ctx->p.cutoff_original, ctx->s3_items, total, d_orig, ld, o);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host_out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(host_out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    for (const auto& v : verdicts) host_out->status[v.first] = v.second;
+    return SVI_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" {
@@ -510,6 +631,16 @@ const char* svi_status_text(int status) {
         case SVI_TRK_NO_MATCHES: return "no matches found";
         case SVI_TRK_DESC: return "descriptor mismatch";
         case SVI_TRK_RANGE: return "out of tracking range";
+        case SVI_EPI_OUT_OF_SIGHT: return "<CFundamentalMatcher>(getVisibleLandmarksFundamental) projection out of sight";
+        case SVI_EPI_VERTICAL: return "<CFundamentalMatcher>(getVisibleLandmarksFundamental) vertical out of sight";
+        case SVI_EPI_NEG_SLOPE: return "<CFundamentalMatcher>(getVisibleLandmarksFundamental) caught bad projection negative slope";
+        case SVI_EPI_POS_SLOPE: return "<CFundamentalMatcher>(getVisibleLandmarksFundamental) caught bad projection positive slope";
+        case SVI_EPI_ZERO_LEN: return "<CFundamentalMatcher>(getVisibleLandmarksFundamental) zero line length";
+        case SVI_EPI_POOL_EMPTY: return "could not find a matching descriptor (empty key point pool)";
+        case SVI_EPI_NO_MATCHES: return "could not find any matches (empty matches pool)";
+        case SVI_EPI_DIST: return "could not find a matching descriptor";
+        case SVI_EPI_ORIG_DIST: return "could not find a matching descriptor (ORIGINAL matching distance too big)";
+        case SVI_EPI_NO_TRANSLATION: return "no translation since detection: epipolar search skipped";
         default: return "unknown status";
     }
 }
@@ -539,6 +670,7 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->trk_img) cudaFree(ctx->trk_img);
+    if (ctx->s3_items) cudaFree(ctx->s3_items);
     {
         void* rp[] = {ctx->roi.resp, ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
                       ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2};
@@ -640,6 +772,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(cudaFuncSetAttribute(track_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(track_stage2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(track_stage2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(track_stage3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     // one shared-memory carve-out for every kernel of the pipeline: back-to-back kernels with different
     // carve-outs make the SMs drain and reconfigure between launches
     {
@@ -648,6 +781,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
                                  (const void*)stereo_match_kernel, (const void*)triangulate_kernel<true>,
                                  (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
                                  (const void*)track_stage2_kernel<true>, (const void*)track_stage2_kernel<false>,
+                                 (const void*)track_stage3_kernel,
                                  (const void*)describe_kernel, (const void*)hamming_match_kernel};
         for (const void* k : kernels)
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1021,6 +1155,14 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
     // ---- stage 2 LEFT, then stage 2 RIGHT, for what is still untracked
     for (int side = 0; side < 2; ++side) {
         rc = track_stage2_side(ctx, l, g, lm, n, T_world_to_left, motion_scaling, side == 0, ld, o, out);
+        if (rc != SVI_SUCCESS) return rc;
+    }
+    // ---- stage 3 (epipolar line in LEFT) when the caller supplied the reference data
+    const bool stage3 = lm->uv_reference_left && lm->desc_reference_left && lm->T_left_to_world_at_detection;
+    if (!stage3 && (lm->uv_reference_left || lm->desc_reference_left || lm->T_left_to_world_at_detection))
+        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: stage 3 needs all three reference arrays");
+    if (stage3) {
+        rc = track_stage3_all(ctx, l, g, lm, n, T_world_to_left, motion_scaling, ld, o, out);
         if (rc != SVI_SUCCESS) return rc;
     }
     CK(cudaMemcpyAsync(out->uv_left, o.uv_l, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));

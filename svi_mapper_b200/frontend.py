@@ -260,7 +260,9 @@ class StereoFrontend:
 
     # -- CFundamentalMatcher::trackManual, stage 1
     def track_landmarks(self, img_left, img_right, T_world_to_left, xyz_world, last_desc_left, last_desc_right,
-                        last_disparity, keypoint_size, motion_scaling: float) -> dict:
+                        last_disparity, keypoint_size, motion_scaling: float, uv_reference_left=None,
+                        desc_reference_left=None, T_left_to_world_at_detection=None) -> dict:
+        """trackManual cascade; stage 3 runs only when the three reference arrays are given."""
         a = self._images(img_left, "img_left")[0]
         b = self._images(img_right, "img_right")[0]
         T = np.ascontiguousarray(np.asarray(T_world_to_left, np.float64).reshape(4, 4))
@@ -273,7 +275,12 @@ class StereoFrontend:
         out = dict(status=np.zeros(n, np.uint8), stage=np.zeros(n, np.uint8), uv_l=np.zeros((n, 2), np.float32),
                    uv_r=np.zeros((n, 2), np.float32), xyz=np.zeros((n, 3), np.float64),
                    desc_l=np.zeros((n, 32), np.uint8), desc_r=np.zeros((n, 32), np.uint8))
-        lm = _lib.Landmarks(_ptr(xw), _ptr(dl), _ptr(dr), _ptr(disp), _ptr(size))
+        uvref = dref = tdet = None
+        if uv_reference_left is not None:
+            uvref = np.ascontiguousarray(np.asarray(uv_reference_left, np.float64).reshape(n, 2))
+            dref = np.ascontiguousarray(np.asarray(desc_reference_left, np.uint8).reshape(n, 32))
+            tdet = np.ascontiguousarray(np.broadcast_to(np.asarray(T_left_to_world_at_detection, np.float64), (n, 4, 4)).copy())
+        lm = _lib.Landmarks(_ptr(xw), _ptr(dl), _ptr(dr), _ptr(disp), _ptr(size), _ptr(uvref), _ptr(dref), _ptr(tdet))
         r = _lib.TrackResult(_ptr(out["status"]), _ptr(out["stage"]), _ptr(out["uv_l"]), _ptr(out["uv_r"]), _ptr(out["xyz"]),
                              _ptr(out["desc_l"]), _ptr(out["desc_r"]))
         self._check(self._lib.svi_track_landmarks(self._ctx, _ptr(a), _ptr(b), self.width, _ptr(T), C.byref(lm), n,

@@ -240,6 +240,46 @@ def test_track_manual_stage2_window_search(vi_cams):
         _compare_tracks(got, ref)
 
 
+def test_track_manual_stage3_epipolar(vi_cams):
+    """Stage 3 (epipolar-line search): stage 2 is disabled through its cut-off so the cascade reaches the line search;
+    four camera motions give horizontal, slanted and radial epipolar lines (sampling along u and along v)."""
+    W, H = vi_cams[0].width, vi_cams[0].height
+    L, R = stereo_pair(W, H, 4000)
+    tri = _tri(vi_cams, cutoff_stage2=0.0)
+    ref0 = o.add_new_landmarks(L, R, tri)
+    ok = np.nonzero(ref0["status"] == 0)[0][:120]
+    disp, lms = _landmarks_from_frame(ref0, ok)
+    for k, lm in zip(ok, lms):
+        lm.update(uv_ref=ref0["uv_l"][k].astype(np.float64), ref_desc_l=ref0["desc_l"][k], T_det_l2w=np.eye(4))
+    seen_u = seen_v = 0
+    with StereoFrontend(*vi_cams, cutoff_stage2=0.0) as fe:
+        for t in ((0.02, 0.0, 0.0), (0.015, 0.01, 0.0), (0.0, 0.0, 0.05), (0.01, 0.03, 0.02)):
+            T = np.eye(4)
+            T[:3, 3] = t
+            ref = o.track_manual_full(L, R, tri, T, lms, 1.5)
+            for lm in lms:
+                pl = o.epipolar_plan(tri, T, lm["T_det_l2w"], lm["uv_ref"], lm["xyz_w"], 1.5)
+                if pl["status"] == 0:
+                    seen_u += pl["along_u"]
+                    seen_v += not pl["along_u"]
+            got = fe.track_landmarks(L, R, T, ref0["xyz"][ok], ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, 1.5,
+                                     uv_reference_left=ref0["uv_l"][ok], desc_reference_left=ref0["desc_l"][ok],
+                                     T_left_to_world_at_detection=np.eye(4))
+            stages = np.bincount([r["stage"] for r in ref], minlength=6)
+            assert stages[5] > 60, stages
+            _compare_tracks(got, ref)
+    assert seen_u > 100 and seen_v > 100
+    # no motion since detection (and stages 1-2 disabled): the essential matrix is undefined, stage 3 is skipped
+    tri0 = _tri(vi_cams, cutoff_stage1=0.0, cutoff_stage2=0.0)
+    ref = o.track_manual_full(L, R, tri0, np.eye(4), lms, 1.5)
+    assert all(r["stage"] == 0 for r in ref) and sum(r["status"] == o.ST_EPI_NO_TRANSLATION for r in ref) > 100
+    with StereoFrontend(*vi_cams, cutoff_stage1=0.0, cutoff_stage2=0.0) as fe:
+        got = fe.track_landmarks(L, R, np.eye(4), ref0["xyz"][ok], ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, 1.5,
+                                 uv_reference_left=ref0["uv_l"][ok], desc_reference_left=ref0["desc_l"][ok],
+                                 T_left_to_world_at_detection=np.eye(4))
+    _compare_tracks(got, ref)
+
+
 def test_device_resident_entry(kitti_cams):
     """svi_stereo_frames_device on torch-owned device memory == the host-buffer entry point."""
     import torch
