@@ -472,7 +472,7 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
 
 
 // ---- stage 3 geometry on the host (CFundamentalMatcher.cpp:1795-1947), plain IEEE double operations in the same
-// order as oracle/frontend_np.py::epipolar_plan
+// order as the CPU restatement the parity tests compare against
 inline void mul3(const double A[3][3], const double B[3][3], double C[3][3]) {
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) C[i][j] = (A[i][0] * B[0][j] + A[i][1] * B[1][j]) + A[i][2] * B[2][j];

@@ -1,5 +1,5 @@
 // CFundamentalMatcher -- image-space half of the reference's src/core/CFundamentalMatcher.{h,cpp}
-// (addNewLandmarks :83-193, trackManual stage 1 :1404-1538, getMaskActiveLandmarks :2043-2073,
+// (addNewLandmarks :83-193, trackManual :1334-2027 (all stages), getMaskActiveLandmarks :2043-2073,
 // visibility bookkeeping :244-263, :2005-2009) with the per-key-point / per-landmark image work done by
 // ONE batched GPU call per frame instead of one OpenCV call per item.  CLandmark keeps the fields the
 // optimisation side reads (src/types/CLandmark.h:35-59); CLandmark::optimize / g2o stay with the caller.
@@ -17,7 +17,8 @@ public:
               const Isometry3d& p_matTransformationLEFTtoWORLD, const Isometry3d& p_matTransformationWORLDtoLEFT,
               const MatrixProjection& p_matProjectionWORLDtoLEFT, const MatrixProjection& p_matProjectionWORLDtoRIGHT, const UIDFrame& p_uIDFrame)
         : uID(p_uID), matDescriptorReferenceLEFT(p_matDescriptorLEFT), matDescriptorReferenceRIGHT(p_matDescriptorRIGHT), dKeyPointSize(p_dKeyPointSize),
-          uIDFrameAtCreation(p_uIDFrame), vecPointXYZInitial(p_matTransformationLEFTtoWORLD * p_vecPointXYZLEFT), vecPointXYZOptimized(vecPointXYZInitial) {
+          uIDFrameAtCreation(p_uIDFrame), vecPointXYZInitial(p_matTransformationLEFTtoWORLD * p_vecPointXYZLEFT), vecPointXYZOptimized(vecPointXYZInitial),
+          vecUVReferenceLEFT{(double)p_ptUVLEFT.x, (double)p_ptUVLEFT.y, 1.0} {
         addMeasurement(p_uIDFrame, p_ptUVLEFT, p_ptUVRIGHT, p_matDescriptorLEFT, p_matDescriptorRIGHT, p_vecPointXYZLEFT, p_matTransformationLEFTtoWORLD,
                        p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT, p_matProjectionWORLDtoRIGHT);
     }
@@ -30,6 +31,7 @@ public:
     const UIDFrame uIDFrameAtCreation;
     const CPoint3DWORLD vecPointXYZInitial;
     CPoint3DWORLD vecPointXYZOptimized;
+    const double vecUVReferenceLEFT[3];   // CPoint2DHomogenized (CLandmark.h:43)
     uint8_t uFailedSubsequentTrackings = 0;
     uint32_t uOptimizationsSuccessful = 0, uOptimizationsFailed = 0;
     bool bIsOptimal = false, bIsCurrentlyVisible = false;
@@ -77,6 +79,8 @@ public:
     std::vector<CLandmark*>::size_type getNumberOfVisibleLandmarks() const { return m_vecVisibleLandmarks.size(); }
     UIDLandmark getNumberOfLandmarksTotal() const { return m_uAvailableLandmarkID; }
     UIDLandmark getNumberOfTracksStage1() const { return m_uNumberOfTracksStage1; }
+    UIDLandmark getNumberOfTracksStage2_1() const { return m_uNumberOfTracksStage2_1; }
+    UIDLandmark getNumberOfTracksStage3() const { return m_uNumberOfTracksStage3; }
     const std::vector<CLandmark*>& getLandmarksWINDOW() const { return m_vecLandmarksWINDOW; }
 
     // :244-254
@@ -162,36 +166,40 @@ public:
         return vecLandmarksNEW->size();
     }
 
-    // trackManual :1334-2027, stage 1 on the GPU for ALL active landmarks in one call; landmarks stage 1 cannot
-    // place are returned in p_vecForStage2 for the caller's stage 2-3, and the
-    // failed-tracking bookkeeping of :1980-2009 is applied to them only once the caller reports them lost.
+    // trackManual :1334-2027: the whole first-success cascade (stage 1 L/R, stage 2 L/R, stage 3) for ALL active
+    // landmarks in ONE GPU call; the visibility / failed-tracking bookkeeping of :1980-2009 follows.
     void trackManual(const UIDFrame p_uFrame, const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT,
                      const Isometry3d& p_matTransformationWORLDtoLEFT, const Isometry3d& p_matTransformationLEFTtoWORLD,
-                     const double& p_dMotionScaling, std::vector<CLandmark*>* p_vecForStage2 = nullptr) {
-        m_uNumberOfTracksStage1 = 0;
+                     const double& p_dMotionScaling) {
+        m_uNumberOfTracksStage1 = m_uNumberOfTracksStage2_1 = m_uNumberOfTracksStage3 = 0;
         const MatrixProjection matProjectionWORLDtoLEFT(m_pCameraLEFT->m_matProjection * p_matTransformationWORLDtoLEFT);
         const MatrixProjection matProjectionWORLDtoRIGHT(m_pCameraRIGHT->m_matProjection * p_matTransformationWORLDtoLEFT);
         std::vector<CLandmark*> vecCandidates;
+        std::vector<const CDetectionPoint*> vecDetectionPointOf;
         for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
             for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
                 if (0 < pLandmark->uOptimizationsFailed) { pLandmark->bIsCurrentlyVisible = false; pLandmark->bIsOptimal = false; }   // :1375-1384
                 else if (0 < pLandmark->uOptimizationsSuccessful && !pLandmark->bIsOptimal) pLandmark->bIsCurrentlyVisible = false;      // :1387-1395
-                else vecCandidates.push_back(pLandmark);
+                else { vecCandidates.push_back(pLandmark); vecDetectionPointOf.push_back(&cDetectionPoint); }
             }
         const int n = (int)vecCandidates.size();
         if (0 < n) {
-            std::vector<double> xyzW(3 * n), xyz(3 * n);
-            std::vector<uint8_t> dL(32 * n), dR(32 * n), oL(32 * n), oR(32 * n), st(n), stage(n);
+            std::vector<double> xyzW(3 * n), xyz(3 * n), uvRef(2 * n), Tdet(16 * n);
+            std::vector<uint8_t> dL(32 * n), dR(32 * n), dRef(32 * n), oL(32 * n), oR(32 * n), st(n), stage(n);
             std::vector<float> disp(n), size(n), uvL(2 * n), uvR(2 * n);
             for (int i = 0; i < n; ++i) {
                 const CLandmark* p = vecCandidates[i];
                 for (int k = 0; k < 3; ++k) xyzW[3 * i + k] = p->vecPointXYZOptimized.v[k];
                 std::memcpy(&dL[32 * i], p->getLastDescriptorLEFT().data(), 32);
                 std::memcpy(&dR[32 * i], p->getLastDescriptorRIGHT().data(), 32);
+                std::memcpy(&dRef[32 * i], p->matDescriptorReferenceLEFT.data(), 32);
                 disp[i] = p->getLastDisparity();
                 size[i] = (float)p->dKeyPointSize;
+                uvRef[2 * i] = p->vecUVReferenceLEFT[0];
+                uvRef[2 * i + 1] = p->vecUVReferenceLEFT[1];
+                std::memcpy(&Tdet[16 * i], vecDetectionPointOf[i]->matTransformationLEFTtoWORLD.m, sizeof(double) * 16);
             }
-            svi_landmarks lm{xyzW.data(), dL.data(), dR.data(), disp.data(), size.data()};
+            svi_landmarks lm{xyzW.data(), dL.data(), dR.data(), disp.data(), size.data(), uvRef.data(), dRef.data(), Tdet.data()};
             svi_track_result r{st.data(), stage.data(), uvL.data(), uvR.data(), xyz.data(), oL.data(), oR.data()};
             m_pGpu->check(svi_track_landmarks(m_pGpu->ctx, p_matImageLEFT.data, p_matImageRIGHT.data, p_matImageLEFT.pitch,
                                               p_matTransformationWORLDtoLEFT.m, &lm, n, p_dMotionScaling, &r));
@@ -207,13 +215,13 @@ public:
                                               CPoint3DCAMERA(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), p_matTransformationLEFTtoWORLD,
                                               p_matTransformationWORLDtoLEFT, matProjectionWORLDtoLEFT, matProjectionWORLDtoRIGHT);
                     m_vecVisibleLandmarks.push_back(pLandmark);
-                    ++m_uNumberOfTracksStage1;
-                } else if (SVI_TRK_OUT_OF_FOV == st[i] || !p_vecForStage2) {
-                    ++pLandmark->uFailedSubsequentTrackings;   // :1996-2001
+                    if (stage[i] <= 2) ++m_uNumberOfTracksStage1;
+                    else if (stage[i] <= 4) ++m_uNumberOfTracksStage2_1;
+                    else ++m_uNumberOfTracksStage3;
+                } else if (SVI_EPI_NO_TRANSLATION != st[i]) {
+                    ++pLandmark->uFailedSubsequentTrackings;   // :1980-1987, :1996-2001
                     pLandmark->bIsCurrentlyVisible = false;
-                } else {
-                    p_vecForStage2->push_back(pLandmark);
-                }
+                }   // no translation since detection: the reference neither tracks nor penalises the landmark (:1804)
             }
         }
         // keep landmarks while failed trackings stay below the limit :2005-2009
@@ -237,7 +245,7 @@ private:
     std::vector<CDetectionPoint> m_vecDetectionPointsActive;
     std::vector<CLandmark*> m_vecVisibleLandmarks, m_vecLandmarksWINDOW;
     std::vector<const CMeasurementLandmark*> m_vecMeasurementsVisible;
-    UIDLandmark m_uAvailableLandmarkID = 0, m_uNumberOfTracksStage1 = 0;
+    UIDLandmark m_uAvailableLandmarkID = 0, m_uNumberOfTracksStage1 = 0, m_uNumberOfTracksStage2_1 = 0, m_uNumberOfTracksStage3 = 0;
 };
 
 #endif

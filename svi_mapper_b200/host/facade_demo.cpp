@@ -42,9 +42,9 @@ int main(int argc, char** argv) {
                          m->ptUVRIGHT.y, m->vecPointXYZLEFT.x(), m->vecPointXYZLEFT.y(), m->vecPointXYZLEFT.z());
         }
         cMatcher.resetVisibilityActiveLandmarks();
-        std::vector<CLandmark*> vecForStage2;
-        cMatcher.trackManual(1, ImageView(L1.data(), W, H), ImageView(R1.data(), W, H), matIdentity, matIdentity, 1.0, &vecForStage2);
-        std::fprintf(out, "TRACKED %lu STAGE2 %zu VISIBLE %zu\n", (unsigned long)cMatcher.getNumberOfTracksStage1(), vecForStage2.size(),
+        cMatcher.trackManual(1, ImageView(L1.data(), W, H), ImageView(R1.data(), W, H), matIdentity, matIdentity, 1.0);
+        std::fprintf(out, "TRACKED %lu STAGE2 %lu STAGE3 %lu VISIBLE %zu\n", (unsigned long)cMatcher.getNumberOfTracksStage1(),
+                     (unsigned long)cMatcher.getNumberOfTracksStage2_1(), (unsigned long)cMatcher.getNumberOfTracksStage3(),
                      cMatcher.getNumberOfVisibleLandmarks());
         for (const CMeasurementLandmark* m : cMatcher.getMeasurementsForVisibleLandmarks())
             std::fprintf(out, "T %lu %.1f %.1f %.1f %.1f %.17g\n", (unsigned long)m->uID, m->ptUVLEFT.x, m->ptUVLEFT.y, m->ptUVRIGHT.x, m->ptUVRIGHT.y,

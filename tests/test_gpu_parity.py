@@ -394,11 +394,15 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
         assert [float(v) for v in row[6:9]] == list(ref["xyz"][i])
     lms = [dict(xyz_w=ref["xyz"][i], last_desc_l=ref["desc_l"][i], last_desc_r=ref["desc_r"][i],
                 last_disparity=np.float32(ref["uv_l"][i, 0] - ref["uv_r"][i, 0]), size=7.0) for i in ok]
-    trk = o.track_manual(L, R, tri, np.eye(4), lms, 1.0)
+    for k, lm in zip(ok, lms):
+        lm.update(uv_ref=ref["uv_l"][k].astype(np.float64), ref_desc_l=ref["desc_l"][k], T_det_l2w=np.eye(4))
+    trk = o.track_manual_full(L, R, tri, np.eye(4), lms, 1.0)
     n_trk = sum(1 for t in trk if t["stage"] > 0)
-    n_fov = sum(1 for t in trk if t["status"] == o.ST_TRK_OUT_OF_FOV)
+    n1 = sum(1 for t in trk if t["stage"] in (1, 2))
+    n2 = sum(1 for t in trk if t["stage"] in (3, 4))
+    n3 = sum(1 for t in trk if t["stage"] == 5)
     head = [l for l in lines if l.startswith("TRACKED")][0].split()
-    assert int(head[1]) == n_trk and int(head[3]) == len(ok) - n_trk - n_fov and int(head[5]) == n_trk
+    assert (int(head[1]), int(head[3]), int(head[5]), int(head[7])) == (n1, n2, n3, n_trk)
     assert n_trk > 0.9 * len(ok)          # static camera: nearly everything is re-found in stage 1
     t_lines = [l.split() for l in lines if l.startswith("T ")]
     tracked = [(k, t) for k, t in enumerate(trk) if t["stage"] > 0]

@@ -160,3 +160,37 @@ def test_oracle_vs_cv2_live():
     img = np.ascontiguousarray(np.tile(tile, (1, 4)))
     np.testing.assert_array_equal(co.gftt(img, 500), o.detect_cv2(img, 500))
     np.testing.assert_array_equal(o.gftt(img, 500), o.detect_cv2(img, 500))
+
+
+def test_track_cascade_oracle_properties():
+    """CPU sanity of the tracking oracle: stage 1 on an unchanged pair, stage 2 after an image shift, stage 3
+    with stage 2 disabled; results respect the reference's compiled-out invariants."""
+    from svi_mapper_b200 import load_camera
+    calib = pathlib.Path(__file__).resolve().parent / "golden" / "calib"
+    cl, cr = load_camera(str(calib / "vi_sensor_left.txt")), load_camera(str(calib / "vi_sensor_right.txt"))
+    L, R = stereo_pair(752, 480, 4000)
+    mk = lambda **kw: o.Triangulator(o.Camera(752, 480, cl.P), o.Camera(752, 480, cr.P), o.StereoParams(max_corners=150, **kw))
+    tri = mk()
+    ref0 = o.add_new_landmarks(L, R, tri)
+    ok = np.nonzero(ref0["status"] == 0)[0][:40]
+    disp = (ref0["uv_l"][ok, 0] - ref0["uv_r"][ok, 0]).astype(np.float32)
+    lms = [dict(xyz_w=ref0["xyz"][i], last_desc_l=ref0["desc_l"][i], last_desc_r=ref0["desc_r"][i], last_disparity=disp[k], size=7.0,
+                uv_ref=ref0["uv_l"][i].astype(np.float64), ref_desc_l=ref0["desc_l"][i], T_det_l2w=np.eye(4)) for k, i in enumerate(ok)]
+    same = o.track_manual_full(L, R, tri, np.eye(4), lms, 1.0)
+    assert sum(r["stage"] == 1 for r in same) >= 38           # unchanged pair, unchanged pose: stage 1 LEFT
+    for r, i in zip(same, ok):
+        if r["stage"] == 1:
+            assert tuple(r["uv_l"]) == tuple(ref0["uv_l"][i]) and tuple(r["uv_r"]) == tuple(ref0["uv_r"][i])
+            np.testing.assert_array_equal(r["xyz"], ref0["xyz"][i])
+    shifted = o.track_manual_full(np.roll(L, (2, 3), (0, 1)), np.roll(R, (2, 3), (0, 1)), tri, np.eye(4), lms, 1.0)
+    st2 = [(r, i) for r, i in zip(shifted, ok) if r["stage"] == 3]
+    assert len(st2) >= 25
+    for r, i in st2:                                          # the window search finds the corner at its shifted place
+        assert tuple(r["uv_l"]) == (ref0["uv_l"][i, 0] + 3, ref0["uv_l"][i, 1] + 2)
+    T = np.eye(4)
+    T[0, 3] = 0.02
+    epi = o.track_manual_full(L, R, mk(cutoff_stage2=0.0), T, lms, 1.5)
+    assert sum(r["stage"] == 5 for r in epi) >= 20
+    for r in same + shifted + epi:
+        if r["stage"]:
+            assert r["uv_l"][1] == r["uv_r"][1] and r["uv_l"][0] > r["uv_r"][0] and r["xyz"][2] > 0
