@@ -435,3 +435,67 @@ def test_stress_frame_global_select_and_long_scanlines(kitti_cams):
     d = ref["uv_l"][ref["status"] == 0, 0] - ref["uv_r"][ref["status"] == 0, 0]
     assert d.max() > 124          # matches beyond the second window really occur
     _compare_frame(got, ref)
+
+
+def test_edge_cases_empty_flat_masked_padded(kitti_cams):
+    """Empty and degenerate inputs: zero frames, a flat image (no corners at all), a fully masked frame, rows
+    padded beyond the width (pitch > W), capacity / argument errors reported loudly."""
+    from svi_mapper_b200 import SviError
+    import ctypes as C
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, R = stereo_pair(W, H, 21)
+    flat = np.full((H, W), 127, np.uint8)
+    tri = _tri(kitti_cams)
+    with StereoFrontend(*kitti_cams, chunk_frames=2) as fe:
+        # flat image: Harris response is identically zero -> no candidates, no key-points; neighbours unaffected
+        res = fe.stereo_frames(np.stack([L, flat, L]), np.stack([R, flat, R]))
+        assert res.n_keypoints[1] == 0 and res.n_detected[1] == 0
+        ref = o.add_new_landmarks(L, R, tri)
+        _compare_frame(res.frame(0), ref)
+        _compare_frame(res.frame(2), ref)
+        assert len(o.gftt(flat, 1000)) == 0
+        # fully masked frame: minMaxLoc over an empty mask, nothing detected
+        zero_mask = np.zeros((H, W), np.uint8)
+        res = fe.stereo_frames(np.stack([L, L]), np.stack([R, R]), np.stack([zero_mask, np.full((H, W), 255, np.uint8)]))
+        assert res.n_keypoints[0] == 0
+        _compare_frame(res.frame(1), ref)
+        assert fe.detect(L, zero_mask)[0].shape == (0, 2)
+        # zero frames is a no-op
+        out = fe.stereo_frames(np.zeros((0, H, W), np.uint8), np.zeros((0, H, W), np.uint8))
+        assert out.n_keypoints.shape == (0,)
+        # padded rows: pitch 1280 > W, frame stride = pitch * H, through the raw C-ABI call
+        pitch = 1280
+        Lp, Rp = np.zeros((2, H, pitch), np.uint8), np.zeros((2, H, pitch), np.uint8)
+        Lp[:, :, :W], Rp[:, :, :W] = L, R
+        Lp[:, :, W:], Rp[:, :, W:] = 255, 0     # garbage in the padding must not matter
+        cap = 1000
+        o_ = dict(n_kp=np.zeros(2, np.int32), n_det=np.zeros(2, np.int32), uv_l=np.zeros((2, cap, 2), np.float32),
+                  uv_r=np.zeros((2, cap, 2), np.float32), xyz=np.zeros((2, cap, 3)), dl=np.zeros((2, cap, 32), np.uint8),
+                  dr=np.zeros((2, cap, 32), np.uint8), dist=np.zeros((2, cap), np.int32), idx=np.zeros((2, cap), np.int32),
+                  st=np.zeros((2, cap), np.uint8))
+        r = _lib.StereoResult(cap, *(o_[k].ctypes.data for k in ("n_kp", "n_det", "uv_l", "uv_r", "xyz", "dl", "dr", "dist", "idx", "st")))
+        fe.stereo_frames_raw(Lp.ctypes.data, Rp.ctypes.data, pitch, pitch * H, 2, r)
+        for f in range(2):
+            k = o_["n_kp"][f]
+            got = dict(uv_l=o_["uv_l"][f, :k], uv_r=o_["uv_r"][f, :k], xyz=o_["xyz"][f, :k], desc_l=o_["dl"][f, :k],
+                       desc_r=o_["dr"][f, :k], dist=o_["dist"][f, :k], idx=o_["idx"][f, :k], status=o_["st"][f, :k])
+            _compare_frame(got, ref)
+        # loud errors: output capacity below maxCorners, pitch below the width, unknown parameter
+        r_small = _lib.StereoResult(10, *(o_[k].ctypes.data for k in ("n_kp", "n_det", "uv_l", "uv_r", "xyz", "dl", "dr", "dist", "idx", "st")))
+        with pytest.raises(SviError, match="capacity_per_frame"):
+            fe.stereo_frames_raw(Lp.ctypes.data, Rp.ctypes.data, pitch, pitch * H, 2, r_small)
+        with pytest.raises(SviError, match="bad argument"):
+            fe.stereo_frames_raw(Lp.ctypes.data, Rp.ctypes.data, W - 1, pitch * H, 2, r)
+        with pytest.raises(SviError, match="max_queries"):
+            fe.describe(L, np.zeros((20000, 2), np.float32))
+    with pytest.raises(TypeError):
+        StereoFrontend(*kitti_cams, not_a_parameter=1)
+    # tracking with zero landmarks and with every landmark outside the field of view
+    with StereoFrontend(*kitti_cams) as fe:
+        out = fe.track_landmarks(L, R, np.eye(4), np.zeros((0, 3)), np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8),
+                                 np.zeros(0, np.float32), 7.0, 1.0)
+        assert out["status"].shape == (0,)
+        far = np.array([[1000.0, 0.0, 5.0], [-1000.0, 3.0, 5.0]])
+        out = fe.track_landmarks(L, R, np.eye(4), far, np.zeros((2, 32), np.uint8), np.zeros((2, 32), np.uint8),
+                                 np.ones(2, np.float32), 7.0, 1.0)
+        assert (out["stage"] == 0).all() and (out["status"] == _lib.SVI_TRK_OUT_OF_FOV).all()
