@@ -25,7 +25,8 @@
 namespace svi {
 
 constexpr signed char kPat[SVI_BRIEF_NTESTS][4] = SVI_BRIEF_PATTERN_INIT;
-__device__ const signed char d_pat[SVI_BRIEF_NTESTS][4] = SVI_BRIEF_PATTERN_INIT;
+__device__ __align__(16) const signed char d_pat[SVI_BRIEF_NTESTS][4] = SVI_BRIEF_PATTERN_INIT;   // rows are 4-byte aligned: read as char4
+__device__ __forceinline__ char4 brief_pattern(int t) { return __ldg(reinterpret_cast<const char4*>(d_pat) + t); }
 
 constexpr int PATCH_ROWS = 2 * kBriefReach + 1;        // 49
 constexpr int PATCH_SLOTS = 64;                        // 2 candidate slots per lane and pass
@@ -104,9 +105,9 @@ __device__ __forceinline__ void brief_at_point(const uint16_t* __restrict__ box,
                                                int cy, int lane, uint32_t (&w)[kDescWords]) {
 #pragma unroll
     for (int j = 0; j < kDescWords; ++j) {
-        const signed char* p = d_pat[32 * j + lane];
-        uint32_t s1 = box[(size_t)(cy + p[0]) * box_pitch + cx + p[1]];
-        uint32_t s2 = box[(size_t)(cy + p[2]) * box_pitch + cx + p[3]];
+        const char4 p = brief_pattern(32 * j + lane);
+        uint32_t s1 = box[(cy + p.x) * box_pitch + cx + p.y];
+        uint32_t s2 = box[(cy + p.z) * box_pitch + cx + p.w];
         w[j] = __brev(__ballot_sync(0xFFFFFFFFu, s1 < s2));
     }
 }
@@ -191,7 +192,14 @@ __device__ __forceinline__ void search_plan(int W, int H, float img_width_f, flo
     //  coordinates the two roundings differ and the reference would read outside its integral image)
     const int ky_r = cv_round_f(border), ky_c = brief_centre(border);
     int i_lo = 0, i_hi = 0;
-    if (ky_r >= kBriefBorder && ky_r < rh - kBriefBorder && ky_c >= kBriefBorder && ky_c < rh - kBriefBorder) {
+    const bool row_ok = ky_r >= kBriefBorder && ky_r < rh - kBriefBorder && ky_c >= kBriefBorder && ky_c < rh - kBriefBorder;
+    if (row_ok && border == (float)ky_r && n_pool < (1 << 22)) {
+        // integral border (every key-point size the reference produces): pool x = ky_r + first + i exactly, both
+        // roundings coincide, and the survivors are the i with 28 <= x < rw - 28
+        const int x0 = ky_r + first;
+        i_lo = min(max(kBriefBorder - x0, 0), n_pool);
+        i_hi = min(max(rw - kBriefBorder - x0, 0), n_pool);
+    } else if (row_ok) {
         for (int i0 = 0; i0 < n_pool; i0 += 32) {
             int i = i0 + lane;
             const float kx = (border + (float)i) + (float)first;
@@ -351,9 +359,9 @@ __device__ __forceinline__ void brief_gather_issue(const uint16_t* __restrict__ 
                                                    int lane, BriefGather& gth) {
 #pragma unroll
     for (int j = 0; j < kDescWords; ++j) {
-        const signed char* p = d_pat[32 * j + lane];
-        gth.s1[j] = __ldg(box + (size_t)(cy + p[0]) * box_pitch + cx + p[1]);
-        gth.s2[j] = __ldg(box + (size_t)(cy + p[2]) * box_pitch + cx + p[3]);
+        const char4 p = brief_pattern(32 * j + lane);
+        gth.s1[j] = __ldg(box + (cy + p.x) * box_pitch + cx + p.y);
+        gth.s2[j] = __ldg(box + (cy + p.z) * box_pitch + cx + p.w);
     }
 }
 __device__ __forceinline__ void brief_gather_finish(const BriefGather& gth, uint32_t (&w)[kDescWords]) {
@@ -686,9 +694,9 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
             if (keep) {
 #pragma unroll 4
                 for (int t = 0; t < SVI_BRIEF_NTESTS; ++t) {
-                    const signed char* p = d_pat[t];
-                    const uint32_t s1 = __ldg(box_this + (size_t)(sy + p[0]) * g.box_pitch + sx + p[1]);
-                    const uint32_t s2 = __ldg(box_this + (size_t)(sy + p[2]) * g.box_pitch + sx + p[3]);
+                    const char4 p = brief_pattern(t);
+                    const uint32_t s1 = __ldg(box_this + (sy + p.x) * g.box_pitch + sx + p.y);
+                    const uint32_t s2 = __ldg(box_this + (sy + p.z) * g.box_pitch + sx + p.w);
                     const uint32_t bit = s1 < s2 ? 1u : 0u;
                     dist += bit ^ ((last_this[t >> 5] >> (31 - (t & 31))) & 1u);
                 }
@@ -816,9 +824,9 @@ track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
             if (keep) {
 #pragma unroll 4
                 for (int t = 0; t < SVI_BRIEF_NTESTS; ++t) {
-                    const signed char* p = d_pat[t];
-                    const uint32_t s1 = __ldg(box_l + (size_t)(sy + p[0]) * g.box_pitch + sx + p[1]);
-                    const uint32_t s2 = __ldg(box_l + (size_t)(sy + p[2]) * g.box_pitch + sx + p[3]);
+                    const char4 p = brief_pattern(t);
+                    const uint32_t s1 = __ldg(box_l + (sy + p.x) * g.box_pitch + sx + p.y);
+                    const uint32_t s2 = __ldg(box_l + (sy + p.z) * g.box_pitch + sx + p.w);
                     dist += (s1 < s2 ? 1u : 0u) ^ ((last_l[t >> 5] >> (31 - (t & 31))) & 1u);
                 }
             }

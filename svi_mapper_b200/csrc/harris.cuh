@@ -283,43 +283,53 @@ nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict_
     const float* R = resp + (size_t)f * in_rows * g.resp_pitch;
     float centre[NMS_ROWS + 2], rowmax[NMS_ROWS + 2];
     const bool xin = gx < W, xl = xin && gx > 0, xr = gx + 1 < W;
+    // out-of-image neighbours are ignored by dilate: -inf; in-image values go through THRESH_TOZERO
+    const float* col = R + gx;
 #pragma unroll
     for (int i = 0; i < NMS_ROWS + 2; ++i) {
         const int gy = y0 - 1 + i;
-        float a = -INFINITY, b = -INFINITY, c = -INFINITY;   // dilate ignores pixels outside the image
-        if (gy >= 0 && gy < H) {
-            const float* row = R + (size_t)gy * g.resp_pitch;
-            if (xl) a = row[gx - 1];
-            if (xin) b = row[gx];
-            if (xr) c = row[gx + 1];
-        }
-        a = (a > thr) ? a : ((a == -INFINITY) ? a : 0.f);
-        b = (b > thr) ? b : ((b == -INFINITY) ? b : 0.f);
-        c = (c > thr) ? c : ((c == -INFINITY) ? c : 0.f);
+        const bool yin = gy >= 0 && gy < H;
+        const float* row = col + (size_t)gy * g.resp_pitch;
+        float a = -INFINITY, b = -INFINITY, c = -INFINITY;
+        if (yin && xl) { a = row[-1]; a = (a > thr) ? a : 0.f; }
+        if (yin && xin) { b = row[0]; b = (b > thr) ? b : 0.f; }
+        if (yin && xr) { c = row[1]; c = (c > thr) ? c : 0.f; }
         centre[i] = b;
         rowmax[i] = fmaxf(fmaxf(a, b), c);
     }
-    __syncthreads();
-    // same-address global atomics serialise in L2: aggregate per warp (ballot), then per CTA (shared
-    // counter), and claim the CTA's slice of the frame's list with ONE global atomic
+    // candidate rows of this thread as a bit mask
+    unsigned mine = 0u;
 #pragma unroll
     for (int k = 0; k < NMS_ROWS; ++k) {
         const int gy = y0 + k;
         const float v = centre[k + 1];
-        bool is_cand = false;
-        if (gx >= 1 && gx < W - 1 && gy >= 1 && gy < H - 1 && v != 0.f) {
-            const float m = fmaxf(fmaxf(rowmax[k], rowmax[k + 1]), rowmax[k + 2]);
-            is_cand = (v == m) && (!mask || mask[(size_t)f * g.img_stride + (size_t)gy * g.img_pitch + gx]);
+        const float m = fmaxf(fmaxf(rowmax[k], rowmax[k + 1]), rowmax[k + 2]);
+        if (v != 0.f && v == m && gy >= 1 && gy < H - 1) mine |= 1u << k;
+    }
+    if (!(gx >= 1 && gx < W - 1)) mine = 0u;
+    if (mine && mask) {
+#pragma unroll
+        for (int k = 0; k < NMS_ROWS; ++k)
+            if (((mine >> k) & 1u) && !mask[(size_t)f * g.img_stride + (size_t)(y0 + k) * g.img_pitch + gx]) mine &= ~(1u << k);
+    }
+    __syncthreads();
+    // same-address global atomics serialise in L2: aggregate per warp (one scan of the per-thread counts), then per
+    // CTA (shared counter), and claim the CTA's slice of the frame's list with ONE global atomic
+    if (__any_sync(0xFFFFFFFFu, mine != 0u)) {
+        const int cnt = __popc(mine);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += u;
         }
-        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_cand);
-        if (ballot) {
-            const int leader = __ffs(ballot) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&s_count, __popc(ballot));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (is_cand)
-                s_keys[base + __popc(ballot & ((1u << lane) - 1u))] =
-                    ((unsigned long long)float_to_ordered(v) << 32) | ((unsigned)gy << 16) | (unsigned)gx;
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&s_count, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+        while (mine) {
+            const int k = __ffs(mine) - 1;
+            mine &= mine - 1u;
+            s_keys[base++] = ((unsigned long long)float_to_ordered(centre[k + 1]) << 32) | ((unsigned)(y0 + k) << 16) | (unsigned)gx;
         }
     }
     __syncthreads();
