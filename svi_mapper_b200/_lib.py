@@ -5,7 +5,10 @@ from __future__ import annotations
 import ctypes as C
 import pathlib
 
-LIB_PATH = pathlib.Path(__file__).resolve().parent / "libsvi_gpu.so"
+import os
+
+# SVI_GPU_LIB selects an alternate build of the same library (kernel tuning experiments)
+LIB_PATH = pathlib.Path(os.environ.get("SVI_GPU_LIB") or (pathlib.Path(__file__).resolve().parent / "libsvi_gpu.so"))
 
 SVI_SUCCESS = 0
 SVI_ERR_INVALID, SVI_ERR_CUDA, SVI_ERR_CAPACITY, SVI_ERR_NO_DEVICE, SVI_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
