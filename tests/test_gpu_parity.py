@@ -499,3 +499,45 @@ def test_edge_cases_empty_flat_masked_padded(kitti_cams):
         out = fe.track_landmarks(L, R, np.eye(4), far, np.zeros((2, 32), np.uint8), np.zeros((2, 32), np.uint8),
                                  np.ones(2, np.float32), 7.0, 1.0)
         assert (out["stage"] == 0).all() and (out["status"] == _lib.SVI_TRK_OUT_OF_FOV).all()
+
+
+def test_harris_on_flat_and_saturated_content(kitti_cams):
+    """Image content where OpenCV's fp64 RUNNING box sums lose exactness (flat / saturated regions next to strong
+    edges): the GPU evaluates the same sums tile-locally.  Pinned here: (1) the GPU response equals the exact fp64
+    window sum rounded once, bit for bit; (2) against OpenCV's operation order it differs only by running-sum
+    residues below 1e-30 in flat regions (where the true sum is 0) or by at most 1 ulp; (3) key-points, descriptors,
+    matches and statuses still equal the OpenCV-order oracle."""
+    import cv2
+    from oracle import c_oracle as co
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    cfg = co.make_config(kitti_cams[0], kitti_cams[1])
+
+    def variants(seed):
+        L, R = stereo_pair(W, H, seed)
+        a, b = L.copy(), R.copy()
+        a[:120], b[:120], a[300:], b[300:] = 255, 255, 0, 0
+        yield a, b                                                      # saturated sky / black ground
+        yield (L // 32 * 32).astype(np.uint8), (R // 32 * 32).astype(np.uint8)   # posterised plateaus
+        d, e = L.copy(), R.copy()
+        cv2.rectangle(d, (200, 80), (500, 300), 255, -1)
+        cv2.rectangle(e, (180, 80), (480, 300), 255, -1)
+        cv2.line(d, (0, 0), (W - 1, H - 1), 0, 3)
+        cv2.line(e, (0, 0), (W - 1, H - 1), 0, 3)
+        yield d, e                                                      # high-contrast shapes
+    n_diff = 0
+    with StereoFrontend(*kitti_cams) as fe:
+        for seed in (1, 9, 10):
+            for L, R in variants(seed):
+                g = fe.harris_response(L)
+                exact = o.harris_response(L, box=o.box7_exact)
+                np.testing.assert_array_equal(g.view(np.uint32), exact.view(np.uint32))
+                cv_order = co.harris_response(L)
+                bad = g.view(np.uint32) != cv_order.view(np.uint32)
+                n_diff += int(bad.sum())
+                if bad.any():
+                    residue = (g[bad] == 0) & (np.abs(cv_order[bad]) < 1e-30)
+                    one_ulp = np.abs(g[bad].view(np.int32).astype(np.int64) - cv_order[bad].view(np.int32).astype(np.int64)) <= 1
+                    assert (residue | one_ulp).all()
+                ref = co.frame(co.stereo_frames(cfg, L, R), 0)
+                _compare_frame(fe.add_new_landmarks(L, R), ref)
+    assert n_diff > 0      # the content really triggers the effect
