@@ -1,0 +1,78 @@
+// CTrackerGT -- the per-frame orchestration of the reference's ground-truth driven tracker
+// (src/core/CTrackerGT.cpp:91-126 process, :137-332 _trackLandmarks) reduced to the calls that touch the
+// stereo front-end: motion scaling, visibility reset, trackManual, the new-landmark trigger and
+// addNewLandmarks.  Display, key-framing, DBoW2 / BTree loop closing, g2o and CLandmark::optimize are
+// the reference's CPU side and are not part of this host layer.
+#ifndef SVI_HOST_CTRACKERGT_H
+#define SVI_HOST_CTRACKERGT_H
+
+#include "CFundamentalMatcher.h"
+
+inline Isometry3d inverseIsometry(const Isometry3d& T) {   // Eigen::Isometry3d::inverse(): R^T, -R^T t
+    Isometry3d I;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) I(r, c) = T(c, r);
+    for (int r = 0; r < 3; ++r) I(r, 3) = -(I(r, 0) * T(0, 3) + I(r, 1) * T(1, 3) + I(r, 2) * T(2, 3));
+    return I;
+}
+
+inline Isometry3d operator*(const Isometry3d& A, const Isometry3d& B) {
+    Isometry3d C;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += A(r, k) * B(k, c);
+            C(r, c) = s + (c == 3 ? A(r, 3) : 0.0);
+        }
+    }
+    return C;
+}
+
+class CTrackerGT {
+public:
+    CTrackerGT(const std::shared_ptr<CStereoCamera> p_pCameraSTEREO, const std::shared_ptr<CGpuContext> p_pGpu)
+        : m_cMatcher(p_pCameraSTEREO, p_pGpu) {}
+
+    // process(imgL, imgR, T_LEFTLAST->LEFTNOW) :91-126; the rotation magnitude is passed in by the caller (the
+    // reference takes it from CMiniVisionToolbox::toOrientationRodrigues of the same transform)
+    void process(const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT, const Isometry3d& p_matTransformationLEFTLASTtoLEFTNOW,
+                 const double p_dRotationNorm = 0.0) {
+        const CPoint3D t(p_matTransformationLEFTLASTtoLEFTNOW(0, 3), p_matTransformationLEFTLASTtoLEFTNOW(1, 3), p_matTransformationLEFTLASTtoLEFTNOW(2, 3));
+        const double dTranslationNorm = std::sqrt(t.x() * t.x() + t.y() * t.y() + t.z() * t.z());
+        const Isometry3d matTransformationWORLDtoLEFT(p_matTransformationLEFTLASTtoLEFTNOW * m_matTransformationWORLDtoLEFTLAST);
+        const Isometry3d matTransformationLEFTtoWORLD(inverseIsometry(matTransformationWORLDtoLEFT));
+        // :157 motion scaling (capped)
+        const double dMotionScaling = std::min(1.0 + (10.0 * p_dRotationNorm + 0.5 * dTranslationNorm), 5.0);
+        m_cMatcher.resetVisibilityActiveLandmarks();                                                               // :160
+        m_cMatcher.trackManual(m_uFrameCount, p_matImageLEFT, p_matImageRIGHT, matTransformationWORLDtoLEFT, matTransformationLEFTtoWORLD,
+                               dMotionScaling);                                                                    // :167-174
+        m_uNumberofVisibleLandmarksLAST = m_cMatcher.getNumberOfVisibleLandmarks();                                // :176-193
+        // (the reference runs CLandmark::optimize for every active landmark here, :197 -- CPU side)
+        if (m_uVisibleLandmarksMinimum > m_uNumberofVisibleLandmarksLAST || m_uMaximumNumberOfFramesWithoutDetection < m_uNumberOfFramesWithoutDetection) {
+            m_uNumberofVisibleLandmarksLAST = m_cMatcher.addNewLandmarks(p_matImageLEFT, p_matImageRIGHT, matTransformationWORLDtoLEFT,
+                                                                         matTransformationLEFTtoWORLD, m_uFrameCount);   // :305-315
+            m_uNumberOfFramesWithoutDetection = 0;
+            ++m_uNumberOfDetections;
+        } else {
+            ++m_uNumberOfFramesWithoutDetection;
+        }
+        m_matTransformationWORLDtoLEFTLAST = matTransformationWORLDtoLEFT;
+        ++m_uFrameCount;
+    }
+
+    CFundamentalMatcher& getMatcher() { return m_cMatcher; }
+    UIDFrame getFrameCount() const { return m_uFrameCount; }
+    uint64_t getNumberOfVisibleLandmarksLAST() const { return m_uNumberofVisibleLandmarksLAST; }
+    uint64_t getNumberOfDetections() const { return m_uNumberOfDetections; }
+
+private:
+    CFundamentalMatcher m_cMatcher;
+    Isometry3d m_matTransformationWORLDtoLEFTLAST;
+    UIDFrame m_uFrameCount = 0;
+    uint64_t m_uNumberofVisibleLandmarksLAST = 0, m_uNumberOfDetections = 0;
+    const uint64_t m_uVisibleLandmarksMinimum = 100;            // CTrackerGT.cpp:29
+    const uint8_t m_uMaximumNumberOfFramesWithoutDetection = 2; // CTrackerGT.h:56
+    uint8_t m_uNumberOfFramesWithoutDetection = 0;
+};
+
+#endif

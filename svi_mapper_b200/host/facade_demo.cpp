@@ -8,7 +8,7 @@
 #include <iostream>
 #include <vector>
 
-#include "CFundamentalMatcher.h"
+#include "CTrackerGT.h"
 
 static std::vector<uint8_t> readRaw(const char* path, size_t n) {
     std::vector<uint8_t> v(n);
@@ -56,6 +56,18 @@ int main(int argc, char** argv) {
             std::fprintf(out, "EXC none\n");
         } catch (const CExceptionNoMatchFound& e) {
             std::fprintf(out, "EXC %s\n", e.what());
+        }
+        // a short sequence through the CTrackerGT orchestration: the same pair shown 6 times while the camera is
+        // reported to move 1 cm per frame along x (tracker_gt.cpp feeds ground-truth poses the same way)
+        CTrackerGT cTracker(CParameterBase::pCameraSTEREO, pGpu);
+        Isometry3d matStep;
+        matStep(0, 3) = 0.01;
+        for (int uFrame = 0; uFrame < 6; ++uFrame) {
+            cTracker.process(ImageView(L0.data(), W, H), ImageView(R0.data(), W, H), uFrame ? matStep : matIdentity);
+            std::fprintf(out, "SEQ %d VISIBLE %lu TOTAL %lu S1 %lu S2 %lu S3 %lu DETECTIONS %lu\n", uFrame,
+                         (unsigned long)cTracker.getNumberOfVisibleLandmarksLAST(), (unsigned long)cTracker.getMatcher().getNumberOfLandmarksTotal(),
+                         (unsigned long)cTracker.getMatcher().getNumberOfTracksStage1(), (unsigned long)cTracker.getMatcher().getNumberOfTracksStage2_1(),
+                         (unsigned long)cTracker.getMatcher().getNumberOfTracksStage3(), (unsigned long)cTracker.getNumberOfDetections());
         }
         std::fclose(out);
     } catch (const std::exception& e) {

@@ -410,7 +410,13 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
         assert int(row[1]) == k
         assert [float(v) for v in row[2:6]] == [float(t["uv_l"][0]), float(t["uv_l"][1]), float(t["uv_r"][0]), float(t["uv_r"][1])]
         assert float(row[6]) == t["xyz"][2]
-    assert lines[-1] == "EXC <CTriangulator>(getPointInLEFT) zero disparity"
+    assert [l for l in lines if l.startswith("EXC")][0] == "EXC <CTriangulator>(getPointInLEFT) zero disparity"
+    # the CTrackerGT-style sequence: frame 0 detects, later frames track (all three stages get used while the claimed
+    # pose drifts away from the unchanged images) and re-detect when the trigger of CTrackerGT.cpp:305 fires
+    seq = [dict(zip(l.split()[2::2], map(int, l.split()[3::2]))) for l in lines if l.startswith("SEQ")]
+    assert len(seq) == 6 and seq[0]["DETECTIONS"] == 1 and seq[0]["TOTAL"] == len(ok)
+    assert all(s["VISIBLE"] > 100 for s in seq) and seq[-1]["DETECTIONS"] >= 2
+    assert sum(s["S1"] + s["S2"] + s["S3"] for s in seq[1:]) > 1000
 
 
 def test_stress_frame_global_select_and_long_scanlines(kitti_cams):
