@@ -159,6 +159,16 @@ int svi_describe(svi_ctx* ctx, const uint8_t* img, size_t pitch, const float* xy
 int svi_match_hamming(svi_ctx* ctx, const uint8_t* query32, int n_query, const uint8_t* train32,
                       int n_train, int32_t* index, int32_t* distance);
 
+/* Sparse epipolar-band matcher (optional mode; not a reference code path -- the reference searches dense scan
+ * lines; this is the key-point-to-key-point form BASELINE.json's stress configuration names and
+ * what cv::BFMatcher::match(query, train, mask) computes with mask(q,t) = |yq - yt| <= band_v && min_disparity <=
+ * xq - xt <= max_disparity).  Per query: first arg-min train index among the admissible trains, its Hamming
+ * distance and the second-best distance (for a ratio test in the caller); -1 where no train is admissible. */
+int svi_match_epipolar(svi_ctx* ctx, const uint8_t* query32, const float* query_xy, int n_query,
+                       const uint8_t* train32, const float* train_xy, int n_train, float band_v,
+                       float min_disparity, float max_disparity, int32_t* index, int32_t* distance,
+                       int32_t* second_distance);
+
 /* Per-query results of the triangulating scan-line searches. */
 typedef struct svi_tri_result {
     float* uv;          /* [n*2] matched point in the searched image */

@@ -345,6 +345,31 @@ def match_hamming(q: np.ndarray, t: np.ndarray):
     return i, int(d[i])
 
 
+def match_epipolar(q_desc, q_xy, t_desc, t_xy, band_v=1.0, min_disp=0.0, max_disp=1e9):
+    """cv::BFMatcher(NORM_HAMMING).match(query, train, mask) with the epipolar-band mask
+    mask[q, t] = |yq - yt| <= band_v and min_disp <= xq - xt <= max_disp, plus the second-best distance.
+    Optional mode (not a reference code path); pinned against cv2 in tests/test_oracle.py."""
+    q_desc, t_desc = np.asarray(q_desc, np.uint8).reshape(-1, 32), np.asarray(t_desc, np.uint8).reshape(-1, 32)
+    q_xy, t_xy = np.asarray(q_xy, F32).reshape(-1, 2), np.asarray(t_xy, F32).reshape(-1, 2)
+    idx = np.full(len(q_desc), -1, np.int32)
+    dist = np.full(len(q_desc), -1, np.int32)
+    second = np.full(len(q_desc), -1, np.int32)
+    for i in range(len(q_desc)):
+        if len(t_desc) == 0:
+            continue
+        d = F32(q_xy[i, 0]) - t_xy[:, 0]
+        ok = (np.abs(F32(q_xy[i, 1]) - t_xy[:, 1]) <= F32(band_v)) & (d >= F32(min_disp)) & (d <= F32(max_disp))
+        cand = np.nonzero(ok)[0]
+        if len(cand) == 0:
+            continue
+        h = hamming(q_desc[i:i + 1], t_desc[cand])
+        j = int(np.argmin(h))
+        idx[i], dist[i] = cand[j], h[j]
+        if len(cand) > 1:
+            second[i] = int(np.partition(h, 1)[1])
+    return idx, dist, second
+
+
 # ----------------------------------------------------------------------------- triangulator
 class Triangulator:
     """CTriangulator (src/core/CTriangulator.cpp)."""

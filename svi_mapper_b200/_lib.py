@@ -22,7 +22,7 @@ SVI_ERR_INVALID, SVI_ERR_CUDA, SVI_ERR_CAPACITY, SVI_ERR_NO_DEVICE, SVI_ERR_UNSU
 EXPORTS = (
     "svi_params_default", "svi_status_text", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
     "svi_stereo_frames", "svi_stereo_frames_device", "svi_harris_response", "svi_detect", "svi_describe",
-    "svi_match_hamming", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
+    "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
     "svi_track_landmarks", "svi_set_profiling", "svi_stage_timings", "svi_config",
 )
 
@@ -98,6 +98,7 @@ def load():
     lib.svi_detect.argtypes = [vp, vp, sz, sz, ci, vp, vp, vp]
     lib.svi_describe.argtypes = [vp, vp, sz, vp, ci, vp, vp]
     lib.svi_match_hamming.argtypes = [vp, vp, ci, vp, ci, vp, vp]
+    lib.svi_match_epipolar.argtypes = [vp, vp, vp, ci, vp, vp, ci, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     lib.svi_triangulate_right.argtypes = [vp, vp, sz, ci, vp, vp, vp, C.c_float, C.POINTER(TriResult)]
     lib.svi_triangulate_left.argtypes = [vp, vp, sz, ci, vp, vp, vp, vp, C.c_float, C.POINTER(TriResult)]
     lib.svi_point_in_left.argtypes = [vp, ci, vp, vp, vp, vp]

@@ -1065,6 +1065,37 @@ int svi_match_hamming(svi_ctx* ctx, const uint8_t* query32, int n_query, const u
     return SVI_SUCCESS;
 }
 
+int svi_match_epipolar(svi_ctx* ctx, const uint8_t* query32, const float* query_xy, int n_query, const uint8_t* train32,
+                       const float* train_xy, int n_train, float band_v, float min_disparity, float max_disparity,
+                       int32_t* index, int32_t* distance, int32_t* second_distance) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!query32 || !query_xy || !index || !distance || !second_distance || n_query < 0 || n_train < 0 ||
+        (n_train > 0 && (!train32 || !train_xy)))
+        return fail(ctx, SVI_ERR_INVALID, "svi_match_epipolar: bad argument");
+    if ((size_t)(n_query + n_train) * 48 + (size_t)n_query * 16 > ctx->arena_bytes)
+        return fail(ctx, SVI_ERR_CAPACITY, "svi_match_epipolar: raise max_queries");
+    if (n_query == 0) return SVI_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->lanes[0].stream;
+    ctx->arena_used = 0;
+    uint8_t* d_q; uint8_t* d_t; float* d_qxy; float* d_txy; int* d_i; int* d_d; int* d_s;
+    UP(d_q, query32, (size_t)n_query * 32);
+    UP(d_qxy, query_xy, (size_t)n_query * 2);
+    UP(d_t, n_train > 0 ? train32 : (const uint8_t*)nullptr, (size_t)std::max(n_train, 1) * 32);
+    UP(d_txy, n_train > 0 ? train_xy : (const float*)nullptr, (size_t)std::max(n_train, 1) * 2);
+    UP(d_i, (const int*)nullptr, (size_t)n_query);
+    UP(d_d, (const int*)nullptr, (size_t)n_query);
+    UP(d_s, (const int*)nullptr, (size_t)n_query);
+    epipolar_match_kernel<<<(n_query + 3) / 4, 128, 0, s>>>(d_q, d_qxy, n_query, d_t, d_txy, n_train, band_v, min_disparity,
+                                                            max_disparity, d_i, d_d, d_s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(index, d_i, sizeof(int) * n_query, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(distance, d_d, sizeof(int) * n_query, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(second_distance, d_s, sizeof(int) * n_query, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVI_SUCCESS;
+}
+
 int svi_triangulate_right(svi_ctx* ctx, const uint8_t* img_right, size_t pitch, int n, const float* top_left,
                           const float* uv_left, const uint8_t* desc_left, float keypoint_size, svi_tri_result* out) {
     if (!ctx) return SVI_ERR_INVALID;

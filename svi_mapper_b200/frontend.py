@@ -201,6 +201,18 @@ class StereoFrontend:
         self._check(self._lib.svi_match_hamming(self._ctx, _ptr(q), len(q), _ptr(t) if len(t) else None, len(t), _ptr(idx), _ptr(dist)))
         return idx, dist
 
+    def match_epipolar(self, query, query_xy, train, train_xy, band_v=1.0, min_disparity=0.0, max_disparity=1e9):
+        """Key-point to key-point matching inside an epipolar row band -> (index, distance, second_distance)."""
+        q = np.ascontiguousarray(np.asarray(query, np.uint8).reshape(-1, 32))
+        t = np.ascontiguousarray(np.asarray(train, np.uint8).reshape(-1, 32))
+        qxy = np.ascontiguousarray(np.asarray(query_xy, np.float32).reshape(len(q), 2))
+        txy = np.ascontiguousarray(np.asarray(train_xy, np.float32).reshape(len(t), 2))
+        idx, dist, second = (np.zeros(len(q), np.int32) for _ in range(3))
+        self._check(self._lib.svi_match_epipolar(self._ctx, _ptr(q), _ptr(qxy), len(q), _ptr(t) if len(t) else None,
+                                                 _ptr(txy) if len(t) else None, len(t), float(band_v), float(min_disparity),
+                                                 float(max_disparity), _ptr(idx), _ptr(dist), _ptr(second)))
+        return idx, dist, second
+
     # -- CTriangulator
     def _tri_out(self, n):
         out = dict(uv=np.zeros((n, 2), np.float32), xyz=np.zeros((n, 3), np.float64), desc=np.zeros((n, 32), np.uint8),

@@ -548,3 +548,27 @@ def test_harris_on_flat_and_saturated_content(kitti_cams):
                 ref = co.frame(co.stereo_frames(cfg, L, R), 0)
                 _compare_frame(fe.add_new_landmarks(L, R), ref)
     assert n_diff > 0      # the content really triggers the effect
+
+
+def test_epipolar_band_matcher(kitti_cams):
+    """Optional sparse-band mode (C5 wording): key-points of both images matched inside a row band with a
+    disparity window; first arg-min, distance and second-best distance equal the oracle, incl. ties and empty bands."""
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, R = stereo_pair(W, H, 31)
+    kl, kr = o.gftt(L, 2000), o.gftt(R, 2000)
+    keep_l, dl = o.brief32(L, kl.astype(np.float32))
+    keep_r, dr = o.brief32(R, kr.astype(np.float32))
+    xl, xr = kl[keep_l].astype(np.float32), kr[keep_r].astype(np.float32)
+    dr[5] = dr[6] = dl[0]                                   # ties: the first admissible index wins
+    xr[5] = xr[6] = xl[0] - np.float32([10, 0])
+    with StereoFrontend(*kitti_cams) as fe:
+        for band, dmin, dmax in ((1.0, 1.0, 60.0), (3.0, 0.0, 1e9), (0.0, 1.0, 60.0)):
+            gi, gd, gs = fe.match_epipolar(dl, xl, dr, xr, band, dmin, dmax)
+            ri, rd, rs = o.match_epipolar(dl, xl, dr, xr, band, dmin, dmax)
+            np.testing.assert_array_equal(gi, ri)
+            np.testing.assert_array_equal(gd, rd)
+            np.testing.assert_array_equal(gs, rs)
+        assert gi[0] == 5 and gd[0] == 0 and gs[0] == 0
+        assert (ri >= 0).sum() > 200 and (ri < 0).sum() > 0
+        gi, gd, gs = fe.match_epipolar(dl[:4], xl[:4], np.zeros((0, 32), np.uint8), np.zeros((0, 2), np.float32))
+        assert (gi == -1).all() and (gd == -1).all() and (gs == -1).all()

@@ -194,3 +194,25 @@ def test_track_cascade_oracle_properties():
     for r in same + shifted + epi:
         if r["stage"]:
             assert r["uv_l"][1] == r["uv_r"][1] and r["uv_l"][0] > r["uv_r"][0] and r["xyz"][2] > 0
+
+
+def test_epipolar_band_matcher_matches_cv2_masked_bfmatcher():
+    """The optional sparse-band mode: oracle == cv2.BFMatcher.match(query, train, mask) with the band mask."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    q, t = rng.integers(0, 256, (120, 32), dtype=np.uint8), rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    t[:40] = q[:40] ^ rng.integers(0, 2, (40, 32), dtype=np.uint8)          # near-duplicates
+    qxy = np.stack([rng.uniform(100, 1200, 120), rng.integers(0, 30, 120)], 1).astype(np.float32)
+    txy = np.stack([rng.uniform(0, 1200, 300), rng.integers(0, 30, 300)], 1).astype(np.float32)
+    band, dmin, dmax = 1.0, 0.0, 400.0
+    idx, dist, second = o.match_epipolar(q, qxy, t, txy, band, dmin, dmax)
+    d = qxy[:, None, 0] - txy[None, :, 0]
+    mask = ((np.abs(qxy[:, None, 1] - txy[None, :, 1]) <= band) & (d >= dmin) & (d <= dmax)).astype(np.uint8)
+    matches = cv2.BFMatcher(cv2.NORM_HAMMING).match(q, t, mask)
+    got = {m.queryIdx: (m.trainIdx, int(m.distance)) for m in matches}
+    for i in range(len(q)):
+        if idx[i] < 0:
+            assert i not in got
+        else:
+            assert got[i] == (idx[i], dist[i])
+            assert second[i] == -1 or second[i] >= dist[i]
