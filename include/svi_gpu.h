@@ -93,7 +93,15 @@ typedef struct svi_params {
     int32_t max_candidates;    /* per-frame capacity of the NMS candidate list (default 16384) */
     int32_t chunk_frames;      /* frames per kernel wave; 0 = library default */
     int32_t max_queries;       /* capacity of the per-query entry points (triangulate_*, describe, track) */
+    /* optional detector mode (NOT a reference code path): 0 = GFTT/Harris as the reference
+     * (default), 1 = FAST-9/16 as cv::FastFeatureDetector(threshold, nonmaxSuppression, TYPE_9_16): every corner
+     * in scan order, no maxCorners cut -- more corners than max_corners is SVI_ERR_CAPACITY */
+    int32_t detector;
+    int32_t fast_threshold;    /* 10 (cv default) */
+    int32_t fast_nonmax;       /* 1 */
 } svi_params;
+
+enum { SVI_DETECTOR_GFTT_HARRIS = 0, SVI_DETECTOR_FAST_9_16 = 1 };
 
 int svi_params_default(svi_params* p);
 const char* svi_status_text(int status);

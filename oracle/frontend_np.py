@@ -271,6 +271,70 @@ def detect_cv2(img, max_corners=1000, quality=0.01, min_distance=7.0, mask=None)
     return np.asarray([[int(kp.pt[0]), int(kp.pt[1])] for kp in kps], np.int32).reshape(-1, 2)
 
 
+# ----------------------------------------------------------------------------- FAST-9/16 (optional detector mode)
+_FAST_RING = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3), (-2, -2), (-3, -1),
+              (-3, 0), (-3, 1), (-2, 2), (-1, 3)]   # (dx, dy) of OpenCV's 16-pixel circle, makeOffsets()
+
+
+def fast9_16(img: np.ndarray, threshold: int = 10, nonmax: bool = True):
+    """cv::FAST(img, kps, threshold, nonmax, TYPE_9_16) restated (OpenCV fast.cpp FAST_t<16> + cornerScore<16>):
+    a pixel is a corner if >= 9 contiguous circle pixels are all darker than v - t or all brighter than v + t;
+    score = largest t for which that still holds; 3x3 non-max suppression with strict >; 3-px border excluded.
+    Returns (xy (n,2) int32 in scan order, score (n,) int32).  NOT a reference code path (the reference detects
+    with GFTT/Harris): optional mode, pinned against cv2.FastFeatureDetector in tests/test_oracle.py."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    t = min(max(int(threshold), 0), 255)
+    v = img.astype(np.int32)
+    ys, xs = np.mgrid[3:h - 3, 3:w - 3]
+    c = v[3:h - 3, 3:w - 3]
+    ring = np.stack([v[3 + dy:h - 3 + dy, 3 + dx:w - 3 + dx] for dx, dy in _FAST_RING], 0)   # (16, H-6, W-6)
+    ring25 = np.concatenate([ring, ring[:9]], 0)
+    d = c[None] - ring25                                                                      # v - ptr[pixel[k]]
+    darker = ring25 < (c - t)[None]
+    brighter = ring25 > (c + t)[None]
+
+    def has_run9(m):
+        run = np.zeros(m.shape[1:], np.int32)
+        best = np.zeros(m.shape[1:], np.int32)
+        for k in range(25):
+            run = np.where(m[k], run + 1, 0)
+            best = np.maximum(best, run)
+        return best >= 9
+    corner = has_run9(darker) | has_run9(brighter)
+    # cornerScore<16>
+    a0 = np.full(c.shape, t, np.int32)
+    for k in range(0, 16, 2):
+        a = np.minimum(np.minimum(d[k + 1], d[k + 2]), d[k + 3])
+        go = a > a0
+        a = np.minimum.reduce([a, d[k + 4], d[k + 5], d[k + 6], d[k + 7], d[k + 8]])
+        upd = np.maximum(np.maximum(a0, np.minimum(a, d[k])), np.minimum(a, d[k + 9]))
+        a0 = np.where(go, upd, a0)
+    b0 = -a0
+    for k in range(0, 16, 2):
+        b = np.maximum.reduce([d[k + 1], d[k + 2], d[k + 3], d[k + 4], d[k + 5]])
+        go = b < b0
+        b = np.maximum.reduce([b, d[k + 6], d[k + 7], d[k + 8]])
+        upd = np.minimum(np.minimum(b0, np.maximum(b, d[k])), np.maximum(b, d[k + 9]))
+        b0 = np.where(go, upd, b0)
+    score_in = (-b0 - 1).astype(np.int32)
+    score = np.zeros((h, w), np.int32)
+    score[3:h - 3, 3:w - 3] = np.where(corner, score_in.astype(np.uint8).astype(np.int32), 0)   # stored as uchar
+    cmask = np.zeros((h, w), bool)
+    cmask[3:h - 3, 3:w - 3] = corner
+    if nonmax:
+        pad = np.zeros((h + 2, w + 2), np.int32)
+        pad[1:-1, 1:-1] = score
+        keep = cmask.copy()
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dy or dx:
+                    keep &= score > pad[1 + dy:h + 1 + dy, 1 + dx:w + 1 + dx]
+        cmask = keep
+    yy, xx = np.nonzero(cmask)
+    return np.stack([xx, yy], 1).astype(np.int32), score[yy, xx]
+
+
 # ----------------------------------------------------------------------------- BRIEF
 def integral(img: np.ndarray) -> np.ndarray:
     """cv::integral(img, CV_32S): (h+1, w+1) int32."""

@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("match_cutoff", C.c_float), ("cutoff_stage1", C.c_float), ("cutoff_stage2", C.c_float),
         ("cutoff_stage3", C.c_float), ("cutoff_original", C.c_float),
         ("max_candidates", C.c_int32), ("chunk_frames", C.c_int32), ("max_queries", C.c_int32),
+        ("detector", C.c_int32), ("fast_threshold", C.c_int32), ("fast_nonmax", C.c_int32),
     ]
 
 

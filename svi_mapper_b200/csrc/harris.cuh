@@ -342,4 +342,113 @@ nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict_
         if (base + i < cand_cap) cand[(size_t)f * cand_cap + base + i] = s_keys[i];
 }
 
+// ------------------------------------------------------------------ FAST-9/16 (optional detector mode)
+// cv::FAST(img, kps, threshold, nonmax, TYPE_9_16) (OpenCV fast.cpp FAST_t<16>, cornerScore<16>): corner test on
+// the 16-pixel circle, score = largest threshold that keeps the corner, 3x3 non-max suppression with strict >,
+// 3-px image border excluded.  Same 64x32 tile + 4-px halo staging as the Harris kernel; the scores of the tile
+// and a 1-px ring around it live in shared memory for the suppression.  Emits keys whose descending order is
+// OpenCV's output order (scan order): high word = ~(y << 16 | x), low word = y << 16 | x.
+__device__ __forceinline__ int fast_ring(const uint8_t (*tile)[U8_P], int ty, int tx, int k) {
+    // (dx, dy) of OpenCV's makeOffsets(), k taken modulo 16
+    constexpr signed char DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr signed char DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    return tile[ty + DY[k & 15]][tx + DX[k & 15]];
+}
+
+__device__ __forceinline__ int fast_corner_score(const uint8_t (*tile)[U8_P], int ty, int tx, int threshold) {
+    const int v = tile[ty][tx];
+    int d[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) d[k] = v - fast_ring(tile, ty, tx, k);
+    int a0 = threshold;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        int a = min(min(d[k + 1], d[k + 2]), d[k + 3]);
+        if (a <= a0) continue;
+        a = min(min(min(a, d[k + 4]), min(d[k + 5], d[k + 6])), min(d[k + 7], d[k + 8]));
+        a0 = max(a0, min(a, d[k]));
+        a0 = max(a0, min(a, d[k + 9]));
+    }
+    int b0 = -a0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        int b = max(max(max(d[k + 1], d[k + 2]), max(d[k + 3], d[k + 4])), d[k + 5]);
+        if (b >= b0) continue;
+        b = max(max(b, d[k + 6]), max(d[k + 7], d[k + 8]));
+        b0 = min(b0, max(b, d[k]));
+        b0 = min(b0, max(b, d[k + 9]));
+    }
+    return -b0 - 1;
+}
+
+__global__ void __launch_bounds__(HT_THREADS)
+fast_candidates_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g, int threshold, int nonmax,
+                       unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
+    __shared__ uint8_t tile[U8_ROWS][U8_P];
+    __shared__ uint16_t score[HT_H + 2][HT_W + 2];      // bit 8 = corner, low byte = score stored as uchar like OpenCV
+    __shared__ unsigned long long s_keys[512];
+    __shared__ int s_count, s_base;
+    const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H, tid = threadIdx.x;
+    if (tid == 0) s_count = 0;
+    load_tile_u8(tile, img + (size_t)f * g.img_stride, g.img_pitch, g.W, g.H, x0, y0);
+    __syncthreads();
+    const int t = min(max(threshold, 0), 255);
+    for (int idx = tid; idx < (HT_H + 2) * (HT_W + 2); idx += HT_THREADS) {
+        const int ly = idx / (HT_W + 2), lx = idx - ly * (HT_W + 2);
+        const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+        uint16_t sc = 0;
+        if (gx >= 3 && gx < g.W - 3 && gy >= 3 && gy < g.H - 3) {
+            const int ty = ly + 3, tx = lx + 3;        // tile origin is (x0 - 4, y0 - 4)
+            const int v = tile[ty][tx];
+            uint32_t dark = 0u, bright = 0u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int p = fast_ring(tile, ty, tx, k);
+                dark |= (uint32_t)(p < v - t) << k;
+                bright |= (uint32_t)(p > v + t) << k;
+            }
+            // >= 9 contiguous set bits on the circle: AND of 9 rotations of the doubled mask
+            uint32_t r = dark | (dark << 16), x = r & (r >> 1);
+            x &= x >> 2; x &= x >> 4; x &= r >> 8;
+            uint32_t r2 = bright | (bright << 16), y = r2 & (r2 >> 1);
+            y &= y >> 2; y &= y >> 4; y &= r2 >> 8;
+            if ((x | y) & 0xFFFFu) sc = 0x100u | (uint16_t)(uint8_t)fast_corner_score(tile, ty, tx, t);
+        }
+        score[ly][lx] = sc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < HT_H * HT_W; idx += HT_THREADS) {
+        const int ly = idx / HT_W, lx = idx - ly * HT_W;
+        const int gx = x0 + lx, gy = y0 + ly;
+        const uint16_t c = score[ly + 1][lx + 1];
+        if (!(c & 0x100u) || gx >= g.W || gy >= g.H) continue;
+        bool keep = true;
+        if (nonmax) {
+            const int sv = c & 0xFF;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+                    if (dy != 1 || dx != 1) keep &= sv > (score[ly + dy][lx + dx] & 0xFF);
+        }
+        if (keep && mask && !mask[(size_t)f * g.img_stride + (size_t)gy * g.img_pitch + gx]) keep = false;
+        if (keep) {
+            const int pos = atomicAdd(&s_count, 1);
+            const unsigned xy = ((unsigned)gy << 16) | (unsigned)gx;
+            if (pos < 512) s_keys[pos] = ((unsigned long long)(0xFFFFFFFFu - xy) << 32) | xy;
+            else {   // more than 512 corners in one tile (cannot happen with nonmax): straight to the global list
+                const int gp = atomicAdd(cand_count + f, 1);
+                if (gp < cand_cap) cand[(size_t)f * cand_cap + gp] = ((unsigned long long)(0xFFFFFFFFu - xy) << 32) | xy;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(s_count, 512);
+    if (n == 0) return;
+    if (tid == 0) s_base = atomicAdd(cand_count + f, n);
+    __syncthreads();
+    for (int i = tid; i < n; i += HT_THREADS)
+        if (s_base + i < cand_cap) cand[(size_t)f * cand_cap + s_base + i] = s_keys[i];
+}
+
 }  // namespace svi

@@ -27,6 +27,7 @@ struct SelectParams {
     int gw, gh;          // grid size
     double min_dist_sq;  // minDistance^2 (cv compares dx*dx+dy*dy < minDistance*minDistance)
     int filter;          // 0 when minDistance < 1 (cv skips the distance filter)
+    int cap_is_error;    // FAST mode: OpenCV returns every corner, so exceeding max_corners must be reported
 };
 
 __device__ __forceinline__ void key_xy(unsigned long long k, int& x, int& y) {
@@ -59,6 +60,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         if (tid == 0) atomicExch(overflow, 1);
         n = sp.cand_cap;
     }
+    if (sp.cap_is_error && n > sp.max_corners && tid == 0) atomicExch(overflow, 3);
     if (kSmem && n > SEL_SMEM_KEYS) {  // host picks the global variant when this can happen
         if (tid == 0) atomicExch(overflow, 2);
         n = SEL_SMEM_KEYS;

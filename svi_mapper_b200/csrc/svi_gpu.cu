@@ -206,15 +206,24 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
     CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, nf);
+    const bool fast = ctx->p.detector == SVI_DETECTOR_FAST_9_16;
     mark(ctx, l);
-    harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf,
-                                                                    l.resp, l.box_l, nullptr, l.frame_max, nullptr, g.H);
+    if (fast) {
+        fast_candidates_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, d_mask, g, ctx->p.fast_threshold, ctx->p.fast_nonmax, l.cand,
+                                                            l.cand_count, ctx->cand_cap);
+        boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, g, l.box_l, nullptr);
+    } else {
+        harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf,
+                                                                        l.resp, l.box_l, nullptr, l.frame_max, nullptr, g.H);
+    }
     mark(ctx, l);
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
-    const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
-    nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
-                                                                 l.cand, l.cand_count, ctx->cand_cap, nullptr, g.H);
+    if (!fast) {
+        const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
+        nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
+                                                       l.cand, l.cand_count, ctx->cand_cap, nullptr, g.H);
+    }
     mark(ctx, l);
     if (ctx->select_smem) {
         select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(
@@ -237,6 +246,10 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
 int check_overflow(svi_ctx* ctx) {
     int h = 0;
     CK(cudaMemcpy(&h, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h == 3) {
+        CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
+        return fail(ctx, SVI_ERR_CAPACITY, "FAST found more corners than svi_params.max_corners in a frame (cv::FAST returns all of them): raise max_corners");
+    }
     if (h) {
         CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
         return fail(ctx, SVI_ERR_CAPACITY,
@@ -611,6 +624,9 @@ int svi_params_default(svi_params* p) {
     p->max_candidates = 16384;
     p->chunk_frames = 0;
     p->max_queries = 16384;
+    p->detector = SVI_DETECTOR_GFTT_HARRIS;
+    p->fast_threshold = 10;
+    p->fast_nonmax = 1;
     return SVI_SUCCESS;
 }
 
@@ -742,6 +758,14 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     sp.cand_cap = cap;
     sp.max_corners = p.max_corners;
     sp.filter = p.min_distance >= 1.0 ? 1 : 0;
+    sp.cap_is_error = 0;
+    if (p.detector == SVI_DETECTOR_FAST_9_16) {   // cv::FAST: no distance filter, no maxCorners cut
+        sp.filter = 0;
+        sp.cap_is_error = 1;
+    } else if (p.detector != SVI_DETECTOR_GFTT_HARRIS) {
+        delete ctx;
+        return fail(nullptr, SVI_ERR_INVALID, "svi_create: unknown detector");
+    }
     sp.min_dist_sq = p.min_distance * p.min_distance;
     int cell = std::max(1, (int)std::ceil(p.min_distance));
     while (((ctx->W + cell - 1) / cell) * ((ctx->H + cell - 1) / cell) > SEL_SMEM_CELLS && cap <= SEL_SMEM_KEYS && cell < 64) ++cell;
@@ -781,7 +805,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
                                  (const void*)stereo_match_kernel, (const void*)triangulate_kernel<true>,
                                  (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
                                  (const void*)track_stage2_kernel<true>, (const void*)track_stage2_kernel<false>,
-                                 (const void*)track_stage3_kernel,
+                                 (const void*)track_stage3_kernel, (const void*)fast_candidates_kernel,
                                  (const void*)describe_kernel, (const void*)hamming_match_kernel};
         for (const void* k : kernels)
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -993,11 +1017,16 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
         CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
         const dim3 tiles((W + HT_W - 1) / HT_W, (H + HT_H - 1) / HT_H, nf);
-        harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                        nullptr, nullptr, l.frame_max, nullptr, g.H);
-        const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
-        nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
-                                                                     l.cand_count, ctx->cand_cap, nullptr, g.H);
+        if (ctx->p.detector == SVI_DETECTOR_FAST_9_16) {
+            fast_candidates_kernel<<<tiles, HT_THREADS, 0, s>>>(l.img_l, d_mask, g, ctx->p.fast_threshold, ctx->p.fast_nonmax, l.cand,
+                                                                l.cand_count, ctx->cand_cap);
+        } else {
+            harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
+                                                                            nullptr, nullptr, l.frame_max, nullptr, g.H);
+            const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
+            nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
+                                                           l.cand_count, ctx->cand_cap, nullptr, g.H);
+        }
         if (ctx->select_smem)
             select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(l.cand, l.cand_count, ctx->sel, nullptr, nullptr,
                                                                                   nullptr, l.det_xy, l.n_det, l.kp_xy, l.n_kp,

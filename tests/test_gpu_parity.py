@@ -572,3 +572,35 @@ def test_epipolar_band_matcher(kitti_cams):
         assert (ri >= 0).sum() > 200 and (ri < 0).sum() > 0
         gi, gd, gs = fe.match_epipolar(dl[:4], xl[:4], np.zeros((0, 32), np.uint8), np.zeros((0, 2), np.float32))
         assert (gi == -1).all() and (gd == -1).all() and (gs == -1).all()
+
+
+def test_fast_detector_mode(kitti_cams):
+    """Optional FAST-9/16 detector mode: corners equal the cv2-pinned oracle in OpenCV's output
+    order, with and without non-max suppression and masks; the stereo pipeline runs on them; exceeding max_corners is
+    a loud capacity error (cv::FAST has no maxCorners cut)."""
+    from svi_mapper_b200 import SviError
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, R = stereo_pair(W, H, 0)
+    tri = _tri(kitti_cams)
+    for thr, nm in ((10, 1), (20, 0), (20, 1)):
+        ref_xy, _ = o.fast9_16(L, thr, bool(nm))
+        assert 200 < len(ref_xy) < 60000
+        with StereoFrontend(*kitti_cams, detector=1, fast_threshold=thr, fast_nonmax=nm, max_corners=60000, max_candidates=65536,
+                            chunk_frames=2) as fe:
+            got = fe.detect(np.stack([L, R]))
+            np.testing.assert_array_equal(got[0].astype(np.int32), ref_xy)
+            np.testing.assert_array_equal(got[1].astype(np.int32), o.fast9_16(R, thr, bool(nm))[0])
+            mask = o.mask_active_landmarks(W, H, ref_xy[::7].astype(np.float32))
+            np.testing.assert_array_equal(fe.detect(L, mask)[0].astype(np.int32), ref_xy[mask[ref_xy[:, 1], ref_xy[:, 0]] != 0])
+            if nm and thr == 20:
+                res = fe.add_new_landmarks(L, R)        # the rest of the path on FAST corners
+                keep, desc_l = o.brief32(L, ref_xy.astype(np.float32))
+                np.testing.assert_array_equal(res["uv_l"].astype(np.int32), ref_xy[keep])
+                np.testing.assert_array_equal(res["desc_l"], desc_l)
+                for u in range(0, len(keep), 9):
+                    x, y = np.float32(ref_xy[keep[u], 0]), np.float32(ref_xy[keep[u], 1])
+                    r = tri.triangulate_right(R, max(np.float32(0), x - np.float32(60) - np.float32(28)), y - np.float32(28), 7.0, (x, y), desc_l[u])
+                    assert res["status"][u] == r["status"] and res["dist"][u] == r.get("dist", -1)
+    with StereoFrontend(*kitti_cams, detector=1, fast_threshold=20, max_corners=1000, max_candidates=65536) as fe:
+        with pytest.raises(SviError, match="FAST found more corners"):
+            fe.detect(L)

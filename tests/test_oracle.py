@@ -216,3 +216,21 @@ def test_epipolar_band_matcher_matches_cv2_masked_bfmatcher():
         else:
             assert got[i] == (idx[i], dist[i])
             assert second[i] == -1 or second[i] >= dist[i]
+
+
+def test_fast_oracle_matches_cv2():
+    """Optional FAST-9/16 mode: the restatement equals cv2.FastFeatureDetector (positions, order, scores)."""
+    cv2 = pytest.importorskip("cv2")
+    L, _ = stereo_pair(320, 240, 5)
+    L2 = L.copy()
+    cv2.rectangle(L2, (40, 40), (120, 100), 255, -1)
+    for img in (L, L2):
+        for t in (5, 20, 40):
+            for nm in (True, False):
+                det = cv2.FastFeatureDetector_create(threshold=t, nonmaxSuppression=nm, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+                kps = det.detect(img)
+                ref = np.array([[int(k.pt[0]), int(k.pt[1])] for k in kps], np.int32).reshape(-1, 2)
+                xy, sc = o.fast9_16(img, t, nm)
+                np.testing.assert_array_equal(xy, ref)
+                if nm:
+                    np.testing.assert_array_equal(sc, np.array([int(k.response) for k in kps], np.int32))
