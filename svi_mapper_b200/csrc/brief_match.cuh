@@ -14,8 +14,8 @@
 // from ONE 32-bit shared-memory load per test point: the u16 box sums of two neighbouring
 // candidates are neighbours in memory.  The 256 test pairs are template constants
 // (brief_pattern_32.h), so every shared-memory offset is an instruction immediate.  Both
-// comparisons of a pair are one 32-bit subtract (values <= 20655 < 2^15 leave the half-word sign
-// bits free): d = b + 0x7FFF7FFF - a has bit 15 / bit 31 set iff a < b in the low / high half.
+// comparisons of a pair are one packed half-precision compare (values <= 20655 < 0x7C00 are
+// positive finite fp16 bit patterns, ordered like the integers): see lt_mask_u16x2.
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <utility>
@@ -134,32 +134,51 @@ __device__ __forceinline__ int hamming_words(const uint32_t (&a)[kDescWords], co
 }
 
 // ------------------------------------------------------------------ unrolled pair tests
+// One 32-bit LDS per test point fetches the box sums of two adjacent candidates.  Box sums are
+// <= 81*255 = 20655 < 0x7C00, i.e. bit patterns of positive finite fp16 numbers, whose order equals the
+// integer order (denormals included, no flush): one packed half-precision compare on the FMA pipe tests
+// both candidates and returns 0xFFFF per true half, so a test costs one compare and one LOP3 that keeps
+// the bit of this test in a 16-test accumulator (low half = even candidate, high half = odd candidate).
+__device__ __forceinline__ uint32_t lt_mask_u16x2(uint32_t a, uint32_t b) {
+    uint32_t m;
+    asm("set.lt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+    return m;
+}
+
 template <int T>
 __device__ __forceinline__ void brief_pair_test(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
-                                                uint32_t& wlo, uint32_t& whi) {
+                                                uint32_t& acc) {
     constexpr int c1 = kPat[T][1] + kBriefReach, c2 = kPat[T][3] + kBriefReach;
     constexpr int o1 = (kPat[T][0] + kBriefReach) * PATCH_WORDS + (c1 >> 1);
     constexpr int o2 = (kPat[T][2] + kBriefReach) * PATCH_WORDS + (c2 >> 1);
+    constexpr uint32_t bit = 0x00010001u << (15 - (T & 15));
     const uint32_t a = (c1 & 1) ? Bl[o1] : Al[o1];
     const uint32_t b = (c2 & 1) ? Bl[o2] : Al[o2];
-    const uint32_t d = b + 0x7FFF7FFFu - a;
-    whi = __funnelshift_l(d, whi, 1);
-    wlo = __funnelshift_l(d << 16, wlo, 1);
+    acc |= lt_mask_u16x2(a, b) & bit;
 }
 
-template <int J, int... I>
+template <int G, int... I>
+__device__ __forceinline__ uint32_t brief_pair_group(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                                     std::integer_sequence<int, I...>) {
+    uint32_t acc = 0u;
+    (brief_pair_test<G * 16 + I>(Al, Bl, acc), ...);
+    return acc;
+}
+
+template <int J>
 __device__ __forceinline__ void brief_pair_word(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
-                                                uint32_t& wlo, uint32_t& whi, std::integer_sequence<int, I...>) {
-    wlo = 0u;
-    whi = 0u;
-    (brief_pair_test<J * 32 + I>(Al, Bl, wlo, whi), ...);
+                                                uint32_t& wlo, uint32_t& whi) {
+    const uint32_t e = brief_pair_group<2 * J>(Al, Bl, std::make_integer_sequence<int, 16>{});      // tests 32J .. 32J+15
+    const uint32_t o = brief_pair_group<2 * J + 1>(Al, Bl, std::make_integer_sequence<int, 16>{});  // tests 32J+16 .. 32J+31
+    wlo = __byte_perm(o, e, 0x5410);   // (e.lo16 << 16) | o.lo16
+    whi = __byte_perm(o, e, 0x7632);   // (e.hi16 << 16) | o.hi16
 }
 
 template <int... J>
 __device__ __forceinline__ void brief_pair_all(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
                                                uint32_t (&wlo)[kDescWords], uint32_t (&whi)[kDescWords],
                                                std::integer_sequence<int, J...>) {
-    (brief_pair_word<J>(Al, Bl, wlo[J], whi[J], std::make_integer_sequence<int, 32>{}), ...);
+    (brief_pair_word<J>(Al, Bl, wlo[J], whi[J]), ...);
 }
 
 struct SearchResult {
