@@ -47,9 +47,12 @@ __device__ __host__ __forceinline__ uint32_t ordered_to_float_bits(uint32_t e) {
     return (e & 0x80000000u) ? (e ^ 0x80000000u) : ~e;
 }
 
-// u8 -> float without the slow I2F path: 0x4B000000 | v is 8388608 + v exactly.
+// u8 -> float in one ALU instruction: a 32-bit signed convert is I2FP (full rate), while the narrow
+// unsigned forms the compiler would pick for a byte go through the slow I2F path.
 __device__ __forceinline__ float u8_to_float(uint32_t v) {
-    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+    float f;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(v));
+    return f;
 }
 
 __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }

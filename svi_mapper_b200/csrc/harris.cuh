@@ -75,19 +75,37 @@ __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint
         }
     }
     __syncthreads();
-    {
-        int x = threadIdx.x % HT_W, oy0 = (threadIdx.x / HT_W) * 8;
-        int gx = x0 + x;
-        int s = 0;
+    // vertical 9-sums, two columns per thread as packed u16 pairs (sums <= 20655, so s + new - old never carries
+    // or borrows across the halves): one 32-bit store per plane and row.  thread = (column pair, 8-row group)
+    if (threadIdx.x < (HT_W / 2) * (HT_H / 8)) {
+        const int xp = (threadIdx.x % (HT_W / 2)) * 2, oy0 = (threadIdx.x / (HT_W / 2)) * 8;
+        const int gx = x0 + xp, rows = min(8, H - (y0 + oy0));
+        if (gx < W && rows > 0) {
+            constexpr int HP = H9_P / 2;   // 33 words per row: conflict-free across the lanes of a warp
+            const uint32_t* col = reinterpret_cast<const uint32_t*>(&h9[0][0]) + oy0 * HP + (xp >> 1);
+            const bool pair2 = xp + 2 < HT_W;   // columns xp+2, xp+3 (for the shifted plane) are inside this tile
+            uint32_t s0 = 0u, s1 = 0u;          // (S(xp), S(xp+1)), (S(xp+2), S(xp+3))
 #pragma unroll
-        for (int i = 0; i < 9; ++i) s += h9[oy0 + i][x];
+            for (int i = 0; i < 9; ++i) { s0 += col[i * HP]; s1 += col[i * HP + 1]; }
+            uint16_t* brow = box + (size_t)(y0 + oy0) * box_pitch + gx;
+            uint16_t* srow = box_shift ? box_shift + (size_t)(y0 + oy0) * box_pitch + gx : nullptr;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k > 0) s += (int)h9[oy0 + k + 8][x] - (int)h9[oy0 + k - 1][x];
-            int gy = y0 + oy0 + k;
-            if (gx < W && gy < H) {
-                box[(size_t)gy * box_pitch + gx] = (uint16_t)s;
-                if (box_shift && gx > 0) box_shift[(size_t)gy * box_pitch + gx - 1] = (uint16_t)s;
+            for (int k = 0; k < 8; ++k) {
+                if (k < rows) {
+                    if (k > 0) {
+                        s0 = s0 + col[(k + 8) * HP] - col[(k - 1) * HP];
+                        s1 = s1 + col[(k + 8) * HP + 1] - col[(k - 1) * HP + 1];
+                    }
+                    *reinterpret_cast<uint32_t*>(brow) = s0;
+                    if (srow) {
+                        // srow[j] = S(gx + j + 1)
+                        if (pair2) *reinterpret_cast<uint32_t*>(srow) = __byte_perm(s0, s1, 0x5432);
+                        else srow[0] = (uint16_t)(s0 >> 16);
+                        if (xp == 0 && gx > 0) srow[-1] = (uint16_t)s0;   // the previous tile's last element
+                        srow += box_pitch;
+                    }
+                    brow += box_pitch;
+                }
             }
         }
     }
@@ -173,18 +191,33 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
         }
     }
     __syncthreads();
-    // ---- REFLECT_101 of the product planes for halo positions outside the image (border tiles only)
-    if (x0 < 3 || y0 < 3 || x0 + HT_W + 3 > W || y0 + HT_H + 3 > H) {
-        for (int idx = tid; idx < COV_ROWS * COV_W; idx += HT_THREADS) {
-            int ly = idx / COV_W, c = idx - ly * COV_W;
-            int gy = y0 - 3 + ly, gx = x0 - 3 + c;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) continue;
-            int sy = reflect101(gy, H) - (y0 - 3), sx = reflect101(gx, W) - (x0 - 3);
-            bool ok = (gy >= -3 && gy < H + 3 && gx >= -3 && gx < W + 3 && sy >= 0 && sy < COV_ROWS && sx >= 0 && sx < COV_W);
+    // ---- REFLECT_101 of the product planes for halo positions outside the image (border tiles only):
+    // at most 3 columns left/right and 3 rows above/below the image are ever read by an in-image output
+    {
+        const int nlc = max(0, 3 - x0), cr0 = W - x0 + 3, nrc = min(max(COV_W - cr0, 0), 3);
+        const int ntr = max(0, 3 - y0), rb0 = H - y0 + 3, nbr = min(max(COV_ROWS - rb0, 0), 3);
+        if (nlc + nrc + ntr + nbr > 0) {
+            auto fix = [&](int ly, int c) {
+                const int gy = y0 - 3 + ly, gx = x0 - 3 + c;
+                const int sy = reflect101(gy, H) - (y0 - 3), sx = reflect101(gx, W) - (x0 - 3);
+                const bool ok = sy >= 0 && sy < COV_ROWS && sx >= 0 && sx < COV_W;
 #pragma unroll
-            for (int p = 0; p < 3; ++p) sm.cov[p][ly][c] = ok ? sm.cov[p][sy][sx] : 0.f;
+                for (int p = 0; p < 3; ++p) sm.cov[p][ly][c] = ok ? sm.cov[p][sy][sx] : 0.f;
+            };
+            const int i8 = tid & 7;            // outside columns of every row: 8 lanes per row
+            if (i8 < nlc + nrc) {
+                const int c = i8 < nlc ? i8 : cr0 + (i8 - nlc);
+                for (int ly = tid >> 3; ly < COV_ROWS; ly += HT_THREADS / 8) {
+                    const int gy = y0 - 3 + ly;
+                    if (gy >= 0 && gy < H) fix(ly, c);
+                }
+            }
+            const int c = tid & 127;           // outside rows, every column (corners included)
+            if (c < COV_W) {
+                for (int i = tid >> 7; i < ntr + nbr; i += HT_THREADS / 128) fix(i < ntr ? i : rb0 + (i - ntr), c);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     // ---- horizontal 7-sums in fp64: one work item = (plane, 16-output segment, row)
     for (int item = tid; item < 3 * (HT_W / HS_SEG) * COV_ROWS; item += HT_THREADS) {
