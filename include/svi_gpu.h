@@ -240,6 +240,20 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
                         size_t pitch, const double* T_world_to_left, const svi_landmarks* lm, int n,
                         double motion_scaling, svi_track_result* out);
 
+/* The same cascade restricted to some of its stages -- what the SV/SVI trackers call separately:
+ *   CFundamentalMatcher::getPoseStereoPosit (src/core/CFundamentalMatcher.cpp:338-757): stages 1 and 2 on the
+ *     optimal landmarks, feeding CSolverStereoPosit                      -> SVI_STAGE_1 | SVI_STAGE_2
+ *   CFundamentalMatcher::trackEpipolar (:760-1332): for landmarks not seen yet in this frame, the epipolar
+ *     search when the camera moved since their detection (:828-1020)     -> SVI_STAGE_3
+ *     and the regional search otherwise (:1022-1290)                     -> SVI_STAGE_2
+ * SVI_STAGE_2 without SVI_STAGE_1 keeps the reference's gate "both projections inside the field of view"
+ * (status SVI_TRK_OUT_OF_FOV otherwise); SVI_STAGE_3 alone has no gate but its own "projection out of sight".
+ * SVI_STAGE_3 needs the three reference arrays of svi_landmarks. */
+enum { SVI_STAGE_1 = 1, SVI_STAGE_2 = 2, SVI_STAGE_3 = 4 };
+int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* img_right,
+                        size_t pitch, const double* T_world_to_left, const svi_landmarks* lm, int n,
+                        double motion_scaling, uint32_t stage_mask, svi_track_result* out);
+
 /* Stage profiling: when enabled, every kernel of the new-landmark path is bracketed by CUDA events
  * on the stream it is launched on.  svi_set_profiling also clears the accumulators;
  * svi_stage_timings waits for the ctx to go idle and returns, per stage, the summed launch

@@ -714,10 +714,22 @@ def track_stage2_side(img_this, img_other, tri: Triangulator, cam_this: Camera, 
     return dict(status=ST_OK, uv_this=in_cam, uv_other=r["uv"], xyz=r["xyz"], desc_this=d_this.copy(), desc_other=r["desc"])
 
 
-def track_manual(img_l, img_r, tri: Triangulator, T_w2l: np.ndarray, landmarks, motion_scaling: float):
+def fov_gate(tri: Triangulator, T_w2l: np.ndarray, landmarks):
+    """The gate in front of stages 1 and 2 (:1416, :1036): both rounded projections inside the field of view."""
+    res = []
+    for lm in landmarks:
+        xyz_l = (T_w2l @ np.append(np.asarray(lm["xyz_w"], np.float64), 1.0))[:3]
+        ok = fov_contains(tri.cl, projection_rounded(tri.cl.P, xyz_l)) and fov_contains(tri.cr, projection_rounded(tri.cr.P, xyz_l))
+        res.append(dict(status=ST_TRK_STAGE1_DIST if ok else ST_TRK_OUT_OF_FOV, stage=0))
+    return res
+
+
+def track_manual(img_l, img_r, tri: Triangulator, T_w2l: np.ndarray, landmarks, motion_scaling: float, stage1: bool = True):
     """trackManual stages 1 and 2 (:1404-1785) as a first-success cascade; stage codes
-    1 = stage 1 LEFT, 2 = stage 1 RIGHT, 3 = stage 2 LEFT, 4 = stage 2 RIGHT, 0 = not tracked (stage 3 is the caller's)."""
-    s1 = track_stage1(img_l, img_r, tri, T_w2l, landmarks, motion_scaling)
+    1 = stage 1 LEFT, 2 = stage 1 RIGHT, 3 = stage 2 LEFT, 4 = stage 2 RIGHT, 0 = not tracked (stage 3 is the caller's).
+    This is also the image part of getPoseStereoPosit (:338-757, the same two stages on the optimal landmarks);
+    stage1=False leaves only the gate and stage 2 = the zero-translation branch of trackEpipolar (:1022-1290)."""
+    s1 = track_stage1(img_l, img_r, tri, T_w2l, landmarks, motion_scaling) if stage1 else fov_gate(tri, T_w2l, landmarks)
     tri_scale = F32(1.0 + motion_scaling)
     out = []
     for lm, r1 in zip(landmarks, s1):
@@ -926,3 +938,99 @@ def track_manual_full(img_l, img_r, tri: Triangulator, T_w2l, landmarks, motion_
             continue
         out[i] = track_stage3(img_l, img_r, tri, T_w2l, lm, motion_scaling)
     return out
+
+
+def track_stages(img_l, img_r, tri: Triangulator, T_w2l, landmarks, motion_scaling: float, stages: int):
+    """svi_track_landmarks_stages: bit 0 = stage 1, bit 1 = stage 2, bit 2 = stage 3.  Stage 3 alone is the
+    moved-camera branch of trackEpipolar (:828-1020): no field-of-view gate in front of it."""
+    if stages & 3:
+        out = track_manual(img_l, img_r, tri, T_w2l, landmarks, motion_scaling, stage1=bool(stages & 1)) if stages & 2 else \
+            track_stage1(img_l, img_r, tri, T_w2l, landmarks, motion_scaling)
+    else:
+        out = [dict(status=ST_TRK_STAGE1_DIST, stage=0) for _ in landmarks]
+    if stages & 4:
+        for i, (lm, r) in enumerate(zip(landmarks, out)):
+            if r["stage"] or r["status"] == ST_TRK_OUT_OF_FOV:
+                continue
+            out[i] = track_stage3(img_l, img_r, tri, T_w2l, lm, motion_scaling)
+    return out
+
+
+# ----------------------------------------------------------------------------- CSolverStereoPosit
+def transformation_from_vector(v):
+    """CMiniVisionToolbox::getTransformationFromVector (src/vision/CMiniVisionToolbox.cpp:354-377): translation
+    v[0:3]; rotation = unit quaternion (sqrt(1-|q|^2), q) with q = v[3:6] when |q|^2 < 1, else identity."""
+    T = np.eye(4)
+    T[:3, 3] = v[:3]
+    x, y, z = v[3:6]
+    n2 = x * x + y * y + z * z
+    if n2 < 1.0:
+        w = math.sqrt(1.0 - n2)
+        T[:3, :3] = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                              [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                              [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return T
+
+
+def solve_stereo_posit(P_l, P_r, T_last, t_imu, T_estimate, matches, min_points=25, min_inliers=15, max_iter=1000,
+                       max_err_inlier=10.0, max_err_avg=9.0, max_risk=2.0, delta=1e-5, min_translation=0.001):
+    """CSolverStereoPosit::getTransformationWORLDtoLEFT (src/optimization/CSolverStereoPosit.cpp:8-170): robust
+    Gauss-Newton on the stereo reprojection error.  matches: list of (xyz_world (3,), uv_l (2,), uv_r (2,)).
+    Returns (T_world_to_left 4x4, None) or (None, reason)."""
+    n = len(matches)
+    if not (min_points < n):
+        return None, "insufficient number of points"
+    P_l, P_r = np.asarray(P_l, np.float64).reshape(3, 4), np.asarray(P_r, np.float64).reshape(3, 4)
+    T = np.array(T_estimate, np.float64).reshape(4, 4).copy()
+    prev = 0.0
+    for _ in range(max_iter):
+        H = np.zeros((6, 6))
+        b = np.zeros(6)
+        total = 0.0
+        inliers = 0
+        for xyz_w, uvl, uvr in matches:
+            p = T[:3, :3] @ np.asarray(xyz_w, np.float64) + T[:3, 3]
+            if not (0.0 < p[2]):
+                continue
+            ph = np.append(p, 1.0)
+            a_l, a_r = P_l @ ph, P_r @ ph
+            cl, cr = a_l[2], a_r[2]
+            e = np.array([a_l[0] / cl - float(uvl[0]), a_l[1] / cl - float(uvl[1]), a_r[0] / cr - float(uvr[0]), a_r[1] / cr - float(uvr[1])])
+            e2 = float(e @ e)
+            w = 1.0
+            if max_err_inlier < e2:
+                w = max_err_inlier / e2
+            else:
+                inliers += 1
+            total += w * e2
+            Jt = np.zeros((4, 6))
+            Jt[:3, :3] = np.eye(3)
+            Jt[:3, 3:] = -2.0 * np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+            Jl = np.array([[1 / cl, 0, -a_l[0] / (cl * cl)], [0, 1 / cl, -a_l[1] / (cl * cl)]])
+            Jr = np.array([[1 / cr, 0, -a_r[0] / (cr * cr)], [0, 1 / cr, -a_r[1] / (cr * cr)]])
+            J = np.vstack([Jl @ P_l @ Jt, Jr @ P_r @ Jt])
+            H += w * (J.T @ J)
+            b += w * (J.T @ e)
+        T = transformation_from_vector(np.linalg.solve(H, -b)) @ T
+        R = T[:3, :3].copy()
+        RtR = R.T @ R
+        RtR[np.diag_indices(3)] -= 1.0
+        T[:3, :3] = R - 0.5 * R @ RtR
+        if delta > abs(prev - total):
+            if max_err_avg < total / n and min_inliers > inliers:
+                return None, "insufficient accuracy"
+            T_last = np.asarray(T_last, np.float64).reshape(4, 4)
+            d = T[:3, 3] - T_last[:3, 3]
+            if min_translation > float(d @ d):
+                T[:3, 3] = T_last[:3, 3]
+            Tinv = np.eye(4)
+            Tinv[:3, :3] = T[:3, :3].T
+            Tinv[:3, 3] = -T[:3, :3].T @ T[:3, 3]
+            Te = np.asarray(T_estimate, np.float64).reshape(4, 4)
+            te_inv = -Te[:3, :3].T @ Te[:3, 3]
+            r = Tinv[:3, 3] - te_inv - np.asarray(t_imu, np.float64)
+            if max_risk < float(r @ r):
+                return None, "inconsistent with prior"
+            return T, None
+        prev = total
+    return None, "system did not converge"

@@ -23,7 +23,7 @@ EXPORTS = (
     "svi_params_default", "svi_status_text", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
     "svi_stereo_frames", "svi_stereo_frames_device", "svi_harris_response", "svi_detect", "svi_describe",
     "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
-    "svi_track_landmarks", "svi_set_profiling", "svi_stage_timings", "svi_config",
+    "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config",
 )
 
 u8p, i32p, f32p, f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
@@ -104,6 +104,7 @@ def load():
     lib.svi_triangulate_left.argtypes = [vp, vp, sz, ci, vp, vp, vp, vp, C.c_float, C.POINTER(TriResult)]
     lib.svi_point_in_left.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.svi_track_landmarks.argtypes = [vp, vp, vp, sz, vp, C.POINTER(Landmarks), ci, C.c_double, C.POINTER(TrackResult)]
+    lib.svi_track_landmarks_stages.argtypes = [vp, vp, vp, sz, vp, C.POINTER(Landmarks), ci, C.c_double, C.c_uint32, C.POINTER(TrackResult)]
     lib.svi_set_profiling.argtypes = [vp, ci]
     lib.svi_stage_timings.argtypes = [vp, C.POINTER(C.c_char_p), f64p, C.POINTER(C.c_int64), ci]
     lib.svi_config.argtypes = [vp, i32p, i32p, i32p]

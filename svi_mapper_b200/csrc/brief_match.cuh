@@ -594,6 +594,7 @@ struct TrackConst {
     double PL[12], PR[12];
     float tri_scale;  // 1 + motion scaling (CFundamentalMatcher.cpp:1363)
     float cutoff1;    // m_dMatchingDistanceCutoffTrackingStage1
+    int stage1_match; // 0: only the field-of-view gate of :1416 (the caller asked for stage 2 without stage 1)
 };
 struct LandmarksDev {
     const double* xyz_w; const uint8_t* desc_l; const uint8_t* desc_r; const float* disparity; const float* size;
@@ -642,7 +643,8 @@ track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restri
     // the single key-point (half, half) of the (8*size+1)^2 ROI must survive BRIEF's border filter
     const int roi_len = (int)(8.f * size + 1.f);
     const bool kp_ok = cv_round_f(half) >= kBriefBorder && cv_round_f(half) < roi_len - kBriefBorder;
-    if (in_fov) {
+    if (in_fov && !k.stage1_match) status = SVI_TRK_STAGE1_DIST;   // untracked, inside both fields of view
+    if (in_fov && k.stage1_match) {
         load_desc(lm.desc_l + (size_t)q * 32, last_l);
         load_desc(lm.desc_r + (size_t)q * 32, last_r);
         // STAGE 1 LEFT :1419-1476 -- descriptor exactly at the projection, then search RIGHT

@@ -738,7 +738,10 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     ctx->box_pitch = align_up(ctx->W, 64);
     const char* env_chunk = std::getenv("SVI_CHUNK_FRAMES");
     const char* env_lanes = std::getenv("SVI_LANES");
-    ctx->chunk = p.chunk_frames > 0 ? p.chunk_frames : (env_chunk ? std::atoi(env_chunk) : 32);
+    // default: 64 KITTI-size frames per launch (measured sweep, profiles/r1_lane_sweep.txt), fewer for larger images so
+    // that the scratch of a lane stays near half a gigabyte
+    const int auto_chunk = (int)std::max<long long>(4, std::min<long long>(64, 30000000LL / ((long long)ctx->W * ctx->H)));
+    ctx->chunk = p.chunk_frames > 0 ? p.chunk_frames : (env_chunk ? std::atoi(env_chunk) : auto_chunk);
     ctx->chunk = std::max(1, std::min(ctx->chunk, 4096));
     ctx->n_lanes = env_lanes ? std::max(1, std::min(std::atoi(env_lanes), kMaxLanes)) : 6;
     ctx->profiling = std::getenv("SVI_PROFILE") != nullptr;
@@ -1163,7 +1166,18 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
                         const double* T_world_to_left, const svi_landmarks* lm, int n, double motion_scaling,
                         svi_track_result* out) {
     if (!ctx) return SVI_ERR_INVALID;
-    if (!img_left || !img_right || !T_world_to_left || !lm || !out || n < 0 || (int)pitch < ctx->W)
+    if (!lm) return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: bad argument");
+    const bool any3 = lm->uv_reference_left || lm->desc_reference_left || lm->T_left_to_world_at_detection;
+    return svi_track_landmarks_stages(ctx, img_left, img_right, pitch, T_world_to_left, lm, n, motion_scaling,
+                                      SVI_STAGE_1 | SVI_STAGE_2 | (any3 ? SVI_STAGE_3 : 0), out);
+}
+
+int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* img_right, size_t pitch,
+                               const double* T_world_to_left, const svi_landmarks* lm, int n, double motion_scaling,
+                               uint32_t stage_mask, svi_track_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!img_left || !img_right || !T_world_to_left || !lm || !out || n < 0 || (int)pitch < ctx->W ||
+        !(stage_mask & (SVI_STAGE_1 | SVI_STAGE_2 | SVI_STAGE_3)) || (stage_mask & ~(uint32_t)(SVI_STAGE_1 | SVI_STAGE_2 | SVI_STAGE_3)))
         return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: bad argument");
     if (!lm->xyz_world || !lm->last_desc_left || !lm->last_desc_right || !lm->last_disparity || !lm->keypoint_size ||
         !out->status || !out->stage || !out->uv_left || !out->uv_right || !out->xyz_left || !out->desc_left || !out->desc_right)
@@ -1203,24 +1217,31 @@ int svi_track_landmarks(svi_ctx* ctx, const uint8_t* img_left, const uint8_t* im
     for (int i = 0; i < 12; ++i) { k.T[i] = T_world_to_left[i]; k.PL[i] = ctx->cam_l.P[i]; k.PR[i] = ctx->cam_r.P[i]; }
     k.tri_scale = (float)(1.0 + motion_scaling);
     k.cutoff1 = ctx->p.cutoff_stage1;
+    k.stage1_match = (stage_mask & SVI_STAGE_1) ? 1 : 0;
     LandmarksDev ld{d_xyzw, d_dl, d_dr, d_disp, d_size};
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, plane);
-    // ---- stage 1 LEFT / RIGHT for every landmark
-    track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
-                                                                                                  ctx->tc, k, ld, n, o);
-    CK(cudaGetLastError());
+    const bool stage3 = (stage_mask & SVI_STAGE_3) != 0;
+    if (stage3 && !(lm->uv_reference_left && lm->desc_reference_left && lm->T_left_to_world_at_detection))
+        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: stage 3 needs all three reference arrays");
+    if (stage_mask & (SVI_STAGE_1 | SVI_STAGE_2)) {
+        // ---- stage 1 LEFT / RIGHT for every landmark (or only its field-of-view gate when stage 2 runs alone)
+        track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
+                                                                                                      ctx->tc, k, ld, n, o);
+        CK(cudaGetLastError());
+    } else {
+        // stage 3 alone (trackEpipolar :828-1020): no gate, every landmark is an untracked candidate
+        CK(cudaMemsetAsync(o.status, SVI_TRK_STAGE1_DIST, (size_t)n, s));
+        CK(cudaMemsetAsync(o.stage, 0, (size_t)n, s));
+    }
     CK(cudaMemcpyAsync(out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     // ---- stage 2 LEFT, then stage 2 RIGHT, for what is still untracked
-    for (int side = 0; side < 2; ++side) {
+    for (int side = 0; side < 2 && (stage_mask & SVI_STAGE_2); ++side) {
         rc = track_stage2_side(ctx, l, g, lm, n, T_world_to_left, motion_scaling, side == 0, ld, o, out);
         if (rc != SVI_SUCCESS) return rc;
     }
-    // ---- stage 3 (epipolar line in LEFT) when the caller supplied the reference data
-    const bool stage3 = lm->uv_reference_left && lm->desc_reference_left && lm->T_left_to_world_at_detection;
-    if (!stage3 && (lm->uv_reference_left || lm->desc_reference_left || lm->T_left_to_world_at_detection))
-        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: stage 3 needs all three reference arrays");
+    // ---- stage 3 (epipolar line in LEFT)
     if (stage3) {
         rc = track_stage3_all(ctx, l, g, lm, n, T_world_to_left, motion_scaling, ld, o, out);
         if (rc != SVI_SUCCESS) return rc;

@@ -273,8 +273,10 @@ class StereoFrontend:
     # -- CFundamentalMatcher::trackManual, stage 1
     def track_landmarks(self, img_left, img_right, T_world_to_left, xyz_world, last_desc_left, last_desc_right,
                         last_disparity, keypoint_size, motion_scaling: float, uv_reference_left=None,
-                        desc_reference_left=None, T_left_to_world_at_detection=None) -> dict:
-        """trackManual cascade; stage 3 runs only when the three reference arrays are given."""
+                        desc_reference_left=None, T_left_to_world_at_detection=None, stages=None) -> dict:
+        """trackManual cascade; stage 3 runs only when the three reference arrays are given.
+        stages (bit 0 = stage 1, bit 1 = stage 2, bit 2 = stage 3) restricts the cascade: 3 = the image part of
+        getPoseStereoPosit, 4 / 2 = the two branches of trackEpipolar (svi_track_landmarks_stages)."""
         a = self._images(img_left, "img_left")[0]
         b = self._images(img_right, "img_right")[0]
         T = np.ascontiguousarray(np.asarray(T_world_to_left, np.float64).reshape(4, 4))
@@ -295,8 +297,12 @@ class StereoFrontend:
         lm = _lib.Landmarks(_ptr(xw), _ptr(dl), _ptr(dr), _ptr(disp), _ptr(size), _ptr(uvref), _ptr(dref), _ptr(tdet))
         r = _lib.TrackResult(_ptr(out["status"]), _ptr(out["stage"]), _ptr(out["uv_l"]), _ptr(out["uv_r"]), _ptr(out["xyz"]),
                              _ptr(out["desc_l"]), _ptr(out["desc_r"]))
-        self._check(self._lib.svi_track_landmarks(self._ctx, _ptr(a), _ptr(b), self.width, _ptr(T), C.byref(lm), n,
-                                                  float(motion_scaling), C.byref(r)))
+        if stages is None:
+            self._check(self._lib.svi_track_landmarks(self._ctx, _ptr(a), _ptr(b), self.width, _ptr(T), C.byref(lm), n,
+                                                      float(motion_scaling), C.byref(r)))
+        else:
+            self._check(self._lib.svi_track_landmarks_stages(self._ctx, _ptr(a), _ptr(b), self.width, _ptr(T), C.byref(lm), n,
+                                                             float(motion_scaling), int(stages), C.byref(r)))
         return out
 
     # -- profiling

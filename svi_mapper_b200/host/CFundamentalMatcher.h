@@ -8,6 +8,7 @@
 
 #include <cmath>
 
+#include "CSolverStereoPosit.h"
 #include "CTriangulator.h"
 
 class CLandmark {
@@ -72,7 +73,8 @@ public:
     CFundamentalMatcher(const std::shared_ptr<CStereoCamera> p_pCameraSTEREO, const std::shared_ptr<CGpuContext> p_pGpu)
         : m_pGpu(p_pGpu), m_pTriangulator(std::make_shared<CTriangulator>(p_pCameraSTEREO, p_pGpu)), m_pCameraLEFT(p_pCameraSTEREO->m_pCameraLEFT),
           m_pCameraRIGHT(p_pCameraSTEREO->m_pCameraRIGHT), m_pCameraSTEREO(p_pCameraSTEREO), m_dMinimumDepthMeters(m_pTriangulator->dDepthMinimumMeters),
-          m_dMaximumDepthMeters(m_pTriangulator->dDepthMaximumMeters) {}
+          m_dMaximumDepthMeters(m_pTriangulator->dDepthMaximumMeters),
+          m_cSolverSterePosit(p_pCameraSTEREO->m_pCameraLEFT->m_matProjection, p_pCameraSTEREO->m_pCameraRIGHT->m_matProjection) {}
     ~CFundamentalMatcher() { for (CLandmark* p : m_vecLandmarksWINDOW) delete p; }
 
     const std::shared_ptr<CTriangulator> getTriangulator() const { return m_pTriangulator; }
@@ -234,6 +236,166 @@ public:
                                          m_vecDetectionPointsActive.end());
     }
 
+    // Gathers what svi_track_landmarks[_stages] reads of a set of landmarks, runs the requested stages in ONE GPU call
+    // and returns the per-landmark verdicts.
+    struct CTrackBatch {
+        std::vector<double> xyz;
+        std::vector<uint8_t> oL, oR, st, stage;
+        std::vector<float> uvL, uvR;
+    };
+    CTrackBatch trackStages(const std::vector<CLandmark*>& p_vecLandmarks, const std::vector<const CDetectionPoint*>& p_vecDetectionPointOf,
+                            const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT, const Isometry3d& p_matTransformationWORLDtoLEFT,
+                            const double& p_dMotionScaling, const uint32_t p_uStageMask) const {
+        const int n = (int)p_vecLandmarks.size();
+        CTrackBatch c;
+        c.xyz.resize(3 * n); c.oL.resize(32 * n); c.oR.resize(32 * n); c.st.resize(n); c.stage.resize(n); c.uvL.resize(2 * n); c.uvR.resize(2 * n);
+        if (0 == n) return c;
+        std::vector<double> xyzW(3 * n), uvRef(2 * n), Tdet(16 * n);
+        std::vector<uint8_t> dL(32 * n), dR(32 * n), dRef(32 * n);
+        std::vector<float> disp(n), size(n);
+        for (int i = 0; i < n; ++i) {
+            const CLandmark* p = p_vecLandmarks[i];
+            for (int k = 0; k < 3; ++k) xyzW[3 * i + k] = p->vecPointXYZOptimized.v[k];
+            std::memcpy(&dL[32 * i], p->getLastDescriptorLEFT().data(), 32);
+            std::memcpy(&dR[32 * i], p->getLastDescriptorRIGHT().data(), 32);
+            std::memcpy(&dRef[32 * i], p->matDescriptorReferenceLEFT.data(), 32);
+            disp[i] = p->getLastDisparity();
+            size[i] = (float)p->dKeyPointSize;
+            uvRef[2 * i] = p->vecUVReferenceLEFT[0];
+            uvRef[2 * i + 1] = p->vecUVReferenceLEFT[1];
+            std::memcpy(&Tdet[16 * i], p_vecDetectionPointOf[i]->matTransformationLEFTtoWORLD.m, sizeof(double) * 16);
+        }
+        const bool bStage3 = 0 != (p_uStageMask & SVI_STAGE_3);
+        svi_landmarks lm{xyzW.data(), dL.data(), dR.data(), disp.data(), size.data(), bStage3 ? uvRef.data() : nullptr,
+                         bStage3 ? dRef.data() : nullptr, bStage3 ? Tdet.data() : nullptr};
+        svi_track_result r{c.st.data(), c.stage.data(), c.uvL.data(), c.uvR.data(), c.xyz.data(), c.oL.data(), c.oR.data()};
+        m_pGpu->check(svi_track_landmarks_stages(m_pGpu->ctx, p_matImageLEFT.data, p_matImageRIGHT.data, p_matImageLEFT.pitch,
+                                                 p_matTransformationWORLDtoLEFT.m, &lm, n, p_dMotionScaling, p_uStageMask, &r));
+        return c;
+    }
+
+    // _addMeasurementToLandmarkSTEREO :2487-2524
+    void _addMeasurementToLandmarkSTEREO(const UIDFrame p_uFrame, CLandmark* p_pLandmark, const Point2f& p_ptUVLEFT, const Point2f& p_ptUVRIGHT,
+                                         const CPoint3DCAMERA& p_vecPointXYZLEFT, const CDescriptor& p_matDescriptorLEFT,
+                                         const CDescriptor& p_matDescriptorRIGHT, const Isometry3d& p_matTransformationLEFTtoWORLD,
+                                         const Isometry3d& p_matTransformationWORLDtoLEFT, const MatrixProjection& p_matProjectionWORLDtoLEFT,
+                                         const MatrixProjection& p_matProjectionWORLDtoRIGHT) {
+        p_pLandmark->bIsCurrentlyVisible = true;
+        p_pLandmark->uFailedSubsequentTrackings = 0;
+        p_pLandmark->addMeasurement(p_uFrame, p_ptUVLEFT, p_ptUVRIGHT, p_matDescriptorLEFT, p_matDescriptorRIGHT, p_vecPointXYZLEFT,
+                                    p_matTransformationLEFTtoWORLD, p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT, p_matProjectionWORLDtoRIGHT);
+        m_vecVisibleLandmarks.push_back(p_pLandmark);
+    }
+
+    // getPoseStereoPosit :338-757: stages 1 and 2 on every OPTIMAL landmark around the pose estimate (one GPU call), the
+    // measurements go to CSolverStereoPosit (CExceptionPoseOptimization on failure, as in the reference), then the
+    // landmarks receive their measurement under the optimised pose.
+    const Isometry3d getPoseStereoPosit(const UIDFrame p_uFrame, const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT,
+                                        const Isometry3d& p_matTransformationEstimateWORLDtoLEFT, const Isometry3d& p_matTransformationWORLDtoLEFTLAST,
+                                        const CPoint3D& /*p_vecRotationIMU*/, const CPoint3D& p_vecTranslationIMU, const double& p_dMotionScaling) {
+        m_uNumberOfTracksStage1 = m_uNumberOfTracksStage2_1 = 0;
+        std::vector<CLandmark*> vecCandidates;
+        std::vector<const CDetectionPoint*> vecDetectionPointOf;
+        for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
+            for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks)
+                if (pLandmark->bIsOptimal) { vecCandidates.push_back(pLandmark); vecDetectionPointOf.push_back(&cDetectionPoint); }
+        const CTrackBatch c(trackStages(vecCandidates, vecDetectionPointOf, p_matImageLEFT, p_matImageRIGHT, p_matTransformationEstimateWORLDtoLEFT,
+                                        p_dMotionScaling, SVI_STAGE_1 | SVI_STAGE_2));
+        std::vector<CSolverStereoPosit::CMatch> vecMeasurementsForStereoPosit;
+        for (size_t i = 0; i < vecCandidates.size(); ++i) {
+            if (0 == c.stage[i]) continue;
+            CDescriptor a, b;
+            std::memcpy(a.data(), &c.oL[32 * i], 32);
+            std::memcpy(b.data(), &c.oR[32 * i], 32);
+            vecMeasurementsForStereoPosit.push_back(CSolverStereoPosit::CMatch(vecCandidates[i], vecCandidates[i]->vecPointXYZOptimized,
+                                                                               CPoint3DCAMERA(c.xyz[3 * i], c.xyz[3 * i + 1], c.xyz[3 * i + 2]),
+                                                                               Point2f(c.uvL[2 * i], c.uvL[2 * i + 1]), Point2f(c.uvR[2 * i], c.uvR[2 * i + 1]), a, b));
+            if (c.stage[i] <= 2) ++m_uNumberOfTracksStage1; else ++m_uNumberOfTracksStage2_1;
+        }
+        const Isometry3d matTransformationWORLDtoLEFT(m_cSolverSterePosit.getTransformationWORLDtoLEFT(
+            p_matTransformationWORLDtoLEFTLAST, p_vecTranslationIMU, p_matTransformationEstimateWORLDtoLEFT, vecMeasurementsForStereoPosit));
+        const MatrixProjection matProjectionWORLDtoLEFT(m_pCameraLEFT->m_matProjection * matTransformationWORLDtoLEFT);
+        const MatrixProjection matProjectionWORLDtoRIGHT(m_pCameraRIGHT->m_matProjection * matTransformationWORLDtoLEFT);
+        const Isometry3d matTransformationLEFTtoWORLD(inverseIsometry(matTransformationWORLDtoLEFT));
+        for (const CSolverStereoPosit::CMatch& cMatchSTEREO : vecMeasurementsForStereoPosit)
+            _addMeasurementToLandmarkSTEREO(p_uFrame, cMatchSTEREO.pLandmark, cMatchSTEREO.ptUVLEFT, cMatchSTEREO.ptUVRIGHT, cMatchSTEREO.vecPointXYZLEFT,
+                                            cMatchSTEREO.matDescriptorLEFT, cMatchSTEREO.matDescriptorRIGHT, matTransformationLEFTtoWORLD,
+                                            matTransformationWORLDtoLEFT, matProjectionWORLDtoLEFT, matProjectionWORLDtoRIGHT);
+        m_vecMeasurementsStereoPositLAST.swap(vecMeasurementsForStereoPosit);
+        return matTransformationWORLDtoLEFT;
+    }
+    const std::vector<CSolverStereoPosit::CMatch>& getMeasurementsStereoPositLAST() const { return m_vecMeasurementsStereoPositLAST; }
+
+    // trackEpipolar :760-1332: the landmarks getPoseStereoPosit did not see.  Where the camera has moved since the
+    // landmark's detection: the epipolar search (stage 3) alone; otherwise: the regional search (stage 2) behind the
+    // field-of-view gate.  Two GPU calls for the whole frame, then the reference's activity bookkeeping.
+    void trackEpipolar(const UIDFrame p_uFrame, const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT,
+                       const Isometry3d& p_matTransformationWORLDtoLEFT, const Isometry3d& p_matTransformationLEFTtoWORLD, const double& p_dMotionScaling) {
+        const MatrixProjection matProjectionWORLDtoLEFT(m_pCameraLEFT->m_matProjection * p_matTransformationWORLDtoLEFT);
+        const MatrixProjection matProjectionWORLDtoRIGHT(m_pCameraRIGHT->m_matProjection * p_matTransformationWORLDtoLEFT);
+        m_uNumberOfTracksStage3 = m_uNumberOfTracksStage2_2 = 0;
+        std::vector<CLandmark*> vecEpipolar, vecRegional, vecDropped;
+        std::vector<const CDetectionPoint*> vecDetectionPointOfEpipolar, vecDetectionPointOfRegional;
+        for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive) {
+            const Isometry3d matTransformationToNow(p_matTransformationWORLDtoLEFT * cDetectionPoint.matTransformationLEFTtoWORLD);   // :800
+            const double dTranslationSquaredNorm = matTransformationToNow(0, 3) * matTransformationToNow(0, 3) + matTransformationToNow(1, 3) * matTransformationToNow(1, 3) +
+                                                   matTransformationToNow(2, 3) * matTransformationToNow(2, 3);
+            for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
+                if (0 < pLandmark->uOptimizationsFailed) { pLandmark->bIsCurrentlyVisible = false; vecDropped.push_back(pLandmark); }                                   // :808-815
+                else if (0 < pLandmark->uOptimizationsSuccessful && !pLandmark->bIsOptimal) { pLandmark->bIsCurrentlyVisible = false; vecDropped.push_back(pLandmark); } // :818-825
+                else if (pLandmark->bIsCurrentlyVisible) continue;                                                                                                       // :830-833
+                else if (0.0 < dTranslationSquaredNorm) { vecEpipolar.push_back(pLandmark); vecDetectionPointOfEpipolar.push_back(&cDetectionPoint); }
+                else { vecRegional.push_back(pLandmark); vecDetectionPointOfRegional.push_back(&cDetectionPoint); }
+            }
+        }
+        auto apply = [&](const std::vector<CLandmark*>& p_vecLandmarks, const CTrackBatch& c, UIDLandmark& p_uCounter) {
+            for (size_t i = 0; i < p_vecLandmarks.size(); ++i) {
+                CLandmark* pLandmark = p_vecLandmarks[i];
+                if (0 < c.stage[i]) {
+                    CDescriptor a, b;
+                    std::memcpy(a.data(), &c.oL[32 * i], 32);
+                    std::memcpy(b.data(), &c.oR[32 * i], 32);
+                    _addMeasurementToLandmarkSTEREO(p_uFrame, pLandmark, Point2f(c.uvL[2 * i], c.uvL[2 * i + 1]), Point2f(c.uvR[2 * i], c.uvR[2 * i + 1]),
+                                                    CPoint3DCAMERA(c.xyz[3 * i], c.xyz[3 * i + 1], c.xyz[3 * i + 2]), a, b, p_matTransformationLEFTtoWORLD,
+                                                    p_matTransformationWORLDtoLEFT, matProjectionWORLDtoLEFT, matProjectionWORLDtoRIGHT);
+                    ++p_uCounter;
+                } else {
+                    ++pLandmark->uFailedSubsequentTrackings;   // :1014-1023, :1281-1289
+                    pLandmark->bIsCurrentlyVisible = false;
+                }
+            }
+        };
+        {
+            const CTrackBatch c(trackStages(vecEpipolar, vecDetectionPointOfEpipolar, p_matImageLEFT, p_matImageRIGHT, p_matTransformationWORLDtoLEFT,
+                                            p_dMotionScaling, SVI_STAGE_3));
+            // the library decides "no translation" on its own product of the two transforms: follow its verdict
+            std::vector<CLandmark*> vecMoved;
+            CTrackBatch m;
+            for (size_t i = 0; i < vecEpipolar.size(); ++i) {
+                if (SVI_EPI_NO_TRANSLATION == c.st[i]) { vecRegional.push_back(vecEpipolar[i]); vecDetectionPointOfRegional.push_back(vecDetectionPointOfEpipolar[i]); continue; }
+                vecMoved.push_back(vecEpipolar[i]);
+                m.st.push_back(c.st[i]); m.stage.push_back(c.stage[i]);
+                m.uvL.insert(m.uvL.end(), &c.uvL[2 * i], &c.uvL[2 * i] + 2); m.uvR.insert(m.uvR.end(), &c.uvR[2 * i], &c.uvR[2 * i] + 2);
+                m.xyz.insert(m.xyz.end(), &c.xyz[3 * i], &c.xyz[3 * i] + 3);
+                m.oL.insert(m.oL.end(), &c.oL[32 * i], &c.oL[32 * i] + 32); m.oR.insert(m.oR.end(), &c.oR[32 * i], &c.oR[32 * i] + 32);
+            }
+            apply(vecMoved, m, m_uNumberOfTracksStage3);
+        }
+        apply(vecRegional, trackStages(vecRegional, vecDetectionPointOfRegional, p_matImageLEFT, p_matImageRIGHT, p_matTransformationWORLDtoLEFT,
+                                       p_dMotionScaling, SVI_STAGE_2), m_uNumberOfTracksStage2_2);
+        // activity :1291-1312: landmarks with a failed / invalid optimisation leave, the others stay while their failed trackings are below the limit
+        for (CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive) {
+            std::vector<CLandmark*>& v = *cDetectionPoint.vecLandmarks;
+            v.erase(std::remove_if(v.begin(), v.end(), [&](CLandmark* p) {
+                        return p->uFailedSubsequentTrackings >= m_uMaximumFailedSubsequentTrackingsPerLandmark ||
+                               std::find(vecDropped.begin(), vecDropped.end(), p) != vecDropped.end(); }), v.end());
+        }
+        m_vecDetectionPointsActive.erase(std::remove_if(m_vecDetectionPointsActive.begin(), m_vecDetectionPointsActive.end(),
+                                                        [](const CDetectionPoint& d) { return d.vecLandmarks->empty(); }),
+                                         m_vecDetectionPointsActive.end());
+    }
+    UIDLandmark getNumberOfTracksStage2_2() const { return m_uNumberOfTracksStage2_2; }
+
 private:
     const std::shared_ptr<CGpuContext> m_pGpu;
     std::shared_ptr<CTriangulator> m_pTriangulator;
@@ -245,7 +407,9 @@ private:
     std::vector<CDetectionPoint> m_vecDetectionPointsActive;
     std::vector<CLandmark*> m_vecVisibleLandmarks, m_vecLandmarksWINDOW;
     std::vector<const CMeasurementLandmark*> m_vecMeasurementsVisible;
-    UIDLandmark m_uAvailableLandmarkID = 0, m_uNumberOfTracksStage1 = 0, m_uNumberOfTracksStage2_1 = 0, m_uNumberOfTracksStage3 = 0;
+    UIDLandmark m_uAvailableLandmarkID = 0, m_uNumberOfTracksStage1 = 0, m_uNumberOfTracksStage2_1 = 0, m_uNumberOfTracksStage2_2 = 0, m_uNumberOfTracksStage3 = 0;
+    CSolverStereoPosit m_cSolverSterePosit;
+    std::vector<CSolverStereoPosit::CMatch> m_vecMeasurementsStereoPositLAST;
 };
 
 #endif

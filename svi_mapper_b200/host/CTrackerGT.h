@@ -8,26 +8,6 @@
 
 #include "CFundamentalMatcher.h"
 
-inline Isometry3d inverseIsometry(const Isometry3d& T) {   // Eigen::Isometry3d::inverse(): R^T, -R^T t
-    Isometry3d I;
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) I(r, c) = T(c, r);
-    for (int r = 0; r < 3; ++r) I(r, 3) = -(I(r, 0) * T(0, 3) + I(r, 1) * T(1, 3) + I(r, 2) * T(2, 3));
-    return I;
-}
-
-inline Isometry3d operator*(const Isometry3d& A, const Isometry3d& B) {
-    Isometry3d C;
-    for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 4; ++c) {
-            double s = 0.0;
-            for (int k = 0; k < 3; ++k) s += A(r, k) * B(k, c);
-            C(r, c) = s + (c == 3 ? A(r, 3) : 0.0);
-        }
-    }
-    return C;
-}
-
 class CTrackerGT {
 public:
     CTrackerGT(const std::shared_ptr<CStereoCamera> p_pCameraSTEREO, const std::shared_ptr<CGpuContext> p_pGpu)

@@ -74,6 +74,26 @@ inline MatrixProjection operator*(const MatrixProjection& P, const Isometry3d& T
     return R;
 }
 
+inline Isometry3d inverseIsometry(const Isometry3d& T) {   // Eigen::Isometry3d::inverse(): R^T, -R^T t
+    Isometry3d I;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) I(r, c) = T(c, r);
+    for (int r = 0; r < 3; ++r) I(r, 3) = -(I(r, 0) * T(0, 3) + I(r, 1) * T(1, 3) + I(r, 2) * T(2, 3));
+    return I;
+}
+
+inline Isometry3d operator*(const Isometry3d& A, const Isometry3d& B) {
+    Isometry3d C;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += A(r, k) * B(k, c);
+            C(r, c) = s + (c == 3 ? A(r, 3) : 0.0);
+        }
+    }
+    return C;
+}
+
 typedef std::array<uint8_t, DESCRIPTOR_SIZE_BYTES> CDescriptor;   // cv::Mat 1x32 CV_8U
 
 struct ImageView {                    // const cv::Mat& (8-bit, single channel)
@@ -124,6 +144,12 @@ public:
     const char* what() const noexcept override { return m_strExceptionDescription.c_str(); }
     const std::string m_strExceptionDescription;
     const int iStatus;   // svi_status of the failing item
+};
+class CExceptionPoseOptimization : public std::exception {   // src/exceptions/CExceptionPoseOptimization.h
+public:
+    explicit CExceptionPoseOptimization(const std::string& p_strExceptionDescription) : m_strExceptionDescription(p_strExceptionDescription) {}
+    const char* what() const noexcept override { return m_strExceptionDescription.c_str(); }
+    const std::string m_strExceptionDescription;
 };
 class CExceptionParameter : public std::exception {
 public:

@@ -1,11 +1,15 @@
 // facade_demo -- drives the C++ host facade the way CTrackerGT::_trackLandmarks drives the reference
 // (src/core/CTrackerGT.cpp:160-174, 305-319): addNewLandmarks on frame 0, trackManual on frame 1.
 // Usage: facade_demo <left_calib> <right_calib> <W> <H> <L0.raw> <R0.raw> <L1.raw> <R1.raw> <out.txt>
-// Writes one line per landmark of frame 0 and one per tracked landmark of frame 1 (parsed by the tests).
+// Writes one line per landmark of frame 0 and one per tracked landmark of frame 1 (parsed by the tests), then
+// drives the SV/SVI entry points getPoseStereoPosit and trackEpipolar (src/core/CTrackerSV.cpp:274,324).
+//        facade_demo --solver <left_calib> <right_calib> <matches.txt>
+// CSolverStereoPosit alone (no GPU work): matches.txt holds "x y z uL vL uR vR" per line, the pose goes to stdout.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "CTrackerGT.h"
@@ -17,7 +21,31 @@ static std::vector<uint8_t> readRaw(const char* path, size_t n) {
     return v;
 }
 
+static int solverMain(char** argv) {
+    try {
+        CParameterBase::loadCameraLEFT(argv[2]);
+        CParameterBase::loadCameraRIGHT(argv[3]);
+        CSolverStereoPosit cSolver(CParameterBase::pCameraLEFT->m_matProjection, CParameterBase::pCameraRIGHT->m_matProjection);
+        std::vector<CSolverStereoPosit::CMatch> vecMatches;
+        std::ifstream f(argv[4]);
+        double x, y, z;
+        float uL, vL, uR, vR;
+        while (f >> x >> y >> z >> uL >> vL >> uR >> vR)
+            vecMatches.push_back(CSolverStereoPosit::CMatch(nullptr, CPoint3D(x, y, z), CPoint3D(), Point2f(uL, vL), Point2f(uR, vR), CDescriptor(), CDescriptor()));
+        const Isometry3d matIdentity;
+        const Isometry3d T(cSolver.getTransformationWORLDtoLEFT(matIdentity, CPoint3D(), matIdentity, vecMatches));
+        for (int i = 0; i < 12; ++i) std::printf("%.17g%c", T.m[i], i == 11 ? '\n' : ' ');
+    } catch (const CExceptionPoseOptimization& e) {
+        std::printf("FAILED %s\n", e.what());
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "facade_demo failed: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 5 && std::string(argv[1]) == "--solver") return solverMain(argv);
     if (argc < 10) { std::fprintf(stderr, "usage: see source\n"); return 2; }
     try {
         CParameterBase::loadCameraLEFT(argv[1]);
@@ -69,6 +97,31 @@ int main(int argc, char** argv) {
                          (unsigned long)cTracker.getMatcher().getNumberOfTracksStage1(), (unsigned long)cTracker.getMatcher().getNumberOfTracksStage2_1(),
                          (unsigned long)cTracker.getMatcher().getNumberOfTracksStage3(), (unsigned long)cTracker.getNumberOfDetections());
         }
+        // the SV/SVI entry points on a fresh matcher: frame 1 = pose from the stereo measurements of stages 1-2, frame 2 =
+        // nothing seen yet and the camera 2 cm away from the detection pose (epipolar branch), frame 3 = nothing seen
+        // yet at the detection pose (regional branch)
+        CFundamentalMatcher cMatcherSV(CParameterBase::pCameraSTEREO, pGpu);
+        cMatcherSV.addNewLandmarks(ImageView(L0.data(), W, H), ImageView(R0.data(), W, H), matIdentity, matIdentity, 0);
+        cMatcherSV.resetVisibilityActiveLandmarks();
+        try {
+            const Isometry3d T(cMatcherSV.getPoseStereoPosit(1, ImageView(L1.data(), W, H), ImageView(R1.data(), W, H), matIdentity, matIdentity, CPoint3D(), CPoint3D(), 1.0));
+            std::fprintf(out, "POSIT %zu S1 %lu S2 %lu VISIBLE %zu POSE", cMatcherSV.getMeasurementsStereoPositLAST().size(), (unsigned long)cMatcherSV.getNumberOfTracksStage1(),
+                         (unsigned long)cMatcherSV.getNumberOfTracksStage2_1(), cMatcherSV.getNumberOfVisibleLandmarks());
+            for (int i = 0; i < 12; ++i) std::fprintf(out, " %.17g", T.m[i]);
+            std::fprintf(out, "\n");
+        } catch (const CExceptionPoseOptimization& e) {
+            std::fprintf(out, "POSIT_FAILED %s\n", e.what());
+        }
+        Isometry3d matMoved;
+        matMoved(0, 3) = 0.02;
+        cMatcherSV.resetVisibilityActiveLandmarks();
+        cMatcherSV.trackEpipolar(2, ImageView(L1.data(), W, H), ImageView(R1.data(), W, H), matMoved, inverseIsometry(matMoved), 1.5);
+        std::fprintf(out, "EPI 2 S3 %lu S22 %lu VISIBLE %zu\n", (unsigned long)cMatcherSV.getNumberOfTracksStage3(), (unsigned long)cMatcherSV.getNumberOfTracksStage2_2(),
+                     cMatcherSV.getNumberOfVisibleLandmarks());
+        cMatcherSV.resetVisibilityActiveLandmarks();
+        cMatcherSV.trackEpipolar(3, ImageView(L1.data(), W, H), ImageView(R1.data(), W, H), matIdentity, matIdentity, 1.0);
+        std::fprintf(out, "EPI 3 S3 %lu S22 %lu VISIBLE %zu\n", (unsigned long)cMatcherSV.getNumberOfTracksStage3(), (unsigned long)cMatcherSV.getNumberOfTracksStage2_2(),
+                     cMatcherSV.getNumberOfVisibleLandmarks());
         std::fclose(out);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "facade_demo failed: %s\n", e.what());

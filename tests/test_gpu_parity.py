@@ -417,6 +417,38 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
     assert len(seq) == 6 and seq[0]["DETECTIONS"] == 1 and seq[0]["TOTAL"] == len(ok)
     assert all(s["VISIBLE"] > 100 for s in seq) and seq[-1]["DETECTIONS"] >= 2
     assert sum(s["S1"] + s["S2"] + s["S3"] for s in seq[1:]) > 1000
+    # SV/SVI entry points: getPoseStereoPosit (stages 1|2 + CSolverStereoPosit), then trackEpipolar's two branches
+    from svi_mapper_b200 import StereoFrontend as FE
+    xyz, dl, dr = ref["xyz"][ok], ref["desc_l"][ok].copy(), ref["desc_r"][ok].copy()
+    disp = (ref["uv_l"][ok, 0] - ref["uv_r"][ok, 0]).astype(np.float32)
+    with FE(*vi_cams) as fe:
+        def run(pose, scaling, stages, sel):
+            return fe.track_landmarks(L, R, pose, xyz[sel], dl[sel], dr[sel], disp[sel], 7.0, scaling, uv_reference_left=ref["uv_l"][ok][sel],
+                                      desc_reference_left=ref["desc_l"][ok][sel], T_left_to_world_at_detection=np.eye(4), stages=stages)
+        every = np.arange(len(ok))
+        g1 = run(np.eye(4), 1.0, 3, every)
+        seen = g1["stage"] > 0
+        posit = [l for l in lines if l.startswith("POSIT")][0].split()
+        assert posit[0] == "POSIT" and int(posit[1]) == seen.sum() and int(posit[3]) == (g1["stage"][seen] <= 2).sum()
+        assert int(posit[5]) == (g1["stage"] >= 3).sum() and int(posit[7]) == seen.sum()
+        matches = [(xyz[i], g1["uv_l"][i], g1["uv_r"][i]) for i in every[seen]]
+        T_ref, why = o.solve_stereo_posit(np.asarray(vi_cams[0].P).reshape(3, 4), np.asarray(vi_cams[1].P).reshape(3, 4), np.eye(4), np.zeros(3), np.eye(4), matches)
+        assert why is None
+        np.testing.assert_allclose(np.array([float(v) for v in posit[9:21]]).reshape(3, 4), T_ref[:3], rtol=0, atol=1e-9)
+
+        def absorb(g, sel):   # addMeasurement: the landmark's last descriptors / disparity follow the new measurement
+            hit = g["stage"] > 0
+            dl[sel[hit]], dr[sel[hit]] = g["desc_l"][hit], g["desc_r"][hit]
+            disp[sel[hit]] = g["uv_l"][hit, 0] - g["uv_r"][hit, 0]
+            return int(hit.sum())
+        absorb(g1, every)
+        moved = np.eye(4)
+        moved[0, 3] = 0.02
+        n3 = absorb(run(moved, 1.5, 4, every), every)
+        epi = [l.split() for l in lines if l.startswith("EPI")]
+        assert [int(epi[0][3]), int(epi[0][5]), int(epi[0][7])] == [n3, 0, n3] and n3 > 0.5 * len(ok)
+        n2 = absorb(run(np.eye(4), 1.0, 2, every), every)
+        assert [int(epi[1][3]), int(epi[1][5]), int(epi[1][7])] == [0, n2, n2] and n2 > 0.5 * len(ok)
 
 
 def test_stress_frame_global_select_and_long_scanlines(kitti_cams):
@@ -604,3 +636,41 @@ def test_fast_detector_mode(kitti_cams):
     with StereoFrontend(*kitti_cams, detector=1, fast_threshold=20, max_corners=1000, max_candidates=65536) as fe:
         with pytest.raises(SviError, match="FAST found more corners"):
             fe.detect(L)
+
+
+def test_track_stage_subsets(vi_cams):
+    """svi_track_landmarks_stages: the pieces of the cascade the SV/SVI trackers call on their own --
+    getPoseStereoPosit = stages 1|2, trackEpipolar = stage 3 alone (camera moved since detection, no field-of-view
+    gate) or stage 2 alone behind the gate (CFundamentalMatcher.cpp:338-757, :760-1332)."""
+    W, H = vi_cams[0].width, vi_cams[0].height
+    L, R = stereo_pair(W, H, 4000)
+    tri = _tri(vi_cams)
+    ref0 = o.add_new_landmarks(L, R, tri)
+    ok = np.nonzero(ref0["status"] == 0)[0][:90]
+    disp, lms = _landmarks_from_frame(ref0, ok)
+    for k, lm in zip(ok, lms):
+        lm.update(uv_ref=ref0["uv_l"][k].astype(np.float64), ref_desc_l=ref0["desc_l"][k], T_det_l2w=np.eye(4))
+    L1, R1 = np.roll(L, (2, 3), axis=(0, 1)), np.roll(R, (2, 3), axis=(0, 1))
+    T = np.eye(4)
+    T[:3, 3] = (0.015, 0.01, 0.0)
+    far = np.eye(4)
+    far[0, 3] = 3.0          # pushes some projections out of the field of view
+    with StereoFrontend(*vi_cams) as fe:
+        def run(a, b, pose, scaling, stages):
+            return fe.track_landmarks(a, b, pose, ref0["xyz"][ok], ref0["desc_l"][ok], ref0["desc_r"][ok], disp, 7.0, scaling,
+                                      uv_reference_left=ref0["uv_l"][ok], desc_reference_left=ref0["desc_l"][ok],
+                                      T_left_to_world_at_detection=np.eye(4), stages=stages)
+        seen = np.zeros(6, int)
+        for a, b, pose, scaling, stages in ((L, R, T, 1.0, 1), (L1, R1, np.eye(4), 1.0, 2), (L1, R1, np.eye(4), 1.0, 3),
+                                            (L, R, T, 1.5, 4), (L, R, far, 1.5, 4), (L, R, far, 1.0, 2), (L1, R1, T, 1.5, 7)):
+            ref = o.track_stages(a, b, tri, pose, lms, scaling, stages)
+            got = run(a, b, pose, scaling, stages)
+            _compare_tracks(got, ref)
+            seen += np.bincount([r["stage"] for r in ref], minlength=6)
+            if stages == 2:
+                assert not any(r["stage"] in (1, 2, 5) for r in ref)
+            if stages == 4:
+                assert not any(r["stage"] in (1, 2, 3, 4) for r in ref)
+        assert seen[1] > 20 and seen[3] > 20 and seen[5] > 40, seen
+        with pytest.raises(Exception):
+            run(L, R, T, 1.0, 0)

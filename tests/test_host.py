@@ -147,3 +147,64 @@ def test_two_rank_partition_over_gloo(tmp_path, calib_dir):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "PARTITION_OK" in outs[0]
+
+
+def test_stereo_posit_solver_cpp_matches_oracle(calib_dir, tmp_path):
+    """CSolverStereoPosit (host C++, the consumer of getPoseStereoPosit) against the numpy restatement of
+    src/optimization/CSolverStereoPosit.cpp:8-170: a perturbed pose is recovered from noisy stereo measurements with
+    outliers, and the reference's failure modes raise the same reasons.  No GPU work."""
+    import pathlib
+    import subprocess
+    from svi_mapper_b200 import load_camera
+    import oracle.frontend_np as o
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    if not exe.exists():
+        from svi_mapper_b200 import build
+        build.build_host_demo()
+    cl, cr = load_camera(calib_dir / "vi_sensor_left.txt"), load_camera(calib_dir / "vi_sensor_right.txt")
+    P_l, P_r = np.asarray(cl.P).reshape(3, 4), np.asarray(cr.P).reshape(3, 4)
+    rng = np.random.default_rng(7)
+
+    def rot(ax, ang):
+        ax = np.asarray(ax, float) / np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+    def run(matches):
+        f = tmp_path / "m.txt"
+        f.write_text("".join(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r} {float(a[0])!r} {float(a[1])!r} {float(b[0])!r} {float(b[1])!r}\n" for p, a, b in matches))
+        r = subprocess.run([str(exe), "--solver", str(calib_dir / "vi_sensor_left.txt"), str(calib_dir / "vi_sensor_right.txt"), str(f)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.strip()
+
+    T_true = np.eye(4)
+    T_true[:3, :3] = rot([0.2, 1.0, 0.1], 0.03)
+    T_true[:3, 3] = [0.06, -0.02, 0.12]
+    pts = np.c_[rng.uniform(-3, 3, 80), rng.uniform(-2, 2, 80), rng.uniform(3, 15, 80)]
+    matches = []
+    for k, p in enumerate(pts):
+        q = np.append(T_true[:3, :3] @ p + T_true[:3, 3], 1.0)
+        a, b = P_l @ q, P_r @ q
+        uvl = np.float32([a[0] / a[2], a[1] / a[2]]) + np.float32(rng.normal(0, 0.3, 2))
+        uvr = np.float32([b[0] / b[2], uvl[1]]) + np.float32([rng.normal(0, 0.3), 0])
+        if k % 13 == 0:
+            uvl += np.float32([25, -18])          # outliers: down-weighted, not rejected
+        matches.append((p, uvl, uvr))
+    T_ref, why = o.solve_stereo_posit(P_l, P_r, np.eye(4), np.zeros(3), np.eye(4), matches)
+    assert why is None and np.abs(T_ref - T_true).max() < 0.02
+    got = np.array([float(v) for v in run(matches).split()]).reshape(3, 4)
+    np.testing.assert_allclose(got, T_ref[:3], rtol=0, atol=1e-9)
+    # too few measurements / prior inconsistent with the result
+    assert run(matches[:25]).startswith("FAILED insufficient number of points: 25")
+    assert o.solve_stereo_posit(P_l, P_r, np.eye(4), np.zeros(3), np.eye(4), matches[:25])[1] == "insufficient number of points"
+    far = [(p + np.array([0.0, 0.0, 0.0]), a, b) for p, a, b in matches]
+    T_big = np.eye(4)
+    T_big[:3, 3] = [2.5, 0, 0]
+    far = []
+    for p in pts:
+        q = np.append(p + T_big[:3, 3], 1.0)
+        a, b = P_l @ q, P_r @ q
+        far.append((p, np.float32([a[0] / a[2], a[1] / a[2]]), np.float32([b[0] / b[2], b[1] / b[2]])))
+    assert o.solve_stereo_posit(P_l, P_r, np.eye(4), np.zeros(3), np.eye(4), far)[1] == "inconsistent with prior"
+    assert run(far).startswith("FAILED inconsistent with prior")
