@@ -1034,3 +1034,47 @@ def solve_stereo_posit(P_l, P_r, T_last, t_imu, T_estimate, matches, min_points=
             return T, None
         prev = total
     return None, "system did not converge"
+
+
+# ----------------------------------------------------------------------------- CLandmark::optimize
+def optimize_landmark(xyz0, measurements, min_measurements=5, max_iter=1000, delta=1e-5, kernel=10.0, max_avg=9.0, min_ratio=0.5):
+    """CLandmark::optimize / _getOptimizedLandmarkSTEREOUV (src/types/CLandmark.cpp:281-296, :447-581).
+    measurements: list of (P_world_to_left 3x4, P_world_to_right 3x4, uv_l, uv_r).
+    Returns dict(xyz, optimal, success, failed): success / failed are the increments of uOptimizationsSuccessful / Failed."""
+    xyz0 = np.asarray(xyz0, np.float64)
+    n = len(measurements)
+    if not (min_measurements < n):
+        return dict(xyz=xyz0, optimal=True, success=0, failed=0)
+    X = np.append(xyz0, 1.0)
+    prev = 0.0
+    for _ in range(max_iter):
+        H = np.zeros((4, 4))
+        b = np.zeros(4)
+        total = 0.0
+        inliers = 0
+        for P_l, P_r, uvl, uvr in measurements:
+            P_l, P_r = np.asarray(P_l, np.float64).reshape(3, 4), np.asarray(P_r, np.float64).reshape(3, 4)
+            a_l, a_r = P_l @ X, P_r @ X
+            cl, cr = a_l[2], a_r[2]
+            e = np.array([a_l[0] / cl - float(uvl[0]), a_l[1] / cl - float(uvl[1]), a_r[0] / cr - float(uvr[0]), a_r[1] / cr - float(uvr[1])])
+            e2 = float(e @ e)
+            w = 1.0
+            if kernel < e2:
+                w = kernel / e2
+            else:
+                inliers += 1
+            total += w * e2
+            Jl = np.array([[1 / cl, 0, -a_l[0] / (cl * cl)], [0, 1 / cl, -a_l[1] / (cl * cl)]])
+            Jr = np.array([[1 / cr, 0, -a_r[0] / (cr * cr)], [0, 1 / cr, -a_r[1] / (cr * cr)]])
+            J = np.vstack([Jl @ P_l, Jr @ P_r])
+            H += w * (J.T @ J)
+            b += w * (J.T @ e)
+        X[:3] += np.linalg.lstsq(H[:, :3], -b, rcond=None)[0]
+        if delta > abs(prev - total):
+            avg = total / n
+            if min_ratio < inliers / n:
+                return dict(xyz=X[:3].copy(), optimal=bool(max_avg > avg), success=1, failed=0, avg=avg)
+            return dict(xyz=xyz0, optimal=False, success=0, failed=1)
+        prev = total
+    return dict(xyz=xyz0, optimal=False, success=0, failed=1)
+

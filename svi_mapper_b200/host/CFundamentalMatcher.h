@@ -2,7 +2,9 @@
 // (addNewLandmarks :83-193, trackManual :1334-2027 (all stages), getMaskActiveLandmarks :2043-2073,
 // visibility bookkeeping :244-263, :2005-2009) with the per-key-point / per-landmark image work done by
 // ONE batched GPU call per frame instead of one OpenCV call per item.  CLandmark keeps the fields the
-// optimisation side reads (src/types/CLandmark.h:35-59); CLandmark::optimize / g2o stay with the caller.
+// optimisation side reads (src/types/CLandmark.h:35-59) and the per-landmark position refinement
+// CLandmark::optimize (src/types/CLandmark.cpp:281-296, :447-581; CPU, a 3-unknown robust Gauss-Newton); g2o
+// stays with the caller.
 #ifndef SVI_HOST_CFUNDAMENTALMATCHER_H
 #define SVI_HOST_CFUNDAMENTALMATCHER_H
 
@@ -19,7 +21,7 @@ public:
               const MatrixProjection& p_matProjectionWORLDtoLEFT, const MatrixProjection& p_matProjectionWORLDtoRIGHT, const UIDFrame& p_uIDFrame)
         : uID(p_uID), matDescriptorReferenceLEFT(p_matDescriptorLEFT), matDescriptorReferenceRIGHT(p_matDescriptorRIGHT), dKeyPointSize(p_dKeyPointSize),
           uIDFrameAtCreation(p_uIDFrame), vecPointXYZInitial(p_matTransformationLEFTtoWORLD * p_vecPointXYZLEFT), vecPointXYZOptimized(vecPointXYZInitial),
-          vecUVReferenceLEFT{(double)p_ptUVLEFT.x, (double)p_ptUVLEFT.y, 1.0} {
+          vecUVReferenceLEFT{(double)p_ptUVLEFT.x, (double)p_ptUVLEFT.y, 1.0}, vecPointXYZMean(vecPointXYZInitial) {
         addMeasurement(p_uIDFrame, p_ptUVLEFT, p_ptUVRIGHT, p_matDescriptorLEFT, p_matDescriptorRIGHT, p_vecPointXYZLEFT, p_matTransformationLEFTtoWORLD,
                        p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT, p_matProjectionWORLDtoRIGHT);
     }
@@ -38,6 +40,15 @@ public:
     bool bIsOptimal = false, bIsCurrentlyVisible = false;
     uint32_t uNumberOfKeyFramePresences = 0;
     std::vector<CDescriptor> vecDescriptorsLEFT, vecDescriptorsRIGHT;
+    CPoint3DWORLD vecPointXYZMean;
+    double dCurrentAverageSquaredError = 0.0;
+    // CLandmark.h:90-98
+    static constexpr uint32_t uCapIterations = 1000;
+    static constexpr double dConvergenceDelta = 1e-5;
+    static constexpr double dMinimumRatioInliersToOutliers = 0.5;
+    static constexpr double dKernelMaximumErrorSquaredPixels = 10.0;
+    static constexpr double dMaximumErrorSquaredAveragePixels = 9.0;
+    static constexpr size_t uMinimumMeasurementsForOptimization = 5;
 
     // src/types/CLandmark.cpp:80-279 without the per-bit statistics (loop-closure data, out of scope)
     void addMeasurement(const UIDFrame&, const Point2f& p_ptUVLEFT, const Point2f& p_ptUVRIGHT, const CDescriptor& p_matDescriptorLEFT,
@@ -46,7 +57,9 @@ public:
                         const MatrixProjection& p_matProjectionWORLDtoRIGHT) {
         vecDescriptorsLEFT.push_back(p_matDescriptorLEFT);
         vecDescriptorsRIGHT.push_back(p_matDescriptorRIGHT);
-        m_vecMeasurements.push_back(new CMeasurementLandmark(uID, p_ptUVLEFT, p_ptUVRIGHT, p_vecXYZLEFT, p_matTransformationLEFTtoWORLD * p_vecXYZLEFT,
+        const CPoint3DWORLD vecXYZWORLD(p_matTransformationLEFTtoWORLD * p_vecXYZLEFT);
+        for (int k = 0; k < 3; ++k) vecPointXYZMean.v[k] = (vecPointXYZMean.v[k] + vecXYZWORLD.v[k]) / 2.0;   // :126
+        m_vecMeasurements.push_back(new CMeasurementLandmark(uID, p_ptUVLEFT, p_ptUVRIGHT, p_vecXYZLEFT, vecXYZWORLD,
                                                              vecPointXYZOptimized, p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT,
                                                              p_matProjectionWORLDtoRIGHT, uOptimizationsSuccessful));
     }
@@ -58,7 +71,98 @@ public:
     const CMeasurementLandmark* getLastMeasurement() const { return m_vecMeasurements.back(); }
     std::vector<CMeasurementLandmark*>::size_type getNumberOfMeasurements() const { return m_vecMeasurements.size(); }
 
+    // optimize :281-296: refine the world position once more than uMinimumMeasurementsForOptimization measurements exist
+    void optimize(const UIDFrame& p_uFrame) {
+        bIsOptimal = false;
+        if (uMinimumMeasurementsForOptimization < m_vecMeasurements.size()) vecPointXYZOptimized = _getOptimizedLandmarkSTEREOUV(p_uFrame, vecPointXYZOptimized);
+        else bIsOptimal = true;
+    }
+
 private:
+    // _getOptimizedLandmarkSTEREOUV :447-581: Gauss-Newton on the stereo reprojection error over all measurements, robust
+    // weights above dKernelMaximumErrorSquaredPixels, the homogeneous coordinate held fixed (4x3 least-squares step)
+    const CPoint3DWORLD _getOptimizedLandmarkSTEREOUV(const UIDFrame&, const CPoint3DWORLD& p_vecInitialGuess) {
+        double X[4] = {p_vecInitialGuess.v[0], p_vecInitialGuess.v[1], p_vecInitialGuess.v[2], 1.0};
+        double dErrorPrevious = 0.0;
+        for (uint32_t uIteration = 0; uIteration < uCapIterations; ++uIteration) {
+            double H[4][4] = {{0}}, b[4] = {0}, dErrorTotal = 0.0;
+            uint32_t uInliers = 0;
+            for (const CMeasurementLandmark* pMeasurement : m_vecMeasurements) {
+                double J[4][4], e[4];
+                const MatrixProjection* P[2] = {&pMeasurement->matProjectionWORLDtoLEFT, &pMeasurement->matProjectionWORLDtoRIGHT};
+                const Point2f uv[2] = {pMeasurement->ptUVLEFT, pMeasurement->ptUVRIGHT};
+                for (int s = 0; s < 2; ++s) {
+                    double a[3];
+                    for (int r = 0; r < 3; ++r) a[r] = (*P[s])(r, 0) * X[0] + (*P[s])(r, 1) * X[1] + (*P[s])(r, 2) * X[2] + (*P[s])(r, 3) * X[3];
+                    const double c = a[2];
+                    e[2 * s] = a[0] / c - uv[s].x;
+                    e[2 * s + 1] = a[1] / c - uv[s].y;
+                    for (int k = 0; k < 4; ++k) {
+                        J[2 * s][k] = (*P[s])(0, k) / c - a[0] / (c * c) * (*P[s])(2, k);
+                        J[2 * s + 1][k] = (*P[s])(1, k) / c - a[1] / (c * c) * (*P[s])(2, k);
+                    }
+                }
+                const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
+                double w = 1.0;
+                if (dKernelMaximumErrorSquaredPixels < e2) w = dKernelMaximumErrorSquaredPixels / e2;
+                else ++uInliers;
+                dErrorTotal += w * e2;
+                for (int i = 0; i < 4; ++i) {
+                    for (int j = 0; j < 4; ++j) H[i][j] += w * (J[0][i] * J[0][j] + J[1][i] * J[1][j] + J[2][i] * J[2][j] + J[3][i] * J[3][j]);
+                    b[i] += w * (J[0][i] * e[0] + J[1][i] * e[1] + J[2][i] * e[2] + J[3][i] * e[3]);
+                }
+            }
+            double dx[3];
+            solveLeastSquares4x3(H, b, dx);   // H.block<4,3>(0,0).householderQr().solve(-b)
+            for (int k = 0; k < 3; ++k) X[k] += dx[k];
+            if (dConvergenceDelta > std::fabs(dErrorPrevious - dErrorTotal)) {
+                const double dErrorAverage = dErrorTotal / m_vecMeasurements.size();
+                if (dMinimumRatioInliersToOutliers < static_cast<double>(uInliers) / m_vecMeasurements.size()) {
+                    ++uOptimizationsSuccessful;
+                    dCurrentAverageSquaredError = dErrorAverage;
+                    if (dMaximumErrorSquaredAveragePixels > dErrorAverage) bIsOptimal = true;
+                    return CPoint3DWORLD(X[0], X[1], X[2]);
+                }
+                ++uOptimizationsFailed;
+                return p_vecInitialGuess;
+            }
+            dErrorPrevious = dErrorTotal;
+        }
+        ++uOptimizationsFailed;
+        return p_vecInitialGuess;
+    }
+    // min || A x + b || for the 4x3 matrix A = first three columns of H, by Householder reflections
+    static void solveLeastSquares4x3(const double (&H)[4][4], const double (&b)[4], double (&x)[3]) {
+        double A[4][3], y[4];
+        for (int i = 0; i < 4; ++i) { for (int j = 0; j < 3; ++j) A[i][j] = H[i][j]; y[i] = -b[i]; }
+        for (int c = 0; c < 3; ++c) {
+            double norm = 0.0;
+            for (int r = c; r < 4; ++r) norm += A[r][c] * A[r][c];
+            norm = std::sqrt(norm);
+            if (0.0 == norm) continue;
+            const double alpha = A[c][c] > 0.0 ? -norm : norm;
+            double v[4] = {0, 0, 0, 0};
+            v[c] = A[c][c] - alpha;
+            for (int r = c + 1; r < 4; ++r) v[r] = A[r][c];
+            double vv = 0.0;
+            for (int r = c; r < 4; ++r) vv += v[r] * v[r];
+            if (0.0 == vv) continue;
+            for (int j = c; j < 3; ++j) {
+                double d = 0.0;
+                for (int r = c; r < 4; ++r) d += v[r] * A[r][j];
+                for (int r = c; r < 4; ++r) A[r][j] -= 2.0 * d / vv * v[r];
+            }
+            double d = 0.0;
+            for (int r = c; r < 4; ++r) d += v[r] * y[r];
+            for (int r = c; r < 4; ++r) y[r] -= 2.0 * d / vv * v[r];
+        }
+        for (int r = 2; r >= 0; --r) {
+            double s2 = y[r];
+            for (int j = r + 1; j < 3; ++j) s2 -= A[r][j] * x[j];
+            x[r] = (0.0 != A[r][r]) ? s2 / A[r][r] : 0.0;
+        }
+    }
+
     std::vector<CMeasurementLandmark*> m_vecMeasurements;
 };
 
@@ -84,6 +188,12 @@ public:
     UIDLandmark getNumberOfTracksStage2_1() const { return m_uNumberOfTracksStage2_1; }
     UIDLandmark getNumberOfTracksStage3() const { return m_uNumberOfTracksStage3; }
     const std::vector<CLandmark*>& getLandmarksWINDOW() const { return m_vecLandmarksWINDOW; }
+
+    // optimizeActiveLandmarks :265-277
+    void optimizeActiveLandmarks(const UIDFrame& p_uFrame) const {
+        for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
+            for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) pLandmark->optimize(p_uFrame);
+    }
 
     // :244-254
     void resetVisibilityActiveLandmarks() {

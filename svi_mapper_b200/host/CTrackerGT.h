@@ -1,8 +1,8 @@
 // CTrackerGT -- the per-frame orchestration of the reference's ground-truth driven tracker
 // (src/core/CTrackerGT.cpp:91-126 process, :137-332 _trackLandmarks) reduced to the calls that touch the
 // stereo front-end: motion scaling, visibility reset, trackManual, the new-landmark trigger and
-// addNewLandmarks.  Display, key-framing, DBoW2 / BTree loop closing, g2o and CLandmark::optimize are
-// the reference's CPU side and are not part of this host layer.
+// addNewLandmarks and the per-frame landmark optimisation.  Display, key-framing, DBoW2 / BTree loop closing and
+// g2o are the reference's CPU side and are not part of this host layer.
 #ifndef SVI_HOST_CTRACKERGT_H
 #define SVI_HOST_CTRACKERGT_H
 
@@ -27,7 +27,7 @@ public:
         m_cMatcher.trackManual(m_uFrameCount, p_matImageLEFT, p_matImageRIGHT, matTransformationWORLDtoLEFT, matTransformationLEFTtoWORLD,
                                dMotionScaling);                                                                    // :167-174
         m_uNumberofVisibleLandmarksLAST = m_cMatcher.getNumberOfVisibleLandmarks();                                // :176-193
-        // (the reference runs CLandmark::optimize for every active landmark here, :197 -- CPU side)
+        m_cMatcher.optimizeActiveLandmarks(m_uFrameCount);                                                         // :197
         if (m_uVisibleLandmarksMinimum > m_uNumberofVisibleLandmarksLAST || m_uMaximumNumberOfFramesWithoutDetection < m_uNumberOfFramesWithoutDetection) {
             m_uNumberofVisibleLandmarksLAST = m_cMatcher.addNewLandmarks(p_matImageLEFT, p_matImageRIGHT, matTransformationWORLDtoLEFT,
                                                                          matTransformationLEFTtoWORLD, m_uFrameCount);   // :305-315

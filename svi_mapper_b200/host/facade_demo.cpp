@@ -5,6 +5,9 @@
 // drives the SV/SVI entry points getPoseStereoPosit and trackEpipolar (src/core/CTrackerSV.cpp:274,324).
 //        facade_demo --solver <left_calib> <right_calib> <matches.txt>
 // CSolverStereoPosit alone (no GPU work): matches.txt holds "x y z uL vL uR vR" per line, the pose goes to stdout.
+//        facade_demo --landmark <measurements.txt>
+// CLandmark::optimize alone (no GPU work): first line "x y z" = first triangulation in the camera frame of measurement 0,
+// then per line 16 numbers of LEFTtoWORLD... see landmarkMain; prints "x y z optimal successful failed".
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -44,8 +47,34 @@ static int solverMain(char** argv) {
     return 0;
 }
 
+// measurements.txt: per line  P_WORLDtoLEFT (12) P_WORLDtoRIGHT (12) uL vL uR vR ; the first line is preceded by the initial
+// world position "x y z".  The landmark is created at identity pose with that position, every line is one addMeasurement.
+static int landmarkMain(char** argv) {
+    std::ifstream f(argv[2]);
+    double x, y, z;
+    f >> x >> y >> z;
+    const Isometry3d matIdentity;
+    CLandmark* pLandmark = nullptr;
+    MatrixProjection PL, PR;
+    float uL, vL, uR, vR;
+    while (true) {
+        for (int i = 0; i < 12; ++i) f >> PL.m[i];
+        for (int i = 0; i < 12; ++i) f >> PR.m[i];
+        if (!(f >> uL >> vL >> uR >> vR)) break;
+        if (!pLandmark) pLandmark = new CLandmark(0, CDescriptor(), CDescriptor(), 7.0, Point2f(uL, vL), Point2f(uR, vR), CPoint3D(x, y, z), matIdentity, matIdentity, PL, PR, 0);
+        else pLandmark->addMeasurement(0, Point2f(uL, vL), Point2f(uR, vR), CDescriptor(), CDescriptor(), CPoint3D(x, y, z), matIdentity, matIdentity, PL, PR);
+    }
+    if (!pLandmark) return 2;
+    pLandmark->optimize(0);
+    std::printf("%.17g %.17g %.17g %d %u %u\n", pLandmark->vecPointXYZOptimized.x(), pLandmark->vecPointXYZOptimized.y(), pLandmark->vecPointXYZOptimized.z(),
+                (int)pLandmark->bIsOptimal, pLandmark->uOptimizationsSuccessful, pLandmark->uOptimizationsFailed);
+    delete pLandmark;
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc == 5 && std::string(argv[1]) == "--solver") return solverMain(argv);
+    if (argc == 3 && std::string(argv[1]) == "--landmark") return landmarkMain(argv);
     if (argc < 10) { std::fprintf(stderr, "usage: see source\n"); return 2; }
     try {
         CParameterBase::loadCameraLEFT(argv[1]);

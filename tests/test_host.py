@@ -208,3 +208,54 @@ def test_stereo_posit_solver_cpp_matches_oracle(calib_dir, tmp_path):
         far.append((p, np.float32([a[0] / a[2], a[1] / a[2]]), np.float32([b[0] / b[2], b[1] / b[2]])))
     assert o.solve_stereo_posit(P_l, P_r, np.eye(4), np.zeros(3), np.eye(4), far)[1] == "inconsistent with prior"
     assert run(far).startswith("FAILED inconsistent with prior")
+
+
+def test_landmark_optimize_cpp_matches_oracle(calib_dir, tmp_path):
+    """CLandmark::optimize (host C++) against the numpy restatement of src/types/CLandmark.cpp:281-296,447-581: a
+    landmark seen from eight poses is pulled from a wrong first triangulation to its true position; too few
+    measurements leave it alone and flag it optimal; a set dominated by outliers counts as a failed optimisation."""
+    import pathlib
+    import subprocess
+    from svi_mapper_b200 import load_camera
+    import oracle.frontend_np as o
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    cl, cr = load_camera(calib_dir / "vi_sensor_left.txt"), load_camera(calib_dir / "vi_sensor_right.txt")
+    P_l, P_r = np.asarray(cl.P).reshape(3, 4), np.asarray(cr.P).reshape(3, 4)
+    rng = np.random.default_rng(3)
+    truth = np.array([0.4, -0.2, 6.0])
+
+    def measurements(n, noise, outlier_every=0):
+        ms = []
+        for k in range(n):
+            T = np.eye(4)
+            T[:3, 3] = [0.03 * k, -0.01 * k, 0.02 * k]
+            Pl, Pr = P_l @ T, P_r @ T
+            a, b = Pl @ np.append(truth, 1), Pr @ np.append(truth, 1)
+            uvl = np.float32([a[0] / a[2], a[1] / a[2]]) + np.float32(rng.normal(0, noise, 2))
+            uvr = np.float32([b[0] / b[2], uvl[1]]) + np.float32([rng.normal(0, noise), 0])
+            if outlier_every and k % outlier_every:
+                uvl += np.float32(rng.uniform(20, 60, 2))
+            ms.append((Pl, Pr, uvl, uvr))
+        return ms
+
+    def run(x0, ms):
+        f = tmp_path / "lm.txt"
+        rows = [" ".join(repr(float(v)) for v in x0)]
+        for Pl, Pr, a, b in ms:
+            rows.append(" ".join(repr(float(v)) for v in list(Pl.ravel()) + list(Pr.ravel()) + [a[0], a[1], b[0], b[1]]))
+        f.write_text("\n".join(rows) + "\n")
+        r = subprocess.run([str(exe), "--landmark", str(f)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        v = r.stdout.split()
+        return np.array([float(t) for t in v[:3]]), int(v[3]), int(v[4]), int(v[5])
+
+    x0 = truth + np.array([0.15, -0.1, 0.8])
+    for ms in (measurements(8, 0.3), measurements(5, 0.3), measurements(9, 0.3, outlier_every=3)):
+        ref = o.optimize_landmark(x0, ms)
+        xyz, optimal, ok, failed = run(x0, ms)
+        assert (optimal, ok, failed) == (int(ref["optimal"]), ref["success"], ref["failed"])
+        np.testing.assert_allclose(xyz, ref["xyz"], rtol=0, atol=1e-7)
+    good = o.optimize_landmark(x0, measurements(8, 0.3))
+    assert good["success"] == 1 and good["optimal"] and np.abs(good["xyz"] - truth).max() < 0.25
+    assert o.optimize_landmark(x0, measurements(5, 0.3)) ["optimal"] and o.optimize_landmark(x0, measurements(9, 0.3, outlier_every=3))["failed"] == 1
+
