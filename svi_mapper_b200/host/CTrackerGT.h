@@ -41,6 +41,7 @@ public:
     }
 
     CFundamentalMatcher& getMatcher() { return m_cMatcher; }
+    const Isometry3d getTransformationLEFTtoWORLD() const { return inverseIsometry(m_matTransformationWORLDtoLEFTLAST); }
     UIDFrame getFrameCount() const { return m_uFrameCount; }
     uint64_t getNumberOfVisibleLandmarksLAST() const { return m_uNumberofVisibleLandmarksLAST; }
     uint64_t getNumberOfDetections() const { return m_uNumberOfDetections; }

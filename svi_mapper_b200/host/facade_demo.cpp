@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "CKeyFrameCloud.h"
 #include "CTrackerGT.h"
 
 static std::vector<uint8_t> readRaw(const char* path, size_t n) {
@@ -47,6 +48,27 @@ static int solverMain(char** argv) {
     return 0;
 }
 
+// --cloud <in.cloud> <out.cloud> <poses.txt>: read a key-frame cloud and write it back; print the relative motions of a
+// KITTI pose file the way tracker_gt.cpp feeds them to the tracker (no GPU work)
+static int cloudMain(char** argv) {
+    try {
+        Isometry3d T;
+        const std::vector<CDescriptorVectorPoint3DWORLD> vecCloud(getCloudFromFile(argv[2], T));
+        saveCloudToFile(argv[3], T, vecCloud);
+        std::printf("POINTS %zu\n", vecCloud.size());
+        const std::vector<Isometry3d> vecPoses(readPosesKITTI(argv[4]));
+        for (size_t i = 0; i < vecPoses.size(); ++i) {
+            const Isometry3d M(i ? getTransformationLEFTLASTtoLEFTNOW(vecPoses[i], vecPoses[i - 1]) : Isometry3d());
+            std::printf("MOTION");
+            for (int k = 0; k < 12; ++k) std::printf(" %.17g", M.m[k]);
+            std::printf("\n");
+        }
+    } catch (const std::exception& e) {
+        std::printf("FAILED %s\n", e.what());
+    }
+    return 0;
+}
+
 // measurements.txt: per line  P_WORLDtoLEFT (12) P_WORLDtoRIGHT (12) uL vL uR vR ; the first line is preceded by the initial
 // world position "x y z".  The landmark is created at identity pose with that position, every line is one addMeasurement.
 static int landmarkMain(char** argv) {
@@ -75,6 +97,7 @@ static int landmarkMain(char** argv) {
 int main(int argc, char** argv) {
     if (argc == 5 && std::string(argv[1]) == "--solver") return solverMain(argv);
     if (argc == 3 && std::string(argv[1]) == "--landmark") return landmarkMain(argv);
+    if (argc == 5 && std::string(argv[1]) == "--cloud") return cloudMain(argv);
     if (argc < 10) { std::fprintf(stderr, "usage: see source\n"); return 2; }
     try {
         CParameterBase::loadCameraLEFT(argv[1]);
@@ -125,6 +148,11 @@ int main(int argc, char** argv) {
                          (unsigned long)cTracker.getNumberOfVisibleLandmarksLAST(), (unsigned long)cTracker.getMatcher().getNumberOfLandmarksTotal(),
                          (unsigned long)cTracker.getMatcher().getNumberOfTracksStage1(), (unsigned long)cTracker.getMatcher().getNumberOfTracksStage2_1(),
                          (unsigned long)cTracker.getMatcher().getNumberOfTracksStage3(), (unsigned long)cTracker.getNumberOfDetections());
+        }
+        if (argc > 10) {   // key-frame cloud of what the sequence tracker sees now (CKeyFrame::saveCloudToFile)
+            std::vector<CLandmark*> vecVisible;
+            for (CLandmark* p : cTracker.getMatcher().getLandmarksWINDOW()) if (p->bIsCurrentlyVisible) vecVisible.push_back(p);
+            saveCloudToFile(argv[10], cTracker.getTransformationLEFTtoWORLD(), getCloudForVisibleOptimizedLandmarks(vecVisible));
         }
         // the SV/SVI entry points on a fresh matcher: frame 1 = pose from the stereo measurements of stages 1-2, frame 2 =
         // nothing seen yet and the camera 2 cm away from the detection pose (epipolar branch), frame 3 = nothing seen

@@ -379,7 +379,8 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
         img.tofile(tmp_path / f"{name}.raw")
     out = tmp_path / "out.txt"
     r = subprocess.run([str(exe), str(calib_dir / "vi_sensor_left.txt"), str(calib_dir / "vi_sensor_right.txt"), str(W), str(H),
-                        str(tmp_path / "L0.raw"), str(tmp_path / "R0.raw"), str(tmp_path / "L0.raw"), str(tmp_path / "R0.raw"), str(out)],
+                        str(tmp_path / "L0.raw"), str(tmp_path / "R0.raw"), str(tmp_path / "L0.raw"), str(tmp_path / "R0.raw"), str(out),
+                        str(tmp_path / "seq.cloud")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lines = out.read_text().splitlines()
@@ -417,6 +418,13 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
     assert len(seq) == 6 and seq[0]["DETECTIONS"] == 1 and seq[0]["TOTAL"] == len(ok)
     assert all(s["VISIBLE"] > 100 for s in seq) and seq[-1]["DETECTIONS"] >= 2
     assert sum(s["S1"] + s["S2"] + s["S3"] for s in seq[1:]) > 1000
+    # the key-frame cloud of the last sequence frame (CKeyFrame::saveCloudToFile format): visible optimal landmarks with
+    # their whole LEFT descriptor history, under the pose the tracker accumulated (5 steps of 1 cm along x)
+    from svi_mapper_b200 import formats
+    T_l2w, cloud = formats.read_cloud(tmp_path / "seq.cloud")
+    np.testing.assert_allclose(T_l2w[:3, 3], [-0.05, 0.0, 0.0], atol=1e-12)
+    assert 0 < len(cloud) <= seq[-1]["VISIBLE"]
+    assert all(len(p["descriptors"]) >= 1 and p["uv_l"][1] == p["uv_r"][1] and p["uv_l"][0] > p["uv_r"][0] and p["xyz_camera"][2] > 0 for p in cloud)
     # SV/SVI entry points: getPoseStereoPosit (stages 1|2 + CSolverStereoPosit), then trackEpipolar's two branches
     from svi_mapper_b200 import StereoFrontend as FE
     xyz, dl, dr = ref["xyz"][ok], ref["desc_l"][ok].copy(), ref["desc_r"][ok].copy()

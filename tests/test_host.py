@@ -259,3 +259,44 @@ def test_landmark_optimize_cpp_matches_oracle(calib_dir, tmp_path):
     assert good["success"] == 1 and good["optimal"] and np.abs(good["xyz"] - truth).max() < 0.25
     assert o.optimize_landmark(x0, measurements(5, 0.3)) ["optimal"] and o.optimize_landmark(x0, measurements(9, 0.3, outlier_every=3))["failed"] == 1
 
+
+
+def test_cloud_and_kitti_pose_formats_roundtrip(tmp_path):
+    """Key-frame .cloud files (src/types/CKeyFrame.cpp:138-270) and KITTI pose lines (tracker_gt.cpp:208-229): the
+    numpy writer, the C++ reader/writer of the host layer and the numpy reader agree byte for byte; truncated files
+    are rejected; the per-frame motions handed to the tracker are inverse(T_i) * T_{i-1}."""
+    import pathlib
+    import subprocess
+    from svi_mapper_b200 import formats
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    rng = np.random.default_rng(11)
+    T = np.eye(4)
+    T[:3, 3] = [1.5, -0.25, 7.0]
+    pts = [dict(xyz_world=rng.normal(size=3), xyz_camera=np.abs(rng.normal(size=3)) + 1, uv_l=np.array([100.0 + k, 50.0]),
+                uv_r=np.array([90.0 + k, 50.0]), descriptors=rng.integers(0, 256, size=(k % 4, 32), dtype=np.uint8)) for k in range(7)]
+    a, b, poses_file = tmp_path / "a.cloud", tmp_path / "b.cloud", tmp_path / "poses.txt"
+    formats.write_cloud(a, T, pts)
+    assert a.stat().st_size == 128 + 8 + sum(80 + 8 + 32 * len(p["descriptors"]) for p in pts)
+    poses = np.tile(np.eye(4), (4, 1, 1))
+    for i in range(4):
+        c, s = np.cos(0.05 * i), np.sin(0.05 * i)
+        poses[i, :3, :3] = [[c, 0, s], [0, 1, 0], [-s, 0, c]]
+        poses[i, :3, 3] = [0.1 * i, 0.0, 0.8 * i]
+    poses_file.write_text("".join(" ".join(repr(float(v)) for v in P[:3].ravel()) + "\n" for P in poses))
+    r = subprocess.run([str(exe), "--cloud", str(a), str(b), str(poses_file)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.splitlines()[0] == "POINTS 7", r.stdout + r.stderr
+    assert a.read_bytes() == b.read_bytes()
+    T2, pts2 = formats.read_cloud(b)
+    np.testing.assert_array_equal(T2, T)
+    for p, q in zip(pts, pts2):
+        for key in ("xyz_world", "xyz_camera", "uv_l", "uv_r", "descriptors"):
+            np.testing.assert_array_equal(np.asarray(p[key]), q[key])
+    motions = np.array([[float(v) for v in l.split()[1:]] for l in r.stdout.splitlines() if l.startswith("MOTION")]).reshape(-1, 3, 4)
+    np.testing.assert_array_equal(formats.read_kitti_poses(poses_file), poses)
+    np.testing.assert_allclose(motions, formats.relative_motions(poses)[:, :3], rtol=0, atol=1e-15)
+    # truncated input
+    (tmp_path / "t.cloud").write_bytes(a.read_bytes()[:-5])
+    with pytest.raises(ValueError):
+        formats.read_cloud(tmp_path / "t.cloud")
+    r = subprocess.run([str(exe), "--cloud", str(tmp_path / "t.cloud"), str(b), str(poses_file)], capture_output=True, text=True)
+    assert r.stdout.startswith("FAILED truncated cloud file")
