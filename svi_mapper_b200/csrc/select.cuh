@@ -9,6 +9,11 @@
 // minDistance, i is REJECTED once some member of hp(i) is ACCEPTED and ACCEPTED once all of
 // hp(i) are REJECTED; iterate to the fixed point.  Decisions are monotone, so reading a
 // neighbour's state while another thread updates it is benign.
+//
+// Priority is the 64-bit key itself, so the peeling needs no sorted input: on the shared-memory path the
+// candidates are first counting-sorted by grid cell (so the 3x3 cell neighbourhood of a candidate is three
+// contiguous runs of keys, no pointer chasing), peeled, and only the ACCEPTED corners (typically under half
+// of the candidates) are compacted and sorted: the bitonic network shrinks with them.
 #pragma once
 #include "common.cuh"
 
@@ -26,13 +31,62 @@ struct SelectParams {
     int cell;            // grid cell edge >= ceil(minDistance)
     int gw, gh;          // grid size
     double min_dist_sq;  // minDistance^2 (cv compares dx*dx+dy*dy < minDistance*minDistance)
+    int min_dist_sq_ceil; // ceil(minDistance^2): for integer d2, d2 < minDistance^2  <=>  d2 < this
+    uint32_t cell_magic; // ceil(2^24 / cell) when cell < 256 (exact x / cell for x < 65536 by one multiply-high), else 0
     int filter;          // 0 when minDistance < 1 (cv skips the distance filter)
     int cap_is_error;    // FAST mode: OpenCV returns every corner, so exceeding max_corners must be reported
 };
 
+__device__ __forceinline__ int cell_of(int v, const SelectParams& sp) {
+    return sp.cell_magic ? (int)__umulhi((uint32_t)v << 8, sp.cell_magic) : v / sp.cell;
+}
+
 __device__ __forceinline__ void key_xy(unsigned long long k, int& x, int& y) {
     x = (int)(k & 0xFFFFu);
     y = (int)((k >> 16) & 0xFFFFu);
+}
+
+// In-place bitonic sort, descending, of n_pad (power of two) keys by the whole CTA.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n_pad, int tid) {
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (n_pad >> 1); t += SEL_THREADS) {
+                int i = 2 * t - (t & (j - 1));
+                int l = i + j;
+                unsigned long long a = keys[i], b = keys[l];
+                bool desc = ((i & k) == 0);
+                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Exclusive scan over the CTA of a packed pair of 32-bit counters; *total receives the CTA sum.
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* wsum,
+                                                                   unsigned long long* total, int tid) {
+    unsigned long long incl = v;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    __syncthreads();   // wsum may still be read from an earlier scan
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        wsum[lane] = wi - w;  // exclusive
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return wsum[wid] + incl - v;
 }
 
 // kSmem: keys/lists in shared memory (n <= SEL_SMEM_KEYS, cells <= SEL_SMEM_CELLS); otherwise
@@ -47,7 +101,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                       const RoiItem* __restrict__ rois) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
-    __shared__ uint32_t block_total;
+    __shared__ unsigned long long scan_total;
     const int f = blockIdx.x, tid = threadIdx.x;
     if (rois) {   // window mode: the bucket grid and the border filter follow the item's rectangle
         sp.W = rois[f].rw;
@@ -69,7 +123,8 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     while (n_pad < n) n_pad <<= 1;
     const int ncells = sp.gw * sp.gh;
 
-    // shared layout: keys[16384] u64 | next16[16384] u16 | state[16384] u8 | head[8192] u32
+    // shared layout: keys[16384] u64 | next16[16384] u16 (cell-sorted path: cell_start u16) | state[16384] u8 |
+    //                head[8192] u32 (cell-sorted path: per-cell counters / cursors)
     unsigned long long* gk = cand + (size_t)f * sp.cand_cap;
     unsigned long long* keys = kSmem ? reinterpret_cast<unsigned long long*>(sel_smem) : gk;
     uint16_t* next16 = reinterpret_cast<uint16_t*>(sel_smem + sizeof(unsigned long long) * SEL_SMEM_KEYS);
@@ -77,36 +132,101 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     uint32_t* head = kSmem ? reinterpret_cast<uint32_t*>(sel_smem + 11 * SEL_SMEM_KEYS)
                            : g_head + (size_t)f * ncells;
     uint32_t* next = kSmem ? nullptr : g_next + (size_t)f * sp.cand_cap;
-    if (kSmem) {
+    const bool peel_first = kSmem && sp.filter;
+    if (peel_first) {
+        // keys are filled by the counting sort below
+    } else if (kSmem) {
         for (int i = tid; i < n_pad; i += SEL_THREADS) keys[i] = (i < n) ? gk[i] : 0ull;
     } else {
         for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
     }
     __syncthreads();
 
-    // ---- bitonic sort, descending
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (n_pad >> 1); t += SEL_THREADS) {
-                int i = 2 * t - (t & (j - 1));
-                int l = i + j;
-                unsigned long long a = keys[i], b = keys[l];
-                bool desc = ((i & k) == 0);
-                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
+    // ---- sort everything up front only where the peeled set cannot be compacted in registers (global path) or
+    //      where nothing is peeled (no distance filter: every candidate is a corner)
+    if (!peel_first) bitonic_sort_desc(keys, n_pad, tid);
+    if (peel_first) {
+        // ---- counting sort of the candidates by grid cell, straight from the global list into `keys`
+        uint16_t* cell_start = next16;            // ncells + 1 <= 8193 entries
+        uint32_t* cursor = head;
+        for (int c = tid; c < ncells; c += SEL_THREADS) cursor[c] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += SEL_THREADS) {
+            int x, y;
+            key_xy(gk[i], x, y);
+            atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
+        }
+        __syncthreads();
+        {
+            const int cper = (ncells + SEL_THREADS - 1) / SEL_THREADS, c0 = tid * cper, c1 = min(c0 + cper, ncells);
+            uint32_t sum = 0;
+            for (int c = c0; c < c1; ++c) sum += cursor[c];
+            uint32_t run = (uint32_t)block_exclusive_scan((unsigned long long)sum, wsum, &scan_total, tid);
+            for (int c = c0; c < c1; ++c) {
+                const uint32_t cnt = cursor[c];
+                cell_start[c] = (uint16_t)run;
+                cursor[c] = run;
+                run += cnt;
             }
-            __syncthreads();
+            if (tid == 0) cell_start[ncells] = (uint16_t)n;   // n <= 16384
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += SEL_THREADS) {
+            const unsigned long long k = gk[i];
+            int x, y;
+            key_xy(k, x, y);
+            const uint32_t pos = atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
+            keys[pos] = k;
+            state[pos] = 0;
+        }
+        __syncthreads();
+        // ---- peel to the fixed point; neighbours = three contiguous key runs
+        for (;;) {
+            int changed = 0;
+            for (int i = tid; i < n; i += SEL_THREADS) {
+                if (state[i] != 0) continue;
+                int x, y;
+                const unsigned long long ki = keys[i];
+                key_xy(ki, x, y);
+                const int cx = cell_of(x, sp), cy = cell_of(y, sp);
+                const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, sp.gw - 1);
+                bool any_acc = false, any_und = false;
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1) && !any_acc; ++yy) {
+                    const int j1 = cell_start[yy * sp.gw + x_hi + 1];
+                    for (int j = cell_start[yy * sp.gw + x_lo]; j < j1; ++j) {
+                        const unsigned long long kj = keys[j];
+                        if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
+                            int px, py;
+                            key_xy(kj, px, py);
+                            const int dx = x - px, dy = y - py;
+                            if (dx * dx + dy * dy < sp.min_dist_sq_ceil) {
+                                const uint8_t s = state[j];
+                                any_acc |= (s == 1);
+                                any_und |= (s == 0);
+                            }
+                        }
+                    }
+                }
+                if (any_acc) { state[i] = 2; changed = 1; }
+                else if (!any_und) { state[i] = 1; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
         }
     }
 
-    // ---- grid cell lists (linked through `next`)
-    for (int c = tid; c < ncells; c += SEL_THREADS) head[c] = SEL_NIL;
-    for (int i = tid; i < n; i += SEL_THREADS) state[i] = 0;
-    __syncthreads();
-    if (sp.filter) {
+    // ---- (sorted path) grid cell lists, linked through `next`
+    if (!peel_first) {
+        for (int c = tid; c < ncells; c += SEL_THREADS) head[c] = SEL_NIL;
+        for (int i = tid; i < n; i += SEL_THREADS) state[i] = 0;
+        __syncthreads();
+    }
+    if (peel_first) {
+        // peeled above
+    } else if (sp.filter) {
         for (int i = tid; i < n; i += SEL_THREADS) {
             int x, y;
             key_xy(keys[i], x, y);
-            int c = (y / sp.cell) * sp.gw + (x / sp.cell);
+            int c = cell_of(y, sp) * sp.gw + cell_of(x, sp);
             uint32_t prev = atomicExch(&head[c], (uint32_t)i);
             if (kSmem) next16[i] = (uint16_t)(prev == SEL_NIL ? 0xFFFFu : prev);
             else next[i] = prev;
@@ -118,18 +238,20 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             for (int i = tid; i < n; i += SEL_THREADS) {
                 if (state[i] != 0) continue;
                 int x, y;
-                key_xy(keys[i], x, y);
-                const int cx = x / sp.cell, cy = y / sp.cell;
+                const unsigned long long ki = keys[i];
+                key_xy(ki, x, y);
+                const int cx = cell_of(x, sp), cy = cell_of(y, sp);
                 bool any_acc = false, any_und = false;
                 for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1); ++yy)
                     for (int xx = max(cx - 1, 0); xx <= min(cx + 1, sp.gw - 1); ++xx) {
                         uint32_t j = head[yy * sp.gw + xx];
                         while (j != SEL_NIL) {
-                            if ((int)j < i) {
+                            const unsigned long long kj = keys[j];
+                            if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
                                 int px, py;
-                                key_xy(keys[j], px, py);
+                                key_xy(kj, px, py);
                                 int dx = x - px, dy = y - py;
-                                if ((double)(dx * dx + dy * dy) < sp.min_dist_sq) {
+                                if (dx * dx + dy * dy < sp.min_dist_sq_ceil) {
                                     uint8_t s = state[j];
                                     any_acc |= (s == 1);
                                     any_und |= (s == 0);
@@ -149,6 +271,34 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         __syncthreads();
     }
 
+    if (peel_first) {
+        // ---- compact the accepted corners (each thread parks its <= 16 keys in registers), sort only those
+        constexpr int PER = SEL_SMEM_KEYS / SEL_THREADS;
+        unsigned long long mine[PER];
+        int cnt = 0;
+        const int b0 = tid * PER;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = b0 + k;
+            const bool acc = i < n && state[i] == 1;
+            mine[k] = acc ? keys[i] : 0ull;     // accepted keys are never 0 (the ordered response of a corner is > 0)
+            cnt += acc;
+        }
+        unsigned long long tot = 0;
+        int rank = (int)block_exclusive_scan((unsigned long long)cnt, wsum, &scan_total, tid);   // ends with a barrier: all reads done
+        tot = scan_total;
+        n = (int)tot;
+        n_pad = 1;
+        while (n_pad < n) n_pad <<= 1;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+            if (mine[k] != 0ull) keys[rank++] = mine[k];
+        for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
+        for (int i = tid; i < n; i += SEL_THREADS) state[i] = 1;
+        __syncthreads();
+        bitonic_sort_desc(keys, n_pad, tid);
+    }
+
     // ---- ranks among accepted corners and among those passing BRIEF's border filter
     const int per = (n + SEL_THREADS - 1) / SEL_THREADS;
     const int i0 = tid * per, i1 = min(i0 + per, n);
@@ -162,30 +312,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         }
     }
     // block exclusive scan of (acc_cnt, kp_cnt) packed as 2 x 32 bit
-    unsigned long long v = ((unsigned long long)kp_cnt << 32) | acc_cnt, incl = v;
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned long long w = wsum[lane], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-            if (lane >= o) wi += u;
-        }
-        wsum[lane] = wi - w;  // exclusive
-        if (lane == 31) {
-            uint32_t tot_acc = (uint32_t)(wi & 0xFFFFFFFFu);
-            block_total = tot_acc;
-        }
-    }
-    __syncthreads();
-    unsigned long long excl = wsum[wid] + incl - v;
+    const unsigned long long excl = block_exclusive_scan(((unsigned long long)kp_cnt << 32) | acc_cnt, wsum, &scan_total, tid);
     uint32_t acc_rank = (uint32_t)(excl & 0xFFFFFFFFu), kp_rank = (uint32_t)(excl >> 32);
     ushort2* det = det_xy + (size_t)f * sp.max_corners;
     ushort2* kp = kp_xy + (size_t)f * sp.max_corners;
@@ -206,7 +333,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     // (or the last accepted one): the thread that writes the last detected corner publishes it.
     {
         uint32_t a0 = (uint32_t)(excl & 0xFFFFFFFFu);
-        uint32_t total = block_total;
+        uint32_t total = (uint32_t)(scan_total & 0xFFFFFFFFu);
         uint32_t limit = min(total, (uint32_t)sp.max_corners);
         if (limit == 0) {
             if (tid == 0) { n_detected[f] = 0; n_keypoints[f] = 0; }

@@ -446,6 +446,7 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
     gr.resp_pitch = r.pitch;
     SelectParams sp = ctx->sel;
     sp.cell = std::max(1, (int)std::ceil(ctx->p.min_distance));
+    sp.cell_magic = sp.cell < 256 ? (uint32_t)(((1u << 24) + sp.cell - 1) / sp.cell) : 0u;
     if (!ctx->select_smem) return fail(ctx, SVI_ERR_UNSUPPORTED, "svi_track_landmarks: stage 2 needs max_candidates <= 16384");
     for (int b0 = 0; b0 < total; b0 += batch) {
         const int nb = std::min(batch, total - b0);
@@ -773,6 +774,8 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     int cell = std::max(1, (int)std::ceil(p.min_distance));
     while (((ctx->W + cell - 1) / cell) * ((ctx->H + cell - 1) / cell) > SEL_SMEM_CELLS && cap <= SEL_SMEM_KEYS && cell < 64) ++cell;
     sp.cell = cell;
+    sp.cell_magic = cell < 256 ? (uint32_t)(((1u << 24) + cell - 1) / cell) : 0u;
+    sp.min_dist_sq_ceil = (int)std::min(std::ceil(sp.min_dist_sq), 2.0e9);
     sp.gw = (ctx->W + cell - 1) / cell;
     sp.gh = (ctx->H + cell - 1) / cell;
     ctx->select_smem = (cap <= SEL_SMEM_KEYS) && (sp.gw * sp.gh <= SEL_SMEM_CELLS);
