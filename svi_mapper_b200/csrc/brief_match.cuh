@@ -374,6 +374,28 @@ struct StereoOutDev {
 struct BriefGather {
     uint16_t s1[kDescWords], s2[kDescWords];
 };
+// The element offsets of this lane's 8 test pairs inside a box-sum plane: the same for every key-point of a
+// frame, so a warp computes them once.
+struct BriefOffsets {
+    int o1[kDescWords], o2[kDescWords];
+};
+__device__ __forceinline__ void brief_offsets_init(BriefOffsets& bo, int box_pitch, int lane) {
+#pragma unroll
+    for (int j = 0; j < kDescWords; ++j) {
+        const char4 p = brief_pattern(32 * j + lane);
+        bo.o1[j] = p.x * box_pitch + p.y;
+        bo.o2[j] = p.z * box_pitch + p.w;
+    }
+}
+__device__ __forceinline__ void brief_gather_issue(const uint16_t* __restrict__ box, int box_pitch, int cx, int cy,
+                                                   const BriefOffsets& bo, BriefGather& gth) {
+    const uint16_t* c = box + cy * box_pitch + cx;
+#pragma unroll
+    for (int j = 0; j < kDescWords; ++j) {
+        gth.s1[j] = __ldg(c + bo.o1[j]);
+        gth.s2[j] = __ldg(c + bo.o2[j]);
+    }
+}
 __device__ __forceinline__ void brief_gather_issue(const uint16_t* __restrict__ box, int box_pitch, int cx, int cy,
                                                    int lane, BriefGather& gth) {
 #pragma unroll
@@ -418,11 +440,13 @@ stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
     ushort2 kp_a = (slot0 + 1 < slot_end) ? kps[slot0 + 1] : kp_b;
     SearchPlan plan_b;
     BriefGather gth_b;
+    BriefOffsets bo;
+    brief_offsets_init(bo, g.box_pitch, lane);
     {
         const float x = (float)kp_b.x, y = (float)kp_b.y;
         plan_right(g, tc, fmaxf(0.f, (x - range) - 4.f * size), y - 4.f * size, size, x, lane, plan_b);
         search_prefetch(plan_b, ps, lane);
-        brief_gather_issue(bl, g.box_pitch, kp_b.x, kp_b.y, lane, gth_b);
+        brief_gather_issue(bl, g.box_pitch, kp_b.x, kp_b.y, bo, gth_b);
     }
     for (int slot = slot0; slot < slot_end; ++slot) {
         // ---- this slot enters stage C
@@ -436,7 +460,7 @@ stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
             kp_b = kp_a;
             const float xn = (float)kp_b.x, yn = (float)kp_b.y;
             plan_right(g, tc, fmaxf(0.f, (xn - range) - 4.f * size), yn - 4.f * size, size, xn, lane, plan_b);
-            brief_gather_issue(bl, g.box_pitch, kp_b.x, kp_b.y, lane, gth_b);
+            brief_gather_issue(bl, g.box_pitch, kp_b.x, kp_b.y, bo, gth_b);
             if (slot + 2 < slot_end) kp_a = kps[slot + 2];
         }
         // ---- stage C
