@@ -30,24 +30,39 @@ struct __align__(16) HarrisSmem {
 };
 static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS * H9_P, "h9 alias");
 
-// Stage the (HT_H+8) x (HT_W+8) u8 tile with REFLECT_101 at the image border.  One thread copies a
-// 12-byte run of one row: the row address and the border test are computed once per run.
+// Stage the (HT_H+8) x (HT_W+8) u8 tile with REFLECT_101 at the image border.  A warp copies whole rows: lane l
+// moves bytes l, l+32, l+64 of a row, so every load instruction of the warp touches one or two 128-byte lines
+// (image rows have no alignment: the pitch is the image width) and every shared store is one wavefront.
 __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_t* __restrict__ img,
                                              int pitch, int W, int H, int x0, int y0) {
-    constexpr int RUN = 12, RUNS = U8_W / RUN;   // 72 = 6 x 12
-    static_assert(U8_W % RUN == 0 && U8_ROWS * RUNS <= HT_THREADS, "tile load mapping");
-    const int t = threadIdx.x;
-    if (t < U8_ROWS * RUNS) {
-        const int ly = t / RUNS, lx0 = (t - ly * RUNS) * RUN;
-        const int gy = reflect101(y0 - 4 + ly, H), gx0 = x0 - 4 + lx0;
-        const uint8_t* row = img + (size_t)gy * pitch;
-        uint8_t* dst = &tile[ly][lx0];
-        if (gx0 >= 0 && gx0 + RUN <= W) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gx0 = x0 - 4;
+    const bool inside = gx0 >= 0 && gx0 + U8_W <= W;   // CTA-uniform
+    constexpr int NW = HT_THREADS / 32, RPW = (U8_ROWS + NW - 1) / NW;   // rows per warp
+    // all loads of the thread are issued before the first store: the global round trip is paid once
+    uint8_t v[RPW][3];
 #pragma unroll
-            for (int i = 0; i < RUN; ++i) dst[i] = __ldg(row + gx0 + i);
+    for (int k = 0; k < RPW; ++k) {
+        const int ly = warp + k * NW;
+        const uint8_t* row = img + (size_t)reflect101(y0 - 4 + min(ly, U8_ROWS - 1), H) * pitch;
+        if (inside) {
+            const uint8_t* src = row + gx0 + lane;
+            v[k][0] = __ldg(src);
+            v[k][1] = __ldg(src + 32);
+            v[k][2] = (lane < U8_W - 64) ? __ldg(src + 64) : (uint8_t)0;
         } else {
+            v[k][0] = __ldg(row + reflect101(gx0 + lane, W));
+            v[k][1] = __ldg(row + reflect101(gx0 + lane + 32, W));
+            v[k][2] = (lane < U8_W - 64) ? __ldg(row + reflect101(gx0 + lane + 64, W)) : (uint8_t)0;
+        }
+    }
 #pragma unroll
-            for (int i = 0; i < RUN; ++i) dst[i] = __ldg(row + reflect101(gx0 + i, W));
+    for (int k = 0; k < RPW; ++k) {
+        const int ly = warp + k * NW;
+        if (ly < U8_ROWS) {
+            tile[ly][lane] = v[k][0];
+            tile[ly][lane + 32] = v[k][1];
+            if (lane < U8_W - 64) tile[ly][lane + 64] = v[k][2];
         }
     }
 }
