@@ -76,17 +76,27 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
 __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint16_t (*h9)[H9_P],
                                                uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift,
                                                int box_pitch, int W, int H, int x0, int y0) {
+    // horizontal 9-sums: one work item = 16 outputs of one tile row; its 24 source bytes arrive as six 32-bit loads
+    // (one shared-memory wavefront each instead of one per byte), the 16 sums leave as eight packed stores
     for (int item = threadIdx.x; item < U8_ROWS * (HT_W / 16); item += HT_THREADS) {
-        int r = item % U8_ROWS, c0 = (item / U8_ROWS) * 16;
-        const uint8_t* row = tile[r] + c0;
-        int s = 0;
+        const int r = item % U8_ROWS, c0 = (item / U8_ROWS) * 16;
+        const uint32_t* row32 = reinterpret_cast<const uint32_t*>(tile[r] + c0);   // U8_P and c0 are multiples of 4
+        uint32_t w[6];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) s += row[i];
-        h9[r][c0] = (uint16_t)s;
+        for (int i = 0; i < 6; ++i) w[i] = row32[i];
+        uint32_t b[24];
 #pragma unroll
-        for (int j = 1; j < 16; ++j) {
-            s += (int)row[j + 8] - (int)row[j - 1];
-            h9[r][c0 + j] = (uint16_t)s;
+        for (int i = 0; i < 24; ++i) b[i] = __byte_perm(w[i >> 2], 0u, 0x4440u + (i & 3));
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s += b[i];
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(&h9[r][c0]);                  // H9_P and c0 are even
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            if (j > 0) s += b[j + 8] - b[j - 1];
+            const uint32_t s1 = s + b[j + 9] - b[j];
+            out32[j >> 1] = s | (s1 << 16);
+            s = s1;
         }
     }
     __syncthreads();
@@ -130,8 +140,8 @@ __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint
 // on the per-query entry points).
 __global__ void __launch_bounds__(HT_THREADS)
 boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift) {
-    __shared__ uint8_t tile[U8_ROWS][U8_P];
-    __shared__ uint16_t h9[U8_ROWS][H9_P];
+    __shared__ __align__(16) uint8_t tile[U8_ROWS][U8_P];
+    __shared__ __align__(16) uint16_t h9[U8_ROWS][H9_P];
     const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
     load_tile_u8(tile, img + (size_t)f * g.img_stride, g.img_pitch, g.W, g.H, x0, y0);
     __syncthreads();
@@ -432,7 +442,7 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t (*tile)[U8_P], in
 __global__ void __launch_bounds__(HT_THREADS)
 fast_candidates_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g, int threshold, int nonmax,
                        unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
-    __shared__ uint8_t tile[U8_ROWS][U8_P];
+    __shared__ __align__(16) uint8_t tile[U8_ROWS][U8_P];
     __shared__ uint16_t score[HT_H + 2][HT_W + 2];      // bit 8 = corner, low byte = score stored as uchar like OpenCV
     __shared__ unsigned long long s_keys[512];
     __shared__ int s_count, s_base;
