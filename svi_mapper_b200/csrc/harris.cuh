@@ -21,6 +21,7 @@ constexpr int COV_P = 73;            // odd pitches: row-per-lane accesses are b
 constexpr int HS_P = 65;
 constexpr int COV_SEG_ROWS = 13;     // 38 rows = 3 segments for the sliding Sobel
 constexpr int HS_SEG = 16;           // horizontal box sums: 16 outputs per work item
+static_assert(COV_ROWS > 32 && COV_ROWS <= 64, "row mapping of the horizontal pass");
 
 struct __align__(16) HarrisSmem {
     double hs[3][COV_ROWS][HS_P];     // horizontal 7-sums, fp64
@@ -246,7 +247,12 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
     }
     // ---- horizontal 7-sums in fp64: one work item = (plane, 16-output segment, row)
     for (int item = tid; item < 3 * (HT_W / HS_SEG) * COV_ROWS; item += HT_THREADS) {
-        const int r = item % COV_ROWS, sgm = (item / COV_ROWS) % (HT_W / HS_SEG), p = item / (COV_ROWS * (HT_W / HS_SEG));
+        // a warp takes 32 consecutive rows of ONE (plane, segment): the row pitches are odd, so its loads and its 64-bit
+        // stores are free of bank conflicts; the rows past 32 of all (plane, segment) pairs follow as a tail
+        constexpr int kCombos = 3 * (HT_W / HS_SEG), kMain = kCombos * 32;
+        const int combo = item < kMain ? item / 32 : (item - kMain) / (COV_ROWS - 32);
+        const int r = item < kMain ? item % 32 : 32 + (item - kMain) % (COV_ROWS - 32);
+        const int sgm = combo % (HT_W / HS_SEG), p = combo / (HT_W / HS_SEG);
         const float* src = &sm.cov[p][r][sgm * HS_SEG];
         double v[HS_SEG + 6];
 #pragma unroll
@@ -268,21 +274,26 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
     {
         const int x = tid % HT_W, oy0 = (tid / HT_W) * 8;
         const int gx = x0 + x;
-        double sa = sm.hs[0][oy0][x], sb = sm.hs[1][oy0][x], sc = sm.hs[2][oy0][x];
+        // the seven rows of the first window stay in registers: they are exactly the rows that leave the window
+        // while it slides over this thread's eight outputs
+        double ra[7], rb[7], rc[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { ra[i] = sm.hs[0][oy0 + i][x]; rb[i] = sm.hs[1][oy0 + i][x]; rc[i] = sm.hs[2][oy0 + i][x]; }
+        double sa = ra[0], sb = rb[0], sc = rc[0];
 #pragma unroll
         for (int i = 1; i < 7; ++i) {
-            sa = __dadd_rn(sa, sm.hs[0][oy0 + i][x]);
-            sb = __dadd_rn(sb, sm.hs[1][oy0 + i][x]);
-            sc = __dadd_rn(sc, sm.hs[2][oy0 + i][x]);
+            sa = __dadd_rn(sa, ra[i]);
+            sb = __dadd_rn(sb, rb[i]);
+            sc = __dadd_rn(sc, rc[i]);
         }
         float* rrow = resp + ((size_t)f * out_rows) * g.resp_pitch;
         const uint8_t* mrow = mask ? mask + (size_t)f * g.img_stride : nullptr;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (k > 0) {
-                sa = __dadd_rn(sa, __dsub_rn(sm.hs[0][oy0 + k + 6][x], sm.hs[0][oy0 + k - 1][x]));
-                sb = __dadd_rn(sb, __dsub_rn(sm.hs[1][oy0 + k + 6][x], sm.hs[1][oy0 + k - 1][x]));
-                sc = __dadd_rn(sc, __dsub_rn(sm.hs[2][oy0 + k + 6][x], sm.hs[2][oy0 + k - 1][x]));
+                sa = __dadd_rn(sa, __dsub_rn(sm.hs[0][oy0 + k + 6][x], ra[k - 1]));
+                sb = __dadd_rn(sb, __dsub_rn(sm.hs[1][oy0 + k + 6][x], rb[k - 1]));
+                sc = __dadd_rn(sc, __dsub_rn(sm.hs[2][oy0 + k + 6][x], rc[k - 1]));
             }
             const int gy = y0 + oy0 + k;
             if (gx < W && gy < H) {
