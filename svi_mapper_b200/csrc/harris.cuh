@@ -332,10 +332,11 @@ __device__ __forceinline__ float gftt_threshold(uint32_t ordered_max, double qua
 // K3: threshold(TOZERO) + 3x3 dilate equality + mask + 1-px image border -> candidate keys.
 // key = ordered(R) << 32 | y << 16 | x ; descending key order == cv's greaterThanPtr order
 // (value desc, then larger address first).
-// One thread owns a column of NMS_ROWS pixels: it issues all 3 x (NMS_ROWS+2) response loads up front
-// (coalesced across the warp, neighbours hit L1), reduces each row to its 3-wide maximum once and
-// reuses it for the three output rows it touches.  No shared memory, no barriers.
-constexpr int NMS_TW = 256, NMS_ROWS = 8;
+// One thread owns a column of NMS_ROWS pixels and loads only that column (NMS_ROWS + 2 values, coalesced across
+// the warp): the vertical 3-maxima are formed in registers, the horizontal ones come from the two neighbouring
+// lanes by shuffle.  Lanes 0 and 31 of every warp are halo columns that only feed their neighbours, so a warp
+// emits 30 columns and a CTA NMS_COLS = 240.  No shared memory and no barriers before the append.
+constexpr int NMS_TW = 256, NMS_ROWS = 8, NMS_COLS = 30 * (NMS_TW / 32);
 __global__ void __launch_bounds__(NMS_TW)
 nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict__ mask, FrameGeom g,
                       double quality, const uint32_t* __restrict__ frame_max,
@@ -344,38 +345,37 @@ nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict_
     // 3x3 NMS leaves at most one candidate per 2x2 block (ties aside); the list is sized for any outcome
     __shared__ unsigned long long s_keys[NMS_TW * NMS_ROWS];
     __shared__ int s_count, s_base;
-    const int f = blockIdx.z, gx = blockIdx.x * NMS_TW + threadIdx.x, y0 = blockIdx.y * NMS_ROWS;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.z, gx = blockIdx.x * NMS_COLS + warp * 30 + lane - 1, y0 = blockIdx.y * NMS_ROWS;
     if (threadIdx.x == 0) s_count = 0;
     const int W = rois ? rois[f].rw : g.W, H = rois ? rois[f].rh : g.H;   // block-uniform
     const float thr = gftt_threshold(frame_max[f], quality);
     const float* R = resp + (size_t)f * in_rows * g.resp_pitch;
-    float centre[NMS_ROWS + 2], rowmax[NMS_ROWS + 2];
-    const bool xin = gx < W, xl = xin && gx > 0, xr = gx + 1 < W;
     // out-of-image neighbours are ignored by dilate: -inf; in-image values go through THRESH_TOZERO
-    const float* col = R + gx;
+    const bool xin = gx >= 0 && gx < W;
+    const float* col = R + (size_t)max(y0 - 1, 0) * g.resp_pitch + (xin ? gx : 0);
+    float t[NMS_ROWS + 2];
 #pragma unroll
     for (int i = 0; i < NMS_ROWS + 2; ++i) {
         const int gy = y0 - 1 + i;
-        const bool yin = gy >= 0 && gy < H;
-        const float* row = col + (size_t)gy * g.resp_pitch;
-        float a = -INFINITY, b = -INFINITY, c = -INFINITY;
-        if (yin && xl) { a = row[-1]; a = (a > thr) ? a : 0.f; }
-        if (yin && xin) { b = row[0]; b = (b > thr) ? b : 0.f; }
-        if (yin && xr) { c = row[1]; c = (c > thr) ? c : 0.f; }
-        centre[i] = b;
-        rowmax[i] = fmaxf(fmaxf(a, b), c);
+        float v = -INFINITY;
+        if (xin && gy >= 0 && gy < H) {
+            v = col[(size_t)(gy - max(y0 - 1, 0)) * g.resp_pitch];
+            v = (v > thr) ? v : 0.f;
+        }
+        t[i] = v;
     }
-    // candidate rows of this thread as a bit mask
     unsigned mine = 0u;
 #pragma unroll
     for (int k = 0; k < NMS_ROWS; ++k) {
+        const float c3 = fmaxf(fmaxf(t[k], t[k + 1]), t[k + 2]);
+        const float l3 = __shfl_up_sync(0xFFFFFFFFu, c3, 1), r3 = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
+        const float m = fmaxf(fmaxf(l3, c3), r3);
+        const float v = t[k + 1];
         const int gy = y0 + k;
-        const float v = centre[k + 1];
-        const float m = fmaxf(fmaxf(rowmax[k], rowmax[k + 1]), rowmax[k + 2]);
         if (v != 0.f && v == m && gy >= 1 && gy < H - 1) mine |= 1u << k;
     }
-    if (!(gx >= 1 && gx < W - 1)) mine = 0u;
+    if (lane == 0 || lane == 31 || !(gx >= 1 && gx < W - 1)) mine = 0u;
     if (mine && mask) {
 #pragma unroll
         for (int k = 0; k < NMS_ROWS; ++k)
@@ -398,7 +398,7 @@ nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict_
         while (mine) {
             const int k = __ffs(mine) - 1;
             mine &= mine - 1u;
-            s_keys[base++] = ((unsigned long long)float_to_ordered(centre[k + 1]) << 32) | ((unsigned)(y0 + k) << 16) | (unsigned)gx;
+            s_keys[base++] = ((unsigned long long)float_to_ordered(t[k + 1]) << 32) | ((unsigned)(y0 + k) << 16) | (unsigned)gx;
         }
     }
     __syncthreads();

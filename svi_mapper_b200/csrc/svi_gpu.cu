@@ -220,7 +220,7 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
     if (!fast) {
-        const dim3 ngrid((g.W + NMS_TW - 1) / NMS_TW, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
+        const dim3 ngrid((g.W + NMS_COLS - 1) / NMS_COLS, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
         nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
                                                        l.cand, l.cand_count, ctx->cand_cap, nullptr, g.H);
     }
@@ -457,7 +457,7 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
         const dim3 tiles((max_w + HT_W - 1) / HT_W, (max_h + HT_H - 1) / HT_H, nb);
         harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(ctx->trk_img, nullptr, gr, ctx->f1, ctx->f0, ctx->kf, r.resp,
                                                                         nullptr, nullptr, r.max, r.rois, r.rows);
-        const dim3 ngrid((max_w + NMS_TW - 1) / NMS_TW, (max_h + NMS_ROWS - 1) / NMS_ROWS, nb);
+        const dim3 ngrid((max_w + NMS_COLS - 1) / NMS_COLS, (max_h + NMS_ROWS - 1) / NMS_ROWS, nb);
         nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(r.resp, nullptr, gr, ctx->p.quality_level, r.max, r.cand, r.cand_count,
                                                        ctx->cand_cap, r.rois, r.rows);
         select_corners_kernel<true><<<nb, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(r.cand, r.cand_count, sp, nullptr, nullptr, nullptr, r.det,
@@ -1029,7 +1029,7 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         } else {
             harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
                                                                             nullptr, nullptr, l.frame_max, nullptr, g.H);
-            const dim3 ngrid((W + NMS_TW - 1) / NMS_TW, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
+            const dim3 ngrid((W + NMS_COLS - 1) / NMS_COLS, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
             nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
                                                            l.cand_count, ctx->cand_cap, nullptr, g.H);
         }
