@@ -353,17 +353,17 @@ nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict_
     const float* R = resp + (size_t)f * in_rows * g.resp_pitch;
     // out-of-image neighbours are ignored by dilate: -inf; in-image values go through THRESH_TOZERO
     const bool xin = gx >= 0 && gx < W;
-    const float* col = R + (size_t)max(y0 - 1, 0) * g.resp_pitch + (xin ? gx : 0);
+    const float* p = R + (ptrdiff_t)(y0 - 1) * g.resp_pitch + (xin ? gx : 0);   // row y0-1 (never read when it is row -1)
     float t[NMS_ROWS + 2];
 #pragma unroll
     for (int i = 0; i < NMS_ROWS + 2; ++i) {
-        const int gy = y0 - 1 + i;
         float v = -INFINITY;
-        if (xin && gy >= 0 && gy < H) {
-            v = col[(size_t)(gy - max(y0 - 1, 0)) * g.resp_pitch];
+        if (xin && (unsigned)(y0 - 1 + i) < (unsigned)H) {
+            v = *p;
             v = (v > thr) ? v : 0.f;
         }
         t[i] = v;
+        p += g.resp_pitch;
     }
     unsigned mine = 0u;
 #pragma unroll
