@@ -296,6 +296,16 @@ def main():
     e2e_value = world * F * args.steps / float(t_e.item())
     h2d = 2 * F * W * H
     d2h = F * cap * BYTES_PER_KEYPOINT + F * 8
+    # what the host link can do on this box: one plain pinned -> device copy of the LEFT batch, best of 3
+    link_gbs = 0.0
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        barrier()
+        c0.record()
+        dL.copy_(hL, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link_gbs = max(link_gbs, hL.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
 
     # the two entry points must agree with each other on the whole batch
     torch.cuda.synchronize()
@@ -357,7 +367,9 @@ def main():
                        "l2_policy": f"inputs {2 * F * W * H / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
                        "keypoints_per_frame": total_kp / F, "matched_per_frame": total_ok / F,
                        "device_vs_host_entry_equal": same},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_gbs_achieved": h2d * (e2e_value / world / F) / 1e9, "h2d_gbs_plain_copy": link_gbs,
+                    "note": "host link bound when h2d_gbs_achieved is close to h2d_gbs_plain_copy (rank 0's link)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
