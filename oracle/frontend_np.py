@@ -15,7 +15,15 @@ What it restates (all file:line relative to /root/reference):
   * CTriangulator::getPointInLEFT                                src/core/CTriangulator.cpp:326-356
   * CFundamentalMatcher::addNewLandmarks                         src/core/CFundamentalMatcher.cpp:83-193
   * CFundamentalMatcher::getMaskActiveLandmarks                  src/core/CFundamentalMatcher.cpp:2043-2073
-  * CFundamentalMatcher::trackManual stage 1                     src/core/CFundamentalMatcher.cpp:1404-1538
+  * CFundamentalMatcher::trackManual stages 1, 2, 3              src/core/CFundamentalMatcher.cpp:1404-1538, 1545-1785,
+    -> track_stage1(), track_manual(), track_stage3(), track_manual_full()                       1786-1993, 2142-2453
+  * getPoseStereoPosit / trackEpipolar (image part)              src/core/CFundamentalMatcher.cpp:338-757, 760-1332
+    -> track_stages()                       (subsets of the same cascade)
+  * CSolverStereoPosit::getTransformationWORLDtoLEFT             src/optimization/CSolverStereoPosit.cpp:8-170
+    -> solve_stereo_posit()
+  * CLandmark::optimize / _getOptimizedLandmarkSTEREOUV          src/types/CLandmark.cpp:281-296, 447-581
+    -> optimize_landmark()
+  * optional modes that the reference does not have: fast9_16() (== cv2.FastFeatureDetector), match_epipolar()
 
 Pinning status: the reference ships no tests and no golden vectors.
   detect        : pinned against cv2 4.13 (setUseOptimized(False), 1 thread) -- tests/test_oracle_cv2.py
