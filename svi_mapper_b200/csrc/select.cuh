@@ -121,6 +121,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     }
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
+    int n_act = n;   // candidates that take part in the peeling (shared-memory path: the top-priority part)
     const int ncells = sp.gw * sp.gh;
 
     // shared layout: keys[16384] u64 | next16[16384] u16 (cell-sorted path: cell_start u16) | state[16384] u8 |
@@ -149,11 +150,43 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         // ---- counting sort of the candidates by grid cell, straight from the global list into `keys`
         uint16_t* cell_start = next16;            // ncells + 1 <= 8193 entries
         uint32_t* cursor = head;
+        // ---- priority cut.  Whether a candidate is accepted depends only on candidates of HIGHER priority, and the
+        // output stops at max_corners accepted corners: peeling the top-priority part of the list gives the exact
+        // head of the accepted sequence.  A 13-bit bucket of the key (sign, exponent, 4 mantissa bits of the response)
+        // is monotone in priority; take the buckets that hold about 2.6 x max_corners candidates, and fall back to
+        // the whole list in the rare case that they yield fewer than max_corners corners.
+        __shared__ uint32_t s_min_bucket;
+        const int target = (int)min((long long)n, (long long)sp.max_corners * 13 / 5 + 256);
+        if (tid == 0) s_min_bucket = 0u;
+        if (n > target) {
+            constexpr int NB = SEL_SMEM_CELLS;   // 8192 buckets in the cursor area
+            for (int b = tid; b < NB; b += SEL_THREADS) cursor[b] = 0u;
+            __syncthreads();
+            for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&cursor[(uint32_t)(gk[i] >> 51) & (NB - 1)], 1u);
+            __syncthreads();
+            constexpr int BPT = NB / SEL_THREADS;   // thread t owns buckets NB-1-BPT*t ... downwards
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < BPT; ++k) sum += cursor[NB - 1 - (tid * BPT + k)];
+            uint32_t above = (uint32_t)block_exclusive_scan((unsigned long long)sum, wsum, &scan_total, tid);
+#pragma unroll
+            for (int k = 0; k < BPT; ++k) {
+                const int b = NB - 1 - (tid * BPT + k);
+                const uint32_t c = cursor[b];
+                if (above < (uint32_t)target && above + c >= (uint32_t)target) s_min_bucket = (uint32_t)b;
+                above += c;
+            }
+        }
+        __syncthreads();
+        for (;;) {   // at most two attempts: cut list, then (rarely) the whole list
+        const uint32_t min_bucket = s_min_bucket;
         for (int c = tid; c < ncells; c += SEL_THREADS) cursor[c] = 0u;
         __syncthreads();
         for (int i = tid; i < n; i += SEL_THREADS) {
+            const unsigned long long k = gk[i];
+            if (((uint32_t)(k >> 51) & (SEL_SMEM_CELLS - 1)) < min_bucket) continue;
             int x, y;
-            key_xy(gk[i], x, y);
+            key_xy(k, x, y);
             atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
         }
         __syncthreads();
@@ -168,11 +201,13 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                 cursor[c] = run;
                 run += cnt;
             }
-            if (tid == 0) cell_start[ncells] = (uint16_t)n;   // n <= 16384
+            n_act = (int)scan_total;                           // candidates taking part in this attempt
+            if (tid == 0) cell_start[ncells] = (uint16_t)n_act;   // n_act <= 16384
         }
         __syncthreads();
         for (int i = tid; i < n; i += SEL_THREADS) {
             const unsigned long long k = gk[i];
+            if (((uint32_t)(k >> 51) & (SEL_SMEM_CELLS - 1)) < min_bucket) continue;
             int x, y;
             key_xy(k, x, y);
             const uint32_t pos = atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
@@ -183,7 +218,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         // ---- peel to the fixed point; neighbours = three contiguous key runs
         for (;;) {
             int changed = 0;
-            for (int i = tid; i < n; i += SEL_THREADS) {
+            for (int i = tid; i < n_act; i += SEL_THREADS) {
                 if (state[i] != 0) continue;
                 int x, y;
                 const unsigned long long ki = keys[i];
@@ -211,6 +246,14 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                 else if (!any_und) { state[i] = 1; changed = 1; }
             }
             if (!__syncthreads_or(changed)) break;
+        }
+        if (min_bucket == 0u) break;   // the whole list was peeled
+        int acc = 0;
+        for (int i = tid; i < n_act; i += SEL_THREADS) acc += (state[i] == 1);
+        block_exclusive_scan((unsigned long long)acc, wsum, &scan_total, tid);
+        if ((int)scan_total >= sp.max_corners) break;   // enough corners from the cut list: exact
+        if (tid == 0) s_min_bucket = 0u;
+        __syncthreads();
         }
     }
 
@@ -280,7 +323,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int i = b0 + k;
-            const bool acc = i < n && state[i] == 1;
+            const bool acc = i < n_act && state[i] == 1;
             mine[k] = acc ? keys[i] : 0ull;     // accepted keys are never 0 (the ordered response of a corner is > 0)
             cnt += acc;
         }

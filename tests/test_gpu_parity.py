@@ -682,3 +682,20 @@ def test_track_stage_subsets(vi_cams):
         assert seen[1] > 20 and seen[3] > 20 and seen[5] > 40, seen
         with pytest.raises(Exception):
             run(L, R, T, 1.0, 0)
+
+
+@pytest.mark.parametrize("min_distance,max_corners", [(12.0, 500), (15.0, 900), (15.0, 1150), (15.0, 2000), (7.0, 3000), (3.0, 400)])
+def test_detect_priority_cut_and_fallback(kitti_cams, min_distance, max_corners):
+    """The selection kernel peels only the top-priority part of the candidate list (about 2.6 x maxCorners candidates)
+    and falls back to the whole list when that part yields fewer than maxCorners corners.  Large minimum distances
+    make the accepted fraction small, so those settings force the fallback ((15, 2000) ends below maxCorners even on the
+    whole list); (7, 3000) needs every candidate anyway and (3, 400) stays on the cut list.  All must equal cv::goodFeaturesToTrack's sequential greedy result."""
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, _ = stereo_pair(W, H, 1000)
+    mask = o.mask_active_landmarks(W, H, np.stack([np.linspace(40, W - 40, 60), np.linspace(30, H - 30, 60)], 1).astype(np.float32))
+    with StereoFrontend(*kitti_cams, max_corners=max_corners, min_distance=min_distance) as fe:
+        for m in (None, mask):
+            ref = o.gftt(L, max_corners, 0.01, min_distance, m)
+            got = fe.detect(L, m)[0]
+            assert len(ref) > 50
+            np.testing.assert_array_equal(got.astype(np.int32), np.asarray(ref, np.int32).reshape(-1, 2))
