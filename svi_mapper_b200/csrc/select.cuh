@@ -23,6 +23,9 @@ constexpr int SEL_THREADS = 1024;
 constexpr int SEL_SMEM_KEYS = 16384;   // keys that fit the shared-memory fast path
 constexpr int SEL_SMEM_CELLS = 8192;
 constexpr uint32_t SEL_NIL = 0xFFFFFFFFu;
+#ifndef SEL_CUT_TENTHS
+#define SEL_CUT_TENTHS 26   // the priority cut keeps about 2.6 x maxCorners candidates
+#endif
 
 struct SelectParams {
     int W, H;
@@ -156,7 +159,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         // is monotone in priority; take the buckets that hold about 2.6 x max_corners candidates, and fall back to
         // the whole list in the rare case that they yield fewer than max_corners corners.
         __shared__ uint32_t s_min_bucket;
-        const int target = (int)min((long long)n, (long long)sp.max_corners * 13 / 5 + 256);
+        const int target = (int)min((long long)n, (long long)sp.max_corners * SEL_CUT_TENTHS / 10 + 256);
         if (tid == 0) s_min_bucket = 0u;
         if (n > target) {
             constexpr int NB = SEL_SMEM_CELLS;   // 8192 buckets in the cursor area
