@@ -418,18 +418,18 @@ __device__ __forceinline__ void brief_gather_finish(const BriefGather& gth, uint
 //   stage C  tests / arg-min / triangulation of slot i from the shared window; the TMA for slot i+1
 //            is issued as soon as the last lane has finished reading the window
 // so every global round trip overlaps the ~1500 shared-memory/ALU instructions of stage C.
-constexpr int MATCH_KP_PER_WARP = 8;
+constexpr int MATCH_KP_PER_WARP = 8;   // for full batches; small calls spread their key-points over more warps (latency)
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
 stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
                     const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float size, float range,
                     const ushort2* __restrict__ kp_xy, const int* __restrict__ n_kp, int max_corners, StereoOutDev out,
-                    int out_frame0) {
+                    int out_frame0, int kp_per_warp) {
     extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.y, slot0 = (blockIdx.x * MATCH_WARPS + warp) * MATCH_KP_PER_WARP;
+    const int f = blockIdx.y, slot0 = (blockIdx.x * MATCH_WARPS + warp) * kp_per_warp;
     const int n = n_kp[f];
     if (slot0 >= n) return;
-    const int slot_end = min(slot0 + MATCH_KP_PER_WARP, n);
+    const int slot_end = min(slot0 + kp_per_warp, n);
     PatchStage ps;
     patch_stage_init(ps, match_smem, &map_r, &map_rs, f * g.H, warp, lane);
     const ushort2* kps = kp_xy + (size_t)f * max_corners;

@@ -28,6 +28,8 @@ using namespace svi;
 namespace {
 
 constexpr int kMaxLanes = 8;
+constexpr int kSmallFrames = 2;          // calls of up to this many frames go through the pinned bounce buffer
+constexpr size_t kOutBytesPerSlot = 8 + 8 + 24 + 32 + 32 + 4 + 4 + 1;   // uv_l uv_r xyz desc_l desc_r dist idx status
 constexpr int kStages = 5;
 const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "nms_candidates", "select_corners", "stereo_match"};
 
@@ -97,6 +99,10 @@ struct svi_ctx {
     } roi;
     Stage3Item* s3_items = nullptr;
     int s3_capacity = 0;
+    // pinned bounce buffer of the small-call path (one or a few frames per call: the tracker's per-frame use)
+    unsigned char* pin = nullptr;
+    size_t pin_bytes = 0;
+    int n_sm = 148;
     // per-query arena
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
@@ -233,11 +239,15 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
             l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     }
     mark(ctx, l);
-    const int kp_per_cta = MATCH_WARPS * MATCH_KP_PER_WARP;
+    // full batches amortise a warp's set-up over MATCH_KP_PER_WARP key-points; a small call (one pair per frame in a
+    // tracker) would leave most SMs idle that way, so it spreads the key-points until two waves of warps exist
+    const long long slots = (long long)nf * ctx->p.max_corners;
+    const int kp_per_warp = (int)std::max<long long>(1, std::min<long long>(MATCH_KP_PER_WARP, slots / (2LL * ctx->n_sm * 9)));
+    const int kp_per_cta = MATCH_WARPS * kp_per_warp;
     const dim3 mgrid((ctx->p.max_corners + kp_per_cta - 1) / kp_per_cta, nf);
     stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size,
                                                                     ctx->p.search_range_px, l.kp_xy, n_kp,
-                                                                    ctx->p.max_corners, out, out_frame0);
+                                                                    ctx->p.max_corners, out, out_frame0, kp_per_warp);
     mark(ctx, l);
     CK(cudaGetLastError());
     return SVI_SUCCESS;
@@ -686,6 +696,7 @@ void svi_destroy(svi_ctx* ctx) {
     }
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->trk_img) cudaFree(ctx->trk_img);
     if (ctx->s3_items) cudaFree(ctx->s3_items);
     {
@@ -732,6 +743,10 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     ctx->cam_l = *left;
     ctx->cam_r = *right;
     ctx->p = p;
+    {
+        int n_sm = 0;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sm > 0) ctx->n_sm = n_sm;
+    }
     ctx->W = (int)left->width;
     ctx->H = (int)left->height;
     ctx->dev_pitch = ctx->W;  // dense rows: staging copies are 1-D DMA transfers at full PCIe rate
@@ -870,6 +885,10 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(dmalloc(&ctx->trk_img, 2 * HH * ctx->dev_pitch));
     ctx->arena_bytes = (size_t)p.max_queries * 512 + (size_t)p.max_corners * 64 + 3 * HH * ctx->dev_pitch + (1 << 20);
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), ctx->arena_bytes));
+    // room for kSmallFrames frames: three image planes in, every output array out
+    ctx->pin_bytes = (size_t)kSmallFrames * (3 * HH * ctx->dev_pitch + (size_t)p.max_corners * kOutBytesPerSlot + 64);
+    if (ctx->pin_bytes <= (64u << 20)) CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->pin), ctx->pin_bytes));
+    else ctx->pin_bytes = 0;
     *out = ctx;
     return SVI_SUCCESS;
 #undef CK
@@ -930,6 +949,53 @@ int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, s
     const size_t dstride = (size_t)H * ctx->dev_pitch;
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, dstride);
     const bool dense = (frame_stride == pitch * (size_t)H);
+    if (n_frames > 0 && n_frames <= std::min(kSmallFrames, ctx->chunk) && ctx->pin) {
+        // ---- small call (the tracker's one pair per frame).  Pageable host buffers make every cudaMemcpyAsync a
+        // blocking staged copy; here the images are packed into the pinned buffer, every transfer is a real async
+        // DMA on the lane's stream, and the outputs come back as one batch that is scattered with memcpy.
+        Lane& l = ctx->lanes[0];
+        cudaStream_t s = l.stream;
+        const int nf = n_frames;
+        const size_t plane = dstride * nf;
+        unsigned char* pin_in = ctx->pin;
+        unsigned char* pin_out = ctx->pin + 3 * (size_t)kSmallFrames * dstride;
+        const uint8_t* srcs[3] = {left, right, masks};
+        uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
+        for (int k = 0; k < 3; ++k) {
+            if (!srcs[k]) continue;
+            unsigned char* stage = pin_in + k * (size_t)kSmallFrames * dstride;
+            for (int f = 0; f < nf; ++f) {
+                const uint8_t* src = srcs[k] + (size_t)f * frame_stride;
+                if ((int)pitch == ctx->dev_pitch) std::memcpy(stage + f * dstride, src, dstride);
+                else for (int y = 0; y < H; ++y) std::memcpy(stage + f * dstride + (size_t)y * ctx->dev_pitch, src + (size_t)y * pitch, W);
+            }
+            CK(cudaMemcpyAsync(dsts[k], stage, plane, cudaMemcpyHostToDevice, s));
+        }
+        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, masks ? l.mask : nullptr, g, nf, l.out, 0, l.n_kp, l.n_det);
+        if (rc != SVI_SUCCESS) return rc;
+        struct Part { const void* dev; void* host; size_t elem; };   // elem = bytes per key-point slot
+        const Part parts[8] = {{l.out.uv_l, out->uv_left, 8}, {l.out.uv_r, out->uv_right, 8}, {l.out.xyz, out->xyz_left, 24},
+                               {l.out.desc_l, out->desc_left, 32}, {l.out.desc_r, out->desc_right, 32}, {l.out.dist, out->distance, 4},
+                               {l.out.idx, out->match_index, 4}, {l.out.status, out->status, 1}};
+        size_t off = 0;
+        for (const Part& q : parts) {
+            CK(cudaMemcpyAsync(pin_out + off, q.dev, (size_t)nf * MC * q.elem, cudaMemcpyDeviceToHost, s));
+            off += (size_t)kSmallFrames * MC * q.elem;
+        }
+        int* pin_cnt = reinterpret_cast<int*>(pin_out + off);
+        CK(cudaMemcpyAsync(pin_cnt, l.n_kp, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pin_cnt + kSmallFrames, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        off = 0;
+        for (const Part& q : parts) {
+            for (int f = 0; f < nf; ++f)
+                std::memcpy(static_cast<unsigned char*>(q.host) + (size_t)f * cap * q.elem, pin_out + off + (size_t)f * MC * q.elem, (size_t)MC * q.elem);
+            off += (size_t)kSmallFrames * MC * q.elem;
+        }
+        std::memcpy(out->n_keypoints, pin_cnt, sizeof(int) * nf);
+        if (out->n_detected) std::memcpy(out->n_detected, pin_cnt + kSmallFrames, sizeof(int) * nf);
+        return check_overflow(ctx);
+    }
     int chunk_id = 0;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk, ++chunk_id) {
         Lane& l = ctx->lanes[chunk_id % ctx->n_lanes];

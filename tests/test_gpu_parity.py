@@ -699,3 +699,44 @@ def test_detect_priority_cut_and_fallback(kitti_cams, min_distance, max_corners)
             got = fe.detect(L, m)[0]
             assert len(ref) > 50
             np.testing.assert_array_equal(got.astype(np.int32), np.asarray(ref, np.int32).reshape(-1, 2))
+
+
+def test_small_call_path_matches_batch_path(kitti_cams):
+    """Calls of one or two pairs (the tracker's per-frame use) go through a pinned bounce buffer and spread the
+    key-points over more warps; they must give what the chunked batch path gives -- also with masks, with an output
+    capacity above maxCorners and with padded image rows."""
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    pairs = [stereo_pair(W, H, 1000 + i) for i in range(5)]
+    Ls, Rs = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    rng = np.random.default_rng(9)
+    masks = np.stack([o.mask_active_landmarks(W, H, np.stack([rng.uniform(0, W, 150), rng.uniform(0, H, 150)], 1)) for _ in range(5)])
+    with StereoFrontend(*kitti_cams) as fe:
+        big = fe.stereo_frames(Ls, Rs, masks)                       # 5 frames: batch path
+        for f0, n in ((0, 1), (1, 2), (3, 2)):
+            small = fe.stereo_frames(Ls[f0:f0 + n], Rs[f0:f0 + n], masks[f0:f0 + n], capacity=1300)
+            for k in range(n):
+                a, b = small.frame(k), big.frame(f0 + k)
+                assert small.n_detected[k] == big.n_detected[f0 + k]
+                ok = b["status"] == 0
+                for key in a:   # the RIGHT-side fields of a key-point without a match are unspecified
+                    sel = ok if key in ("uv_r", "xyz", "desc_r") else slice(None)
+                    np.testing.assert_array_equal(a[key][sel], b[key][sel])
+        # padded rows (pitch > W) through the one-pair call, raw C-ABI arguments
+        from svi_mapper_b200 import _lib
+        pitch = W + 23
+        padL, padR = np.zeros((H, pitch), np.uint8), np.zeros((H, pitch), np.uint8)
+        padL[:, :W], padR[:, :W] = Ls[0], Rs[0]
+        cap = fe.max_corners
+        o_ = dict(n_kp=np.zeros(1, np.int32), n_det=np.zeros(1, np.int32), uv_l=np.zeros((cap, 2), np.float32), uv_r=np.zeros((cap, 2), np.float32),
+                  xyz=np.zeros((cap, 3)), dl=np.zeros((cap, 32), np.uint8), dr=np.zeros((cap, 32), np.uint8), dist=np.zeros(cap, np.int32),
+                  idx=np.zeros(cap, np.int32), st=np.zeros(cap, np.uint8))
+        r = _lib.StereoResult(cap, *(a.ctypes.data for a in (o_["n_kp"], o_["n_det"], o_["uv_l"], o_["uv_r"], o_["xyz"], o_["dl"], o_["dr"],
+                                                              o_["dist"], o_["idx"], o_["st"])))
+        fe.stereo_frames_raw(padL.ctypes.data, padR.ctypes.data, pitch, pitch * H, 1, r)
+        ref = fe.stereo_frames(Ls[:1], Rs[:1]).frame(0)
+        n = int(o_["n_kp"][0])
+        assert n == len(ref["status"])
+        for key, arr in (("uv_l", o_["uv_l"]), ("uv_r", o_["uv_r"]), ("xyz", o_["xyz"]), ("desc_l", o_["dl"]), ("desc_r", o_["dr"]),
+                         ("dist", o_["dist"]), ("idx", o_["idx"]), ("status", o_["st"])):
+            sel = (ref["status"] == 0) if key in ("uv_r", "xyz", "desc_r") else slice(None)
+            np.testing.assert_array_equal(arr[:n][sel], ref[key][sel])
