@@ -22,6 +22,9 @@ namespace svi {
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_SMEM_KEYS = 16384;   // keys that fit the shared-memory fast path
 constexpr int SEL_SMEM_CELLS = 8192;
+constexpr int SEL_SMALL_THREADS = 256, SEL_SMALL_KEYS = 2048, SEL_SMALL_CELLS = 2048;   // window-mode configuration
+__host__ __device__ constexpr int select_smem_bytes(int keys, int cells) { return 11 * keys + 4 * cells; }
+__host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 constexpr uint32_t SEL_NIL = 0xFFFFFFFFu;
 #ifndef SEL_CUT_TENTHS
 #define SEL_CUT_TENTHS 26   // the priority cut keeps about 2.6 x maxCorners candidates
@@ -50,10 +53,11 @@ __device__ __forceinline__ void key_xy(unsigned long long k, int& x, int& y) {
 }
 
 // In-place bitonic sort, descending, of n_pad (power of two) keys by the whole CTA.
+template <int T>
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n_pad, int tid) {
     for (int k = 2; k <= n_pad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (n_pad >> 1); t += SEL_THREADS) {
+            for (int t = tid; t < (n_pad >> 1); t += T) {
                 int i = 2 * t - (t & (j - 1));
                 int l = i + j;
                 unsigned long long a = keys[i], b = keys[l];
@@ -66,6 +70,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
 }
 
 // Exclusive scan over the CTA of a packed pair of 32-bit counters; *total receives the CTA sum.
+template <int T>
 __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* wsum,
                                                                    unsigned long long* total, int tid) {
     unsigned long long incl = v;
@@ -79,13 +84,13 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        unsigned long long w = wsum[lane], wi = w;
+        unsigned long long w = lane < T / 32 ? wsum[lane] : 0ull, wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, o);
             if (lane >= o) wi += u;
         }
-        wsum[lane] = wi - w;  // exclusive
+        if (lane < T / 32) wsum[lane] = wi - w;  // exclusive
         if (lane == 31) *total = wi;
     }
     __syncthreads();
@@ -94,14 +99,19 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 
 // kSmem: keys/lists in shared memory (n <= SEL_SMEM_KEYS, cells <= SEL_SMEM_CELLS); otherwise
 // they live in the per-frame global scratch (stress-size frames).
-template <bool kSmem>
+// The big configuration (1024 threads, 16384 keys, 8192 cells, 208 KB) owns an SM: right for whole frames.  The
+// tracker's stage 2 runs the detector on thousands of small windows per frame; for those the small configuration
+// (256 threads, 2048 keys, 2048 cells, 30 KB) keeps seven CTAs on an SM.  A window that does not fit the small
+// configuration sets defer[f] and is picked up by a second launch of the big one (run_if).
+template <bool kSmem, int SEL_THREADS = 1024, int SEL_SMEM_KEYS = 16384, int SEL_SMEM_CELLS = 8192>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
                       SelectParams sp, uint32_t* __restrict__ g_head, uint32_t* __restrict__ g_next,
                       uint8_t* __restrict__ g_state, ushort2* __restrict__ det_xy,
                       int* __restrict__ n_detected, ushort2* __restrict__ kp_xy,
                       int* __restrict__ n_keypoints, int* __restrict__ overflow,
-                      const RoiItem* __restrict__ rois) {
+                      const RoiItem* __restrict__ rois, int* __restrict__ defer = nullptr,
+                      const int* __restrict__ run_if = nullptr) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
     __shared__ unsigned long long scan_total;
@@ -112,7 +122,12 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         sp.gw = (sp.W + sp.cell - 1) / sp.cell;
         sp.gh = (sp.H + sp.cell - 1) / sp.cell;
     }
+    if (run_if && !run_if[f]) return;
     int n = cand_count[f];
+    if (defer && (n > SEL_SMEM_KEYS || sp.gw * sp.gh > SEL_SMEM_CELLS)) {   // CTA-uniform
+        if (tid == 0) defer[f] = 1;
+        return;
+    }
     if (n > sp.cand_cap) {
         if (tid == 0) atomicExch(overflow, 1);
         n = sp.cand_cap;
@@ -133,7 +148,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     unsigned long long* keys = kSmem ? reinterpret_cast<unsigned long long*>(sel_smem) : gk;
     uint16_t* next16 = reinterpret_cast<uint16_t*>(sel_smem + sizeof(unsigned long long) * SEL_SMEM_KEYS);
     uint8_t* state = kSmem ? reinterpret_cast<uint8_t*>(next16 + SEL_SMEM_KEYS) : g_state + (size_t)f * sp.cand_cap;
-    uint32_t* head = kSmem ? reinterpret_cast<uint32_t*>(sel_smem + 11 * SEL_SMEM_KEYS)
+    uint32_t* head = kSmem ? reinterpret_cast<uint32_t*>(sel_smem + 11 * SEL_SMEM_KEYS)   // = select_smem_bytes() - 4 * cells
                            : g_head + (size_t)f * ncells;
     uint32_t* next = kSmem ? nullptr : g_next + (size_t)f * sp.cand_cap;
     const bool peel_first = kSmem && sp.filter;
@@ -148,7 +163,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
 
     // ---- sort everything up front only where the peeled set cannot be compacted in registers (global path) or
     //      where nothing is peeled (no distance filter: every candidate is a corner)
-    if (!peel_first) bitonic_sort_desc(keys, n_pad, tid);
+    if (!peel_first) bitonic_sort_desc<SEL_THREADS>(keys, n_pad, tid);
     if (peel_first) {
         // ---- counting sort of the candidates by grid cell, straight from the global list into `keys`
         uint16_t* cell_start = next16;            // ncells + 1 <= 8193 entries
@@ -159,19 +174,20 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         // is monotone in priority; take the buckets that hold about 2.6 x max_corners candidates, and fall back to
         // the whole list in the rare case that they yield fewer than max_corners corners.
         __shared__ uint32_t s_min_bucket;
+        constexpr int kBucketShift = 64 - ilog2(SEL_SMEM_CELLS);   // top bits of the key: sign, exponent, leading mantissa bits
         const int target = (int)min((long long)n, (long long)sp.max_corners * SEL_CUT_TENTHS / 10 + 256);
         if (tid == 0) s_min_bucket = 0u;
         if (n > target) {
-            constexpr int NB = SEL_SMEM_CELLS;   // 8192 buckets in the cursor area
+            constexpr int NB = SEL_SMEM_CELLS;   // one bucket per entry of the cursor area
             for (int b = tid; b < NB; b += SEL_THREADS) cursor[b] = 0u;
             __syncthreads();
-            for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&cursor[(uint32_t)(gk[i] >> 51) & (NB - 1)], 1u);
+            for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&cursor[(uint32_t)(gk[i] >> kBucketShift)], 1u);
             __syncthreads();
             constexpr int BPT = NB / SEL_THREADS;   // thread t owns buckets NB-1-BPT*t ... downwards
             uint32_t sum = 0;
 #pragma unroll
             for (int k = 0; k < BPT; ++k) sum += cursor[NB - 1 - (tid * BPT + k)];
-            uint32_t above = (uint32_t)block_exclusive_scan((unsigned long long)sum, wsum, &scan_total, tid);
+            uint32_t above = (uint32_t)block_exclusive_scan<SEL_THREADS>((unsigned long long)sum, wsum, &scan_total, tid);
 #pragma unroll
             for (int k = 0; k < BPT; ++k) {
                 const int b = NB - 1 - (tid * BPT + k);
@@ -187,7 +203,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         __syncthreads();
         for (int i = tid; i < n; i += SEL_THREADS) {
             const unsigned long long k = gk[i];
-            if (((uint32_t)(k >> 51) & (SEL_SMEM_CELLS - 1)) < min_bucket) continue;
+            if ((uint32_t)(k >> kBucketShift) < min_bucket) continue;
             int x, y;
             key_xy(k, x, y);
             atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
@@ -197,7 +213,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             const int cper = (ncells + SEL_THREADS - 1) / SEL_THREADS, c0 = tid * cper, c1 = min(c0 + cper, ncells);
             uint32_t sum = 0;
             for (int c = c0; c < c1; ++c) sum += cursor[c];
-            uint32_t run = (uint32_t)block_exclusive_scan((unsigned long long)sum, wsum, &scan_total, tid);
+            uint32_t run = (uint32_t)block_exclusive_scan<SEL_THREADS>((unsigned long long)sum, wsum, &scan_total, tid);
             for (int c = c0; c < c1; ++c) {
                 const uint32_t cnt = cursor[c];
                 cell_start[c] = (uint16_t)run;
@@ -210,7 +226,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         __syncthreads();
         for (int i = tid; i < n; i += SEL_THREADS) {
             const unsigned long long k = gk[i];
-            if (((uint32_t)(k >> 51) & (SEL_SMEM_CELLS - 1)) < min_bucket) continue;
+            if ((uint32_t)(k >> kBucketShift) < min_bucket) continue;
             int x, y;
             key_xy(k, x, y);
             const uint32_t pos = atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
@@ -253,7 +269,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         if (min_bucket == 0u) break;   // the whole list was peeled
         int acc = 0;
         for (int i = tid; i < n_act; i += SEL_THREADS) acc += (state[i] == 1);
-        block_exclusive_scan((unsigned long long)acc, wsum, &scan_total, tid);
+        block_exclusive_scan<SEL_THREADS>((unsigned long long)acc, wsum, &scan_total, tid);
         if ((int)scan_total >= sp.max_corners) break;   // enough corners from the cut list: exact
         if (tid == 0) s_min_bucket = 0u;
         __syncthreads();
@@ -331,7 +347,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             cnt += acc;
         }
         unsigned long long tot = 0;
-        int rank = (int)block_exclusive_scan((unsigned long long)cnt, wsum, &scan_total, tid);   // ends with a barrier: all reads done
+        int rank = (int)block_exclusive_scan<SEL_THREADS>((unsigned long long)cnt, wsum, &scan_total, tid);   // ends with a barrier: all reads done
         tot = scan_total;
         n = (int)tot;
         n_pad = 1;
@@ -342,7 +358,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
         for (int i = tid; i < n; i += SEL_THREADS) state[i] = 1;
         __syncthreads();
-        bitonic_sort_desc(keys, n_pad, tid);
+        bitonic_sort_desc<SEL_THREADS>(keys, n_pad, tid);
     }
 
     // ---- ranks among accepted corners and among those passing BRIEF's border filter
@@ -358,7 +374,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         }
     }
     // block exclusive scan of (acc_cnt, kp_cnt) packed as 2 x 32 bit
-    const unsigned long long excl = block_exclusive_scan(((unsigned long long)kp_cnt << 32) | acc_cnt, wsum, &scan_total, tid);
+    const unsigned long long excl = block_exclusive_scan<SEL_THREADS>(((unsigned long long)kp_cnt << 32) | acc_cnt, wsum, &scan_total, tid);
     uint32_t acc_rank = (uint32_t)(excl & 0xFFFFFFFFu), kp_rank = (uint32_t)(excl >> 32);
     ushort2* det = det_xy + (size_t)f * sp.max_corners;
     ushort2* kp = kp_xy + (size_t)f * sp.max_corners;

@@ -96,6 +96,7 @@ struct svi_ctx {
         int* n_kp = nullptr;
         RoiItem* rois = nullptr;
         Stage2Item* s2 = nullptr;
+        int* defer = nullptr;   // windows that do not fit the small selection configuration
     } roi;
     Stage3Item* s3_items = nullptr;
     int s3_capacity = 0;
@@ -368,7 +369,7 @@ inline float host_projection(const double* P, int row, const double* p) {
 int ensure_roi_scratch(svi_ctx* ctx, int items, int rows, int pitch) {
     svi_ctx::RoiScratch& r = ctx->roi;
     if (items <= r.items && rows <= r.rows && pitch <= r.pitch) return SVI_SUCCESS;
-    void* rp[] = {r.resp, r.max, r.cand_count, r.cand, r.det, r.kp, r.n_det, r.n_kp, r.rois, r.s2};
+    void* rp[] = {r.resp, r.max, r.cand_count, r.cand, r.det, r.kp, r.n_det, r.n_kp, r.rois, r.s2, r.defer};
     for (void* q : rp) if (q) cudaFree(q);
     r = svi_ctx::RoiScratch();
     items = std::max(items, 64);
@@ -383,6 +384,7 @@ int ensure_roi_scratch(svi_ctx* ctx, int items, int rows, int pitch) {
     CK(dmalloc(&r.n_kp, (size_t)items));
     CK(dmalloc(&r.rois, (size_t)items));
     CK(dmalloc(&r.s2, (size_t)items));
+    CK(dmalloc(&r.defer, (size_t)items));
     r.items = items; r.rows = rows; r.pitch = pitch;
     return SVI_SUCCESS;
 }
@@ -464,14 +466,20 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
         CK(cudaMemcpyAsync(r.s2, items.data() + b0, sizeof(Stage2Item) * nb, cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(r.max, 0, sizeof(uint32_t) * nb, s));
         CK(cudaMemsetAsync(r.cand_count, 0, sizeof(int) * nb, s));
+        CK(cudaMemsetAsync(r.defer, 0, sizeof(int) * nb, s));
         const dim3 tiles((max_w + HT_W - 1) / HT_W, (max_h + HT_H - 1) / HT_H, nb);
         harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(ctx->trk_img, nullptr, gr, ctx->f1, ctx->f0, ctx->kf, r.resp,
                                                                         nullptr, nullptr, r.max, r.rois, r.rows);
         const dim3 ngrid((max_w + NMS_COLS - 1) / NMS_COLS, (max_h + NMS_ROWS - 1) / NMS_ROWS, nb);
         nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(r.resp, nullptr, gr, ctx->p.quality_level, r.max, r.cand, r.cand_count,
                                                        ctx->cand_cap, r.rois, r.rows);
+        // thousands of small windows: seven small-configuration CTAs per SM; the rare window that does not fit is
+        // deferred to the frame-size configuration (its CTAs return at once for every other window)
+        select_corners_kernel<true, SEL_SMALL_THREADS, SEL_SMALL_KEYS, SEL_SMALL_CELLS>
+            <<<nb, SEL_SMALL_THREADS, select_smem_bytes(SEL_SMALL_KEYS, SEL_SMALL_CELLS), s>>>(
+                r.cand, r.cand_count, sp, nullptr, nullptr, nullptr, r.det, r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, r.defer, nullptr);
         select_corners_kernel<true><<<nb, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(r.cand, r.cand_count, sp, nullptr, nullptr, nullptr, r.det,
-                                                                              r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois);
+                                                                              r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, nullptr, r.defer);
         const int blocks = (nb + MATCH_WARPS - 1) / MATCH_WARPS;
         if (left)
             track_stage2_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage2,
@@ -701,7 +709,7 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->s3_items) cudaFree(ctx->s3_items);
     {
         void* rp[] = {ctx->roi.resp, ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
-                      ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2};
+                      ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2, ctx->roi.defer};
         for (void* q : rp) if (q) cudaFree(q);
     }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
