@@ -103,6 +103,11 @@ struct svi_ctx {
     // pinned bounce buffer of the small-call path (one or a few frames per call: the tracker's per-frame use)
     unsigned char* pin = nullptr;
     size_t pin_bytes = 0;
+    // pinned mirror of the per-query arena: uploads and result downloads of the per-query / tracking entry points bounce
+    // through it, so that pageable caller buffers never turn a transfer into a blocking staged copy
+    unsigned char* pin_arena = nullptr;
+    struct Pending { void* host; const unsigned char* pinned; size_t bytes; };
+    std::vector<Pending> pending;
     int n_sm = 148;
     // per-query arena
     unsigned char* arena = nullptr;
@@ -284,9 +289,17 @@ cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<vo
 // ---- per-query entry points: one image (or pair) staged in lane 0, queries in the arena ----
 namespace {
 int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, uint16_t* d_box_shift,
-              cudaStream_t s) {
+              cudaStream_t s, int pin_plane = 0) {
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
-    CK(cudaMemcpy2DAsync(d_img, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
+    const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
+    if (ctx->pin && pin_plane >= 0 && (size_t)(pin_plane + 1) * plane <= ctx->pin_bytes) {
+        unsigned char* stage = ctx->pin + (size_t)pin_plane * plane;
+        if ((int)pitch == ctx->dev_pitch) std::memcpy(stage, img, plane);
+        else for (int y = 0; y < ctx->H; ++y) std::memcpy(stage + (size_t)y * ctx->dev_pitch, img + (size_t)y * pitch, ctx->W);
+        CK(cudaMemcpyAsync(d_img, stage, plane, cudaMemcpyHostToDevice, s));
+    } else {
+        CK(cudaMemcpy2DAsync(d_img, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
+    }
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_img, g, d_box, d_box_shift);
     CK(cudaGetLastError());
@@ -296,7 +309,31 @@ template <typename T>
 int upload(svi_ctx* ctx, T** d, const T* h, size_t count, cudaStream_t s) {
     *d = static_cast<T*>(arena_alloc(ctx, count * sizeof(T)));
     if (!*d) return fail(ctx, SVI_ERR_CAPACITY, "query arena exhausted: raise svi_params.max_queries");
-    if (h) CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (h && ctx->pin_arena) {
+        unsigned char* mirror = ctx->pin_arena + (reinterpret_cast<unsigned char*>(*d) - ctx->arena);
+        std::memcpy(mirror, h, count * sizeof(T));
+        CK(cudaMemcpyAsync(*d, mirror, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    } else if (h) {
+        CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    return SVI_SUCCESS;
+}
+// Result array that lives in the arena -> caller's buffer: async copy into the pinned mirror now, memcpy after the sync.
+int download(svi_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t s) {
+    const unsigned char* d = static_cast<const unsigned char*>(dev);
+    if (ctx->pin_arena && d >= ctx->arena && d + bytes <= ctx->arena + ctx->arena_bytes) {
+        unsigned char* mirror = ctx->pin_arena + (d - ctx->arena);
+        CK(cudaMemcpyAsync(mirror, dev, bytes, cudaMemcpyDeviceToHost, s));
+        ctx->pending.push_back({host, mirror, bytes});
+    } else {
+        CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    return SVI_SUCCESS;
+}
+int flush_downloads(svi_ctx* ctx, cudaStream_t s) {
+    CK(cudaStreamSynchronize(s));
+    for (const svi_ctx::Pending& q : ctx->pending) std::memcpy(q.host, q.pinned, q.bytes);
+    ctx->pending.clear();
     return SVI_SUCCESS;
 }
 #define UP(d, h, count)                                        \
@@ -319,7 +356,7 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
     CK(cudaSetDevice(ctx->device));
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
-    ctx->arena_used = 0;
+    ctx->arena_used = 0; ctx->pending.clear();
     int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     float* d_range = nullptr; float* d_tl; float* d_uv; uint8_t* d_desc;
@@ -705,6 +742,7 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->pin_arena) cudaFreeHost(ctx->pin_arena);
     if (ctx->trk_img) cudaFree(ctx->trk_img);
     if (ctx->s3_items) cudaFree(ctx->s3_items);
     {
@@ -893,6 +931,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(dmalloc(&ctx->trk_img, 2 * HH * ctx->dev_pitch));
     ctx->arena_bytes = (size_t)p.max_queries * 512 + (size_t)p.max_corners * 64 + 3 * HH * ctx->dev_pitch + (1 << 20);
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), ctx->arena_bytes));
+    if (ctx->arena_bytes <= (64u << 20)) CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->pin_arena), ctx->arena_bytes));
     // room for kSmallFrames frames: three image planes in, every output array out
     ctx->pin_bytes = (size_t)kSmallFrames * (3 * HH * ctx->dev_pitch + (size_t)p.max_corners * kOutBytesPerSlot + 64);
     if (ctx->pin_bytes <= (64u << 20)) CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->pin), ctx->pin_bytes));
@@ -1135,7 +1174,7 @@ int svi_describe(svi_ctx* ctx, const uint8_t* img, size_t pitch, const float* xy
     CK(cudaSetDevice(ctx->device));
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
-    ctx->arena_used = 0;
+    ctx->arena_used = 0; ctx->pending.clear();
     int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     float* d_xy; uint8_t* d_desc; uint8_t* d_kept;
@@ -1160,7 +1199,7 @@ int svi_match_hamming(svi_ctx* ctx, const uint8_t* query32, int n_query, const u
     if (n_query == 0) return SVI_SUCCESS;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->lanes[0].stream;
-    ctx->arena_used = 0;
+    ctx->arena_used = 0; ctx->pending.clear();
     uint8_t* d_q; uint8_t* d_t; int* d_i; int* d_d;
     UP(d_q, query32, (size_t)n_query * 32);
     UP(d_t, n_train > 0 ? train32 : (const uint8_t*)nullptr, (size_t)std::max(n_train, 1) * 32);
@@ -1186,7 +1225,7 @@ int svi_match_epipolar(svi_ctx* ctx, const uint8_t* query32, const float* query_
     if (n_query == 0) return SVI_SUCCESS;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->lanes[0].stream;
-    ctx->arena_used = 0;
+    ctx->arena_used = 0; ctx->pending.clear();
     uint8_t* d_q; uint8_t* d_t; float* d_qxy; float* d_txy; int* d_i; int* d_d; int* d_s;
     UP(d_q, query32, (size_t)n_query * 32);
     UP(d_qxy, query_xy, (size_t)n_query * 2);
@@ -1225,7 +1264,7 @@ int svi_point_in_left(svi_ctx* ctx, int n, const float* uv_left, const float* uv
     if (n == 0) return SVI_SUCCESS;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->lanes[0].stream;
-    ctx->arena_used = 0;
+    ctx->arena_used = 0; ctx->pending.clear();
     float* d_l; float* d_r; double* d_xyz; uint8_t* d_st;
     UP(d_l, uv_left, (size_t)n * 2);
     UP(d_r, uv_right, (size_t)n * 2);
@@ -1264,12 +1303,12 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     CK(cudaSetDevice(ctx->device));
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
-    ctx->arena_used = 0;
+    ctx->arena_used = 0; ctx->pending.clear();
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
     // both images as planes 0 / 1 of one buffer (the window-mode detector indexes them by plane)
     int rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
-    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s);
+    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s, 1);
     if (rc != SVI_SUCCESS) return rc;
     double* d_xyzw; uint8_t* d_dl; uint8_t* d_dr; float* d_disp; float* d_size;
     UP(d_xyzw, lm->xyz_world, (size_t)n * 3);
@@ -1323,12 +1362,13 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         rc = track_stage3_all(ctx, l, g, lm, n, T_world_to_left, motion_scaling, ld, o, out);
         if (rc != SVI_SUCCESS) return rc;
     }
-    CK(cudaMemcpyAsync(out->uv_left, o.uv_l, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out->uv_right, o.uv_r, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out->xyz_left, o.xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out->desc_left, o.desc_l, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out->desc_right, o.desc_r, (size_t)32 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    int rd = download(ctx, out->uv_left, o.uv_l, sizeof(float) * 2 * n, s);
+    if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_right, o.uv_r, sizeof(float) * 2 * n, s);
+    if (rd == SVI_SUCCESS) rd = download(ctx, out->xyz_left, o.xyz, sizeof(double) * 3 * n, s);
+    if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_left, o.desc_l, (size_t)32 * n, s);
+    if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_right, o.desc_r, (size_t)32 * n, s);
+    if (rd == SVI_SUCCESS) rd = flush_downloads(ctx, s);
+    if (rd != SVI_SUCCESS) return rd;
     return check_overflow(ctx);
 }
 
