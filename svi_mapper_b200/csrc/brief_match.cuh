@@ -762,32 +762,23 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
     if (nd > 0) {
         status = SVI_TRK_NO_MATCHES;
         const ushort2* corners = det_xy + (size_t)i * max_corners;
-        for (int k0 = 0; k0 < nd; k0 += 32) {
-            const int k = k0 + lane;
-            bool keep = false;
-            int sx = 0, sy = 0;
-            if (k < nd) {
-                const ushort2 c = corners[k];
-                const float px = (float)c.x + half, py = (float)c.y + half;
-                const int rx = cv_round_f(px), ry = cv_round_f(py), cx = brief_centre(px), cy = brief_centre(py);
-                keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder &&
-                       cx >= kBriefBorder && cx < it.gw - kBriefBorder && cy >= kBriefBorder && cy < it.gh - kBriefBorder;
-                sx = it.gx + cx;
-                sy = it.gy + cy;
-            }
-            uint32_t dist = 0;
-            if (keep) {
-#pragma unroll 4
-                for (int t = 0; t < SVI_BRIEF_NTESTS; ++t) {
-                    const char4 p = brief_pattern(t);
-                    const uint32_t s1 = __ldg(box_this + (sy + p.x) * g.box_pitch + sx + p.y);
-                    const uint32_t s2 = __ldg(box_this + (sy + p.z) * g.box_pitch + sx + p.w);
-                    const uint32_t bit = s1 < s2 ? 1u : 0u;
-                    dist += bit ^ ((last_this[t >> 5] >> (31 - (t & 31))) & 1u);
-                }
-            }
-            const uint32_t key = keep ? ((dist << 16) | (uint32_t)k) : 0xFFFFFFFFu;
-            best = min(best, warp_min_u32(key));   // smaller k wins ties: BFMatcher's first minimum in pool order
+        // lanes = tests: a window holds a few dozen corners at most, so one corner at a time with the 256 tests spread
+        // over the warp (8 rounds of 2 gathers per lane, pattern offsets computed once) beats one corner per lane
+        BriefOffsets bo;
+        brief_offsets_init(bo, g.box_pitch, lane);
+        for (int k = 0; k < nd; ++k) {
+            const ushort2 c = corners[k];
+            const float px = (float)c.x + half, py = (float)c.y + half;
+            const int rx = cv_round_f(px), ry = cv_round_f(py), cx = brief_centre(px), cy = brief_centre(py);
+            const bool keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder &&
+                              cx >= kBriefBorder && cx < it.gw - kBriefBorder && cy >= kBriefBorder && cy < it.gh - kBriefBorder;
+            if (!keep) continue;   // warp-uniform
+            BriefGather gth;
+            brief_gather_issue(box_this, g.box_pitch, it.gx + cx, it.gy + cy, bo, gth);
+            uint32_t w[kDescWords];
+            brief_gather_finish(gth, w);
+            const uint32_t key = ((uint32_t)hamming_words(w, last_this) << 16) | (uint32_t)k;
+            best = min(best, key);   // smaller k wins ties: BFMatcher's first minimum in pool order
         }
     }
     SearchResult r;
