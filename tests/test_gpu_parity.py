@@ -740,3 +740,31 @@ def test_small_call_path_matches_batch_path(kitti_cams):
                          ("dist", o_["dist"]), ("idx", o_["idx"]), ("status", o_["st"])):
             sel = (ref["status"] == 0) if key in ("uv_r", "xyz", "desc_r") else slice(None)
             np.testing.assert_array_equal(arr[:n][sel], ref[key][sel])
+
+
+def test_large_batch_against_c_oracle(kitti_cams):
+    """160 distinct pairs (more than two chunks on every lane pattern), maxCorners 2000: every frame of the batch path equals
+    the C restatement of the reference run on all host threads -- key-points, descriptors, matches, statuses bit for bit."""
+    from oracle import c_oracle as co
+    from svi_mapper_b200.synth import stereo_batch_torch
+    import torch
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    n = 160
+    dL, dR = stereo_batch_torch(n, W, H, seed=7000, device=torch.device("cuda", 0))
+    Ls, Rs = dL.cpu().numpy(), dR.cpu().numpy()
+    cfg = co.make_config(kitti_cams[0], kitti_cams[1], max_corners=2000)
+    ref = co.stereo_frames(cfg, Ls, Rs, n_threads=co.host_threads())
+    with StereoFrontend(*kitti_cams, max_corners=2000) as fe:
+        got = fe.stereo_frames(Ls, Rs)
+    total = 0
+    for f in range(n):
+        r, g_ = co.frame(ref, f), got.frame(f)
+        assert len(r["status"]) == len(g_["status"]) > 1000
+        for k in ("uv_l", "desc_l", "status", "dist", "idx"):
+            np.testing.assert_array_equal(g_[k], r[k], err_msg=f"frame {f} {k}")
+        ok = r["status"] == 0
+        np.testing.assert_array_equal(g_["uv_r"][ok], r["uv_r"][ok])
+        np.testing.assert_array_equal(g_["desc_r"][ok], r["desc_r"][ok])
+        np.testing.assert_array_equal(g_["xyz"][ok], r["xyz"][ok])
+        total += int(ok.sum())
+    assert total > 150 * n
