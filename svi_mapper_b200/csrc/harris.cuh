@@ -37,33 +37,43 @@ static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS
 __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_t* __restrict__ img,
                                              int pitch, int W, int H, int x0, int y0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gx0 = x0 - 4;
-    const bool inside = gx0 >= 0 && gx0 + U8_W <= W;   // CTA-uniform
+    const int gx0 = x0 - 4, gy0 = y0 - 4;
+    const bool inside_x = gx0 >= 0 && gx0 + U8_W <= W;        // CTA-uniform
+    const bool inside_y = gy0 >= 0 && gy0 + U8_ROWS <= H;     // CTA-uniform
     constexpr int NW = HT_THREADS / 32, RPW = (U8_ROWS + NW - 1) / NW;   // rows per warp
-    // all loads of the thread are issued before the first store: the global round trip is paid once
+    // all loads of the thread are issued before the first store: the global round trip is paid once.
+    // 32-bit element offsets inside the frame; the three loads of a row share one address register.
     uint8_t v[RPW][3];
+    if (inside_x) {
+        const uint8_t* col = img + gx0 + lane;
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {
-        const int ly = warp + k * NW;
-        const uint8_t* row = img + (size_t)reflect101(y0 - 4 + min(ly, U8_ROWS - 1), H) * pitch;
-        if (inside) {
-            const uint8_t* src = row + gx0 + lane;
+        for (int k = 0; k < RPW; ++k) {
+            const int ly = min(warp + k * NW, U8_ROWS - 1);
+            const int ry = inside_y ? gy0 + ly : reflect101(gy0 + ly, H);
+            const uint8_t* src = col + ry * pitch;
             v[k][0] = __ldg(src);
             v[k][1] = __ldg(src + 32);
             v[k][2] = (lane < U8_W - 64) ? __ldg(src + 64) : (uint8_t)0;
-        } else {
-            v[k][0] = __ldg(row + reflect101(gx0 + lane, W));
-            v[k][1] = __ldg(row + reflect101(gx0 + lane + 32, W));
-            v[k][2] = (lane < U8_W - 64) ? __ldg(row + reflect101(gx0 + lane + 64, W)) : (uint8_t)0;
+        }
+    } else {
+        const int c0 = reflect101(gx0 + lane, W), c1 = reflect101(gx0 + lane + 32, W), c2 = reflect101(gx0 + lane + 64, W);
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+            const int ly = min(warp + k * NW, U8_ROWS - 1);
+            const uint8_t* row = img + reflect101(gy0 + ly, H) * pitch;
+            v[k][0] = __ldg(row + c0);
+            v[k][1] = __ldg(row + c1);
+            v[k][2] = (lane < U8_W - 64) ? __ldg(row + c2) : (uint8_t)0;
         }
     }
 #pragma unroll
     for (int k = 0; k < RPW; ++k) {
         const int ly = warp + k * NW;
         if (ly < U8_ROWS) {
-            tile[ly][lane] = v[k][0];
-            tile[ly][lane + 32] = v[k][1];
-            if (lane < U8_W - 64) tile[ly][lane + 64] = v[k][2];
+            uint8_t* dst = &tile[ly][lane];
+            dst[0] = v[k][0];
+            dst[32] = v[k][1];
+            if (lane < U8_W - 64) dst[64] = v[k][2];
         }
     }
 }
