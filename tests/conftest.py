@@ -14,6 +14,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_artifacts():
+    """A fresh checkout has no binaries (they are git-ignored): build the library, the C++ facade demo and the C checker
+    once per session (nvcc cross-compiles without a GPU; nothing is rebuilt when the files are up to date)."""
+    from svi_mapper_b200 import build as b
+    if b.needs_build():
+        b.build_library()
+    if not (ROOT / "svi_mapper_b200" / "host" / "facade_demo").exists():
+        b.build_host_demo()
+    from oracle import c_oracle
+    if not (ROOT / "oracle" / "libsvi_oracle.so").exists():
+        c_oracle.build(native=False)
+
+
 @pytest.fixture(scope="session")
 def calib_dir():
     return CALIB
