@@ -17,6 +17,7 @@
 
 #include "CKeyFrameCloud.h"
 #include "CTrackerGT.h"
+#include "CTrackerSV.h"
 
 static std::vector<uint8_t> readRaw(const char* path, size_t n) {
     std::vector<uint8_t> v(n);
@@ -179,6 +180,19 @@ int main(int argc, char** argv) {
         cMatcherSV.trackEpipolar(3, ImageView(L1.data(), W, H), ImageView(R1.data(), W, H), matIdentity, matIdentity, 1.0);
         std::fprintf(out, "EPI 3 S3 %lu S22 %lu VISIBLE %zu\n", (unsigned long)cMatcherSV.getNumberOfTracksStage3(), (unsigned long)cMatcherSV.getNumberOfTracksStage2_2(),
                      cMatcherSV.getNumberOfVisibleLandmarks());
+        // the stereo-only tracker: no ground truth, the pose comes from the stereo measurements.  The scene is static (the
+        // same pair every frame), so the recovered pose has to stay at the origin while landmarks are detected, tracked,
+        // optimised and re-detected.
+        CTrackerSV cTrackerSV(CParameterBase::pCameraSTEREO, pGpu);
+        for (int uFrame = 0; uFrame < 12; ++uFrame) {
+            cTrackerSV.process(ImageView(L0.data(), W, H), ImageView(R0.data(), W, H));
+            const Isometry3d& T = cTrackerSV.getTransformationWORLDtoLEFT();
+            std::fprintf(out, "SV %d VISIBLE %lu TOTAL %lu S1 %lu S2 %lu S3 %lu S22 %lu DETECTIONS %lu POSE %s T %.9g %.9g %.9g\n", uFrame,
+                         (unsigned long)cTrackerSV.getNumberOfVisibleLandmarksLAST(), (unsigned long)cTrackerSV.getMatcher().getNumberOfLandmarksTotal(),
+                         (unsigned long)cTrackerSV.getMatcher().getNumberOfTracksStage1(), (unsigned long)cTrackerSV.getMatcher().getNumberOfTracksStage2_1(),
+                         (unsigned long)cTrackerSV.getMatcher().getNumberOfTracksStage3(), (unsigned long)cTrackerSV.getMatcher().getNumberOfTracksStage2_2(),
+                         (unsigned long)cTrackerSV.getNumberOfDetections(), cTrackerSV.getPoseSource().c_str(), T(0, 3), T(1, 3), T(2, 3));
+        }
         std::fclose(out);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "facade_demo failed: %s\n", e.what());

@@ -418,6 +418,16 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
     assert len(seq) == 6 and seq[0]["DETECTIONS"] == 1 and seq[0]["TOTAL"] == len(ok)
     assert all(s["VISIBLE"] > 100 for s in seq) and seq[-1]["DETECTIONS"] >= 2
     assert sum(s["S1"] + s["S2"] + s["S3"] for s in seq[1:]) > 1000
+    # the stereo-only tracker (CTrackerSV orchestration): frame 0 has no landmarks (pose = prior, detection), from frame 1 on
+    # the pose comes from CSolverStereoPosit over the stage-1/2 measurements; the scene is static, so it stays at the origin
+    sv = [l.split() for l in lines if l.startswith("SV ")]
+    assert len(sv) == 12
+    svd = [dict(zip(r[2:16:2], map(int, r[3:16:2]))) for r in sv]
+    assert svd[0]["DETECTIONS"] == 1 and svd[0]["TOTAL"] == len(ok) and sv[0][17] == "prior"
+    assert all(r[17] == "posit" for r in sv[1:]), [r[17] for r in sv]
+    assert all(d["S1"] > 0.9 * len(ok) for d in svd[1:3]) and all(d["VISIBLE"] > 100 for d in svd)
+    assert all(abs(float(v)) < 1e-6 for r in sv for v in r[19:22])
+    assert svd[-1]["DETECTIONS"] >= 2          # the trigger of CTrackerSV.cpp:468 fires again after three frames
     # the key-frame cloud of the last sequence frame (CKeyFrame::saveCloudToFile format): visible optimal landmarks with
     # their whole LEFT descriptor history, under the pose the tracker accumulated (5 steps of 1 cm along x)
     from svi_mapper_b200 import formats
