@@ -115,7 +115,8 @@ const char* svi_last_error(const svi_ctx* ctx); /* ctx may be NULL: last create 
 int svi_device_count(void);
 
 /* SoA result of the new-landmark path, caller-owned.  Slot (f, i) lives at index
- * f*capacity_per_frame + i; slots i >= n_keypoints[f] are untouched. 113 bytes per key-point. */
+ * f*capacity_per_frame + i; only slots i < n_keypoints[f] carry results -- the content of the slots
+ * behind them (up to max_corners per frame) is unspecified after the call.  113 bytes per key-point. */
 typedef struct svi_stereo_result {
     int32_t capacity_per_frame; /* in: >= params.max_corners */
     int32_t* n_keypoints;       /* [n_frames] corners that survived BRIEF's 28-px border filter */
@@ -147,6 +148,13 @@ int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, s
 int svi_stereo_frames_device(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
                              size_t frame_stride, int n_frames, const uint8_t* masks_or_null,
                              const svi_stereo_result* out, void* cuda_stream);
+
+/* Capacity check for work enqueued by svi_stereo_frames_device (every host-buffer entry point does it
+ * itself before returning): waits for the ctx's streams, then returns SVI_ERR_CAPACITY (and clears the
+ * condition) if any frame since the last check produced more candidates than svi_params.max_candidates
+ * (or, in FAST mode, more corners than max_corners) -- the results of such a frame are zero key-points,
+ * never a silently truncated list.  SVI_SUCCESS otherwise. */
+int svi_check_overflow(svi_ctx* ctx);
 
 /* cv::cornerHarris(img, 7, 3, k) as GFTTDetector runs it (response plane, fp32, W*H). */
 int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* response);

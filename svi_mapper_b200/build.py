@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",          # Harris must round every fp32 op on its own (cv2 parity)
     "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-ffp-contract=off",   # host-side fp64 geometry: same rounding as the kernels, whatever -march is used
 ]
 
 
@@ -59,12 +60,14 @@ def build_library(force: bool = False, verbose: bool = False) -> pathlib.Path:
     return LIB
 
 
-def build_host_demo() -> pathlib.Path:
-    """g++ build of the C++ host facade's demo driver (links libsvi_gpu.so through an $ORIGIN rpath)."""
+def build_host_demo(out: pathlib.Path | None = None, flags=("-O2", "-ffp-contract=off")) -> pathlib.Path:
+    """g++ build of the C++ host facade's demo driver (links libsvi_gpu.so through an rpath).  The documented build
+    line carries -ffp-contract=off; the headers also pin it themselves (pragma), so that the reference's own
+    `-O3 -march=native` (CMakeLists.txt:51) gives the same numbers -- tests build it that way too."""
     host = PKG / "host"
-    exe = host / "facade_demo"
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", str(exe), str(host / "facade_demo.cpp"),
-           "-L" + str(PKG), "-lsvi_gpu", "-Wl,-rpath,$ORIGIN/.."]
+    exe = out or host / "facade_demo"
+    cmd = ["g++", "-std=c++17", *flags, "-Wall", "-Wextra", "-o", str(exe), str(host / "facade_demo.cpp"),
+           "-L" + str(PKG), "-lsvi_gpu", "-Wl,-rpath," + str(PKG)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)

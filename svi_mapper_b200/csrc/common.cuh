@@ -47,6 +47,13 @@ __device__ __host__ __forceinline__ uint32_t ordered_to_float_bits(uint32_t e) {
     return (e & 0x80000000u) ? (e ^ 0x80000000u) : ~e;
 }
 
+// Threshold as cv::goodFeaturesToTrack computes it: minMaxLoc gives a double, threshold()
+// converts (double)max * qualityLevel to float for the 32F image.
+__device__ __forceinline__ float gftt_threshold(uint32_t ordered_max, double quality) {
+    if (ordered_max == 0u) return 0.f;  // empty mask: minMaxLoc leaves maxVal = 0
+    return (float)((double)__uint_as_float(ordered_to_float_bits(ordered_max)) * quality);
+}
+
 // u8 -> float in one ALU instruction: a 32-bit signed convert is I2FP (full rate), while the narrow
 // unsigned forms the compiler would pick for a byte go through the slow I2F path.
 __device__ __forceinline__ float u8_to_float(uint32_t v) {

@@ -1,16 +1,27 @@
 // harris.cuh -- detection front half: Harris response (bit-exact to cv::cornerHarris with
-// optimisations off), 9x9 box-sum images for BRIEF, threshold + 3x3 NMS candidate extraction.
+// optimisations off), 9x9 box-sum images for BRIEF, 3x3 NMS candidate extraction -- one kernel, the
+// response never leaves the SM.
 //
 // Replaces, for cv::GFTTDetector::create(1000, 0.01, 7.0, 7, true)->detect
 // (reference src/core/CFundamentalMatcher.cpp:18,101), the OpenCV calls cornerHarris
 // (Sobel x2, covariance products, 7x7 boxFilter), minMaxLoc, threshold(TOZERO), dilate 3x3 and
 // the candidate collection loop of goodFeaturesToTrack; arithmetic order from SURVEY.md App. A.
+//
+// goodFeaturesToTrack's candidate test "R' != 0 and R' == dilate3x3(R')" with R' = TOZERO(R, thr),
+// thr = float(double(max R) * quality), equals "R > thr and R >= its 8 raw neighbours" (thresholding is
+// monotone), and thr > 0 whenever there is a candidate at all.  A CTA therefore emits the local maxima
+// of its response tile that exceed the threshold of the TILE's own maximum (<= the frame's, so nothing
+// is lost, and the emitted list is deterministic); the exact frame threshold is applied to the keys by
+// select_corners_kernel once the frame maximum is final.  Response tiles overlap by one pixel on each
+// side (stride 62 x 30 for a 64 x 32 tile) so that every candidate sees its 8 neighbours on chip.
 #pragma once
 #include "common.cuh"
 
 namespace svi {
 
 constexpr int HT_W = 64, HT_H = 32, HT_THREADS = 256;
+constexpr int HT_SX = HT_W - 2, HT_SY = HT_H - 2;   // tile stride of the Harris kernel: candidates = tile interior
+constexpr int HT_MAX_KEYS = HT_SX * HT_SY;          // a plateau can make every interior pixel a local maximum
 constexpr int U8_W = HT_W + 8;       // u8 tile: 4-px halo (1 Sobel + 3 box; also the 9x9 box sum)
 constexpr int U8_P = U8_W + 4;       // 19 words per row: row-per-lane walks are bank-conflict free
 constexpr int H9_P = HT_W + 2;       // 33 words per row, same reason
@@ -28,8 +39,11 @@ struct __align__(16) HarrisSmem {
     float cov[3][COV_ROWS][COV_P];    // Dx*Dx, Dx*Dy, Dy*Dy (fp32); reused as the 9-sum rows (u16)
     uint8_t tile[U8_ROWS][U8_P];
     uint32_t red[HT_THREADS / 32];
+    int key_count, key_base;
 };
 static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS * H9_P, "h9 alias");
+static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(float) * HT_H * HT_W, "response tile alias");
+static_assert(sizeof(double) * 3 * COV_ROWS * HS_P >= sizeof(unsigned long long) * HT_MAX_KEYS, "key list alias");
 
 // Stage the (HT_H+8) x (HT_W+8) u8 tile with REFLECT_101 at the image border.  A warp copies whole rows: lane l
 // moves bytes l, l+32, l+64 of a row, so every load instruction of the warp touches one or two 128-byte lines
@@ -84,9 +98,7 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
 // `box_shift` (optional) receives the same plane stored one element to the left,
 // box_shift[y][x] = S(y, x+1): TMA tile loads must start on a 16-byte boundary, so the match
 // kernels fetch their odd-aligned copy of a window from this plane at the same aligned address.
-__device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint16_t (*h9)[H9_P],
-                                               uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift,
-                                               int box_pitch, int W, int H, int x0, int y0) {
+__device__ __forceinline__ void box9_rows(const uint8_t (*tile)[U8_P], uint16_t (*h9)[H9_P]) {
     // horizontal 9-sums: one work item = 16 outputs of one tile row; its 24 source bytes arrive as six 32-bit loads
     // (one shared-memory wavefront each instead of one per byte), the 16 sums leave as eight packed stores
     for (int item = threadIdx.x; item < U8_ROWS * (HT_W / 16); item += HT_THREADS) {
@@ -110,7 +122,10 @@ __device__ __forceinline__ void box9_from_tile(const uint8_t (*tile)[U8_P], uint
             s = s1;
         }
     }
-    __syncthreads();
+}
+// (a __syncthreads() separates the two halves)
+__device__ __forceinline__ void box9_cols(const uint16_t (*h9)[H9_P], uint16_t* __restrict__ box,
+                                          uint16_t* __restrict__ box_shift, int box_pitch, int W, int H, int x0, int y0) {
     // vertical 9-sums, two columns per thread as packed u16 pairs (sums <= 20655, so s + new - old never carries
     // or borrows across the halves): one 32-bit store per plane and row.  thread = (column pair, 8-row group)
     if (threadIdx.x < (HT_W / 2) * (HT_H / 8)) {
@@ -157,27 +172,36 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
     load_tile_u8(tile, img + (size_t)f * g.img_stride, g.img_pitch, g.W, g.H, x0, y0);
     __syncthreads();
     const size_t fo = (size_t)f * g.H * g.box_pitch;
-    box9_from_tile(tile, h9, box + fo, box_shift ? box_shift + fo : nullptr, g.box_pitch, g.W, g.H, x0, y0);
+    box9_rows(tile, h9);
+    __syncthreads();
+    box9_cols(h9, box + fo, box_shift ? box_shift + fo : nullptr, g.box_pitch, g.W, g.H, x0, y0);
 }
 
-// K1: Harris response + per-frame masked maximum + LEFT box-sum image, one 64x32 tile per CTA.
+// K1: Harris response + per-frame masked maximum + 3x3 NMS candidates + LEFT box-sum image; one 64x32 response
+// tile per CTA, tiles HT_SX x HT_SY apart (the tile interior is the CTA's share of the candidates).
 //   Sobel:  r = p[x+1]-p[x-1];  Dx = (r[y-1]+r[y+1])*f1 + r[y]*f0
 //                           q = (p[x-1]*f1 + p[x]*f0) + p[x+1]*f1;  Dy = q[y+1]-q[y-1]
 //   every op rounded to fp32 on its own (explicit _rn intrinsics, never an FMA).
 //   Box 7x7 (A.2): products accumulated in fp64, REFLECT_101 on the PRODUCT planes, one rounding
 //   to fp32.  Harris (A.3): R = (a*c - b*b) - (k*(a+c))*(a+c) in fp32.
+//   Candidates (A.4): R > 0, R > thr(tile max), R >= its 8 neighbours (neighbours outside the image are
+//   ignored, as cv::dilate does), mask != 0, 1-px image border excluded.
+//   key = ordered(R) << 32 | y << 16 | x ; descending key order == cv's greaterThanPtr order
+//   (value desc, then larger address first).
 // With `rois` the z-th CTA layer works on the window rois[z] of image plane rois[z].plane instead of
 // frame z: the Sobel filters still read the real pixels around the window (OpenCV ROI semantics without
-// BORDER_ISOLATED), while the product planes reflect at the WINDOW edge and the maximum is window-local
-// -- exactly what cv::cornerHarris / goodFeaturesToTrack do on img(roi).  Output plane z has `out_rows` rows.
+// BORDER_ISOLATED), while the product planes reflect at the WINDOW edge and the maximum / NMS are window-local
+// -- exactly what cv::cornerHarris / goodFeaturesToTrack do on img(roi); key coordinates are window-local.
+// `resp` (optional, svi_harris_response only) receives the response plane, `out_rows` rows per z.
 __global__ void __launch_bounds__(HT_THREADS, 2)
 harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
-                  float f1, float f0, float kf, float* __restrict__ resp, uint16_t* __restrict__ box,
+                  float f1, float f0, float kf, double quality, float* __restrict__ resp, uint16_t* __restrict__ box,
                   uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max,
+                  unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap,
                   const RoiItem* __restrict__ rois, int out_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarrisSmem& sm = *reinterpret_cast<HarrisSmem*>(smem_raw);
-    const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
+    const int f = blockIdx.z, x0 = blockIdx.x * HT_SX, y0 = blockIdx.y * HT_SY;
     const int tid = threadIdx.x;
     // W x H is the rectangle the detector sees (frame or window), (ox, oy) its origin in the image
     int W = g.W, H = g.H, ox = 0, oy = 0;
@@ -186,8 +210,11 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
         const RoiItem it = rois[f];
         W = it.rw; H = it.rh; ox = it.rx; oy = it.ry;
         im = img + (size_t)it.plane * g.img_stride;
-        if (x0 >= W || y0 >= H) return;
     }
+    // a tile without interior pixels inside the 1-px border has no candidates, and every pixel it holds also
+    // belongs to a neighbouring tile (maximum, box sums); tile (0, 0) always runs
+    if ((blockIdx.x > 0 && x0 + 1 > W - 2) || (blockIdx.y > 0 && y0 + 1 > H - 2)) return;
+    if (tid == 0) sm.key_count = 0;
 
     load_tile_u8(sm.tile, im, g.img_pitch, g.W, g.H, ox + x0, oy + y0);
     __syncthreads();
@@ -279,11 +306,15 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
         }
     }
     __syncthreads();
-    // ---- vertical 7-sums + Harris: thread = (column, 8-row segment)
+    // ---- vertical 7-sums + Harris: thread = (column, 8-row segment); the responses stay in registers and go to a
+    //      shared tile (the product planes are dead) for the neighbourhood test
     uint32_t local_max = 0u;
+    float rv[8];
+    unsigned mbits = 0u;   // pixels of this thread that the mask admits
+    float (*Rs)[HT_W] = reinterpret_cast<float(*)[HT_W]>(&sm.cov[0][0][0]);
+    const int x = tid % HT_W, oy0 = (tid / HT_W) * 8;
+    const int gx = x0 + x;
     {
-        const int x = tid % HT_W, oy0 = (tid / HT_W) * 8;
-        const int gx = x0 + x;
         // the seven rows of the first window stay in registers: they are exactly the rows that leave the window
         // while it slides over this thread's eight outputs
         double ra[7], rb[7], rc[7];
@@ -296,7 +327,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
             sb = __dadd_rn(sb, rb[i]);
             sc = __dadd_rn(sc, rc[i]);
         }
-        float* rrow = resp + ((size_t)f * out_rows) * g.resp_pitch;
+        float* rrow = resp ? resp + ((size_t)f * out_rows) * g.resp_pitch : nullptr;
         const uint8_t* mrow = mask ? mask + (size_t)f * g.img_stride : nullptr;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -306,119 +337,114 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
                 sc = __dadd_rn(sc, __dsub_rn(sm.hs[2][oy0 + k + 6][x], rc[k - 1]));
             }
             const int gy = y0 + oy0 + k;
+            float R = -INFINITY;   // outside the image: ignored by the neighbourhood maximum
             if (gx < W && gy < H) {
                 float a = __double2float_rn(sa), b = __double2float_rn(sb), c = __double2float_rn(sc);
                 float det = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b));
                 float tr = __fadd_rn(a, c);
-                float R = __fsub_rn(det, __fmul_rn(__fmul_rn(kf, tr), tr));
-                rrow[(size_t)gy * g.resp_pitch + gx] = R;
-                if (!mrow || mrow[(size_t)gy * g.img_pitch + gx]) local_max = max(local_max, float_to_ordered(R));
+                R = __fsub_rn(det, __fmul_rn(__fmul_rn(kf, tr), tr));
+                if (rrow) rrow[(size_t)gy * g.resp_pitch + gx] = R;
+                if (!mrow || mrow[(size_t)gy * g.img_pitch + gx]) {
+                    local_max = max(local_max, float_to_ordered(R));
+                    mbits |= 1u << k;
+                }
             }
+            rv[k] = R;
+            Rs[oy0 + k][x] = R;
         }
     }
     local_max = warp_max_u32(local_max);
     if ((tid & 31) == 0) sm.red[tid >> 5] = local_max;
-    __syncthreads();   // also: cov no longer read -> may be reused for the 9-sum rows
-    if (tid == 0) {
-        uint32_t m = 0;
+    __syncthreads();   // response tile complete; hs and the product planes are dead
+    uint32_t tile_max = 0u;
 #pragma unroll
-        for (int i = 0; i < HT_THREADS / 32; ++i) m = max(m, sm.red[i]);
-        if (m) atomicMax(frame_max + f, m);
+    for (int i = 0; i < HT_THREADS / 32; ++i) tile_max = max(tile_max, sm.red[i]);
+    if (tid == 0 && tile_max) atomicMax(frame_max + f, tile_max);
+
+    // ---- 3x3 non-maximum suppression on the tile interior.  A thread owns 8 rows of one column: the vertical
+    //      3-maxima come from its registers plus the rows above / below in the shared tile, the horizontal ones
+    //      from the neighbouring lanes by shuffle (the column across the warp boundary from the shared tile).
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(&sm.hs[0][0][0]);
+    if (cand) {
+        const int lane = tid & 31;
+        const float thr = gftt_threshold(tile_max, quality);
+        const float up = oy0 > 0 ? Rs[oy0 - 1][x] : -INFINITY;
+        const float dn = oy0 + 8 < HT_H ? Rs[oy0 + 8][x] : -INFINITY;
+        float c3[8], e3[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            c3[k] = fmaxf(fmaxf(k > 0 ? rv[k - 1] : up, rv[k]), k < 7 ? rv[k + 1] : dn);
+            e3[k] = -INFINITY;
+        }
+        if (lane == 0 || lane == 31) {
+            const int xn = lane == 0 ? x - 1 : x + 1;
+            if (xn >= 0 && xn < HT_W) {
+                float t[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const int row = oy0 - 1 + i;
+                    t[i] = (row >= 0 && row < HT_H) ? Rs[row][xn] : -INFINITY;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e3[k] = fmaxf(fmaxf(t[k], t[k + 1]), t[k + 2]);
+            }
+        }
+        unsigned mine = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float l3 = __shfl_up_sync(0xFFFFFFFFu, c3[k], 1), r3 = __shfl_down_sync(0xFFFFFFFFu, c3[k], 1);
+            if (lane == 0) l3 = e3[k];
+            if (lane == 31) r3 = e3[k];
+            const float v = rv[k];
+            if (v > 0.f && v > thr && v == fmaxf(fmaxf(l3, c3[k]), r3)) mine |= 1u << k;
+        }
+        mine &= mbits;
+        // tile interior, 1-px image border excluded (gx >= 1 and gy >= 1 follow from x >= 1, ly >= 1)
+        {
+            unsigned rows_ok = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int ly = oy0 + k;
+                if (ly >= 1 && ly <= HT_H - 2 && y0 + ly <= H - 2) rows_ok |= 1u << k;
+            }
+            if (!(x >= 1 && x <= HT_W - 2 && gx <= W - 2)) rows_ok = 0u;
+            mine &= rows_ok;
+        }
+        // same-address atomics serialise: aggregate per warp (one scan of the per-thread counts), then per CTA
+        // (shared counter); the CTA claims its slice of the frame's list with ONE global atomic below
+        if (__any_sync(0xFFFFFFFFu, mine != 0u)) {
+            const int cnt = __popc(mine);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&sm.key_count, incl);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((mine >> k) & 1u)
+                    s_keys[base++] = ((unsigned long long)float_to_ordered(rv[k]) << 32) | ((unsigned)(y0 + oy0 + k) << 16) | (unsigned)gx;
+        }
     }
-    if (box) {   // whole-frame mode only
+    __syncthreads();   // key list complete; the response tile is dead -> its memory becomes the 9-sum rows
+    const int n_keys = sm.key_count;
+    if (tid == 0 && n_keys) sm.key_base = atomicAdd(cand_count + f, n_keys);
+    uint16_t (*h9)[H9_P] = reinterpret_cast<uint16_t(*)[H9_P]>(&sm.cov[0][0][0]);
+    if (box) box9_rows(sm.tile, h9);   // whole-frame mode only
+    __syncthreads();
+    if (n_keys) {
+        const int base = sm.key_base;
+        unsigned long long* dst = cand + (size_t)f * cand_cap;
+        for (int i = tid; i < n_keys; i += HT_THREADS)
+            if (base + i < cand_cap) dst[base + i] = s_keys[i];   // an overflowing list is reported by select_corners_kernel
+    }
+    if (box) {
         const size_t fo = (size_t)f * H * g.box_pitch;
-        box9_from_tile(sm.tile, reinterpret_cast<uint16_t(*)[H9_P]>(&sm.cov[0][0][0]), box + fo,
-                       box_shift ? box_shift + fo : nullptr, g.box_pitch, W, H, x0, y0);
+        box9_cols(h9, box + fo, box_shift ? box_shift + fo : nullptr, g.box_pitch, W, H, x0, y0);
     }
-}
-
-// Threshold as cv::goodFeaturesToTrack computes it: minMaxLoc gives a double, threshold()
-// converts (double)max * qualityLevel to float for the 32F image.
-__device__ __forceinline__ float gftt_threshold(uint32_t ordered_max, double quality) {
-    if (ordered_max == 0u) return 0.f;  // empty mask: minMaxLoc leaves maxVal = 0
-    return (float)((double)__uint_as_float(ordered_to_float_bits(ordered_max)) * quality);
-}
-
-// K3: threshold(TOZERO) + 3x3 dilate equality + mask + 1-px image border -> candidate keys.
-// key = ordered(R) << 32 | y << 16 | x ; descending key order == cv's greaterThanPtr order
-// (value desc, then larger address first).
-// One thread owns a column of NMS_ROWS pixels and loads only that column (NMS_ROWS + 2 values, coalesced across
-// the warp): the vertical 3-maxima are formed in registers, the horizontal ones come from the two neighbouring
-// lanes by shuffle.  Lanes 0 and 31 of every warp are halo columns that only feed their neighbours, so a warp
-// emits 30 columns and a CTA NMS_COLS = 240.  No shared memory and no barriers before the append.
-constexpr int NMS_TW = 256, NMS_ROWS = 8, NMS_COLS = 30 * (NMS_TW / 32);
-__global__ void __launch_bounds__(NMS_TW)
-nms_candidates_kernel(const float* __restrict__ resp, const uint8_t* __restrict__ mask, FrameGeom g,
-                      double quality, const uint32_t* __restrict__ frame_max,
-                      unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap,
-                      const RoiItem* __restrict__ rois, int in_rows) {
-    // 3x3 NMS leaves at most one candidate per 2x2 block (ties aside); the list is sized for any outcome
-    __shared__ unsigned long long s_keys[NMS_TW * NMS_ROWS];
-    __shared__ int s_count, s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.z, gx = blockIdx.x * NMS_COLS + warp * 30 + lane - 1, y0 = blockIdx.y * NMS_ROWS;
-    if (threadIdx.x == 0) s_count = 0;
-    const int W = rois ? rois[f].rw : g.W, H = rois ? rois[f].rh : g.H;   // block-uniform
-    const float thr = gftt_threshold(frame_max[f], quality);
-    const float* R = resp + (size_t)f * in_rows * g.resp_pitch;
-    // out-of-image neighbours are ignored by dilate: -inf; in-image values go through THRESH_TOZERO
-    const bool xin = gx >= 0 && gx < W;
-    const float* p = R + (ptrdiff_t)(y0 - 1) * g.resp_pitch + (xin ? gx : 0);   // row y0-1 (never read when it is row -1)
-    float t[NMS_ROWS + 2];
-#pragma unroll
-    for (int i = 0; i < NMS_ROWS + 2; ++i) {
-        float v = -INFINITY;
-        if (xin && (unsigned)(y0 - 1 + i) < (unsigned)H) {
-            v = *p;
-            v = (v > thr) ? v : 0.f;
-        }
-        t[i] = v;
-        p += g.resp_pitch;
-    }
-    unsigned mine = 0u;
-#pragma unroll
-    for (int k = 0; k < NMS_ROWS; ++k) {
-        const float c3 = fmaxf(fmaxf(t[k], t[k + 1]), t[k + 2]);
-        const float l3 = __shfl_up_sync(0xFFFFFFFFu, c3, 1), r3 = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
-        const float m = fmaxf(fmaxf(l3, c3), r3);
-        const float v = t[k + 1];
-        const int gy = y0 + k;
-        if (v != 0.f && v == m && gy >= 1 && gy < H - 1) mine |= 1u << k;
-    }
-    if (lane == 0 || lane == 31 || !(gx >= 1 && gx < W - 1)) mine = 0u;
-    if (mine && mask) {
-#pragma unroll
-        for (int k = 0; k < NMS_ROWS; ++k)
-            if (((mine >> k) & 1u) && !mask[(size_t)f * g.img_stride + (size_t)(y0 + k) * g.img_pitch + gx]) mine &= ~(1u << k);
-    }
-    __syncthreads();
-    // same-address global atomics serialise in L2: aggregate per warp (one scan of the per-thread counts), then per
-    // CTA (shared counter), and claim the CTA's slice of the frame's list with ONE global atomic
-    if (__any_sync(0xFFFFFFFFu, mine != 0u)) {
-        const int cnt = __popc(mine);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        int base = 0;
-        if (lane == 31) base = atomicAdd(&s_count, incl);
-        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
-        while (mine) {
-            const int k = __ffs(mine) - 1;
-            mine &= mine - 1u;
-            s_keys[base++] = ((unsigned long long)float_to_ordered(t[k + 1]) << 32) | ((unsigned)(y0 + k) << 16) | (unsigned)gx;
-        }
-    }
-    __syncthreads();
-    const int n = s_count;
-    if (n == 0) return;
-    if (threadIdx.x == 0) s_base = atomicAdd(cand_count + f, n);
-    __syncthreads();
-    const int base = s_base;
-    for (int i = threadIdx.x; i < n; i += NMS_TW)
-        if (base + i < cand_cap) cand[(size_t)f * cand_cap + base + i] = s_keys[i];
 }
 
 // ------------------------------------------------------------------ FAST-9/16 (optional detector mode)

@@ -32,7 +32,9 @@ constexpr uint32_t SEL_NIL = 0xFFFFFFFFu;
 
 struct SelectParams {
     int W, H;
-    int cand_cap;        // per-frame stride of `cand` (power of two)
+    int raw_cap;         // per-frame stride and capacity of `cand`: the local maxima the Harris kernel emits
+    int cand_cap;        // capacity for the candidates that pass the frame's quality threshold (power of two)
+    double quality;      // qualityLevel of goodFeaturesToTrack
     int max_corners;
     int cell;            // grid cell edge >= ceil(minDistance)
     int gw, gh;          // grid size
@@ -106,6 +108,7 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
 template <bool kSmem, int SEL_THREADS = 1024, int SEL_SMEM_KEYS = 16384, int SEL_SMEM_CELLS = 8192>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
+                      const uint32_t* __restrict__ frame_max,
                       SelectParams sp, uint32_t* __restrict__ g_head, uint32_t* __restrict__ g_next,
                       uint8_t* __restrict__ g_state, ushort2* __restrict__ det_xy,
                       int* __restrict__ n_detected, ushort2* __restrict__ kp_xy,
@@ -115,6 +118,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
     __shared__ unsigned long long scan_total;
+    __shared__ uint32_t s_fill;
     const int f = blockIdx.x, tid = threadIdx.x;
     if (rois) {   // window mode: the bucket grid and the border filter follow the item's rectangle
         sp.W = rois[f].rw;
@@ -123,20 +127,34 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         sp.gh = (sp.H + sp.cell - 1) / sp.cell;
     }
     if (run_if && !run_if[f]) return;
-    int n = cand_count[f];
+    // The list holds the local maxima above the threshold of their TILE's maximum; goodFeaturesToTrack keeps the
+    // ones above the threshold of the FRAME's maximum (final by now): R > thr  <=>  ordered(R) > ordered(thr).
+    // frame_max == nullptr (FAST mode): every key is a corner.
+    int n_raw = cand_count[f];
+    if (n_raw > sp.raw_cap) {
+        if (tid == 0) atomicExch(overflow, 1);
+        n_raw = sp.raw_cap;
+    }
+    unsigned long long* gk = cand + (size_t)f * sp.raw_cap;
+    const uint32_t thr_ord = frame_max ? float_to_ordered(gftt_threshold(frame_max[f], sp.quality)) : 0u;
+    auto live = [thr_ord](unsigned long long k) { return (uint32_t)(k >> 32) > thr_ord; };
+    int n;
+    {
+        int c = 0;
+        for (int i = tid; i < n_raw; i += SEL_THREADS) c += live(gk[i]) ? 1 : 0;
+        block_exclusive_scan<SEL_THREADS>((unsigned long long)c, wsum, &scan_total, tid);
+        n = (int)scan_total;
+    }
     if (defer && (n > SEL_SMEM_KEYS || sp.gw * sp.gh > SEL_SMEM_CELLS)) {   // CTA-uniform
         if (tid == 0) defer[f] = 1;
         return;
     }
-    if (n > sp.cand_cap) {
-        if (tid == 0) atomicExch(overflow, 1);
-        n = sp.cand_cap;
+    if (n > sp.cand_cap || (kSmem && (n > SEL_SMEM_KEYS || sp.gw * sp.gh > SEL_SMEM_CELLS))) {
+        // more candidates than the ctx was sized for: reported as SVI_ERR_CAPACITY by the host, never a silent cut
+        if (tid == 0) { atomicExch(overflow, n > sp.cand_cap ? 1 : 2); n_detected[f] = 0; n_keypoints[f] = 0; }
+        return;
     }
     if (sp.cap_is_error && n > sp.max_corners && tid == 0) atomicExch(overflow, 3);
-    if (kSmem && n > SEL_SMEM_KEYS) {  // host picks the global variant when this can happen
-        if (tid == 0) atomicExch(overflow, 2);
-        n = SEL_SMEM_KEYS;
-    }
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     int n_act = n;   // candidates that take part in the peeling (shared-memory path: the top-priority part)
@@ -144,7 +162,6 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
 
     // shared layout: keys[16384] u64 | next16[16384] u16 (cell-sorted path: cell_start u16) | state[16384] u8 |
     //                head[8192] u32 (cell-sorted path: per-cell counters / cursors)
-    unsigned long long* gk = cand + (size_t)f * sp.cand_cap;
     unsigned long long* keys = kSmem ? reinterpret_cast<unsigned long long*>(sel_smem) : gk;
     uint16_t* next16 = reinterpret_cast<uint16_t*>(sel_smem + sizeof(unsigned long long) * SEL_SMEM_KEYS);
     uint8_t* state = kSmem ? reinterpret_cast<uint8_t*>(next16 + SEL_SMEM_KEYS) : g_state + (size_t)f * sp.cand_cap;
@@ -155,9 +172,20 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     if (peel_first) {
         // keys are filled by the counting sort below
     } else if (kSmem) {
-        for (int i = tid; i < n_pad; i += SEL_THREADS) keys[i] = (i < n) ? gk[i] : 0ull;
-    } else {
+        // compact the live keys into shared memory (any order: they are sorted next)
+        if (tid == 0) s_fill = 0u;
         for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
+        __syncthreads();
+        for (int i = tid; i < n_raw; i += SEL_THREADS) {
+            const unsigned long long k = gk[i];
+            if (live(k)) keys[atomicAdd(&s_fill, 1u)] = k;
+        }
+    } else {
+        // global variant: sort the raw list in place with the dead keys zeroed (they sink to the end)
+        n_pad = 1;
+        while (n_pad < n_raw) n_pad <<= 1;
+        for (int i = tid; i < n_pad; i += SEL_THREADS)
+            if (i >= n_raw || !live(keys[i])) keys[i] = 0ull;
     }
     __syncthreads();
 
@@ -181,7 +209,10 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             constexpr int NB = SEL_SMEM_CELLS;   // one bucket per entry of the cursor area
             for (int b = tid; b < NB; b += SEL_THREADS) cursor[b] = 0u;
             __syncthreads();
-            for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&cursor[(uint32_t)(gk[i] >> kBucketShift)], 1u);
+            for (int i = tid; i < n_raw; i += SEL_THREADS) {
+                const unsigned long long k = gk[i];
+                if (live(k)) atomicAdd(&cursor[(uint32_t)(k >> kBucketShift)], 1u);
+            }
             __syncthreads();
             constexpr int BPT = NB / SEL_THREADS;   // thread t owns buckets NB-1-BPT*t ... downwards
             uint32_t sum = 0;
@@ -201,9 +232,9 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         const uint32_t min_bucket = s_min_bucket;
         for (int c = tid; c < ncells; c += SEL_THREADS) cursor[c] = 0u;
         __syncthreads();
-        for (int i = tid; i < n; i += SEL_THREADS) {
+        for (int i = tid; i < n_raw; i += SEL_THREADS) {
             const unsigned long long k = gk[i];
-            if ((uint32_t)(k >> kBucketShift) < min_bucket) continue;
+            if ((uint32_t)(k >> kBucketShift) < min_bucket || !live(k)) continue;
             int x, y;
             key_xy(k, x, y);
             atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
@@ -224,9 +255,9 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             if (tid == 0) cell_start[ncells] = (uint16_t)n_act;   // n_act <= 16384
         }
         __syncthreads();
-        for (int i = tid; i < n; i += SEL_THREADS) {
+        for (int i = tid; i < n_raw; i += SEL_THREADS) {
             const unsigned long long k = gk[i];
-            if ((uint32_t)(k >> kBucketShift) < min_bucket) continue;
+            if ((uint32_t)(k >> kBucketShift) < min_bucket || !live(k)) continue;
             int x, y;
             key_xy(k, x, y);
             const uint32_t pos = atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);

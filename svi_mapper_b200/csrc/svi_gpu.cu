@@ -3,10 +3,8 @@
 //
 // Execution model.  A batch of independent stereo pairs is cut into chunks of `chunk_frames`
 // frames; chunk c runs on lane c % n_lanes.  A lane is one CUDA stream plus the scratch of one
-// chunk (response plane, two box-sum planes, candidate lists), sized so that the scratch of all
-// lanes stays resident in the B200's 126 MB L2 between the producing and the consuming kernel;
-// different lanes overlap each other's copies, wide kernels (Harris, match) and the
-// one-CTA-per-frame selection kernel.
+// chunk (box-sum planes of both images, candidate lists, corner lists); different lanes overlap
+// each other's copies, wide kernels (Harris, match) and the one-CTA-per-frame selection kernel.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -30,15 +28,15 @@ namespace {
 constexpr int kMaxLanes = 8;
 constexpr int kSmallFrames = 2;          // calls of up to this many frames go through the pinned bounce buffer
 constexpr size_t kOutBytesPerSlot = 8 + 8 + 24 + 32 + 32 + 4 + 4 + 1;   // uv_l uv_r xyz desc_l desc_r dist idx status
-constexpr int kStages = 5;
-const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "nms_candidates", "select_corners", "stereo_match"};
+constexpr int kStages = 4;
+const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "select_corners", "stereo_match"};
+constexpr int kRawFactor = 4;   // the Harris kernel's list (local maxima above the TILE threshold) vs max_candidates
 
 std::string g_create_error;
 
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    float* resp = nullptr;
     uint16_t* box_l = nullptr;   // S(y,x) of LEFT
     uint16_t* box_r = nullptr;   // S(y,x) of RIGHT
     uint16_t* box_ls = nullptr;  // planes stored shifted by one element, S(y,x+1): the odd-aligned TMA copies
@@ -73,7 +71,8 @@ struct svi_ctx {
     int dev_pitch = 0;   // bytes per row of the staged images
     int resp_pitch = 0, box_pitch = 0;
     int chunk = 0, n_lanes = 0;
-    int cand_cap = 0;
+    int cand_cap = 0, raw_cap = 0;
+    float* resp_one = nullptr;   // svi_harris_response only: one W x H plane
     bool select_smem = true;
     SelectParams sel{};
     TriConst tc{};
@@ -85,8 +84,7 @@ struct svi_ctx {
     // window-mode detector of stage 2 (grown on demand)
     uint8_t* trk_img = nullptr;
     struct RoiScratch {
-        int items = 0, rows = 0, pitch = 0;
-        float* resp = nullptr;
+        int items = 0;
         uint32_t* max = nullptr;
         int* cand_count = nullptr;
         unsigned long long* cand = nullptr;
@@ -113,8 +111,8 @@ struct svi_ctx {
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
     bool profiling = false;
-    double stage_ms[kStages] = {0, 0, 0, 0, 0};
-    long stage_launches[kStages] = {0, 0, 0, 0, 0};
+    double stage_ms[kStages] = {0, 0, 0, 0};
+    long stage_launches[kStages] = {0, 0, 0, 0};
     std::string err;
 };
 
@@ -133,6 +131,11 @@ int fail(svi_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// grid of the Harris kernel: response tiles HT_SX x HT_SY apart, the tile interiors cover columns 1..W-2, rows 1..H-2
+inline dim3 harris_grid(int W, int H, int layers) {
+    return dim3((unsigned)std::max(1, (W - 2 + HT_SX - 1) / HT_SX), (unsigned)std::max(1, (H - 2 + HT_SY - 1) / HT_SY), (unsigned)layers);
+}
 
 FrameGeom make_geom(const svi_ctx* c, int img_pitch, size_t img_stride) {
     FrameGeom g;
@@ -181,12 +184,18 @@ bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch
     return true;
 }
 
-cudaEvent_t lane_event(Lane& l) {
-    if (l.ev_used == l.ev.size()) {
+// Stage-boundary events come from a per-lane pool that svi_set_profiling fills ahead of time (kEventPool events per
+// lane), so that no event is created inside a timed region; the pool still grows if a step needs more.
+constexpr size_t kEventPool = 1024;
+void reserve_events(Lane& l, size_t count) {
+    while (l.ev.size() < count) {
         cudaEvent_t e;
-        cudaEventCreate(&e);
+        if (cudaEventCreate(&e) != cudaSuccess) break;
         l.ev.push_back(e);
     }
+}
+cudaEvent_t lane_event(Lane& l) {
+    if (l.ev_used == l.ev.size()) reserve_events(l, l.ev.size() + 64);
     return l.ev[l.ev_used++];
 }
 
@@ -222,27 +231,23 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     mark(ctx, l);
     if (fast) {
         fast_candidates_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, d_mask, g, ctx->p.fast_threshold, ctx->p.fast_nonmax, l.cand,
-                                                            l.cand_count, ctx->cand_cap);
+                                                            l.cand_count, ctx->raw_cap);
         boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, g, l.box_l, nullptr);
     } else {
-        harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf,
-                                                                        l.resp, l.box_l, nullptr, l.frame_max, nullptr, g.H);
+        harris_box_kernel<<<harris_grid(g.W, g.H, nf), HT_THREADS, sizeof(HarrisSmem), s>>>(
+            d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, l.box_l, nullptr, l.frame_max, l.cand,
+            l.cand_count, ctx->raw_cap, nullptr, g.H);
     }
     mark(ctx, l);
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
-    if (!fast) {
-        const dim3 ngrid((g.W + NMS_COLS - 1) / NMS_COLS, (g.H + NMS_ROWS - 1) / NMS_ROWS, nf);
-        nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max,
-                                                       l.cand, l.cand_count, ctx->cand_cap, nullptr, g.H);
-    }
-    mark(ctx, l);
+    const uint32_t* fmax = fast ? nullptr : l.frame_max;
     if (ctx->select_smem) {
         select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(
-            l.cand, l.cand_count, ctx->sel, nullptr, nullptr, nullptr, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
+            l.cand, l.cand_count, fmax, ctx->sel, nullptr, nullptr, nullptr, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     } else {
         select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(
-            l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
+            l.cand, l.cand_count, fmax, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     }
     mark(ctx, l);
     // full batches amortise a warp's set-up over MATCH_KP_PER_WARP key-points; a small call (one pair per frame in a
@@ -403,18 +408,20 @@ inline float host_projection(const double* P, int row, const double* p) {
     return std::round(static_cast<float>(h / w));
 }
 
-int ensure_roi_scratch(svi_ctx* ctx, int items, int rows, int pitch) {
+constexpr int kRoiRawCap = 8192;   // local maxima per stage-2 window (windows are at most ~240 x 240 px)
+constexpr int kRoiBatch = 4096;    // windows per wave of the window-mode detector
+
+int ensure_roi_scratch(svi_ctx* ctx, int items) {
     svi_ctx::RoiScratch& r = ctx->roi;
-    if (items <= r.items && rows <= r.rows && pitch <= r.pitch) return SVI_SUCCESS;
-    void* rp[] = {r.resp, r.max, r.cand_count, r.cand, r.det, r.kp, r.n_det, r.n_kp, r.rois, r.s2, r.defer};
+    if (items <= r.items) return SVI_SUCCESS;
+    void* rp[] = {r.max, r.cand_count, r.cand, r.det, r.kp, r.n_det, r.n_kp, r.rois, r.s2, r.defer};
     for (void* q : rp) if (q) cudaFree(q);
     r = svi_ctx::RoiScratch();
     items = std::max(items, 64);
     const size_t MC = (size_t)ctx->p.max_corners;
-    CK(dmalloc(&r.resp, (size_t)items * rows * pitch));
     CK(dmalloc(&r.max, (size_t)items));
     CK(dmalloc(&r.cand_count, (size_t)items));
-    CK(dmalloc(&r.cand, (size_t)items * ctx->cand_cap));
+    CK(dmalloc(&r.cand, (size_t)items * kRoiRawCap));
     CK(dmalloc(&r.det, (size_t)items * MC));
     CK(dmalloc(&r.kp, (size_t)items * MC));
     CK(dmalloc(&r.n_det, (size_t)items));
@@ -422,7 +429,7 @@ int ensure_roi_scratch(svi_ctx* ctx, int items, int rows, int pitch) {
     CK(dmalloc(&r.rois, (size_t)items));
     CK(dmalloc(&r.s2, (size_t)items));
     CK(dmalloc(&r.defer, (size_t)items));
-    r.items = items; r.rows = rows; r.pitch = pitch;
+    r.items = items;
     return SVI_SUCCESS;
 }
 
@@ -484,16 +491,13 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
         CK(cudaStreamSynchronize(s));
         return SVI_SUCCESS;
     }
-    const int pitch = align_up(max_w, 32), rows = max_h;
-    // bound the response scratch to ~256 MB per batch
-    const size_t plane_bytes = (size_t)rows * pitch * sizeof(float);
-    const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)total, (256u << 20) / plane_bytes));
-    int rc = ensure_roi_scratch(ctx, batch, rows, pitch);
+    const int batch = std::min(total, kRoiBatch);
+    int rc = ensure_roi_scratch(ctx, batch);
     if (rc != SVI_SUCCESS) return rc;
     svi_ctx::RoiScratch& r = ctx->roi;
-    FrameGeom gr = g;
-    gr.resp_pitch = r.pitch;
     SelectParams sp = ctx->sel;
+    sp.raw_cap = kRoiRawCap;
+    sp.cand_cap = std::min(ctx->cand_cap, kRoiRawCap);
     sp.cell = std::max(1, (int)std::ceil(ctx->p.min_distance));
     sp.cell_magic = sp.cell < 256 ? (uint32_t)(((1u << 24) + sp.cell - 1) / sp.cell) : 0u;
     if (!ctx->select_smem) return fail(ctx, SVI_ERR_UNSUPPORTED, "svi_track_landmarks: stage 2 needs max_candidates <= 16384");
@@ -504,18 +508,15 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landm
         CK(cudaMemsetAsync(r.max, 0, sizeof(uint32_t) * nb, s));
         CK(cudaMemsetAsync(r.cand_count, 0, sizeof(int) * nb, s));
         CK(cudaMemsetAsync(r.defer, 0, sizeof(int) * nb, s));
-        const dim3 tiles((max_w + HT_W - 1) / HT_W, (max_h + HT_H - 1) / HT_H, nb);
-        harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(ctx->trk_img, nullptr, gr, ctx->f1, ctx->f0, ctx->kf, r.resp,
-                                                                        nullptr, nullptr, r.max, r.rois, r.rows);
-        const dim3 ngrid((max_w + NMS_COLS - 1) / NMS_COLS, (max_h + NMS_ROWS - 1) / NMS_ROWS, nb);
-        nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(r.resp, nullptr, gr, ctx->p.quality_level, r.max, r.cand, r.cand_count,
-                                                       ctx->cand_cap, r.rois, r.rows);
+        harris_box_kernel<<<harris_grid(max_w, max_h, nb), HT_THREADS, sizeof(HarrisSmem), s>>>(
+            ctx->trk_img, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, r.max, r.cand,
+            r.cand_count, kRoiRawCap, r.rois, 0);
         // thousands of small windows: seven small-configuration CTAs per SM; the rare window that does not fit is
         // deferred to the frame-size configuration (its CTAs return at once for every other window)
         select_corners_kernel<true, SEL_SMALL_THREADS, SEL_SMALL_KEYS, SEL_SMALL_CELLS>
             <<<nb, SEL_SMALL_THREADS, select_smem_bytes(SEL_SMALL_KEYS, SEL_SMALL_CELLS), s>>>(
-                r.cand, r.cand_count, sp, nullptr, nullptr, nullptr, r.det, r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, r.defer, nullptr);
-        select_corners_kernel<true><<<nb, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(r.cand, r.cand_count, sp, nullptr, nullptr, nullptr, r.det,
+                r.cand, r.cand_count, r.max, sp, nullptr, nullptr, nullptr, r.det, r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, r.defer, nullptr);
+        select_corners_kernel<true><<<nb, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(r.cand, r.cand_count, r.max, sp, nullptr, nullptr, nullptr, r.det,
                                                                               r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, nullptr, r.defer);
         const int blocks = (nb + MATCH_WARPS - 1) / MATCH_WARPS;
         if (left)
@@ -731,7 +732,7 @@ void svi_destroy(svi_ctx* ctx) {
     for (int i = 0; i < kMaxLanes; ++i) {
         Lane& l = ctx->lanes[i];
         if (l.stream) cudaStreamSynchronize(l.stream);
-        void* ptrs[] = {l.resp, l.box_l, l.box_r, l.box_ls, l.box_rs, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
+        void* ptrs[] = {l.box_l, l.box_r, l.box_ls, l.box_rs, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
                         l.g_head, l.g_next, l.g_state, l.img_l, l.img_r, l.mask, l.out.uv_l, l.out.uv_r, l.out.xyz,
                         l.out.desc_l, l.out.desc_r, l.out.dist, l.out.idx, l.out.status};
         for (void* p : ptrs) if (p) cudaFree(p);
@@ -745,8 +746,9 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->pin_arena) cudaFreeHost(ctx->pin_arena);
     if (ctx->trk_img) cudaFree(ctx->trk_img);
     if (ctx->s3_items) cudaFree(ctx->s3_items);
+    if (ctx->resp_one) cudaFree(ctx->resp_one);
     {
-        void* rp[] = {ctx->roi.resp, ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
+        void* rp[] = {ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
                       ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2, ctx->roi.defer};
         for (void* q : rp) if (q) cudaFree(q);
     }
@@ -810,6 +812,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     int cap = 1024;
     while (cap < p.max_candidates) cap <<= 1;
     ctx->cand_cap = cap;
+    ctx->raw_cap = cap * kRawFactor;
 
     // cornerHarris scale: 1 / ((1 << (ksize-1)) * blockSize) / 255 for 8-bit input (ksize 3, block 7)
     const double scale = 1.0 / (4.0 * 7.0 * 255.0);
@@ -821,6 +824,8 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     SelectParams& sp = ctx->sel;
     sp.W = ctx->W; sp.H = ctx->H;
     sp.cand_cap = cap;
+    sp.raw_cap = cap * kRawFactor;
+    sp.quality = p.quality_level;
     sp.max_corners = p.max_corners;
     sp.filter = p.min_distance >= 1.0 ? 1 : 0;
     sp.cap_is_error = 0;
@@ -867,7 +872,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     // one shared-memory carve-out for every kernel of the pipeline: back-to-back kernels with different
     // carve-outs make the SMs drain and reconfigure between launches
     {
-        const void* kernels[] = {(const void*)harris_box_kernel, (const void*)boxsum9_kernel, (const void*)nms_candidates_kernel,
+        const void* kernels[] = {(const void*)harris_box_kernel, (const void*)boxsum9_kernel,
                                  (const void*)select_corners_kernel<true>, (const void*)select_corners_kernel<false>,
                                  (const void*)stereo_match_kernel, (const void*)triangulate_kernel<true>,
                                  (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
@@ -883,7 +888,6 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         Lane& l = ctx->lanes[i];
         CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-        CK(dmalloc(&l.resp, C * HH * ctx->resp_pitch));
         CK(dmalloc(&l.box_l, C * HH * ctx->box_pitch));
         CK(dmalloc(&l.box_r, C * HH * ctx->box_pitch));
         CK(dmalloc(&l.box_ls, C * HH * ctx->box_pitch));
@@ -902,7 +906,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         }
         CK(dmalloc(&l.frame_max, C));
         CK(dmalloc(&l.cand_count, C));
-        CK(dmalloc(&l.cand, C * cap));
+        CK(dmalloc(&l.cand, C * (size_t)ctx->raw_cap));
         CK(dmalloc(&l.det_xy, C * MC));
         CK(dmalloc(&l.kp_xy, C * MC));
         CK(dmalloc(&l.n_det, C));
@@ -966,20 +970,22 @@ int svi_stereo_frames_device(svi_ctx* ctx, const uint8_t* left, const uint8_t* r
     o.uv_l = out->uv_left; o.uv_r = out->uv_right; o.xyz = out->xyz_left;
     o.desc_l = out->desc_left; o.desc_r = out->desc_right;
     o.dist = out->distance; o.idx = out->match_index; o.status = out->status;
-    int chunk_id = 0;
+    int chunk_id = 0, rc = SVI_SUCCESS;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk, ++chunk_id) {
         Lane& l = ctx->lanes[chunk_id % ctx->n_lanes];
         const int nf = std::min(ctx->chunk, n_frames - f0);
         int* n_det = out->n_detected ? out->n_detected + f0 : l.n_det;
-        int rc = run_pipeline(ctx, l, left + (size_t)f0 * frame_stride, right + (size_t)f0 * frame_stride,
-                              masks ? masks + (size_t)f0 * frame_stride : nullptr, g, nf, o, f0, out->n_keypoints + f0, n_det);
-        if (rc != SVI_SUCCESS) return rc;
+        rc = run_pipeline(ctx, l, left + (size_t)f0 * frame_stride, right + (size_t)f0 * frame_stride,
+                          masks ? masks + (size_t)f0 * frame_stride : nullptr, g, nf, o, f0, out->n_keypoints + f0, n_det);
+        if (rc != SVI_SUCCESS) break;
     }
+    // join the lanes back into the caller's stream -- also after a failure, so that nothing queued so far can outlive
+    // the caller's next use of its buffers
     for (int i = 0; i < ctx->n_lanes; ++i) {
-        CK(cudaEventRecord(ctx->lanes[i].done, ctx->lanes[i].stream));
-        CK(cudaStreamWaitEvent(user, ctx->lanes[i].done, 0));
+        if (cudaEventRecord(ctx->lanes[i].done, ctx->lanes[i].stream) == cudaSuccess)
+            cudaStreamWaitEvent(user, ctx->lanes[i].done, 0);
     }
-    return SVI_SUCCESS;
+    return rc;
 }
 
 int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch, size_t frame_stride,
@@ -1102,11 +1108,12 @@ int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* r
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
     CK(cudaMemcpy2DAsync(l.img_l, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t), s));
-    const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
-    harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                    nullptr, nullptr, l.frame_max, nullptr, g.H);
+    if (!ctx->resp_one) CK(dmalloc(&ctx->resp_one, (size_t)ctx->H * ctx->resp_pitch));
+    harris_box_kernel<<<harris_grid(g.W, g.H, 1), HT_THREADS, sizeof(HarrisSmem), s>>>(
+        l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, ctx->resp_one, nullptr, nullptr, l.frame_max, nullptr,
+        nullptr, 0, nullptr, g.H);
     CK(cudaGetLastError());
-    CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, l.resp, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
+    CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, ctx->resp_one, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
                          ctx->H, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return SVI_SUCCESS;
@@ -1136,22 +1143,22 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
         CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
         const dim3 tiles((W + HT_W - 1) / HT_W, (H + HT_H - 1) / HT_H, nf);
-        if (ctx->p.detector == SVI_DETECTOR_FAST_9_16) {
+        const bool fast = ctx->p.detector == SVI_DETECTOR_FAST_9_16;
+        if (fast) {
             fast_candidates_kernel<<<tiles, HT_THREADS, 0, s>>>(l.img_l, d_mask, g, ctx->p.fast_threshold, ctx->p.fast_nonmax, l.cand,
-                                                                l.cand_count, ctx->cand_cap);
+                                                                l.cand_count, ctx->raw_cap);
         } else {
-            harris_box_kernel<<<tiles, HT_THREADS, sizeof(HarrisSmem), s>>>(l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, l.resp,
-                                                                            nullptr, nullptr, l.frame_max, nullptr, g.H);
-            const dim3 ngrid((W + NMS_COLS - 1) / NMS_COLS, (H + NMS_ROWS - 1) / NMS_ROWS, nf);
-            nms_candidates_kernel<<<ngrid, NMS_TW, 0, s>>>(l.resp, d_mask, g, ctx->p.quality_level, l.frame_max, l.cand,
-                                                           l.cand_count, ctx->cand_cap, nullptr, g.H);
+            harris_box_kernel<<<harris_grid(W, H, nf), HT_THREADS, sizeof(HarrisSmem), s>>>(
+                l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, l.frame_max, l.cand,
+                l.cand_count, ctx->raw_cap, nullptr, g.H);
         }
+        const uint32_t* fmax = fast ? nullptr : l.frame_max;
         if (ctx->select_smem)
-            select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(l.cand, l.cand_count, ctx->sel, nullptr, nullptr,
+            select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(l.cand, l.cand_count, fmax, ctx->sel, nullptr, nullptr,
                                                                                   nullptr, l.det_xy, l.n_det, l.kp_xy, l.n_kp,
                                                                                   ctx->d_overflow, nullptr);
         else
-            select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(l.cand, l.cand_count, ctx->sel, l.g_head, l.g_next, l.g_state,
+            select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(l.cand, l.cand_count, fmax, ctx->sel, l.g_head, l.g_next, l.g_state,
                                                                    l.det_xy, l.n_det, l.kp_xy, l.n_kp, ctx->d_overflow, nullptr);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_xy.data(), l.det_xy, sizeof(ushort2) * (size_t)nf * MC, cudaMemcpyDeviceToHost, s));
@@ -1299,6 +1306,13 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         !out->status || !out->stage || !out->uv_left || !out->uv_right || !out->xyz_left || !out->desc_left || !out->desc_right)
         return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: null array");
     if (n > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_track_landmarks: n > max_queries");
+    // the reference computes the scaling as min(1 + ..., 5) (CTrackerGT.cpp:157) and asserts it positive; the search
+    // windows grow with it, so an absurd value is rejected here instead of producing image-sized windows
+    if (!(motion_scaling >= 0.0 && motion_scaling <= 16.0))
+        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: motion_scaling must be within [0, 16]");
+    const bool stage3 = (stage_mask & SVI_STAGE_3) != 0;
+    if (stage3 && !(lm->uv_reference_left && lm->desc_reference_left && lm->T_left_to_world_at_detection))
+        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: stage 3 needs all three reference arrays");
     if (n == 0) return SVI_SUCCESS;
     CK(cudaSetDevice(ctx->device));
     Lane& l = ctx->lanes[0];
@@ -1336,9 +1350,6 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     k.stage1_match = (stage_mask & SVI_STAGE_1) ? 1 : 0;
     LandmarksDev ld{d_xyzw, d_dl, d_dr, d_disp, d_size};
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, plane);
-    const bool stage3 = (stage_mask & SVI_STAGE_3) != 0;
-    if (stage3 && !(lm->uv_reference_left && lm->desc_reference_left && lm->T_left_to_world_at_detection))
-        return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: stage 3 needs all three reference arrays");
     if (stage_mask & (SVI_STAGE_1 | SVI_STAGE_2)) {
         // ---- stage 1 LEFT / RIGHT for every landmark (or only its field-of-view gate when stage 2 runs alone)
         track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
@@ -1378,7 +1389,16 @@ int svi_set_profiling(svi_ctx* ctx, int enable) {
     collect_timings(ctx);
     for (int s = 0; s < kStages; ++s) { ctx->stage_ms[s] = 0.0; ctx->stage_launches[s] = 0; }
     ctx->profiling = enable != 0;
+    if (ctx->profiling)
+        for (int i = 0; i < ctx->n_lanes; ++i) reserve_events(ctx->lanes[i], kEventPool);
     return SVI_SUCCESS;
+}
+
+int svi_check_overflow(svi_ctx* ctx) {
+    if (!ctx) return SVI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < ctx->n_lanes; ++i) CK(cudaStreamSynchronize(ctx->lanes[i].stream));
+    return check_overflow(ctx);
 }
 
 int svi_stage_timings(svi_ctx* ctx, const char** names, double* total_ms, int64_t* launches, int capacity) {

@@ -168,6 +168,11 @@ class StereoFrontend:
         self._check(self._lib.svi_stereo_frames_device(self._ctx, left_ptr, right_ptr, pitch, frame_stride, n_frames,
                                                        masks_ptr, C.byref(result), stream or None))
 
+    def check_overflow(self):
+        """svi_check_overflow: synchronise and raise SviError(SVI_ERR_CAPACITY) if a frame enqueued through
+        stereo_frames_device overflowed a candidate list."""
+        self._check(self._lib.svi_check_overflow(self._ctx))
+
     # -- detector / extractor / matcher pieces
     def harris_response(self, img) -> np.ndarray:
         a = self._images(img, "img")[0]

@@ -13,6 +13,16 @@
 #include "CSolverStereoPosit.h"
 #include "CTriangulator.h"
 
+// Pinned arithmetic: every product and sum below rounds on its own, in the written order (the GPU kernels and the CPU
+// oracle do the same), whatever flags the including project uses -- the reference builds with -O3 -march=native
+// (CMakeLists.txt:51), where GCC's default -ffp-contract=fast would fuse a*b + c into an FMA.
+#if defined(__clang__)
+#pragma clang fp contract(off)
+#elif defined(__GNUC__)
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+#endif
+
 class CLandmark {
 public:
     CLandmark(const UIDLandmark& p_uID, const CDescriptor& p_matDescriptorLEFT, const CDescriptor& p_matDescriptorRIGHT, const double& p_dKeyPointSize,
@@ -522,4 +532,7 @@ private:
     std::vector<CSolverStereoPosit::CMatch> m_vecMeasurementsStereoPositLAST;
 };
 
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC pop_options
+#endif
 #endif

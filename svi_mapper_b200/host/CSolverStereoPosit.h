@@ -14,6 +14,16 @@
 
 #include "Types.h"
 
+// Pinned arithmetic: every product and sum below rounds on its own, in the written order (the GPU kernels and the CPU
+// oracle do the same), whatever flags the including project uses -- the reference builds with -O3 -march=native
+// (CMakeLists.txt:51), where GCC's default -ffp-contract=fast would fuse a*b + c into an FMA.
+#if defined(__clang__)
+#pragma clang fp contract(off)
+#elif defined(__GNUC__)
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+#endif
+
 class CLandmark;
 
 class CSolverStereoPosit {
@@ -157,4 +167,7 @@ private:
     const double m_dMinimumTranslationMetersL2 = 0.001;
 };
 
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC pop_options
+#endif
 #endif

@@ -9,6 +9,16 @@
 
 #include "CFundamentalMatcher.h"
 
+// Pinned arithmetic: every product and sum below rounds on its own, in the written order (the GPU kernels and the CPU
+// oracle do the same), whatever flags the including project uses -- the reference builds with -O3 -march=native
+// (CMakeLists.txt:51), where GCC's default -ffp-contract=fast would fuse a*b + c into an FMA.
+#if defined(__clang__)
+#pragma clang fp contract(off)
+#elif defined(__GNUC__)
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+#endif
+
 // cv::Rodrigues(R) for the motion-scaling term: rotation vector (axis * angle) of a rotation matrix
 inline CPoint3D toOrientationRodrigues(const Isometry3d& T) {
     const double dTrace = T(0, 0) + T(1, 1) + T(2, 2);
@@ -101,4 +111,7 @@ private:
     UIDFrame m_uNumberOfFramesWithoutDetection = 0;
 };
 
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC pop_options
+#endif
 #endif

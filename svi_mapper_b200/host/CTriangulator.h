@@ -12,6 +12,16 @@
 #include "../../include/svi_gpu.h"
 #include "CPinholeCamera.h"
 
+// Pinned arithmetic: every product and sum below rounds on its own, in the written order (the GPU kernels and the CPU
+// oracle do the same), whatever flags the including project uses -- the reference builds with -O3 -march=native
+// (CMakeLists.txt:51), where GCC's default -ffp-contract=fast would fuse a*b + c into an FMA.
+#if defined(__clang__)
+#pragma clang fp contract(off)
+#elif defined(__GNUC__)
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+#endif
+
 class CGpuContext {   // owns one svi_ctx (one per host thread and GPU)
 public:
     CGpuContext(const std::shared_ptr<CStereoCamera> p_pStereoCamera, const svi_params* p_pParams = nullptr, int p_iDevice = 0) {
@@ -114,4 +124,7 @@ private:
     };
 };
 
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC pop_options
+#endif
 #endif

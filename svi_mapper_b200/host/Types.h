@@ -14,6 +14,16 @@
 #include <string>
 #include <vector>
 
+// Pinned arithmetic: every product and sum below rounds on its own, in the written order (the GPU kernels and the CPU
+// oracle do the same), whatever flags the including project uses -- the reference builds with -O3 -march=native
+// (CMakeLists.txt:51), where GCC's default -ffp-contract=fast would fuse a*b + c into an FMA.
+#if defined(__clang__)
+#pragma clang fp contract(off)
+#elif defined(__GNUC__)
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+#endif
+
 #define DESCRIPTOR_SIZE_BITS 256
 #define DESCRIPTOR_SIZE_BYTES (DESCRIPTOR_SIZE_BITS / 8)
 
@@ -50,6 +60,36 @@ struct MatrixProjection {             // Eigen::Matrix<double,3,4>, row-major he
     double m[12] = {0};
     double operator()(int r, int c) const { return m[4 * r + c]; }
     double& operator()(int r, int c) { return m[4 * r + c]; }
+};
+
+struct Matrix3d {                     // Eigen::Matrix3d, row-major here
+    double m[9] = {0};
+    double operator()(int r, int c) const { return m[3 * r + c]; }
+    double& operator()(int r, int c) { return m[3 * r + c]; }
+    Matrix3d transpose() const {
+        Matrix3d t;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) t(r, c) = (*this)(c, r);
+        return t;
+    }
+    Matrix3d inverse() const {        // adjugate / determinant (Eigen's closed form for fixed 3x3); singular -> inf / nan like Eigen
+        auto cof = [&](int i, int j) {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            return (*this)(i1, j1) * (*this)(i2, j2) - (*this)(i1, j2) * (*this)(i2, j1);
+        };
+        const double det = (cof(0, 0) * (*this)(0, 0) + cof(1, 0) * (*this)(1, 0)) + cof(2, 0) * (*this)(2, 0);
+        const double inv_det = 1.0 / det;
+        Matrix3d r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) r(i, j) = cof(j, i) * inv_det;
+        return r;
+    }
+};
+
+struct Vector4d {                     // Eigen::Vector4d
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    double operator()(int i) const { return v[i]; }
+    double& operator()(int i) { return v[i]; }
 };
 
 struct Isometry3d {                   // Eigen::Isometry3d as a row-major 4x4
@@ -158,4 +198,7 @@ public:
     const std::string m_strExceptionDescription;
 };
 
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC pop_options
+#endif
 #endif

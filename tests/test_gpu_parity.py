@@ -4,7 +4,7 @@ same seeded inputs.  Integer / byte / index outputs must be bit-exact; xyz withi
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("built_library", "built_oracle")]
 
 from oracle import frontend_np as o
 from svi_mapper_b200 import StereoFrontend, _lib
@@ -384,6 +384,17 @@ def test_cpp_host_facade(vi_cams, calib_dir, tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lines = out.read_text().splitlines()
+    # the same facade compiled the way the reference compiles (-O3 -march=native, CMakeLists.txt:51; FMA contraction is
+    # what -march=native would add): the headers pin fp-contract themselves, so every printed number is identical
+    from svi_mapper_b200 import build as bld
+    exe_native = bld.build_host_demo(tmp_path / "facade_demo_native", flags=("-O3", "-march=native"))
+    out_n = tmp_path / "out_native.txt"
+    rn = subprocess.run([str(exe_native)] + [str(a) for a in (calib_dir / "vi_sensor_left.txt", calib_dir / "vi_sensor_right.txt", W, H,
+                        tmp_path / "L0.raw", tmp_path / "R0.raw", tmp_path / "L0.raw", tmp_path / "R0.raw", out_n, tmp_path / "seq_n.cloud")],
+                        capture_output=True, text=True)
+    assert rn.returncode == 0, rn.stderr
+    assert out_n.read_text() == out.read_text()
+    assert (tmp_path / "seq_n.cloud").read_bytes() == (tmp_path / "seq.cloud").read_bytes()
     tri = _tri(vi_cams)
     ref = o.add_new_landmarks(L, R, tri)
     ok = np.nonzero(ref["status"] == 0)[0]
@@ -778,3 +789,36 @@ def test_large_batch_against_c_oracle(kitti_cams):
         np.testing.assert_array_equal(g_["xyz"][ok], r["xyz"][ok])
         total += int(ok.sum())
     assert total > 150 * n
+
+
+def test_candidate_overflow_is_reported_on_both_entry_points(kitti_cams):
+    """A ctx sized too small for a frame's candidates never truncates silently: the host entry point returns
+    SVI_ERR_CAPACITY, the device-resident one reports it through svi_check_overflow, and the condition is cleared."""
+    import torch
+    from svi_mapper_b200 import SviError
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    L, R = stereo_pair(W, H, 11)
+    with StereoFrontend(*kitti_cams, max_candidates=1024) as fe:   # ~8000 candidates per textured KITTI-size frame
+        with pytest.raises(SviError) as e:
+            fe.stereo_frames(L, R)
+        assert e.value.code == _lib.SVI_ERR_CAPACITY
+        fe.check_overflow()                                        # cleared by the failing call
+        dev = torch.device("cuda", 0)
+        dL, dR = torch.from_numpy(L).to(dev)[None].contiguous(), torch.from_numpy(R).to(dev)[None].contiguous()
+        cap = fe.max_corners
+        t = dict(n_kp=torch.full((1,), -1, dtype=torch.int32, device=dev), uv_l=torch.zeros(1, cap, 2, device=dev),
+                 uv_r=torch.zeros(1, cap, 2, device=dev), xyz=torch.zeros(1, cap, 3, dtype=torch.float64, device=dev),
+                 dl=torch.zeros(1, cap, 32, dtype=torch.uint8, device=dev), dr=torch.zeros(1, cap, 32, dtype=torch.uint8, device=dev),
+                 dist=torch.zeros(1, cap, dtype=torch.int32, device=dev), idx=torch.zeros(1, cap, dtype=torch.int32, device=dev),
+                 st=torch.zeros(1, cap, dtype=torch.uint8, device=dev))
+        r = _lib.StereoResult(cap, t["n_kp"].data_ptr(), None, t["uv_l"].data_ptr(), t["uv_r"].data_ptr(), t["xyz"].data_ptr(),
+                              t["dl"].data_ptr(), t["dr"].data_ptr(), t["dist"].data_ptr(), t["idx"].data_ptr(), t["st"].data_ptr())
+        fe.stereo_frames_device(dL.data_ptr(), dR.data_ptr(), W, W * H, 1, r, stream=torch.cuda.current_stream().cuda_stream)
+        with pytest.raises(SviError) as e:
+            fe.check_overflow()
+        assert e.value.code == _lib.SVI_ERR_CAPACITY
+        assert int(t["n_kp"].cpu()[0]) == 0                        # an overflowing frame yields no key-points at all
+        fe.check_overflow()
+    with StereoFrontend(*kitti_cams) as fe:                         # default sizing: the same frame is fine
+        assert fe.stereo_frames(L, R).n_keypoints[0] > 500
+        fe.check_overflow()

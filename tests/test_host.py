@@ -14,6 +14,8 @@ import pytest
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 
+pytestmark = pytest.mark.usefixtures("built_library", "built_oracle")
+
 
 def test_calibration_values(calib_dir):
     from svi_mapper_b200 import construct_camera_stereo, load_camera
@@ -44,6 +46,26 @@ def test_calibration_errors(tmp_path, calib_dir):
     p.write_text(txt.replace("uWidthPixels 1241", "uWidthPixels abc"))
     with pytest.raises(ValueError):
         load_camera(str(p))
+
+
+def test_cpp_parameter_base_requires_the_reference_keys(calib_dir, tmp_path):
+    """CParameterBase::loadCameraLEFT/RIGHT (src/utility/CParameterBase.h:169-226) reads eight keys and throws
+    CExceptionParameter("cannot find parameter: <key>") when one is missing; the C++ host layer rejects the same files
+    (driven through facade_demo --solver, which loads both cameras first; no GPU work)."""
+    exe = ROOT / "svi_mapper_b200" / "host" / "facade_demo"
+    txt = (calib_dir / "vi_sensor_left.txt").read_text()
+    right = str(calib_dir / "vi_sensor_right.txt")
+    (tmp_path / "m.txt").write_text("")
+    for key in ("uWidthPixels", "uHeightPixels", "matProjection", "matIntrinsic", "dFocalLengthMeters", "vecDistortionCoefficients",
+                "matRectification"):
+        bad = tmp_path / f"no_{key}.txt"
+        bad.write_text(txt.replace(key, key + "X"))
+        r = subprocess.run([str(exe), "--solver", str(bad), right, str(tmp_path / "m.txt")], capture_output=True, text=True)
+        assert r.returncode == 1 and f"cannot find parameter: {key}" in r.stderr, (key, r.stderr)
+    r = subprocess.run([str(exe), "--solver", str(tmp_path / "missing.txt"), right, str(tmp_path / "m.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "unable to open file" in r.stderr
+    ok = subprocess.run([str(exe), "--solver", str(calib_dir / "vi_sensor_left.txt"), right, str(tmp_path / "m.txt")], capture_output=True, text=True)
+    assert ok.returncode == 0 and ok.stdout.startswith("FAILED insufficient number of points")
 
 
 def test_library_exports_every_declared_symbol():

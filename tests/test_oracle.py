@@ -10,6 +10,8 @@ from oracle import c_oracle as co
 from oracle import frontend_np as o
 from svi_mapper_b200.synth import stereo_pair
 
+pytestmark = pytest.mark.usefixtures("built_oracle")
+
 GOLD = pathlib.Path(__file__).resolve().parent / "golden" / "stereo_320x240.npz"
 
 
