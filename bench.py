@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=4096, help="stereo pairs per rank per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="tuning aid: only the device-resident measurement (no e2e, no CPU baseline); not a bench line")
     return ap.parse_args()
 
 
@@ -265,6 +266,15 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     value = world * F * args.steps / (ms_max * 1e-3)
+
+    if args.device_only:
+        if rank == 0:
+            print(json.dumps({"device_only": True, "value": value, "ms_per_step": ms_max / args.steps, "clocks": clocks,
+                              "stage_ms": {k: v["total_ms"] for k, v in stages.items()}}), flush=True)
+        fe.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the host-buffer C-ABI call: pinned host in, pinned host out, every step
     hL = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True).copy_(dL)

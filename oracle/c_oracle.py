@@ -24,6 +24,22 @@ class Result(C.Structure):
                 ("match_index", C.c_void_p), ("status", C.c_void_p)]
 
 
+class TrackParams(C.Structure):
+    _fields_ = [("cutoff_stage1", C.c_float), ("cutoff_stage2", C.c_float), ("cutoff_stage3", C.c_float), ("cutoff_original", C.c_float),
+                ("epipolar_base_length", C.c_double), ("block_size_stage2", C.c_int32)]
+
+
+class Landmarks(C.Structure):
+    _fields_ = [("xyz_world", C.c_void_p), ("last_desc_left", C.c_void_p), ("last_desc_right", C.c_void_p), ("last_disparity", C.c_void_p),
+                ("keypoint_size", C.c_void_p), ("uv_reference_left", C.c_void_p), ("desc_reference_left", C.c_void_p),
+                ("T_left_to_world_at_detection", C.c_void_p)]
+
+
+class TrackResult(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("stage", C.c_void_p), ("uv_left", C.c_void_p), ("uv_right", C.c_void_p), ("xyz_left", C.c_void_p),
+                ("desc_left", C.c_void_p), ("desc_right", C.c_void_p)]
+
+
 def build(native: bool = False) -> pathlib.Path:
     target = "libsvi_oracle_native.so" if native else "libsvi_oracle.so"
     r = subprocess.run(["make", "-C", str(HERE), "native" if native else "all"], capture_output=True, text=True)
@@ -35,15 +51,19 @@ def build(native: bool = False) -> pathlib.Path:
 _libs: dict = {}
 
 
-def load(native: bool = False):
-    """Load (building if needed and possible) the oracle library."""
-    key = bool(native)
+def load(native=False):
+    """Load (building if needed and possible) the oracle library.  `native` may also be the path of a variant built
+    around another BRIEF pair table (svi_mapper_b200.build.build_with_table)."""
+    key = native if isinstance(native, bool) else str(native)
     if key in _libs:
         return _libs[key]
-    path = HERE / ("libsvi_oracle_native.so" if native else "libsvi_oracle.so")
-    src = HERE / "svi_oracle.c"
-    if not path.exists() or path.stat().st_mtime < src.stat().st_mtime:
-        path = build(native)
+    if isinstance(native, bool):
+        path = HERE / ("libsvi_oracle_native.so" if native else "libsvi_oracle.so")
+        src = HERE / "svi_oracle.c"
+        if not path.exists() or path.stat().st_mtime < src.stat().st_mtime:
+            path = build(native)
+    else:
+        path = pathlib.Path(native)
     lib = C.CDLL(str(path))
     vp, ci, cf = C.c_void_p, C.c_int, C.c_float
     lib.svo_harris_response.argtypes = [vp, ci, ci, ci, C.c_double, vp]
@@ -54,6 +74,11 @@ def load(native: bool = False):
     lib.svo_triangulate_right.argtypes = [C.POINTER(Config), vp, ci, cf, cf, cf, vp, vp, vp, vp, vp, vp, vp]
     lib.svo_triangulate_left.argtypes = [C.POINTER(Config), vp, ci, cf, cf, cf, cf, vp, vp, vp, vp, vp, vp, vp]
     lib.svo_stereo_frames_mt.argtypes = [C.POINTER(Config), vp, vp, ci, C.c_size_t, ci, vp, C.POINTER(Result), vp, vp, ci]
+    lib.svo_harris_response_roi.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, C.c_double, vp]
+    lib.svo_gftt_roi.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, C.c_double, C.c_double, vp, ci]
+    lib.svo_track_params_default.argtypes = [C.POINTER(TrackParams)]
+    lib.svo_track_landmarks.argtypes = [C.POINTER(Config), C.POINTER(TrackParams), vp, vp, ci, vp, C.POINTER(Landmarks), ci, C.c_double,
+                                        C.c_uint, C.POINTER(TrackResult), ci]
     _libs[key] = lib
     return lib
 
@@ -123,6 +148,45 @@ def stereo_frames(cfg: Config, left: np.ndarray, right: np.ndarray, masks=None, 
     rc = load(native).svo_stereo_frames_mt(C.byref(cfg), L.ctypes.data, R.ctypes.data, w, w * h, n,
                                            M.ctypes.data if M is not None else None, C.byref(r),
                                            out["n_keypoints"].ctypes.data, out["n_detected"].ctypes.data, int(n_threads))
+    assert rc == 0
+    return out
+
+
+def track_landmarks(cfg: Config, img_left, img_right, T_world_to_left, xyz_world, last_desc_left, last_desc_right, last_disparity,
+                    keypoint_size, motion_scaling: float, uv_reference_left=None, desc_reference_left=None,
+                    T_left_to_world_at_detection=None, stages=None, n_threads: int = 1, native=False, **cutoffs) -> dict:
+    """svo_track_landmarks: CFundamentalMatcher::trackManual (all stages) for n landmarks of one pair; the same arguments
+    and result keys as StereoFrontend.track_landmarks.  cutoffs: cutoff_stage1 / 2 / 3 / cutoff_original overrides."""
+    lib = load(native)
+    a = np.ascontiguousarray(img_left, np.uint8)
+    b = np.ascontiguousarray(img_right, np.uint8)
+    h, w = a.shape
+    T = np.ascontiguousarray(np.asarray(T_world_to_left, np.float64).reshape(4, 4))
+    xw = np.ascontiguousarray(np.asarray(xyz_world, np.float64).reshape(-1, 3))
+    n = len(xw)
+    dl = np.ascontiguousarray(np.asarray(last_desc_left, np.uint8).reshape(n, 32))
+    dr = np.ascontiguousarray(np.asarray(last_desc_right, np.uint8).reshape(n, 32))
+    disp = np.ascontiguousarray(np.asarray(last_disparity, np.float32).reshape(n))
+    size = np.ascontiguousarray(np.broadcast_to(np.asarray(keypoint_size, np.float32), (n,)).copy())
+    uvref = dref = tdet = None
+    if uv_reference_left is not None:
+        uvref = np.ascontiguousarray(np.asarray(uv_reference_left, np.float64).reshape(n, 2))
+        dref = np.ascontiguousarray(np.asarray(desc_reference_left, np.uint8).reshape(n, 32))
+        tdet = np.ascontiguousarray(np.broadcast_to(np.asarray(T_left_to_world_at_detection, np.float64), (n, 4, 4)).copy())
+    if stages is None:
+        stages = 3 | (4 if uvref is not None else 0)
+    out = dict(status=np.zeros(n, np.uint8), stage=np.zeros(n, np.uint8), uv_l=np.zeros((n, 2), np.float32),
+               uv_r=np.zeros((n, 2), np.float32), xyz=np.zeros((n, 3), np.float64), desc_l=np.zeros((n, 32), np.uint8),
+               desc_r=np.zeros((n, 32), np.uint8))
+    p = lambda x: x.ctypes.data if x is not None else None
+    lm = Landmarks(p(xw), p(dl), p(dr), p(disp), p(size), p(uvref), p(dref), p(tdet))
+    r = TrackResult(p(out["status"]), p(out["stage"]), p(out["uv_l"]), p(out["uv_r"]), p(out["xyz"]), p(out["desc_l"]), p(out["desc_r"]))
+    tp = TrackParams()
+    lib.svo_track_params_default(C.byref(tp))
+    for k, v in cutoffs.items():
+        setattr(tp, k, v)
+    rc = lib.svo_track_landmarks(C.byref(cfg), C.byref(tp), a.ctypes.data, b.ctypes.data, w, T.ctypes.data, C.byref(lm), n,
+                                 float(motion_scaling), int(stages), C.byref(r), int(n_threads))
     assert rc == 0
     return out
 

@@ -71,18 +71,23 @@ class TrackResult(C.Structure):
 
 
 _lib = None
+_others: dict = {}
 
 
-def load():
-    """Load libsvi_gpu.so once; raise with a build hint if it is absent."""
+def load(path=None):
+    """Load libsvi_gpu.so once; raise with a build hint if it is absent.  `path` loads another build of the same
+    library (a variant compiled around a different BRIEF pair table, a tuning experiment) beside the default one."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    if path is not None and str(path) in _others:
+        return _others[str(path)]
+    lib_path = pathlib.Path(path) if path is not None else LIB_PATH
+    if not lib_path.exists():
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m svi_mapper_b200.build` "
+            f"{lib_path} is missing: build it with `python -m svi_mapper_b200.build` "
             "(svi_mapper_b200 has no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
     lib.svi_params_default.argtypes = [C.POINTER(Params)]
     lib.svi_status_text.argtypes = [ci]
@@ -111,5 +116,8 @@ def load():
     lib.svi_config.argtypes = [vp, i32p, i32p, i32p]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = header/library mismatch
-    _lib = lib
+    if path is None:
+        _lib = lib
+    else:
+        _others[str(path)] = lib
     return lib

@@ -40,16 +40,22 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in sources())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> pathlib.Path:
+def build_library(force: bool = False, verbose: bool = False, out: pathlib.Path | None = None, defines=(),
+                  pattern_header: pathlib.Path | None = None) -> pathlib.Path:
+    """nvcc build of libsvi_gpu.so.  `out` / `defines` / `pattern_header` build a variant next to the product library:
+    tuning experiments (-DNAME=value) and libraries with another BRIEF pair table (tools/gen_pattern_header.py --table)."""
     sys.path.insert(0, str(ROOT / "tools"))
     try:
         import gen_pattern_header
-        gen_pattern_header.main()
+        gen_pattern_header.main([])
     finally:
         sys.path.pop(0)
-    if not force and not needs_build():
+    lib = pathlib.Path(out) if out else LIB
+    if not force and not out and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "svi_gpu.cu")]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", str(lib), str(CSRC / "svi_gpu.cu")]
+    if pattern_header:
+        cmd.insert(1, f"-DSVI_BRIEF_PATTERN_HEADER=\"{pattern_header}\"")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,7 +63,7 @@ def build_library(force: bool = False, verbose: bool = False) -> pathlib.Path:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return lib
 
 
 def build_host_demo(out: pathlib.Path | None = None, flags=("-O2", "-ffp-contract=off")) -> pathlib.Path:
@@ -74,6 +80,60 @@ def build_host_demo(out: pathlib.Path | None = None, flags=("-O2", "-ffp-contrac
     return exe
 
 
+ALT_TABLES = {"alt_random": ROOT / "tests" / "golden" / "patterns" / "alt_random.txt",
+              "alt_adversarial": ROOT / "tests" / "golden" / "patterns" / "alt_adversarial.txt"}
+ALT_DIR = ROOT / "build" / "alt"   # git-ignored, travels to the GPU box with the snapshot
+
+
+def build_with_table(table: pathlib.Path, out_dir: pathlib.Path) -> dict:
+    """libsvi_gpu.so and the C checker (oracle/svi_oracle.c) compiled around another BRIEF pair table -- the
+    one-command table swap: header from the text table, then the two ordinary build lines with
+    -DSVI_BRIEF_PATTERN_HEADER pointing at it.  Returns the paths."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    try:
+        import gen_pattern_header
+    finally:
+        sys.path.pop(0)
+    out_dir = pathlib.Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    hdr = out_dir / "brief_pattern_32.h"
+    gen_pattern_header.write(table, hdr)
+    lib = build_library(force=True, out=out_dir / "libsvi_gpu.so", pattern_header=hdr)
+    orc = out_dir / "libsvi_oracle.so"
+    cmd = ["gcc", "-O3", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", f"-DSVI_BRIEF_PATTERN_HEADER=\"{hdr}\"",
+           "-shared", "-o", str(orc), str(ROOT / "oracle" / "svi_oracle.c"), "-lm", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + r.stdout + r.stderr)
+    return {"table": pathlib.Path(table), "header": hdr, "lib": lib, "oracle": orc}
+
+
+def build_alt_tables(force: bool = False) -> dict:
+    """The two test tables of tests/golden/patterns (see tools/make_alt_patterns.py), built once."""
+    out = {}
+    newest = max(p.stat().st_mtime for p in sources() + [ROOT / "oracle" / "svi_oracle.c"])
+    for name, table in ALT_TABLES.items():
+        d = ALT_DIR / name
+        have = all((d / f).exists() and (d / f).stat().st_mtime >= max(newest, table.stat().st_mtime) for f in ("libsvi_gpu.so", "libsvi_oracle.so"))
+        out[name] = ({"table": table, "header": d / "brief_pattern_32.h", "lib": d / "libsvi_gpu.so", "oracle": d / "libsvi_oracle.so"}
+                     if have and not force else build_with_table(table, d))
+    return out
+
+
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    print(build_host_demo())
+    import argparse
+    ap = argparse.ArgumentParser(description="build libsvi_gpu.so (+ the facade demo); --table/--lib builds a variant around another BRIEF pair table")
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-v", action="store_true")
+    ap.add_argument("--table")
+    ap.add_argument("--lib", help="output directory of the variant (libsvi_gpu.so, libsvi_oracle.so, brief_pattern_32.h)")
+    ap.add_argument("-D", action="append", default=[], help="extra -D for a tuning variant; needs --out")
+    ap.add_argument("--out", help="output path of a tuning variant")
+    a = ap.parse_args()
+    if a.table:
+        print(build_with_table(pathlib.Path(a.table), pathlib.Path(a.lib or (ALT_DIR / pathlib.Path(a.table).stem))))
+    elif a.out:
+        print(build_library(force=True, verbose=a.v, out=pathlib.Path(a.out), defines=a.D))
+    else:
+        print(build_library(force=a.force, verbose=a.v))
+        print(build_host_demo())

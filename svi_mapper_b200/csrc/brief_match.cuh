@@ -19,7 +19,11 @@
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <utility>
+#ifdef SVI_BRIEF_PATTERN_HEADER   // another pair table (tools/gen_pattern_header.py --table ... --out ...)
+#include SVI_BRIEF_PATTERN_HEADER
+#else
 #include "brief_pattern_32.h"
+#endif
 #include "common.cuh"
 
 namespace svi {

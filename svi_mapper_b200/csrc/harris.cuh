@@ -20,6 +20,9 @@
 namespace svi {
 
 constexpr int HT_W = 64, HT_H = 32, HT_THREADS = 256;
+#ifndef HARRIS_CTAS_PER_SM
+#define HARRIS_CTAS_PER_SM 4
+#endif
 constexpr int HT_SX = HT_W - 2, HT_SY = HT_H - 2;   // tile stride of the Harris kernel: candidates = tile interior
 constexpr int HT_MAX_KEYS = HT_SX * HT_SY;          // a plateau can make every interior pixel a local maximum
 constexpr int U8_W = HT_W + 8;       // u8 tile: 4-px halo (1 Sobel + 3 box; also the 9x9 box sum)
@@ -31,11 +34,14 @@ constexpr int COV_ROWS = HT_H + 6;
 constexpr int COV_P = 73;            // odd pitches: row-per-lane accesses are bank-conflict free
 constexpr int HS_P = 65;
 constexpr int COV_SEG_ROWS = 13;     // 38 rows = 3 segments for the sliding Sobel
-constexpr int HS_SEG = 16;           // horizontal box sums: 16 outputs per work item
+constexpr int HS_SEG = 11;           // horizontal box sums: 11 outputs per work item, 6 segments x 38 rows = 228 items
+constexpr int HS_NSEG = (HT_W + HS_SEG - 1) / HS_SEG;
+static_assert(HS_NSEG * COV_ROWS <= HT_THREADS, "one horizontal work item per thread");
+static_assert((HS_NSEG - 1) * HS_SEG + HS_SEG + 6 <= COV_P, "the last segment's loads stay inside the padded row");
 static_assert(COV_ROWS > 32 && COV_ROWS <= 64, "row mapping of the horizontal pass");
 
 struct __align__(16) HarrisSmem {
-    double hs[3][COV_ROWS][HS_P];     // horizontal 7-sums, fp64
+    double hs[COV_ROWS][HS_P];        // horizontal 7-sums of ONE product plane, fp64
     float cov[3][COV_ROWS][COV_P];    // Dx*Dx, Dx*Dy, Dy*Dy (fp32); reused as the 9-sum rows (u16)
     uint8_t tile[U8_ROWS][U8_P];
     uint32_t red[HT_THREADS / 32];
@@ -43,7 +49,7 @@ struct __align__(16) HarrisSmem {
 };
 static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(uint16_t) * U8_ROWS * H9_P, "h9 alias");
 static_assert(sizeof(float) * 3 * COV_ROWS * COV_P >= sizeof(float) * HT_H * HT_W, "response tile alias");
-static_assert(sizeof(double) * 3 * COV_ROWS * HS_P >= sizeof(unsigned long long) * HT_MAX_KEYS, "key list alias");
+static_assert(sizeof(double) * COV_ROWS * HS_P >= sizeof(unsigned long long) * HT_MAX_KEYS, "key list alias");
 
 // Stage the (HT_H+8) x (HT_W+8) u8 tile with REFLECT_101 at the image border.  A warp copies whole rows: lane l
 // moves bytes l, l+32, l+64 of a row, so every load instruction of the warp touches one or two 128-byte lines
@@ -193,7 +199,7 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
 // BORDER_ISOLATED), while the product planes reflect at the WINDOW edge and the maximum / NMS are window-local
 // -- exactly what cv::cornerHarris / goodFeaturesToTrack do on img(roi); key coordinates are window-local.
 // `resp` (optional, svi_harris_response only) receives the response plane, `out_rows` rows per z.
-__global__ void __launch_bounds__(HT_THREADS, 2)
+__global__ void __launch_bounds__(HT_THREADS, HARRIS_CTAS_PER_SM)
 harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
                   float f1, float f0, float kf, double quality, float* __restrict__ resp, uint16_t* __restrict__ box,
                   uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max,
@@ -282,70 +288,73 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
             __syncthreads();
         }
     }
-    // ---- horizontal 7-sums in fp64: one work item = (plane, 16-output segment, row)
-    for (int item = tid; item < 3 * (HT_W / HS_SEG) * COV_ROWS; item += HT_THREADS) {
-        // a warp takes 32 consecutive rows of ONE (plane, segment): the row pitches are odd, so its loads and its 64-bit
-        // stores are free of bank conflicts; the rows past 32 of all (plane, segment) pairs follow as a tail
-        constexpr int kCombos = 3 * (HT_W / HS_SEG), kMain = kCombos * 32;
-        const int combo = item < kMain ? item / 32 : (item - kMain) / (COV_ROWS - 32);
-        const int r = item < kMain ? item % 32 : 32 + (item - kMain) % (COV_ROWS - 32);
-        const int sgm = combo % (HT_W / HS_SEG), p = combo / (HT_W / HS_SEG);
-        const float* src = &sm.cov[p][r][sgm * HS_SEG];
-        double v[HS_SEG + 6];
+    // ---- 7x7 box sums in fp64, one product plane at a time through ONE plane of horizontal sums (the three planes
+    //      at once would be 59 KB and hold the SM at two CTAs; this way four fit):
+    //        horizontal 7-sums: work item = (row, HS_SEG-output segment), a warp takes 32 consecutive rows of one
+    //          segment -- the row pitches are odd, so its loads and 64-bit stores are free of bank conflicts; the six
+    //          rows past 32 follow in the seventh warp
+    //        vertical 7-sums:   thread = (column, 8-row segment); the seven rows of the first window stay in
+    //          registers: they are exactly the rows that leave the window while it slides over the eight outputs
+    const int x = tid % HT_W, oy0 = (tid / HT_W) * 8;
+    const int gx = x0 + x;
+    float bsum[3][8];
 #pragma unroll
-        for (int i = 0; i < HS_SEG + 6; ++i) v[i] = (double)src[i];
-        double s = v[0];
+    for (int p = 0; p < 3; ++p) {
+        if (p > 0) __syncthreads();   // every thread has finished reading the previous plane's sums
+        if (tid < HS_NSEG * COV_ROWS) {
+            const int sgm = tid < HS_NSEG * 32 ? tid >> 5 : (tid - HS_NSEG * 32) / (COV_ROWS - 32);
+            const int r = tid < HS_NSEG * 32 ? tid & 31 : 32 + (tid - HS_NSEG * 32) % (COV_ROWS - 32);
+            const float* src = &sm.cov[p][r][sgm * HS_SEG];
+            double v[HS_SEG + 6];
 #pragma unroll
-        for (int i = 1; i < 7; ++i) s = __dadd_rn(s, v[i]);
-        double* dst = &sm.hs[p][r][sgm * HS_SEG];
-        dst[0] = s;
+            for (int i = 0; i < HS_SEG + 6; ++i) v[i] = (double)src[i];   // the last segment reads into the row padding: unused sums
+            double s = v[0];
 #pragma unroll
-        for (int j = 1; j < HS_SEG; ++j) {
-            s = __dadd_rn(s, __dsub_rn(v[j + 6], v[j - 1]));
-            dst[j] = s;
+            for (int i = 1; i < 7; ++i) s = __dadd_rn(s, v[i]);
+            double* dst = &sm.hs[r][sgm * HS_SEG];
+            dst[0] = s;
+#pragma unroll
+            for (int j = 1; j < HS_SEG; ++j) {
+                s = __dadd_rn(s, __dsub_rn(v[j + 6], v[j - 1]));
+                if (sgm * HS_SEG + j < HT_W) dst[j] = s;
+            }
+        }
+        __syncthreads();
+        double rw[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) rw[i] = sm.hs[oy0 + i][x];
+        double sv = rw[0];
+#pragma unroll
+        for (int i = 1; i < 7; ++i) sv = __dadd_rn(sv, rw[i]);
+        bsum[p][0] = __double2float_rn(sv);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            sv = __dadd_rn(sv, __dsub_rn(sm.hs[oy0 + k + 6][x], rw[k - 1]));
+            bsum[p][k] = __double2float_rn(sv);
         }
     }
-    __syncthreads();
-    // ---- vertical 7-sums + Harris: thread = (column, 8-row segment); the responses stay in registers and go to a
-    //      shared tile (the product planes are dead) for the neighbourhood test
-    uint32_t local_max = 0u;
+    // ---- Harris; the responses stay in registers and go to a shared tile (the product planes are dead) for the
+    //      neighbourhood test
+    float lmax = -INFINITY;
     float rv[8];
     unsigned mbits = 0u;   // pixels of this thread that the mask admits
     float (*Rs)[HT_W] = reinterpret_cast<float(*)[HT_W]>(&sm.cov[0][0][0]);
-    const int x = tid % HT_W, oy0 = (tid / HT_W) * 8;
-    const int gx = x0 + x;
     {
-        // the seven rows of the first window stay in registers: they are exactly the rows that leave the window
-        // while it slides over this thread's eight outputs
-        double ra[7], rb[7], rc[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) { ra[i] = sm.hs[0][oy0 + i][x]; rb[i] = sm.hs[1][oy0 + i][x]; rc[i] = sm.hs[2][oy0 + i][x]; }
-        double sa = ra[0], sb = rb[0], sc = rc[0];
-#pragma unroll
-        for (int i = 1; i < 7; ++i) {
-            sa = __dadd_rn(sa, ra[i]);
-            sb = __dadd_rn(sb, rb[i]);
-            sc = __dadd_rn(sc, rc[i]);
-        }
         float* rrow = resp ? resp + ((size_t)f * out_rows) * g.resp_pitch : nullptr;
         const uint8_t* mrow = mask ? mask + (size_t)f * g.img_stride : nullptr;
+        const int rows_in = min(8, H - (y0 + oy0));   // rows of this thread inside the image (<= 0: none)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (k > 0) {
-                sa = __dadd_rn(sa, __dsub_rn(sm.hs[0][oy0 + k + 6][x], ra[k - 1]));
-                sb = __dadd_rn(sb, __dsub_rn(sm.hs[1][oy0 + k + 6][x], rb[k - 1]));
-                sc = __dadd_rn(sc, __dsub_rn(sm.hs[2][oy0 + k + 6][x], rc[k - 1]));
-            }
-            const int gy = y0 + oy0 + k;
             float R = -INFINITY;   // outside the image: ignored by the neighbourhood maximum
-            if (gx < W && gy < H) {
-                float a = __double2float_rn(sa), b = __double2float_rn(sb), c = __double2float_rn(sc);
-                float det = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b));
-                float tr = __fadd_rn(a, c);
+            if (gx < W && k < rows_in) {
+                const float a = bsum[0][k], b = bsum[1][k], c = bsum[2][k];
+                const float det = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b));
+                const float tr = __fadd_rn(a, c);
                 R = __fsub_rn(det, __fmul_rn(__fmul_rn(kf, tr), tr));
+                const int gy = y0 + oy0 + k;
                 if (rrow) rrow[(size_t)gy * g.resp_pitch + gx] = R;
                 if (!mrow || mrow[(size_t)gy * g.img_pitch + gx]) {
-                    local_max = max(local_max, float_to_ordered(R));
+                    lmax = fmaxf(lmax, R);
                     mbits |= 1u << k;
                 }
             }
@@ -353,6 +362,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
             Rs[oy0 + k][x] = R;
         }
     }
+    uint32_t local_max = lmax == -INFINITY ? 0u : float_to_ordered(lmax);   // 0 = no admitted pixel
     local_max = warp_max_u32(local_max);
     if ((tid & 31) == 0) sm.red[tid >> 5] = local_max;
     __syncthreads();   // response tile complete; hs and the product planes are dead
@@ -364,7 +374,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
     // ---- 3x3 non-maximum suppression on the tile interior.  A thread owns 8 rows of one column: the vertical
     //      3-maxima come from its registers plus the rows above / below in the shared tile, the horizontal ones
     //      from the neighbouring lanes by shuffle (the column across the warp boundary from the shared tile).
-    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(&sm.hs[0][0][0]);
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(&sm.hs[0][0]);
     if (cand) {
         const int lane = tid & 31;
         const float thr = gftt_threshold(tile_max, quality);
@@ -389,6 +399,16 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
                 for (int k = 0; k < 8; ++k) e3[k] = fmaxf(fmaxf(t[k], t[k + 1]), t[k + 2]);
             }
         }
+        // candidate rows of this thread: tile interior (rows 1 .. HT_H-2) inside the image minus its 1-px border
+        // (y <= H-2); bit k = row oy0 + k.  Columns: tile interior, x <= W-2 (x >= 1 and y >= 1 follow from the tile).
+        unsigned allowed = 0u;
+        {
+            const int k_lo = oy0 == 0 ? 1 : 0;
+            const int k_hi = min(min(7, HT_H - 2 - oy0), H - 2 - y0 - oy0);
+            if (k_hi >= k_lo && x >= 1 && x <= HT_W - 2 && gx <= W - 2) allowed = (0xFFu >> (7 - k_hi)) & (0xFFu << k_lo);
+        }
+        allowed &= mbits;
+        const float thr0 = fmaxf(thr, 0.f);   // a candidate has R' = R > thr and R' != 0; thr >= 0 whenever max R > 0
         unsigned mine = 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -396,20 +416,9 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
             if (lane == 0) l3 = e3[k];
             if (lane == 31) r3 = e3[k];
             const float v = rv[k];
-            if (v > 0.f && v > thr && v == fmaxf(fmaxf(l3, c3[k]), r3)) mine |= 1u << k;
+            if (v > thr0 && v == fmaxf(fmaxf(l3, c3[k]), r3)) mine |= 1u << k;
         }
-        mine &= mbits;
-        // tile interior, 1-px image border excluded (gx >= 1 and gy >= 1 follow from x >= 1, ly >= 1)
-        {
-            unsigned rows_ok = 0u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ly = oy0 + k;
-                if (ly >= 1 && ly <= HT_H - 2 && y0 + ly <= H - 2) rows_ok |= 1u << k;
-            }
-            if (!(x >= 1 && x <= HT_W - 2 && gx <= W - 2)) rows_ok = 0u;
-            mine &= rows_ok;
-        }
+        mine &= allowed;
         // same-address atomics serialise: aggregate per warp (one scan of the per-thread counts), then per CTA
         // (shared counter); the CTA claims its slice of the frame's list with ONE global atomic below
         if (__any_sync(0xFFFFFFFFu, mine != 0u)) {
@@ -423,10 +432,15 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
             int base = 0;
             if (lane == 31) base = atomicAdd(&sm.key_count, incl);
             base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+            const unsigned yx0 = ((unsigned)(y0 + oy0) << 16) | (unsigned)gx;
+            while (mine) {   // a thread rarely holds more than one local maximum
+                const int k = __ffs(mine) - 1;
+                mine &= mine - 1u;
+                float v = rv[0];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((mine >> k) & 1u)
-                    s_keys[base++] = ((unsigned long long)float_to_ordered(rv[k]) << 32) | ((unsigned)(y0 + oy0 + k) << 16) | (unsigned)gx;
+                for (int i = 1; i < 8; ++i) v = (k == i) ? rv[i] : v;
+                s_keys[base++] = ((unsigned long long)float_to_ordered(v) << 32) | (yx0 + ((unsigned)k << 16));
+            }
         }
     }
     __syncthreads();   // key list complete; the response tile is dead -> its memory becomes the 9-sum rows

@@ -81,9 +81,10 @@ class StereoFrontend:
     """One svi_ctx: the GPU-side replacement of CTriangulator + the image-space half of
     CFundamentalMatcher for one stereo camera on one device."""
 
-    def __init__(self, cam_left, cam_right, device: int = 0, **overrides):
-        self._lib = _lib.load()
-        self.params = default_params()
+    def __init__(self, cam_left, cam_right, device: int = 0, lib_path=None, **overrides):
+        self._lib = _lib.load(lib_path)   # lib_path: another build of libsvi_gpu.so (e.g. a different BRIEF pair table)
+        self.params = _lib.Params()
+        self._lib.svi_params_default(C.byref(self.params))
         for k, v in overrides.items():
             if not hasattr(self.params, k):
                 raise TypeError(f"unknown svi_params field {k!r}")
