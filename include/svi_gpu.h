@@ -156,6 +156,20 @@ int svi_stereo_frames_device(svi_ctx* ctx, const uint8_t* left, const uint8_t* r
  * never a silently truncated list.  SVI_SUCCESS otherwise. */
 int svi_check_overflow(svi_ctx* ctx);
 
+/* CFundamentalMatcher::getMaskActiveLandmarks (src/core/CFundamentalMatcher.cpp:2043-2073) on the device: a
+ * W x H plane of 255 with, per centre, the filled radius-7 disc of zeros that
+ * cv::circle(mask, Point(cvRound(x), cvRound(y)), 7, Scalar(0), -1) draws (149 px; m_uFeatureRadiusForMask,
+ * CFundamentalMatcher.h:70).  centres_xy = n_centres x (x, y): last LEFT detection of a visible landmark or the
+ * projection of an invisible one (the caller's bookkeeping).  The plane is returned to `mask` (pitch bytes per
+ * row) -- for display / inspection; the new-landmark path below never needs it on the host. */
+int svi_mask_active_landmarks(svi_ctx* ctx, const float* centres_xy, int n_centres, uint8_t* mask, size_t pitch);
+
+/* addNewLandmarks for ONE pair with the detection mask of getMaskActiveLandmarks built on the device from the
+ * landmark centres: 8 bytes per active landmark go to the GPU instead of a W x H mask plane.  Same outputs as
+ * svi_stereo_frames(..., n_frames = 1, mask, out). */
+int svi_stereo_frame_masked(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                            const float* centres_xy, int n_centres, svi_stereo_result* out);
+
 /* cv::cornerHarris(img, 7, 3, k) as GFTTDetector runs it (response plane, fp32, W*H). */
 int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* response);
 

@@ -48,6 +48,20 @@ def build(native: bool = False) -> pathlib.Path:
     return HERE / target
 
 
+def build_variant(pattern_header: pathlib.Path, out: pathlib.Path) -> pathlib.Path:
+    """The checker compiled around another BRIEF pair table (header from tools/gen_pattern_header.py --table)."""
+    out = pathlib.Path(out)
+    src = HERE / "svi_oracle.c"
+    if out.exists() and out.stat().st_mtime >= max(src.stat().st_mtime, pathlib.Path(pattern_header).stat().st_mtime):
+        return out
+    cmd = ["gcc", "-O3", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", f'-DSVI_BRIEF_PATTERN_HEADER="{pattern_header}"',
+           "-shared", "-o", str(out), str(src), "-lm", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle variant build failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 _libs: dict = {}
 
 

@@ -21,7 +21,7 @@ SVI_ERR_INVALID, SVI_ERR_CUDA, SVI_ERR_CAPACITY, SVI_ERR_NO_DEVICE, SVI_ERR_UNSU
 
 EXPORTS = (
     "svi_params_default", "svi_status_text", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
-    "svi_stereo_frames", "svi_stereo_frames_device", "svi_check_overflow", "svi_harris_response", "svi_detect", "svi_describe",
+    "svi_stereo_frames", "svi_stereo_frames_device", "svi_check_overflow", "svi_mask_active_landmarks", "svi_stereo_frame_masked", "svi_harris_response", "svi_detect", "svi_describe",
     "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
     "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config",
 )
@@ -101,6 +101,8 @@ def load(path=None):
     lib.svi_stereo_frames.argtypes = [vp, vp, vp, sz, sz, ci, vp, C.POINTER(StereoResult)]
     lib.svi_stereo_frames_device.argtypes = [vp, vp, vp, sz, sz, ci, vp, C.POINTER(StereoResult), vp]
     lib.svi_check_overflow.argtypes = [vp]
+    lib.svi_mask_active_landmarks.argtypes = [vp, vp, ci, vp, sz]
+    lib.svi_stereo_frame_masked.argtypes = [vp, vp, vp, sz, vp, ci, C.POINTER(StereoResult)]
     lib.svi_harris_response.argtypes = [vp, vp, sz, vp]
     lib.svi_detect.argtypes = [vp, vp, sz, sz, ci, vp, vp, vp]
     lib.svi_describe.argtypes = [vp, vp, sz, vp, ci, vp, vp]

@@ -86,9 +86,8 @@ ALT_DIR = ROOT / "build" / "alt"   # git-ignored, travels to the GPU box with th
 
 
 def build_with_table(table: pathlib.Path, out_dir: pathlib.Path) -> dict:
-    """libsvi_gpu.so and the C checker (oracle/svi_oracle.c) compiled around another BRIEF pair table -- the
-    one-command table swap: header from the text table, then the two ordinary build lines with
-    -DSVI_BRIEF_PATTERN_HEADER pointing at it.  Returns the paths."""
+    """libsvi_gpu.so compiled around another BRIEF pair table -- the one-command table swap: header from the text
+    table, then the ordinary build line with -DSVI_BRIEF_PATTERN_HEADER pointing at it.  Returns the paths."""
     sys.path.insert(0, str(ROOT / "tools"))
     try:
         import gen_pattern_header
@@ -99,24 +98,18 @@ def build_with_table(table: pathlib.Path, out_dir: pathlib.Path) -> dict:
     hdr = out_dir / "brief_pattern_32.h"
     gen_pattern_header.write(table, hdr)
     lib = build_library(force=True, out=out_dir / "libsvi_gpu.so", pattern_header=hdr)
-    orc = out_dir / "libsvi_oracle.so"
-    cmd = ["gcc", "-O3", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", f"-DSVI_BRIEF_PATTERN_HEADER=\"{hdr}\"",
-           "-shared", "-o", str(orc), str(ROOT / "oracle" / "svi_oracle.c"), "-lm", "-lpthread"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("gcc failed:\n" + r.stdout + r.stderr)
-    return {"table": pathlib.Path(table), "header": hdr, "lib": lib, "oracle": orc}
+    return {"table": pathlib.Path(table), "header": hdr, "lib": lib}
 
 
 def build_alt_tables(force: bool = False) -> dict:
     """The two test tables of tests/golden/patterns (see tools/make_alt_patterns.py), built once."""
     out = {}
-    newest = max(p.stat().st_mtime for p in sources() + [ROOT / "oracle" / "svi_oracle.c"])
+    newest = max(p.stat().st_mtime for p in sources())
     for name, table in ALT_TABLES.items():
         d = ALT_DIR / name
-        have = all((d / f).exists() and (d / f).stat().st_mtime >= max(newest, table.stat().st_mtime) for f in ("libsvi_gpu.so", "libsvi_oracle.so"))
-        out[name] = ({"table": table, "header": d / "brief_pattern_32.h", "lib": d / "libsvi_gpu.so", "oracle": d / "libsvi_oracle.so"}
-                     if have and not force else build_with_table(table, d))
+        lib = d / "libsvi_gpu.so"
+        have = lib.exists() and lib.stat().st_mtime >= max(newest, table.stat().st_mtime)
+        out[name] = {"table": table, "header": d / "brief_pattern_32.h", "lib": lib} if have and not force else build_with_table(table, d)
     return out
 
 
@@ -126,7 +119,7 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("-v", action="store_true")
     ap.add_argument("--table")
-    ap.add_argument("--lib", help="output directory of the variant (libsvi_gpu.so, libsvi_oracle.so, brief_pattern_32.h)")
+    ap.add_argument("--lib", help="output directory of the variant (libsvi_gpu.so, brief_pattern_32.h)")
     ap.add_argument("-D", action="append", default=[], help="extra -D for a tuning variant; needs --out")
     ap.add_argument("--out", help="output path of a tuning variant")
     a = ap.parse_args()

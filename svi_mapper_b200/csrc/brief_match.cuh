@@ -745,12 +745,12 @@ template <bool kLeft>
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
 track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant__ CUtensorMap map_other,
                     const __grid_constant__ CUtensorMap map_other_s, FrameGeom g, TriConst tc, float cutoff2,
-                    const Stage2Item* __restrict__ items, int n_items, const ushort2* __restrict__ det_xy,
+                    const Stage2Item* __restrict__ items, const int* __restrict__ n_items, const ushort2* __restrict__ det_xy,
                     const int* __restrict__ n_det, int max_corners, LandmarksDev lm, TrackOutDev out) {
     extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * MATCH_WARPS + warp;
-    if (i >= n_items) return;
+    if (i >= *n_items) return;   // the item list was compacted on the device
     const Stage2Item it = items[i];
     const int q = it.q;
     PatchStage ps;
@@ -851,16 +851,16 @@ __device__ __forceinline__ void epipolar_sample(const Stage3Item& it, int i, dou
 }
 
 // _getMatchSampleRecursiveU/V + _getMatch (:2142-2397) and _addMeasurementToLandmarkLEFT (:2399-2453):
-// the line geometry (coefficients, clipped range, sampling direction) comes from the host; one warp per item.
+// the line geometry (coefficients, clipped range, sampling direction) comes from stage3_plan_kernel; one warp per item.
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
 track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
                     const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float cutoff3, float cutoff_orig,
-                    const Stage3Item* __restrict__ items, int n_items, const uint8_t* __restrict__ desc_orig,
+                    const Stage3Item* __restrict__ items, const int* __restrict__ n_items, const uint8_t* __restrict__ desc_orig,
                     LandmarksDev lm, TrackOutDev out) {
     extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * MATCH_WARPS + warp;
-    if (idx >= n_items) return;
+    if (idx >= *n_items) return;   // the item list was compacted on the device
     const Stage3Item it = items[idx];
     const int q = it.q, n = it.count;
     PatchStage ps;

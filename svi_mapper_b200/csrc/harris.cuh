@@ -198,13 +198,14 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
 // frame z: the Sobel filters still read the real pixels around the window (OpenCV ROI semantics without
 // BORDER_ISOLATED), while the product planes reflect at the WINDOW edge and the maximum / NMS are window-local
 // -- exactly what cv::cornerHarris / goodFeaturesToTrack do on img(roi); key coordinates are window-local.
+// `n_rois` (optional) points at the number of valid window items.
 // `resp` (optional, svi_harris_response only) receives the response plane, `out_rows` rows per z.
 __global__ void __launch_bounds__(HT_THREADS, HARRIS_CTAS_PER_SM)
 harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
                   float f1, float f0, float kf, double quality, float* __restrict__ resp, uint16_t* __restrict__ box,
                   uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max,
                   unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap,
-                  const RoiItem* __restrict__ rois, int out_rows) {
+                  const RoiItem* __restrict__ rois, const int* __restrict__ n_rois, int out_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarrisSmem& sm = *reinterpret_cast<HarrisSmem*>(smem_raw);
     const int f = blockIdx.z, x0 = blockIdx.x * HT_SX, y0 = blockIdx.y * HT_SY;
@@ -213,6 +214,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
     int W = g.W, H = g.H, ox = 0, oy = 0;
     const uint8_t* im = img + (size_t)f * g.img_stride;
     if (rois) {
+        if (n_rois && f >= *n_rois) return;   // the item list was compacted on the device: layers past its end are idle
         const RoiItem it = rois[f];
         W = it.rw; H = it.rh; ox = it.rx; oy = it.ry;
         im = img + (size_t)it.plane * g.img_stride;

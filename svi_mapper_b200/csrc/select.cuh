@@ -114,12 +114,13 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                       int* __restrict__ n_detected, ushort2* __restrict__ kp_xy,
                       int* __restrict__ n_keypoints, int* __restrict__ overflow,
                       const RoiItem* __restrict__ rois, int* __restrict__ defer = nullptr,
-                      const int* __restrict__ run_if = nullptr) {
+                      const int* __restrict__ run_if = nullptr, const int* __restrict__ n_items = nullptr) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
     __shared__ unsigned long long scan_total;
     __shared__ uint32_t s_fill;
     const int f = blockIdx.x, tid = threadIdx.x;
+    if (n_items && f >= *n_items) return;   // window mode with a device-side item count
     if (rois) {   // window mode: the bucket grid and the border filter follow the item's rectangle
         sp.W = rois[f].rw;
         sp.H = rois[f].rh;

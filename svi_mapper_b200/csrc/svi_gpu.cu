@@ -20,6 +20,7 @@
 #include "brief_match.cuh"
 #include "harris.cuh"
 #include "select.cuh"
+#include "track_plan.cuh"
 
 using namespace svi;
 
@@ -95,9 +96,9 @@ struct svi_ctx {
         RoiItem* rois = nullptr;
         Stage2Item* s2 = nullptr;
         int* defer = nullptr;   // windows that do not fit the small selection configuration
+        int* counters = nullptr;  // device-side item counts: stage 2 LEFT, stage 2 RIGHT, stage 3
     } roi;
     Stage3Item* s3_items = nullptr;
-    int s3_capacity = 0;
     // pinned bounce buffer of the small-call path (one or a few frames per call: the tracker's per-frame use)
     unsigned char* pin = nullptr;
     size_t pin_bytes = 0;
@@ -236,7 +237,7 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     } else {
         harris_box_kernel<<<harris_grid(g.W, g.H, nf), HT_THREADS, sizeof(HarrisSmem), s>>>(
             d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, l.box_l, nullptr, l.frame_max, l.cand,
-            l.cand_count, ctx->raw_cap, nullptr, g.H);
+            l.cand_count, ctx->raw_cap, nullptr, nullptr, g.H);
     }
     mark(ctx, l);
     boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
@@ -350,6 +351,84 @@ int flush_downloads(svi_ctx* ctx, cudaStream_t s) {
 
 
 namespace {
+// getMaskActiveLandmarks on the device: lane.mask (plane 0) = 255 with a radius-7 disc of zeros per centre.
+int build_mask(svi_ctx* ctx, Lane& l, const float* centres, int n_centres) {
+    cudaStream_t s = l.stream;
+    const size_t bytes = (size_t)ctx->H * ctx->dev_pitch;
+    mask_fill_kernel<<<(unsigned)((bytes / 16 + 256) / 256), 256, 0, s>>>(l.mask, bytes);
+    if (n_centres > 0) {
+        ctx->arena_used = 0; ctx->pending.clear();
+        float* d_c;
+        UP(d_c, centres, (size_t)n_centres * 2);
+        mask_discs_kernel<<<(n_centres * 15 + 255) / 256, 256, 0, s>>>(l.mask, ctx->W, ctx->H, ctx->dev_pitch, d_c, n_centres);
+    }
+    CK(cudaGetLastError());
+    return SVI_SUCCESS;
+}
+
+// ---- small call (the tracker's one pair per frame).  Pageable host buffers make every cudaMemcpyAsync a blocking
+// staged copy; here the images are packed into the pinned buffer, every transfer is a real async DMA on the lane's
+// stream, and the outputs come back as one batch that is scattered with memcpy.  The detection mask is either the
+// caller's plane(s) or -- with `centres` -- built on the device from the landmark centres
+// (getMaskActiveLandmarks, CFundamentalMatcher.cpp:2043-2073): 8 bytes per landmark go up instead of a W x H plane.
+int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch, size_t frame_stride, int n_frames,
+               const uint8_t* masks, const float* centres, int n_centres, svi_stereo_result* out) {
+    const int W = ctx->W, H = ctx->H, MC = ctx->p.max_corners, cap = out->capacity_per_frame;
+    const size_t dstride = (size_t)H * ctx->dev_pitch;
+    const FrameGeom g = make_geom(ctx, ctx->dev_pitch, dstride);
+    {
+        Lane& l = ctx->lanes[0];
+        cudaStream_t s = l.stream;
+        const int nf = n_frames;
+        const size_t plane = dstride * nf;
+        unsigned char* pin_in = ctx->pin;
+        unsigned char* pin_out = ctx->pin + 3 * (size_t)kSmallFrames * dstride;
+        const uint8_t* srcs[3] = {left, right, masks};
+        uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
+        for (int k = 0; k < 3; ++k) {
+            if (!srcs[k]) continue;
+            unsigned char* stage = pin_in + k * (size_t)kSmallFrames * dstride;
+            for (int f = 0; f < nf; ++f) {
+                const uint8_t* src = srcs[k] + (size_t)f * frame_stride;
+                if ((int)pitch == ctx->dev_pitch) std::memcpy(stage + f * dstride, src, dstride);
+                else for (int y = 0; y < H; ++y) std::memcpy(stage + f * dstride + (size_t)y * ctx->dev_pitch, src + (size_t)y * pitch, W);
+            }
+            CK(cudaMemcpyAsync(dsts[k], stage, plane, cudaMemcpyHostToDevice, s));
+        }
+        bool have_mask = masks != nullptr;
+        if (centres) {
+            int rc = build_mask(ctx, l, centres, n_centres);
+            if (rc != SVI_SUCCESS) return rc;
+            have_mask = true;
+        }
+        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, l.out, 0, l.n_kp, l.n_det);
+        if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
+        struct Part { const void* dev; void* host; size_t elem; };   // elem = bytes per key-point slot
+        const Part parts[8] = {{l.out.uv_l, out->uv_left, 8}, {l.out.uv_r, out->uv_right, 8}, {l.out.xyz, out->xyz_left, 24},
+                               {l.out.desc_l, out->desc_left, 32}, {l.out.desc_r, out->desc_right, 32}, {l.out.dist, out->distance, 4},
+                               {l.out.idx, out->match_index, 4}, {l.out.status, out->status, 1}};
+        size_t off = 0;
+        for (const Part& q : parts) {
+            CK(cudaMemcpyAsync(pin_out + off, q.dev, (size_t)nf * MC * q.elem, cudaMemcpyDeviceToHost, s));
+            off += (size_t)kSmallFrames * MC * q.elem;
+        }
+        int* pin_cnt = reinterpret_cast<int*>(pin_out + off);
+        CK(cudaMemcpyAsync(pin_cnt, l.n_kp, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pin_cnt + kSmallFrames, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        off = 0;
+        for (const Part& q : parts) {   // only the live slots reach the caller's arrays
+            for (int f = 0; f < nf; ++f)
+                std::memcpy(static_cast<unsigned char*>(q.host) + (size_t)f * cap * q.elem, pin_out + off + (size_t)f * MC * q.elem,
+                            (size_t)std::min(std::max(pin_cnt[f], 0), MC) * q.elem);
+            off += (size_t)kSmallFrames * MC * q.elem;
+        }
+        std::memcpy(out->n_keypoints, pin_cnt, sizeof(int) * nf);
+        if (out->n_detected) std::memcpy(out->n_detected, pin_cnt + kSmallFrames, sizeof(int) * nf);
+        return check_overflow(ctx);
+    }
+}
+
 int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_t pitch, int n, const float* search_range,
                        const float* top_left, const float* uv_ref, const uint8_t* desc_ref, float size, svi_tri_result* out) {
     if (!img || !top_left || !uv_ref || !desc_ref || !out || n < 0 || (int)pitch < ctx->W || (left_search && !search_range))
@@ -401,23 +480,15 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
 
 namespace {
 
-// std::round / cvRound helpers for the host-side window arithmetic of stage 2 (plain IEEE double/float ops)
-inline float host_projection(const double* P, int row, const double* p) {
-    const double h = ((P[4 * row] * p[0] + P[4 * row + 1] * p[1]) + P[4 * row + 2] * p[2]) + P[4 * row + 3];
-    const double w = ((P[8] * p[0] + P[9] * p[1]) + P[10] * p[2]) + P[11];
-    return std::round(static_cast<float>(h / w));
-}
+constexpr int kRoiRawCap = 8192;   // local maxima per stage-2 window (windows are at most ~600 x 600 px at the largest scaling)
+constexpr int kRoiBatch = 4096;    // landmarks per wave of the window-mode detector
 
-constexpr int kRoiRawCap = 8192;   // local maxima per stage-2 window (windows are at most ~240 x 240 px)
-constexpr int kRoiBatch = 4096;    // windows per wave of the window-mode detector
-
-int ensure_roi_scratch(svi_ctx* ctx, int items) {
+// Scratch of the tracking cascade: allocated once, at the first tracking call, sized from max_queries; never
+// reallocated or freed inside a call.
+int ensure_track_scratch(svi_ctx* ctx) {
     svi_ctx::RoiScratch& r = ctx->roi;
-    if (items <= r.items) return SVI_SUCCESS;
-    void* rp[] = {r.max, r.cand_count, r.cand, r.det, r.kp, r.n_det, r.n_kp, r.rois, r.s2, r.defer};
-    for (void* q : rp) if (q) cudaFree(q);
-    r = svi_ctx::RoiScratch();
-    items = std::max(items, 64);
+    if (r.items) return SVI_SUCCESS;
+    const int items = std::min(std::max(ctx->p.max_queries, 64), kRoiBatch);
     const size_t MC = (size_t)ctx->p.max_corners;
     CK(dmalloc(&r.max, (size_t)items));
     CK(dmalloc(&r.cand_count, (size_t)items));
@@ -429,233 +500,86 @@ int ensure_roi_scratch(svi_ctx* ctx, int items) {
     CK(dmalloc(&r.rois, (size_t)items));
     CK(dmalloc(&r.s2, (size_t)items));
     CK(dmalloc(&r.defer, (size_t)items));
+    CK(dmalloc(&r.counters, 4));
+    CK(dmalloc(&ctx->s3_items, (size_t)std::max(ctx->p.max_queries, 64)));
     r.items = items;
     return SVI_SUCCESS;
 }
 
-// One side of trackManual stage 2 for every landmark that is still untracked (host_out->stage == 0 and not
-// out of the field of view).  The window arithmetic of :1548-1575 runs here on the host; detection inside the
-// windows, description, matching and triangulation run on the GPU; statuses come back into host_out.
-int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landmarks* lm, int n, const double* T,
-                      double motion_scaling, bool left, const LandmarksDev& ld, const TrackOutDev& o, svi_track_result* host_out) {
+TrackPlanConst make_plan(const svi_ctx* ctx, const double* T, const svi_camera& cam, double motion_scaling) {
+    TrackPlanConst k;
+    for (int i = 0; i < 12; ++i) { k.T[i] = T[i]; k.P[i] = cam.P[i]; }
+    k.motion_scaling = motion_scaling;
+    k.W = ctx->W; k.H = ctx->H;
+    k.block = 15;        // m_uSearchBlockSizePoseOptimization (CFundamentalMatcher.h:95)
+    k.epi_base = 15.0;   // m_dEpipolarLineBaseLength (CFundamentalMatcher.h:92)
+    return k;
+}
+
+// One side of trackManual stage 2 for every landmark that is still untracked, entirely enqueued on the lane's stream:
+// window arithmetic (:1548-1575) in stage2_plan_kernel, GFTT inside the windows (window-mode Harris + selection),
+// description, matching and triangulation in track_stage2_kernel.  Landmarks go through in waves of kRoiBatch.
+int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, int n, const double* T, double motion_scaling, bool left,
+                      const LandmarksDev& ld, const TrackOutDev& o) {
     cudaStream_t s = l.stream;
     const svi_camera& cam = left ? ctx->cam_l : ctx->cam_r;
-    const double cx = cam.P[2], cy = cam.P[6];
-    const int W = ctx->W, H = ctx->H;
-    const float tri_scale = (float)(1.0 + motion_scaling);
-    std::vector<RoiItem> rois;
-    std::vector<Stage2Item> items;
-    std::vector<int> no_window;   // landmarks whose window is empty: GFTT on an empty image finds nothing
-    int max_w = 0, max_h = 0;
-    for (int q = 0; q < n; ++q) {
-        if (host_out->stage[q] != 0 || host_out->status[q] == SVI_TRK_OUT_OF_FOV) continue;
-        const double* pw = lm->xyz_world + 3 * q;
-        double p[3];
-        for (int r = 0; r < 3; ++r) p[r] = ((T[4 * r] * pw[0] + T[4 * r + 1] * pw[1]) + T[4 * r + 2] * pw[2]) + T[4 * r + 3];
-        const float u = host_projection(cam.P, 0, p), v = host_projection(cam.P, 1, p);
-        const float size = lm->keypoint_size[q], half = 4.f * size;
-        // :1548-1558 half sizes round(round(w + scaling) * 15), corners clamped, cv::Rect(Point2f, Point2f)
-        const double su = std::round(std::sqrt(std::fabs((double)u - cx)) / 10.0 + motion_scaling);
-        const double sv = std::round(std::sqrt(std::fabs((double)v - cy)) / 10.0 + motion_scaling);
-        const double hw = std::round(su * 15.0), hh = std::round(sv * 15.0);
-        const float ul_x = (float)std::max((double)u - hw, 0.0), ul_y = (float)std::max((double)v - hh, 0.0);
-        const float lr_x = (float)std::min((double)u + hw, (double)W), lr_y = (float)std::min((double)v + hh, (double)H);
-        const int rx = (int)std::lrintf(ul_x), ry = (int)std::lrintf(ul_y);
-        const int rw = (int)std::lrintf(lr_x) - rx, rh = (int)std::lrintf(lr_y) - ry;
-        if (rw <= 0 || rh <= 0 || rx < 0 || ry < 0 || rx + rw > W || ry + rh > H) {
-            host_out->status[q] = SVI_TRK_NO_FEATURES;
-            no_window.push_back(q);
-            continue;
-        }
-        // :1572-1575 window grown by 4*size and clamped
-        const float g_ulx = std::max(ul_x - half, 0.0f), g_uly = std::max(ul_y - half, 0.0f);
-        const float g_lrx = std::min(lr_x + half, (float)W), g_lry = std::min(lr_y + half, (float)H);
-        Stage2Item it;
-        it.q = q;
-        it.gx = (int)std::lrintf(g_ulx); it.gy = (int)std::lrintf(g_uly);
-        it.gw = (int)std::lrintf(g_lrx) - it.gx; it.gh = (int)std::lrintf(g_lry) - it.gy;
-        it.ul_x = ul_x; it.ul_y = ul_y;
-        it.search = tri_scale * lm->last_disparity[q];
-        it.size = size;
-        items.push_back(it);
-        rois.push_back(RoiItem{left ? 0 : 1, rx, ry, rw, rh});
-        max_w = std::max(max_w, rw);
-        max_h = std::max(max_h, rh);
-    }
-    const int total = (int)items.size();
-    if (total == 0) {
-        for (int q : no_window) {
-            const uint8_t st = SVI_TRK_NO_FEATURES;
-            CK(cudaMemcpyAsync(o.status + q, &st, 1, cudaMemcpyHostToDevice, s));
-        }
-        CK(cudaStreamSynchronize(s));
-        return SVI_SUCCESS;
-    }
-    const int batch = std::min(total, kRoiBatch);
-    int rc = ensure_roi_scratch(ctx, batch);
-    if (rc != SVI_SUCCESS) return rc;
     svi_ctx::RoiScratch& r = ctx->roi;
+    if (!ctx->select_smem) return fail(ctx, SVI_ERR_UNSUPPORTED, "svi_track_landmarks: stage 2 needs max_candidates <= 16384");
+    const TrackPlanConst k = make_plan(ctx, T, cam, motion_scaling);
+    // upper bound of the window size (the grid of the window-mode detector): the principal weight is largest at the
+    // image edge that is farthest from the principal point
+    const double cx = cam.P[2], cy = cam.P[6];
+    const double su = std::round(std::sqrt(std::max(std::fabs(cx), std::fabs((double)ctx->W - cx))) / 10.0 + motion_scaling);
+    const double sv = std::round(std::sqrt(std::max(std::fabs(cy), std::fabs((double)ctx->H - cy))) / 10.0 + motion_scaling);
+    const int max_w = std::min(ctx->W, 2 * (int)std::round(su * 15.0) + 2), max_h = std::min(ctx->H, 2 * (int)std::round(sv * 15.0) + 2);
+    if (max_w <= 0 || max_h <= 0) return SVI_SUCCESS;   // no window can exist: the plan kernel reports "no features" per landmark
     SelectParams sp = ctx->sel;
     sp.raw_cap = kRoiRawCap;
     sp.cand_cap = std::min(ctx->cand_cap, kRoiRawCap);
     sp.cell = std::max(1, (int)std::ceil(ctx->p.min_distance));
     sp.cell_magic = sp.cell < 256 ? (uint32_t)(((1u << 24) + sp.cell - 1) / sp.cell) : 0u;
-    if (!ctx->select_smem) return fail(ctx, SVI_ERR_UNSUPPORTED, "svi_track_landmarks: stage 2 needs max_candidates <= 16384");
-    for (int b0 = 0; b0 < total; b0 += batch) {
-        const int nb = std::min(batch, total - b0);
-        CK(cudaMemcpyAsync(r.rois, rois.data() + b0, sizeof(RoiItem) * nb, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(r.s2, items.data() + b0, sizeof(Stage2Item) * nb, cudaMemcpyHostToDevice, s));
+    int* n_items = r.counters + (left ? 0 : 1);
+    for (int q0 = 0; q0 < n; q0 += r.items) {
+        const int nb = std::min(r.items, n - q0);
+        CK(cudaMemsetAsync(n_items, 0, sizeof(int), s));
         CK(cudaMemsetAsync(r.max, 0, sizeof(uint32_t) * nb, s));
         CK(cudaMemsetAsync(r.cand_count, 0, sizeof(int) * nb, s));
         CK(cudaMemsetAsync(r.defer, 0, sizeof(int) * nb, s));
+        stage2_plan_kernel<<<(nb + 127) / 128, 128, 0, s>>>(k, left ? 0 : 1, (float)(1.0 + motion_scaling), ld, q0, q0 + nb, o, r.rois, r.s2, n_items);
         harris_box_kernel<<<harris_grid(max_w, max_h, nb), HT_THREADS, sizeof(HarrisSmem), s>>>(
             ctx->trk_img, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, r.max, r.cand,
-            r.cand_count, kRoiRawCap, r.rois, 0);
+            r.cand_count, kRoiRawCap, r.rois, n_items, 0);
         // thousands of small windows: seven small-configuration CTAs per SM; the rare window that does not fit is
         // deferred to the frame-size configuration (its CTAs return at once for every other window)
         select_corners_kernel<true, SEL_SMALL_THREADS, SEL_SMALL_KEYS, SEL_SMALL_CELLS>
             <<<nb, SEL_SMALL_THREADS, select_smem_bytes(SEL_SMALL_KEYS, SEL_SMALL_CELLS), s>>>(
-                r.cand, r.cand_count, r.max, sp, nullptr, nullptr, nullptr, r.det, r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, r.defer, nullptr);
+                r.cand, r.cand_count, r.max, sp, nullptr, nullptr, nullptr, r.det, r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, r.defer, nullptr, n_items);
         select_corners_kernel<true><<<nb, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(r.cand, r.cand_count, r.max, sp, nullptr, nullptr, nullptr, r.det,
-                                                                              r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, nullptr, r.defer);
+                                                                              r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, nullptr, r.defer, n_items);
         const int blocks = (nb + MATCH_WARPS - 1) / MATCH_WARPS;
         if (left)
             track_stage2_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage2,
-                                                                                  r.s2, nb, r.det, r.n_det, ctx->p.max_corners, ld, o);
+                                                                                  r.s2, n_items, r.det, r.n_det, ctx->p.max_corners, ld, o);
         else
             track_stage2_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_r, l.map_l, l.map_ls, g, ctx->tc, ctx->p.cutoff_stage2,
-                                                                                   r.s2, nb, r.det, r.n_det, ctx->p.max_corners, ld, o);
+                                                                                   r.s2, n_items, r.det, r.n_det, ctx->p.max_corners, ld, o);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(s));   // the batch's item arrays are reused by the next batch
     }
-    CK(cudaMemcpyAsync(host_out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(host_out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    for (int q : no_window) {   // keep the host-side verdicts in both copies of the status array
-        host_out->status[q] = SVI_TRK_NO_FEATURES;
-        const uint8_t st = SVI_TRK_NO_FEATURES;
-        CK(cudaMemcpyAsync(o.status + q, &st, 1, cudaMemcpyHostToDevice, s));
-    }
-    CK(cudaStreamSynchronize(s));
     return SVI_SUCCESS;
 }
 
-
-// ---- stage 3 geometry on the host (CFundamentalMatcher.cpp:1795-1947), plain IEEE double operations in the same
-// order as the CPU restatement the parity tests compare against
-inline void mul3(const double A[3][3], const double B[3][3], double C[3][3]) {
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) C[i][j] = (A[i][0] * B[0][j] + A[i][1] * B[1][j]) + A[i][2] * B[2][j];
-}
-
-inline void inv3(const double m[3][3], double out[3][3]) {   // adjugate / determinant (Eigen's fixed 3x3 closed form)
-    auto cof = [&](int i, int j) {
-        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-        return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
-    };
-    const double c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
-    const double det = (c0 * m[0][0] + c1 * m[1][0]) + c2 * m[2][0];
-    const double inv_det = 1.0 / det;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) out[i][j] = cof(j, i) * inv_det;
-}
-
-// Returns SVI_OK and fills `it`, or the svi_status of the failing check.
-int epipolar_plan(const svi_ctx* ctx, const double* Tw, const double* Td, const double* uv_ref, const double* pw,
-                  double motion_scaling, Stage3Item& it) {
-    double R[3][3], t[3];
-    for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) R[i][j] = (Tw[4 * i] * Td[j] + Tw[4 * i + 1] * Td[4 + j]) + Tw[4 * i + 2] * Td[8 + j];
-        t[i] = ((Tw[4 * i] * Td[3] + Tw[4 * i + 1] * Td[7]) + Tw[4 * i + 2] * Td[11]) + Tw[4 * i + 3];
-    }
-    if (!(0.0 < (t[0] * t[0] + t[1] * t[1]) + t[2] * t[2])) return SVI_EPI_NO_TRANSLATION;
-    const double S[3][3] = {{0.0, -t[2], t[1]}, {t[2], 0.0, -t[0]}, {-t[1], t[0], 0.0}};
-    double E[3][3], K[3][3], Ki[3][3], KiT[3][3], A[3][3], F[3][3];
-    mul3(R, S, E);
-    const double* P = ctx->cam_l.P;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) K[i][j] = P[4 * i + j];
-    inv3(K, Ki);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) KiT[i][j] = Ki[j][i];
-    mul3(KiT, E, A);
-    mul3(A, Ki, F);
-    double c[3];
-    for (int i = 0; i < 3; ++i) c[i] = (F[i][0] * uv_ref[0] + F[i][1] * uv_ref[1]) + F[i][2] * 1.0;
-    double p[3];
-    for (int r = 0; r < 3; ++r) p[r] = ((Tw[4 * r] * pw[0] + Tw[4 * r + 1] * pw[1]) + Tw[4 * r + 2] * pw[2]) + Tw[4 * r + 3];
-    const float pu = host_projection(P, 0, p), pv = host_projection(P, 1, p);
-    const int Wi = ctx->W, Hi = ctx->H;
-    if (!(pu >= 28.f && pu < (float)(Wi - 28) && pv >= 28.f && pv < (float)(Hi - 28))) return SVI_EPI_OUT_OF_SIGHT;
-    const double W = (double)Wi, H = (double)Hi;
-    const double half = 10.0 * motion_scaling;
-    const double wu = std::sqrt(std::fabs((double)pu - P[2])) / 10.0, wv = std::sqrt(std::fabs((double)pv - P[6])) / 10.0;
-    const double hl_u = 15.0 + wu * half, hl_v = 15.0 + wv * half;   // m_dEpipolarLineBaseLength = 15 (CFundamentalMatcher.h:92)
-    auto curve_v = [&](double u) { return -(c[0] * u + c[2]) / c[1]; };
-    auto curve_u = [&](double v) { return -(c[1] * v + c[2]) / c[0]; };
-    const double u_min_raw = std::max((double)pu - hl_u, 0.0), u_max_raw = std::min((double)pu + hl_u, W);
-    const double v_min_raw = curve_v(u_min_raw), v_max_raw = curve_v(u_max_raw);
-    if ((0.0 > v_min_raw && 0.0 > v_max_raw) || (H < v_min_raw && H < v_max_raw)) return SVI_EPI_VERTICAL;
-    const double v_lim_min = std::max((double)pv - hl_v, 0.0), v_lim_max = std::min((double)pv + hl_v, H);
-    double u_min = u_min_raw, u_max = u_max_raw, v_for_min, v_for_max;
-    if (v_min_raw < v_max_raw) {
-        if (v_lim_min > v_max_raw || v_lim_max < v_min_raw) return SVI_EPI_NEG_SLOPE;
-        if (v_lim_min > v_min_raw) { v_for_min = v_lim_min; u_min = curve_u(v_for_min); } else v_for_min = v_min_raw;
-        if (v_lim_max < v_max_raw) { v_for_max = v_lim_max; u_max = curve_u(v_for_max); } else v_for_max = v_max_raw;
-    } else {
-        if (v_lim_min > v_min_raw || v_lim_max < v_max_raw) return SVI_EPI_POS_SLOPE;
-        if (v_lim_min > v_max_raw) { v_for_min = v_lim_min; u_max = curve_u(v_for_min); } else v_for_min = v_max_raw;
-        if (v_lim_max < v_min_raw) { v_for_max = v_lim_max; u_min = curve_u(v_for_max); } else v_for_max = v_min_raw;
-    }
-    const double du = u_max - u_min, dv = v_for_max - v_for_min;
-    // the reference converts these to uint32_t; negative / non-finite values are undefined there
-    if (!(std::isfinite(du) && std::isfinite(dv)) || du < 0.0 || dv < 0.0 || du >= 65536.0 || dv >= 65536.0) return SVI_EPI_ZERO_LEN;
-    const int delta_u = (int)du, delta_v = (int)dv;
-    if (delta_u == 0 && delta_v == 0) return SVI_EPI_ZERO_LEN;
-    it.along_u = delta_v < delta_u ? 1 : 0;
-    it.count = it.along_u ? delta_u : delta_v;
-    it.start = it.along_u ? u_min : v_for_min;
-    it.c0 = c[0]; it.c1 = c[1]; it.c2 = c[2];
-    return SVI_OK;
-}
-
-int track_stage3_all(svi_ctx* ctx, Lane& l, const FrameGeom& g, const svi_landmarks* lm, int n, const double* T,
-                     double motion_scaling, const LandmarksDev& ld, const TrackOutDev& o, svi_track_result* host_out) {
+// Stage 3 (epipolar line in LEFT): line geometry per landmark in stage3_plan_kernel (:1795-1947), sampling / matching /
+// triangulation in track_stage3_kernel, both enqueued on the lane's stream.
+int track_stage3_all(svi_ctx* ctx, Lane& l, const FrameGeom& g, int n, const double* T, double motion_scaling, const LandmarksDev& ld,
+                     const Stage3Extra& ex, const uint8_t* d_orig, const TrackOutDev& o) {
     cudaStream_t s = l.stream;
-    std::vector<Stage3Item> items;
-    std::vector<std::pair<int, uint8_t>> verdicts;   // landmarks decided by the host-side geometry checks
-    for (int q = 0; q < n; ++q) {
-        if (host_out->stage[q] != 0 || host_out->status[q] == SVI_TRK_OUT_OF_FOV) continue;
-        Stage3Item it;
-        it.q = q;
-        it.size = lm->keypoint_size[q];
-        it.search = (float)((1.0 + motion_scaling) * (double)lm->last_disparity[q]);   // :2415
-        const int st = epipolar_plan(ctx, T, lm->T_left_to_world_at_detection + 16 * (size_t)q, lm->uv_reference_left + 2 * (size_t)q,
-                                     lm->xyz_world + 3 * (size_t)q, motion_scaling, it);
-        if (st == SVI_OK) items.push_back(it);
-        else verdicts.emplace_back(q, (uint8_t)st);
-    }
-    const int total = (int)items.size();
-    if (total > 0) {
-        if (total > ctx->s3_capacity) {
-            if (ctx->s3_items) cudaFree(ctx->s3_items);
-            ctx->s3_items = nullptr;
-            ctx->s3_capacity = 0;
-            CK(dmalloc(&ctx->s3_items, (size_t)total));
-            ctx->s3_capacity = total;
-        }
-        uint8_t* d_orig = static_cast<uint8_t*>(arena_alloc(ctx, (size_t)n * 32));
-        if (!d_orig) return fail(ctx, SVI_ERR_CAPACITY, "query arena exhausted: raise svi_params.max_queries");
-        CK(cudaMemcpyAsync(d_orig, lm->desc_reference_left, (size_t)n * 32, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->s3_items, items.data(), sizeof(Stage3Item) * total, cudaMemcpyHostToDevice, s));
-        track_stage3_kernel<<<(total + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(
-            l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage3, ctx->p.cutoff_original, ctx->s3_items, total, d_orig, ld, o);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host_out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(host_out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-    }
-    for (const auto& v : verdicts) host_out->status[v.first] = v.second;
+    int* n_items = ctx->roi.counters + 2;
+    const TrackPlanConst k = make_plan(ctx, T, ctx->cam_l, motion_scaling);
+    CK(cudaMemsetAsync(n_items, 0, sizeof(int), s));
+    stage3_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(k, ld, ex, n, o, ctx->s3_items, n_items);
+    track_stage3_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(
+        l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage3, ctx->p.cutoff_original, ctx->s3_items, n_items, d_orig, ld, o);
+    CK(cudaGetLastError());
     return SVI_SUCCESS;
 }
 
@@ -749,7 +673,7 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->resp_one) cudaFree(ctx->resp_one);
     {
         void* rp[] = {ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
-                      ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2, ctx->roi.defer};
+                      ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2, ctx->roi.defer, ctx->roi.counters};
         for (void* q : rp) if (q) cudaFree(q);
     }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
@@ -1002,53 +926,8 @@ int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, s
     const size_t dstride = (size_t)H * ctx->dev_pitch;
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, dstride);
     const bool dense = (frame_stride == pitch * (size_t)H);
-    if (n_frames > 0 && n_frames <= std::min(kSmallFrames, ctx->chunk) && ctx->pin) {
-        // ---- small call (the tracker's one pair per frame).  Pageable host buffers make every cudaMemcpyAsync a
-        // blocking staged copy; here the images are packed into the pinned buffer, every transfer is a real async
-        // DMA on the lane's stream, and the outputs come back as one batch that is scattered with memcpy.
-        Lane& l = ctx->lanes[0];
-        cudaStream_t s = l.stream;
-        const int nf = n_frames;
-        const size_t plane = dstride * nf;
-        unsigned char* pin_in = ctx->pin;
-        unsigned char* pin_out = ctx->pin + 3 * (size_t)kSmallFrames * dstride;
-        const uint8_t* srcs[3] = {left, right, masks};
-        uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
-        for (int k = 0; k < 3; ++k) {
-            if (!srcs[k]) continue;
-            unsigned char* stage = pin_in + k * (size_t)kSmallFrames * dstride;
-            for (int f = 0; f < nf; ++f) {
-                const uint8_t* src = srcs[k] + (size_t)f * frame_stride;
-                if ((int)pitch == ctx->dev_pitch) std::memcpy(stage + f * dstride, src, dstride);
-                else for (int y = 0; y < H; ++y) std::memcpy(stage + f * dstride + (size_t)y * ctx->dev_pitch, src + (size_t)y * pitch, W);
-            }
-            CK(cudaMemcpyAsync(dsts[k], stage, plane, cudaMemcpyHostToDevice, s));
-        }
-        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, masks ? l.mask : nullptr, g, nf, l.out, 0, l.n_kp, l.n_det);
-        if (rc != SVI_SUCCESS) return rc;
-        struct Part { const void* dev; void* host; size_t elem; };   // elem = bytes per key-point slot
-        const Part parts[8] = {{l.out.uv_l, out->uv_left, 8}, {l.out.uv_r, out->uv_right, 8}, {l.out.xyz, out->xyz_left, 24},
-                               {l.out.desc_l, out->desc_left, 32}, {l.out.desc_r, out->desc_right, 32}, {l.out.dist, out->distance, 4},
-                               {l.out.idx, out->match_index, 4}, {l.out.status, out->status, 1}};
-        size_t off = 0;
-        for (const Part& q : parts) {
-            CK(cudaMemcpyAsync(pin_out + off, q.dev, (size_t)nf * MC * q.elem, cudaMemcpyDeviceToHost, s));
-            off += (size_t)kSmallFrames * MC * q.elem;
-        }
-        int* pin_cnt = reinterpret_cast<int*>(pin_out + off);
-        CK(cudaMemcpyAsync(pin_cnt, l.n_kp, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(pin_cnt + kSmallFrames, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        off = 0;
-        for (const Part& q : parts) {
-            for (int f = 0; f < nf; ++f)
-                std::memcpy(static_cast<unsigned char*>(q.host) + (size_t)f * cap * q.elem, pin_out + off + (size_t)f * MC * q.elem, (size_t)MC * q.elem);
-            off += (size_t)kSmallFrames * MC * q.elem;
-        }
-        std::memcpy(out->n_keypoints, pin_cnt, sizeof(int) * nf);
-        if (out->n_detected) std::memcpy(out->n_detected, pin_cnt + kSmallFrames, sizeof(int) * nf);
-        return check_overflow(ctx);
-    }
+    if (n_frames > 0 && n_frames <= std::min(kSmallFrames, ctx->chunk) && ctx->pin)
+        return small_call(ctx, left, right, pitch, frame_stride, n_frames, masks, nullptr, 0, out);
     int chunk_id = 0;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk, ++chunk_id) {
         Lane& l = ctx->lanes[chunk_id % ctx->n_lanes];
@@ -1099,6 +978,37 @@ int svi_stereo_frames(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, s
     return check_overflow(ctx);
 }
 
+int svi_mask_active_landmarks(svi_ctx* ctx, const float* centres_xy, int n_centres, uint8_t* mask, size_t pitch) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!mask || n_centres < 0 || (n_centres > 0 && !centres_xy) || (int)pitch < ctx->W)
+        return fail(ctx, SVI_ERR_INVALID, "svi_mask_active_landmarks: bad argument");
+    if (n_centres > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_mask_active_landmarks: n_centres > max_queries");
+    CK(cudaSetDevice(ctx->device));
+    Lane& l = ctx->lanes[0];
+    int rc = build_mask(ctx, l, centres_xy, n_centres);
+    if (rc != SVI_SUCCESS) return rc;
+    CK(cudaMemcpy2DAsync(mask, pitch, l.mask, ctx->dev_pitch, ctx->W, ctx->H, cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaStreamSynchronize(l.stream));
+    return SVI_SUCCESS;
+}
+
+int svi_stereo_frame_masked(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch, const float* centres_xy,
+                            int n_centres, svi_stereo_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!left || !right || !out || n_centres < 0 || (n_centres > 0 && !centres_xy) || (int)pitch < ctx->W)
+        return fail(ctx, SVI_ERR_INVALID, "svi_stereo_frame_masked: bad argument");
+    if (out->capacity_per_frame < ctx->p.max_corners) return fail(ctx, SVI_ERR_CAPACITY, "svi_stereo_frame_masked: capacity_per_frame < max_corners");
+    if (!out->n_keypoints || !out->uv_left || !out->uv_right || !out->xyz_left || !out->desc_left || !out->desc_right ||
+        !out->distance || !out->match_index || !out->status)
+        return fail(ctx, SVI_ERR_INVALID, "svi_stereo_frame_masked: null output array");
+    if (n_centres > ctx->p.max_queries) return fail(ctx, SVI_ERR_CAPACITY, "svi_stereo_frame_masked: n_centres > max_queries");
+    if (!ctx->pin) return fail(ctx, SVI_ERR_UNSUPPORTED, "svi_stereo_frame_masked: frame too large for the pinned bounce buffer");
+    CK(cudaSetDevice(ctx->device));
+    static const float kNone[2] = {-1.0e9f, -1.0e9f};   // no landmark yet: an all-255 mask
+    return small_call(ctx, left, right, pitch, pitch * (size_t)ctx->H, 1, nullptr, n_centres > 0 ? centres_xy : kNone,
+                      n_centres > 0 ? n_centres : 1, out);
+}
+
 int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* response) {
     if (!ctx) return SVI_ERR_INVALID;
     if (!img || !response || (int)pitch < ctx->W) return fail(ctx, SVI_ERR_INVALID, "svi_harris_response: bad argument");
@@ -1111,7 +1021,7 @@ int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* r
     if (!ctx->resp_one) CK(dmalloc(&ctx->resp_one, (size_t)ctx->H * ctx->resp_pitch));
     harris_box_kernel<<<harris_grid(g.W, g.H, 1), HT_THREADS, sizeof(HarrisSmem), s>>>(
         l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, ctx->resp_one, nullptr, nullptr, l.frame_max, nullptr,
-        nullptr, 0, nullptr, g.H);
+        nullptr, 0, nullptr, nullptr, g.H);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, ctx->resp_one, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
                          ctx->H, cudaMemcpyDeviceToHost, s));
@@ -1150,7 +1060,7 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
         } else {
             harris_box_kernel<<<harris_grid(W, H, nf), HT_THREADS, sizeof(HarrisSmem), s>>>(
                 l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, l.frame_max, l.cand,
-                l.cand_count, ctx->raw_cap, nullptr, g.H);
+                l.cand_count, ctx->raw_cap, nullptr, nullptr, g.H);
         }
         const uint32_t* fmax = fast ? nullptr : l.frame_max;
         if (ctx->select_smem)
@@ -1315,12 +1225,14 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         return fail(ctx, SVI_ERR_INVALID, "svi_track_landmarks: stage 3 needs all three reference arrays");
     if (n == 0) return SVI_SUCCESS;
     CK(cudaSetDevice(ctx->device));
+    int rc = ensure_track_scratch(ctx);
+    if (rc != SVI_SUCCESS) return rc;
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0; ctx->pending.clear();
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
     // both images as planes 0 / 1 of one buffer (the window-mode detector indexes them by plane)
-    int rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
+    rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s, 1);
     if (rc != SVI_SUCCESS) return rc;
@@ -1330,6 +1242,15 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     UP(d_dr, lm->last_desc_right, (size_t)n * 32);
     UP(d_disp, lm->last_disparity, (size_t)n);
     UP(d_size, lm->keypoint_size, (size_t)n);
+    Stage3Extra ex{nullptr, nullptr};
+    uint8_t* d_orig = nullptr;
+    if (stage3) {
+        double* d_uvref; double* d_tdet;
+        UP(d_uvref, lm->uv_reference_left, (size_t)n * 2);
+        UP(d_tdet, lm->T_left_to_world_at_detection, (size_t)n * 16);
+        UP(d_orig, lm->desc_reference_left, (size_t)n * 32);
+        ex.uv_ref = d_uvref; ex.T_det = d_tdet;
+    }
     TrackOutDev o;
     UP(o.status, (const uint8_t*)nullptr, (size_t)n);
     UP(o.stage, (const uint8_t*)nullptr, (size_t)n);
@@ -1350,6 +1271,8 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     k.stage1_match = (stage_mask & SVI_STAGE_1) ? 1 : 0;
     LandmarksDev ld{d_xyzw, d_dl, d_dr, d_disp, d_size};
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, plane);
+    // The whole cascade is ONE stream of kernels: every stage reads the stage / status bytes the previous one left on
+    // the device and plans its own work items there; the host only waits once, for the results.
     if (stage_mask & (SVI_STAGE_1 | SVI_STAGE_2)) {
         // ---- stage 1 LEFT / RIGHT for every landmark (or only its field-of-view gate when stage 2 runs alone)
         track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
@@ -1360,25 +1283,25 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         CK(cudaMemsetAsync(o.status, SVI_TRK_STAGE1_DIST, (size_t)n, s));
         CK(cudaMemsetAsync(o.stage, 0, (size_t)n, s));
     }
-    CK(cudaMemcpyAsync(out->status, o.status, (size_t)n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out->stage, o.stage, (size_t)n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     // ---- stage 2 LEFT, then stage 2 RIGHT, for what is still untracked
     for (int side = 0; side < 2 && (stage_mask & SVI_STAGE_2); ++side) {
-        rc = track_stage2_side(ctx, l, g, lm, n, T_world_to_left, motion_scaling, side == 0, ld, o, out);
-        if (rc != SVI_SUCCESS) return rc;
+        rc = track_stage2_side(ctx, l, g, n, T_world_to_left, motion_scaling, side == 0, ld, o);
+        if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
     }
     // ---- stage 3 (epipolar line in LEFT)
     if (stage3) {
-        rc = track_stage3_all(ctx, l, g, lm, n, T_world_to_left, motion_scaling, ld, o, out);
-        if (rc != SVI_SUCCESS) return rc;
+        rc = track_stage3_all(ctx, l, g, n, T_world_to_left, motion_scaling, ld, ex, d_orig, o);
+        if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
     }
-    int rd = download(ctx, out->uv_left, o.uv_l, sizeof(float) * 2 * n, s);
+    int rd = download(ctx, out->status, o.status, (size_t)n, s);
+    if (rd == SVI_SUCCESS) rd = download(ctx, out->stage, o.stage, (size_t)n, s);
+    if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_left, o.uv_l, sizeof(float) * 2 * n, s);
     if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_right, o.uv_r, sizeof(float) * 2 * n, s);
     if (rd == SVI_SUCCESS) rd = download(ctx, out->xyz_left, o.xyz, sizeof(double) * 3 * n, s);
     if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_left, o.desc_l, (size_t)32 * n, s);
     if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_right, o.desc_r, (size_t)32 * n, s);
     if (rd == SVI_SUCCESS) rd = flush_downloads(ctx, s);
+    else cudaStreamSynchronize(s);
     if (rd != SVI_SUCCESS) return rd;
     return check_overflow(ctx);
 }

@@ -154,9 +154,34 @@ class StereoFrontend:
                                                 _ptr(M), C.byref(r)))
         return out
 
-    def add_new_landmarks(self, img_left, img_right, mask=None) -> dict:
-        """One pair; per-key-point arrays in the reference's iteration order."""
-        return self.stereo_frames(img_left, img_right, mask).frame(0)
+    def add_new_landmarks(self, img_left, img_right, mask=None, mask_centres=None) -> dict:
+        """One pair; per-key-point arrays in the reference's iteration order.  mask_centres (n, 2): the detection mask
+        of getMaskActiveLandmarks is built on the GPU from these landmark centres (svi_stereo_frame_masked)."""
+        if mask_centres is None:
+            return self.stereo_frames(img_left, img_right, mask).frame(0)
+        if mask is not None:
+            raise ValueError("give either a mask plane or mask centres")
+        L, R = self._images(img_left, "left"), self._images(img_right, "right")
+        c = np.ascontiguousarray(np.asarray(mask_centres, np.float32).reshape(-1, 2))
+        cap = self.max_corners
+        out = StereoFrames(
+            n_keypoints=np.zeros(1, np.int32), n_detected=np.zeros(1, np.int32),
+            uv_left=np.zeros((1, cap, 2), np.float32), uv_right=np.zeros((1, cap, 2), np.float32),
+            xyz_left=np.zeros((1, cap, 3), np.float64), desc_left=np.zeros((1, cap, 32), np.uint8),
+            desc_right=np.zeros((1, cap, 32), np.uint8), distance=np.full((1, cap), -1, np.int32),
+            match_index=np.full((1, cap), -1, np.int32), status=np.zeros((1, cap), np.uint8))
+        r = _lib.StereoResult(cap, _ptr(out.n_keypoints), _ptr(out.n_detected), _ptr(out.uv_left), _ptr(out.uv_right),
+                              _ptr(out.xyz_left), _ptr(out.desc_left), _ptr(out.desc_right), _ptr(out.distance),
+                              _ptr(out.match_index), _ptr(out.status))
+        self._check(self._lib.svi_stereo_frame_masked(self._ctx, _ptr(L), _ptr(R), self.width, _ptr(c) if len(c) else None, len(c), C.byref(r)))
+        return out.frame(0)
+
+    def mask_active_landmarks(self, centres) -> np.ndarray:
+        """getMaskActiveLandmarks: (H, W) u8 plane, 255 with radius-7 zero discs at the centres (built on the GPU)."""
+        c = np.ascontiguousarray(np.asarray(centres, np.float32).reshape(-1, 2))
+        m = np.empty((self.height, self.width), np.uint8)
+        self._check(self._lib.svi_mask_active_landmarks(self._ctx, _ptr(c) if len(c) else None, len(c), _ptr(m), self.width))
+        return m
 
     def stereo_frames_raw(self, left_ptr, right_ptr, pitch, frame_stride, n_frames, result: _lib.StereoResult, masks_ptr=None):
         """svi_stereo_frames on caller-managed HOST memory given as raw addresses (e.g. pinned torch tensors)."""

@@ -217,56 +217,54 @@ public:
         return m_vecMeasurementsVisible;
     }
 
-    // getMaskActiveLandmarks :2043-2073: 255 everywhere, filled radius-7 zero discs (cv::circle stencil)
-    std::vector<uint8_t> getMaskActiveLandmarks(const Isometry3d& p_matTransformationWORLDtoLEFT) const {
-        const int W = m_pCameraSTEREO->m_uPixelWidth, H = m_pCameraSTEREO->m_uPixelHeight;
-        std::vector<uint8_t> matMaskDetection((size_t)W * H, 255);
-        static const int arrHalfWidth[15] = {0, 3, 4, 5, 6, 6, 6, 7, 6, 6, 6, 5, 4, 3, 0};
+    // The centres getMaskActiveLandmarks :2043-2073 draws its discs at: the last LEFT detection of a visible landmark
+    // (:2057), the projection of an invisible one (getUV, :2062-2065).
+    std::vector<Point2f> getMaskCentres(const Isometry3d& p_matTransformationWORLDtoLEFT) const {
+        std::vector<Point2f> vecCentres;
         for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
             for (const CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
-                Point2f ptCenter;
-                if (pLandmark->bIsCurrentlyVisible) ptCenter = pLandmark->getLastDetectionLEFT();
+                if (pLandmark->bIsCurrentlyVisible) vecCentres.push_back(pLandmark->getLastDetectionLEFT());
                 else {
                     const CPoint3DCAMERA p(p_matTransformationWORLDtoLEFT * pLandmark->vecPointXYZOptimized);
                     const MatrixProjection& P = m_pCameraLEFT->m_matProjection;
                     const double w = P(2, 0) * p.x() + P(2, 1) * p.y() + P(2, 2) * p.z() + P(2, 3);
-                    ptCenter = Point2f((float)((P(0, 0) * p.x() + P(0, 1) * p.y() + P(0, 2) * p.z() + P(0, 3)) / w),
-                                       (float)((P(1, 0) * p.x() + P(1, 1) * p.y() + P(1, 2) * p.z() + P(1, 3)) / w));
-                }
-                const long cx = std::lrint(ptCenter.x), cy = std::lrint(ptCenter.y);
-                for (int dy = -7; dy <= 7; ++dy) {
-                    const long y = cy + dy;
-                    if (y < 0 || y >= H) continue;
-                    const long x0 = std::max(cx - arrHalfWidth[dy + 7], 0L), x1 = std::min(cx + arrHalfWidth[dy + 7], (long)W - 1);
-                    for (long x = x0; x <= x1; ++x) matMaskDetection[(size_t)y * W + x] = 0;
+                    vecCentres.push_back(Point2f((float)((P(0, 0) * p.x() + P(0, 1) * p.y() + P(0, 2) * p.z() + P(0, 3)) / w),
+                                                 (float)((P(1, 0) * p.x() + P(1, 1) * p.y() + P(1, 2) * p.z() + P(1, 3)) / w)));
                 }
             }
+        return vecCentres;
+    }
+    // 255 everywhere, filled radius-7 zero discs (cv::circle, m_uFeatureRadiusForMask): stamped on the GPU
+    // (svi_mask_active_landmarks); the plane only comes back for callers that want to look at it
+    std::vector<uint8_t> getMaskForCentres(const std::vector<Point2f>& p_vecCentres) const {
+        const int W = m_pCameraSTEREO->m_uPixelWidth, H = m_pCameraSTEREO->m_uPixelHeight;
+        std::vector<uint8_t> matMaskDetection((size_t)W * H, 255);
+        static_assert(sizeof(Point2f) == 2 * sizeof(float), "Point2f is two packed floats");
+        m_pGpu->check(svi_mask_active_landmarks(m_pGpu->ctx, p_vecCentres.empty() ? nullptr : &p_vecCentres[0].x, (int)p_vecCentres.size(),
+                                                matMaskDetection.data(), (size_t)W));
         return matMaskDetection;
     }
+    std::vector<uint8_t> getMaskActiveLandmarks(const Isometry3d& p_matTransformationWORLDtoLEFT) const {
+        return getMaskForCentres(getMaskCentres(p_matTransformationWORLDtoLEFT));
+    }
 
-    // addNewLandmarks :83-193: mask -> detect -> describe -> per-key-point scan-line triangulation, one GPU call
+    // addNewLandmarks :83-193: mask -> detect -> describe -> per-key-point scan-line triangulation, one GPU call; the
+    // mask is built on the device from the landmark centres (8 bytes per landmark instead of a W x H plane upload)
     std::vector<CLandmark*>::size_type addNewLandmarks(const ImageView& p_matImageLEFT, const ImageView& p_matImageRIGHT,
                                                        const Isometry3d& p_matTransformationWORLDtoLEFT,
                                                        const Isometry3d& p_matTransformationLEFTtoWORLD, const UIDFrame& p_uIDFrame) {
         const MatrixProjection matProjectionWORLDtoLEFT(m_pCameraLEFT->m_matProjection * p_matTransformationWORLDtoLEFT);
         const MatrixProjection matProjectionWORLDtoRIGHT(m_pCameraRIGHT->m_matProjection * p_matTransformationWORLDtoLEFT);
-        const std::vector<uint8_t> matMask(getMaskActiveLandmarks(p_matTransformationWORLDtoLEFT));
-        const int W = m_pCameraSTEREO->m_uPixelWidth, H = m_pCameraSTEREO->m_uPixelHeight, cap = m_pGpu->params.max_corners;
-        // the mask shares the images' pitch: repack if the caller's rows are padded
-        std::vector<uint8_t> matMaskPitched;
-        const uint8_t* pMask = matMask.data();
-        if (p_matImageLEFT.pitch != (size_t)W) {
-            matMaskPitched.assign(p_matImageLEFT.pitch * H, 255);
-            for (int y = 0; y < H; ++y) std::memcpy(&matMaskPitched[y * p_matImageLEFT.pitch], &matMask[(size_t)y * W], W);
-            pMask = matMaskPitched.data();
-        }
+        const std::vector<Point2f> vecCentres(getMaskCentres(p_matTransformationWORLDtoLEFT));
+        const int cap = m_pGpu->params.max_corners;
         int32_t nKeyPoints = 0, nDetected = 0;
         std::vector<float> uvL(2 * cap), uvR(2 * cap);
         std::vector<double> xyz(3 * cap);
         std::vector<uint8_t> dL(32 * cap), dR(32 * cap), st(cap);
         std::vector<int32_t> dist(cap), idx(cap);
         svi_stereo_result r{cap, &nKeyPoints, &nDetected, uvL.data(), uvR.data(), xyz.data(), dL.data(), dR.data(), dist.data(), idx.data(), st.data()};
-        m_pGpu->check(svi_stereo_frames(m_pGpu->ctx, p_matImageLEFT.data, p_matImageRIGHT.data, p_matImageLEFT.pitch, p_matImageLEFT.pitch * H, 1, pMask, &r));
+        m_pGpu->check(svi_stereo_frame_masked(m_pGpu->ctx, p_matImageLEFT.data, p_matImageRIGHT.data, p_matImageLEFT.pitch,
+                                              vecCentres.empty() ? nullptr : &vecCentres[0].x, (int)vecCentres.size(), &r));
 
         std::shared_ptr<std::vector<CLandmark*>> vecLandmarksNEW(std::make_shared<std::vector<CLandmark*>>());
         for (int32_t u = 0; u < nKeyPoints; ++u) {

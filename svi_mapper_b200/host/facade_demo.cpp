@@ -95,8 +95,32 @@ static int landmarkMain(char** argv) {
     return 0;
 }
 
+// --mask <left_calib> <right_calib> <centres.txt> <out.raw>: the detection mask of getMaskActiveLandmarks for the given
+// centres ("x y" per line), written as a W x H u8 plane -- pinned against cv2.circle golden data by the tests
+static int maskMain(char** argv) {
+    try {
+        CParameterBase::loadCameraLEFT(argv[2]);
+        CParameterBase::loadCameraRIGHT(argv[3]);
+        CParameterBase::constructCameraSTEREO(CPoint3D(-0.54, 0.0, 0.0));
+        auto pGpu = std::make_shared<CGpuContext>(CParameterBase::pCameraSTEREO);
+        CFundamentalMatcher cMatcher(CParameterBase::pCameraSTEREO, pGpu);
+        std::vector<Point2f> vecCentres;
+        std::ifstream f(argv[4]);
+        float x, y;
+        while (f >> x >> y) vecCentres.push_back(Point2f(x, y));
+        const std::vector<uint8_t> matMask(cMatcher.getMaskForCentres(vecCentres));
+        std::ofstream o(argv[5], std::ios::binary);
+        o.write(reinterpret_cast<const char*>(matMask.data()), (std::streamsize)matMask.size());
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "facade_demo failed: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc == 5 && std::string(argv[1]) == "--solver") return solverMain(argv);
+    if (argc == 6 && std::string(argv[1]) == "--mask") return maskMain(argv);
     if (argc == 3 && std::string(argv[1]) == "--landmark") return landmarkMain(argv);
     if (argc == 5 && std::string(argv[1]) == "--cloud") return cloudMain(argv);
     if (argc < 10) { std::fprintf(stderr, "usage: see source\n"); return 2; }

@@ -843,7 +843,8 @@ def test_other_pair_tables(vi_cams, kitti_cams, table):
     tests, the gather kernels and the C-ABI end to end."""
     from oracle import c_oracle as co
     from svi_mapper_b200 import build as bld
-    alt = bld.build_alt_tables()[table]
+    alt = dict(bld.build_alt_tables()[table])
+    alt["oracle"] = co.build_variant(alt["header"], alt["header"].parent / "libsvi_oracle.so")
     for cams, seed, mc in ((kitti_cams, 0, 1000), (vi_cams, 4000, 1000)):
         W, H = cams[0].width, cams[0].height
         L, R = stereo_pair(W, H, seed)
@@ -899,3 +900,39 @@ def test_track_cascade_full_landmark_set_vs_c_port(vi_cams):
             _c_vs_gpu_tracks(fe.track_landmarks(a, b, T, *args, scaling, **kw), want)
             seen += np.bincount(want["stage"], minlength=6)
     assert seen[1] > 1000 and seen[3] > 500 and seen[5] > 50, seen
+
+
+def test_detection_mask_on_gpu_matches_cv2_circle(kitti_cams, calib_dir, tmp_path):
+    """getMaskActiveLandmarks (CFundamentalMatcher.cpp:2043-2073) stamped by the GPU stencil kernel == the cv2.circle
+    golden plane (tests/golden/stereo_320x240.npz: 60 centres incl. discs cut by every image edge), through the C-ABI
+    and through the C++ facade (facade_demo --mask); addNewLandmarks with device-built mask == with an uploaded plane."""
+    import pathlib
+    import subprocess
+    from svi_mapper_b200.calib import PinholeCamera
+    gold = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "stereo_320x240.npz")
+    small = [PinholeCamera(c.label, 320, 240, c.P, c.K, c.focal_length_m, c.distortion, c.rectification) for c in kitti_cams]
+    with StereoFrontend(*small) as fe:
+        np.testing.assert_array_equal(fe.mask_active_landmarks(gold["mask_centres"]), gold["mask"])
+        assert (fe.mask_active_landmarks(np.zeros((0, 2), np.float32)) == 255).all()
+        far = np.array([[1e9, 5.0], [np.nan, 3.0], [-1e12, -1e12], [160.4, 120.6]], np.float32)   # projections at infinity draw nothing
+        np.testing.assert_array_equal(fe.mask_active_landmarks(far), o.mask_active_landmarks(320, 240, [(160.4, 120.6)]))
+        # new landmarks under the mask: centres on the device == the same plane uploaded by the caller
+        a = fe.add_new_landmarks(gold["left"], gold["right"], mask=gold["mask"])
+        b = fe.add_new_landmarks(gold["left"], gold["right"], mask_centres=gold["mask_centres"])
+        c = fe.add_new_landmarks(gold["left"], gold["right"], mask_centres=np.zeros((0, 2), np.float32))
+        d = fe.add_new_landmarks(gold["left"], gold["right"])
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+            np.testing.assert_array_equal(c[k], d[k], err_msg=k)
+        assert len(a["status"]) > 50 and len(a["status"]) != len(d["status"])
+        np.testing.assert_array_equal(d["uv_l"], gold["frame_uv_l"])
+    # the C++ facade draws the same plane (one implementation: the kernel)
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    for side in ("left", "right"):
+        txt = (calib_dir / f"kitti_00_{side}.txt").read_text().replace("uWidthPixels 1241", "uWidthPixels 320").replace("uHeightPixels 376", "uHeightPixels 240")
+        (tmp_path / f"{side}.txt").write_text(txt)
+    np.savetxt(tmp_path / "centres.txt", gold["mask_centres"], fmt="%.9g")
+    r = subprocess.run([str(exe), "--mask", str(tmp_path / "left.txt"), str(tmp_path / "right.txt"), str(tmp_path / "centres.txt"), str(tmp_path / "mask.raw")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    np.testing.assert_array_equal(np.fromfile(tmp_path / "mask.raw", np.uint8).reshape(240, 320), gold["mask"])
