@@ -936,3 +936,52 @@ def test_detection_mask_on_gpu_matches_cv2_circle(kitti_cams, calib_dir, tmp_pat
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     np.testing.assert_array_equal(np.fromfile(tmp_path / "mask.raw", np.uint8).reshape(240, 320), gold["mask"])
+
+
+class _CpuBackend:
+    """SequenceTracker backend over the C restatement (checker side of the sequence tests)."""
+
+    def __init__(self, cfg, threads):
+        from oracle import c_oracle as co
+        self.co, self.cfg, self.threads = co, cfg, threads
+
+    def track(self, L, R, T, s, scaling, size):
+        return self.co.track_landmarks(self.cfg, L, R, T, s["xyz_w"], s["last_desc_l"], s["last_desc_r"], s["last_disp"], size, scaling,
+                                       uv_reference_left=s["uv_ref"], desc_reference_left=s["ref_desc_l"],
+                                       T_left_to_world_at_detection=s["T_det"], n_threads=self.threads)
+
+    def add_new(self, L, R, centres):
+        m = o.mask_active_landmarks(L.shape[1], L.shape[0], centres)[None] if len(centres) else None
+        return self.co.frame(self.co.stereo_frames(self.cfg, L, R, masks=m), 0)
+
+
+def test_sequence_tracking_in_lockstep_with_cpu_port(vi_cams):
+    """BASELINE configs[2] in small: a rendered vi_sensor sequence (static world, smooth trajectory) run through the
+    per-frame loop of CTrackerGT::_trackLandmarks -- trackManual on every active landmark, visibility / failure
+    bookkeeping, retirement, re-detection under the device-built mask -- once over the GPU front-end and once over the C
+    port, with the landmark state fed forward.  Every frame's tracking result, new-landmark result and bookkeeping
+    record must be identical (so the two sequences never diverge), and all three stages must occur."""
+    from oracle import c_oracle as co
+    from svi_mapper_b200.sequence import GpuBackend, SequenceTracker, render_sequence
+    n = 14
+    L, R, T = render_sequence(vi_cams[0], vi_cams[1], n)
+    cfg = co.make_config(vi_cams[0], vi_cams[1], max_corners=1000)
+    total = np.zeros(6, np.int64)
+    with StereoFrontend(*vi_cams) as fe:
+        g, c = SequenceTracker(GpuBackend(fe), vi_cams[0]), SequenceTracker(_CpuBackend(cfg, co.host_threads()), vi_cams[0])
+        for t in range(n):
+            rg, rc = g.process(L[t], R[t], T[t]), c.process(L[t], R[t], T[t])
+            assert rg == rc, (t, rg, rc)
+            if rg["tracked"]:
+                _c_vs_gpu_tracks(g.last_track, c.last_track)
+            if rg["new"]:
+                for k in ("uv_l", "desc_l", "status"):
+                    np.testing.assert_array_equal(g.last_new[k], c.last_new[k], err_msg=k)
+                ok = c.last_new["status"] == 0
+                for k in ("uv_r", "desc_r", "xyz"):
+                    np.testing.assert_array_equal(g.last_new[k][ok], c.last_new[k][ok], err_msg=k)
+            for k in g.s:
+                np.testing.assert_array_equal(g.s[k], c.s[k], err_msg=k)
+            total += np.asarray(rg["stages"])
+    assert g.n_active > 1500 and total[1] > 5000 and total[3] + total[4] > 100 and total[5] > 100, (g.n_active, total)
+    assert sum(r["new"] > 0 for r in g.log) >= 3          # the re-detection trigger of CTrackerGT.cpp:305 fired repeatedly
