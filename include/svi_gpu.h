@@ -277,11 +277,33 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
                         double motion_scaling, uint32_t stage_mask, svi_track_result* out);
 
 /* Stage profiling: when enabled, every kernel of the new-landmark path is bracketed by CUDA events
- * on the stream it is launched on.  svi_set_profiling also clears the accumulators;
- * svi_stage_timings waits for the ctx to go idle and returns, per stage, the summed launch
- * duration in ms and the number of launches (arrays of length >= 5; returns the stage count). */
+ * on the stream it is launched on (the events come from a pool filled here, none is created while
+ * work is being timed).  enable = 1: the lanes keep overlapping, a bracket also contains other lanes'
+ * kernels; enable = 2: svi_stereo_frames_device runs every chunk on ONE lane, so each bracket is the
+ * exclusive duration of one kernel (what the roofline record uses -- slower overall, not for timing
+ * the step).  svi_set_profiling also clears the accumulators; svi_stage_timings waits for the ctx to
+ * go idle and returns, per stage, the summed launch duration in ms and the number of launches
+ * (arrays of length >= 4; returns the stage count). */
 int svi_set_profiling(svi_ctx* ctx, int enable);
 int svi_stage_timings(svi_ctx* ctx, const char** names, double* total_ms, int64_t* launches, int capacity);
+
+/* Frame-partitioned batches over the GPUs of one box (stereo pairs are independent:
+ * CFundamentalMatcher::addNewLandmarks keeps no state between pairs, src/core/CFundamentalMatcher.cpp:83-193,
+ * CTriangulator is const).  svi_multi owns one svi_ctx per listed device (devices == NULL: 0 .. n_devices-1; a
+ * device may be listed more than once).  svi_multi_stereo_frames cuts the n_frames pairs into contiguous ranges
+ * [g*F/G, (g+1)*F/G) (svi_multi_frame_range), runs every range through its own ctx on its own host thread and
+ * writes disjoint slices of the caller's host arrays -- no collective, no peer access; the outputs are
+ * byte-for-byte those of svi_stereo_frames on one device.  Pinned host buffers keep the copies asynchronous. */
+typedef struct svi_multi svi_multi;
+int svi_multi_create(const svi_camera* left, const svi_camera* right, const svi_params* params,
+                     const int* devices, int n_devices, svi_multi** out);
+void svi_multi_destroy(svi_multi* m);
+const char* svi_multi_last_error(const svi_multi* m); /* m may be NULL: last create error */
+int svi_multi_device_count(const svi_multi* m);
+int svi_multi_frame_range(const svi_multi* m, int n_frames, int part, int* first, int* count);
+int svi_multi_stereo_frames(svi_multi* m, const uint8_t* left, const uint8_t* right, size_t pitch,
+                            size_t frame_stride, int n_frames, const uint8_t* masks_or_null,
+                            svi_stereo_result* out);
 
 /* How this ctx was configured: frames per kernel wave, number of stream lanes, whether corner
  * selection runs out of shared memory (1) or the global-memory variant for very large frames (0). */

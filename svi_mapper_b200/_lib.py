@@ -24,6 +24,8 @@ EXPORTS = (
     "svi_stereo_frames", "svi_stereo_frames_device", "svi_check_overflow", "svi_mask_active_landmarks", "svi_stereo_frame_masked", "svi_harris_response", "svi_detect", "svi_describe",
     "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
     "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config",
+    "svi_multi_create", "svi_multi_destroy", "svi_multi_last_error", "svi_multi_device_count", "svi_multi_frame_range",
+    "svi_multi_stereo_frames",
 )
 
 u8p, i32p, f32p, f64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
@@ -116,6 +118,14 @@ def load(path=None):
     lib.svi_set_profiling.argtypes = [vp, ci]
     lib.svi_stage_timings.argtypes = [vp, C.POINTER(C.c_char_p), f64p, C.POINTER(C.c_int64), ci]
     lib.svi_config.argtypes = [vp, i32p, i32p, i32p]
+    lib.svi_multi_create.argtypes = [C.POINTER(Camera), C.POINTER(Camera), C.POINTER(Params), i32p, ci, C.POINTER(vp)]
+    lib.svi_multi_destroy.argtypes = [vp]
+    lib.svi_multi_destroy.restype = None
+    lib.svi_multi_last_error.argtypes = [vp]
+    lib.svi_multi_last_error.restype = C.c_char_p
+    lib.svi_multi_device_count.argtypes = [vp]
+    lib.svi_multi_frame_range.argtypes = [vp, ci, ci, i32p, i32p]
+    lib.svi_multi_stereo_frames.argtypes = [vp, vp, vp, sz, sz, ci, vp, C.POINTER(StereoResult)]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = header/library mismatch
     if path is None:

@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",          # Harris must round every fp32 op on its own (cv2 parity)
     "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-pthread",           # svi_multi: one host thread per GPU
     "-Xcompiler", "-ffp-contract=off",   # host-side fp64 geometry: same rounding as the kernels, whatever -march is used
 ]
 

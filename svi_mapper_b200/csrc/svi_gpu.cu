@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/svi_gpu.h"
@@ -112,6 +113,7 @@ struct svi_ctx {
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
     bool profiling = false;
+    bool serial = false;   // profiling mode 2: every chunk on lane 0, so that the stage events bracket ONE kernel each
     double stage_ms[kStages] = {0, 0, 0, 0};
     long stage_launches[kStages] = {0, 0, 0, 0};
     std::string err;
@@ -896,7 +898,7 @@ int svi_stereo_frames_device(svi_ctx* ctx, const uint8_t* left, const uint8_t* r
     o.dist = out->distance; o.idx = out->match_index; o.status = out->status;
     int chunk_id = 0, rc = SVI_SUCCESS;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->chunk, ++chunk_id) {
-        Lane& l = ctx->lanes[chunk_id % ctx->n_lanes];
+        Lane& l = ctx->lanes[ctx->serial ? 0 : chunk_id % ctx->n_lanes];
         const int nf = std::min(ctx->chunk, n_frames - f0);
         int* n_det = out->n_detected ? out->n_detected + f0 : l.n_det;
         rc = run_pipeline(ctx, l, left + (size_t)f0 * frame_stride, right + (size_t)f0 * frame_stride,
@@ -1312,8 +1314,9 @@ int svi_set_profiling(svi_ctx* ctx, int enable) {
     collect_timings(ctx);
     for (int s = 0; s < kStages; ++s) { ctx->stage_ms[s] = 0.0; ctx->stage_launches[s] = 0; }
     ctx->profiling = enable != 0;
+    ctx->serial = enable == 2;
     if (ctx->profiling)
-        for (int i = 0; i < ctx->n_lanes; ++i) reserve_events(ctx->lanes[i], kEventPool);
+        for (int i = 0; i < ctx->n_lanes; ++i) reserve_events(ctx->lanes[i], ctx->serial && i == 0 ? 8 * kEventPool : kEventPool);
     return SVI_SUCCESS;
 }
 
@@ -1335,6 +1338,93 @@ int svi_stage_timings(svi_ctx* ctx, const char** names, double* total_ms, int64_
         launches[i] = ctx->stage_launches[i];
     }
     return n;
+}
+
+// ---- frame-partitioned batches over several GPUs: stereo pairs are independent, so a batch of F
+// frames is cut into contiguous ranges [g*F/G, (g+1)*F/G), one per device; each range runs through its own svi_ctx on
+// its own host thread and writes a disjoint slice of the caller's arrays.  No collective, no peer access: the result is
+// byte-for-byte the one a single device produces.
+struct svi_multi {
+    std::vector<svi_ctx*> ctx;
+    std::vector<int> devices;
+    std::string err;
+};
+
+int svi_multi_create(const svi_camera* left, const svi_camera* right, const svi_params* params, const int* devices, int n_devices,
+                     svi_multi** out) {
+    if (!left || !right || !out || n_devices < 1 || n_devices > 64) return fail(nullptr, SVI_ERR_INVALID, "svi_multi_create: bad argument");
+    *out = nullptr;
+    svi_multi* m = new svi_multi();
+    for (int g = 0; g < n_devices; ++g) {
+        svi_ctx* c = nullptr;
+        const int dev = devices ? devices[g] : g;
+        const int rc = svi_create(left, right, params, dev, &c);
+        if (rc != SVI_SUCCESS) {   // g_create_error holds the reason
+            for (svi_ctx* q : m->ctx) svi_destroy(q);
+            delete m;
+            return rc;
+        }
+        m->ctx.push_back(c);
+        m->devices.push_back(dev);
+    }
+    *out = m;
+    return SVI_SUCCESS;
+}
+
+void svi_multi_destroy(svi_multi* m) {
+    if (!m) return;
+    for (svi_ctx* c : m->ctx) svi_destroy(c);
+    delete m;
+}
+
+const char* svi_multi_last_error(const svi_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+int svi_multi_device_count(const svi_multi* m) { return m ? (int)m->ctx.size() : 0; }
+
+int svi_multi_frame_range(const svi_multi* m, int n_frames, int part, int* first, int* count) {
+    if (!m || !first || !count || n_frames < 0 || part < 0 || part >= (int)m->ctx.size()) return SVI_ERR_INVALID;
+    const long long G = (long long)m->ctx.size();
+    const long long f0 = (long long)part * n_frames / G, f1 = (long long)(part + 1) * n_frames / G;
+    *first = (int)f0;
+    *count = (int)(f1 - f0);
+    return SVI_SUCCESS;
+}
+
+int svi_multi_stereo_frames(svi_multi* m, const uint8_t* left, const uint8_t* right, size_t pitch, size_t frame_stride, int n_frames,
+                            const uint8_t* masks, svi_stereo_result* out) {
+    if (!m) return SVI_ERR_INVALID;
+    if (!left || !right || !out || n_frames < 0) { m->err = "svi_multi_stereo_frames: bad argument"; return SVI_ERR_INVALID; }
+    const int G = (int)m->ctx.size();
+    std::vector<int> rc(G, SVI_SUCCESS);
+    std::vector<std::thread> workers;
+    const size_t cap = (size_t)out->capacity_per_frame;
+    for (int g = 0; g < G; ++g) {
+        int f0 = 0, nf = 0;
+        svi_multi_frame_range(m, n_frames, g, &f0, &nf);
+        if (nf == 0) continue;
+        workers.emplace_back([=, &rc]() {
+            svi_stereo_result sub = *out;   // the same arrays, advanced to this range's first frame
+            const size_t o0 = (size_t)f0 * cap;
+            sub.n_keypoints = out->n_keypoints ? out->n_keypoints + f0 : nullptr;
+            sub.n_detected = out->n_detected ? out->n_detected + f0 : nullptr;
+            sub.uv_left = out->uv_left ? out->uv_left + o0 * 2 : nullptr;
+            sub.uv_right = out->uv_right ? out->uv_right + o0 * 2 : nullptr;
+            sub.xyz_left = out->xyz_left ? out->xyz_left + o0 * 3 : nullptr;
+            sub.desc_left = out->desc_left ? out->desc_left + o0 * 32 : nullptr;
+            sub.desc_right = out->desc_right ? out->desc_right + o0 * 32 : nullptr;
+            sub.distance = out->distance ? out->distance + o0 : nullptr;
+            sub.match_index = out->match_index ? out->match_index + o0 : nullptr;
+            sub.status = out->status ? out->status + o0 : nullptr;
+            rc[g] = svi_stereo_frames(m->ctx[g], left + (size_t)f0 * frame_stride, right + (size_t)f0 * frame_stride, pitch, frame_stride, nf,
+                                      masks ? masks + (size_t)f0 * frame_stride : nullptr, &sub);
+        });
+    }
+    for (std::thread& t : workers) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rc[g] != SVI_SUCCESS) {
+            m->err = "device " + std::to_string(m->devices[g]) + ": " + svi_last_error(m->ctx[g]);
+            return rc[g];
+        }
+    return SVI_SUCCESS;
 }
 
 int svi_config(const svi_ctx* ctx, int32_t* chunk_frames, int32_t* n_lanes, int32_t* select_in_smem) {

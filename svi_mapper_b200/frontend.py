@@ -337,8 +337,9 @@ class StereoFrontend:
         return out
 
     # -- profiling
-    def set_profiling(self, enable: bool):
-        self._check(self._lib.svi_set_profiling(self._ctx, int(bool(enable))))
+    def set_profiling(self, enable):
+        """0 / False: off; 1 / True: stage events with overlapping lanes; 2: one lane, exclusive per-kernel durations."""
+        self._check(self._lib.svi_set_profiling(self._ctx, int(enable)))
 
     def stage_timings(self) -> dict:
         names = (C.c_char_p * 8)()

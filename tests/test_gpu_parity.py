@@ -985,3 +985,45 @@ def test_sequence_tracking_in_lockstep_with_cpu_port(vi_cams):
             total += np.asarray(rg["stages"])
     assert g.n_active > 1500 and total[1] > 5000 and total[3] + total[4] > 100 and total[5] > 100, (g.n_active, total)
     assert sum(r["new"] > 0 for r in g.log) >= 3          # the re-detection trigger of CTrackerGT.cpp:305 fired repeatedly
+
+
+def _same_stereo(a, b, n):
+    np.testing.assert_array_equal(a.n_keypoints, b.n_keypoints)
+    np.testing.assert_array_equal(a.n_detected, b.n_detected)
+    for f in range(n):
+        fa, fb = a.frame(f), b.frame(f)
+        for k in ("uv_l", "desc_l", "status", "dist", "idx"):
+            assert fa[k].tobytes() == fb[k].tobytes(), (f, k)
+        ok = fa["status"] == 0
+        for k in ("uv_r", "desc_r", "xyz"):
+            assert fa[k][ok].tobytes() == fb[k][ok].tobytes(), (f, k)
+
+
+def test_multi_gpu_driver_equals_single_device(kitti1112_cams):
+    """svi_multi (one host thread + one svi_ctx per device, contiguous frame ranges, disjoint output slices) returns
+    byte-for-byte what one device returns.  On a box with >= 2 GPUs the ranges really run on different
+    devices; with one GPU the same driver runs two contexts of device 0 side by side (same code path, same threads)."""
+    import torch
+    W, H = kitti1112_cams[0].width, kitti1112_cams[0].height
+    n = 37                                               # not divisible by 2, 3 or 4: ragged ranges
+    pairs = [stereo_pair(W, H, 2000 + i) for i in range(6)]
+    L = np.stack([pairs[i % 6][0] for i in range(n)])
+    R = np.stack([pairs[i % 6][1] for i in range(n)])
+    for i in range(n):                                   # make every frame distinct
+        L[i, :, : 8 + i] = L[i, :, : 8 + i][:, ::-1]
+    masks = np.full((n, H, W), 255, np.uint8)
+    masks[::3, 100:200, 300:700] = 0
+    from svi_mapper_b200 import MultiFrontend
+    with StereoFrontend(*kitti1112_cams, chunk_frames=8) as fe:
+        one = fe.stereo_frames(L, R, masks)
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 1 % ndev], [0, 1 % ndev, 2 % ndev], [d % ndev for d in range(4)], [0]):
+        with MultiFrontend(*kitti1112_cams, devices=devices, chunk_frames=8) as mf:
+            assert [mf.frame_range(n, g) for g in range(len(devices))] == [((g * n) // len(devices), ((g + 1) * n) // len(devices)) for g in range(len(devices))]
+            _same_stereo(mf.stereo_frames(L, R, masks), one, n)
+            _same_stereo(mf.stereo_frames(L[:1], R[:1], masks[:1]), fe_one_frame(kitti1112_cams, L[:1], R[:1], masks[:1]), 1)   # fewer frames than devices
+
+
+def fe_one_frame(cams, L, R, M):
+    with StereoFrontend(*cams, chunk_frames=8) as fe:
+        return fe.stereo_frames(L, R, M)
