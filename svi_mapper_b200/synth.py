@@ -74,7 +74,7 @@ def stereo_pair(width: int, height: int, seed: int, d_min=1, d_max=55):
     return np.ascontiguousarray(left), np.ascontiguousarray(right)
 
 
-def stereo_batch_torch(n_frames: int, width: int, height: int, seed: int, device="cuda"):
+def stereo_batch_torch(n_frames: int, width: int, height: int, seed: int, device="cuda", d_max: int = 55):
     """Batch of n_frames distinct pairs generated on `device` with torch ops.
 
     Same recipe as stereo_pair (3 blurred noise layers, block disparities 1..55, +-2 noise)
@@ -107,7 +107,7 @@ def stereo_batch_torch(n_frames: int, width: int, height: int, seed: int, device
         hi = acc.amax(dim=(2, 3), keepdim=True)
         left = torch.round((acc - lo) / (hi - lo) * 255.0).to(torch.uint8).squeeze(1)
         by, bx = 4, 8
-        d_blocks = torch.randint(1, 56, (n, by, bx), device=device, generator=g)
+        d_blocks = torch.randint(1, d_max + 1, (n, by, bx), device=device, generator=g)
         ys = torch.clamp((torch.arange(height, device=device) * by) // height, max=by - 1)
         xs = torch.clamp((torch.arange(width, device=device) * bx) // width, max=bx - 1)
         d = d_blocks[:, ys][:, :, xs]
@@ -120,3 +120,22 @@ def stereo_batch_torch(n_frames: int, width: int, height: int, seed: int, device
         outs_l.append(left.contiguous())
         outs_r.append(right.clamp_(0, 255).to(torch.uint8).contiguous())
     return torch.cat(outs_l), torch.cat(outs_r)
+
+
+def stereo_frames_range_torch(first: int, count: int, width: int, height: int, base_seed: int, device="cuda", d_max: int = 55):
+    """Frames [first, first + count) of an endless synthetic stream: the stream is generated in blocks (64 frames, 8 for
+    multi-megapixel images) with one seeded generator per block, so the content of frame i does not depend on how a batch
+    is partitioned over GPUs -- the multi-GPU runs of a fixed batch (BASELINE.json configs[3]) see the same frames as one GPU."""
+    import torch
+
+    block = 64 if width * height <= 2_000_000 else 8
+    ls, rs = [], []
+    if count <= 0:
+        e = torch.zeros((0, height, width), dtype=torch.uint8, device=device)
+        return e, e.clone()
+    for b in range(first // block, (first + count - 1) // block + 1):
+        l, r = stereo_batch_torch(block, width, height, seed=base_seed * 1000003 + b, device=device, d_max=d_max)
+        lo, hi = max(first, b * block) - b * block, min(first + count, (b + 1) * block) - b * block
+        ls.append(l[lo:hi])
+        rs.append(r[lo:hi])
+    return torch.cat(ls).contiguous(), torch.cat(rs).contiguous()

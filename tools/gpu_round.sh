@@ -1,17 +1,22 @@
 #!/bin/bash
-# One GPU-box session: parity tests, the default bench line, the ncu launch list and one --set full capture of the
-# four kernels of the new-landmark path.  Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
+# One GPU-box session: parity tests, the default bench line, every BASELINE configuration, the ncu launch list and one
+# --set full capture of the four kernels of the new-landmark path.  Usage (repo root, under gpurun): bash tools/gpu_round.sh <tag> [quick]
 set -u
 TAG=${1:-run}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
-echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
-tail -5 $OUT/${TAG}_pytest.log
-timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
-echo "bench exit $?"
-cat $OUT/${TAG}_bench.json
+echo "pytest exit $?"; tail -4 $OUT/${TAG}_pytest.log
+timeout 600 python bench.py > $OUT/${TAG}_bench_c2.json 2> $OUT/${TAG}_bench_c2.err
+echo "bench c2 exit $?"; cut -c1-400 $OUT/${TAG}_bench_c2.json
+if [ "${2:-}" != "quick" ]; then
+  for C in c1 c3 c4 c5; do
+    timeout 900 python bench.py --config $C > $OUT/${TAG}_bench_$C.json 2> $OUT/${TAG}_bench_$C.err
+    echo "bench $C exit $?"; cut -c1-300 $OUT/${TAG}_bench_$C.json; tail -2 $OUT/${TAG}_bench_$C.err
+  done
+  timeout 600 python bench.py --impl reference > $OUT/${TAG}_ref_c2.json 2>/dev/null
+fi
 SMALL="python bench.py --frames 256 --steps 1 --warmup 3 --no-cpu-baseline"
 if $SMALL > $OUT/${TAG}_plain.log 2>&1; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'harris|boxsum|select|stereo_match' -s 32 -c 64 \
