@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true", help="tuning aid: only the device-resident measurement; not a bench line")
     ap.add_argument("--device-order", default=None, help="comma list: CUDA device of local rank i (placement experiments)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node (placement experiments)")
     a = ap.parse_args()
     a.cfg = dict(CONFIGS[a.config])
     if a.frames is not None:
@@ -167,6 +168,21 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Bind this process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned buffer is allocated, so that
+    the staging memory of every rank lives on the NUMA node its PCIe root port hangs off -- with all ranks on one node the
+    host-to-device streams of a multi-GPU run meet on the inter-socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus [{cpus[0]}..{cpus[-1]}]"
+    except Exception as e:   # no NVML / not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
 
 
 def metric_name(name, cams):
@@ -477,7 +493,7 @@ def run_batch(args, rank, world, dev_index):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": cfg["what"], "name": args.config, "frames_per_step_total": total_frames, "frames_this_rank": F,
-                       "chunk_frames": chunk, "lanes": fcfg["n_lanes"],
+                       "chunk_frames": chunk, "lanes": fcfg["n_lanes"], "device": dev_index, "cpu_affinity": args.numa,
                        "l2_policy": (f"inputs {2 * F * W * H / 1e9:.2f} GB per step and rank >> 126 MB L2 (no flush needed)" if 2 * F * W * H > 4e8 else
                                      "the pair fits the L2: value = back-to-back calls on resident inputs; e2e brings new bytes from the host every call"),
                        "keypoints_per_frame": total_kp / max(len(nk), 1), "matched_per_frame": total_ok / max(len(nk), 1),
@@ -657,6 +673,8 @@ def main():
         order = [int(v) for v in args.device_order.split(",")]
         dev_index = order[local_rank % len(order)]
     torch.cuda.set_device(dev_index)
+    # multi-GPU runs only: a single rank keeps every host core (its cpu_baseline leg uses them all)
+    args.numa = bind_to_gpu_numa_node(dev_index) if (world > 1 and not args.no_numa_bind) else "all cpus"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev_index))
