@@ -668,7 +668,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
-    dev_index = local_rank
+    # Placement: on this pool's 8-GPU boxes GPUs 0-3 and 4-7 hang off two host uplinks of ~116 and ~142 GB/s
+    # (profiles/r2_h2d_matrix.json: four neighbouring GPUs share 116 GB/s, four strided ones get 217 GB/s), so a job of
+    # N < 8 ranks spreads its ranks over the visible devices (N=2 -> 0,4; N=4 -> 0,2,4,6) instead of packing them on 0..N-1.
+    n_visible = torch.cuda.device_count()
+    dev_index = local_rank * (n_visible // world) if (world <= n_visible and n_visible % world == 0) else local_rank % n_visible
     if args.device_order:
         order = [int(v) for v in args.device_order.split(",")]
         dev_index = order[local_rank % len(order)]

@@ -198,6 +198,17 @@ public:
     UIDLandmark getNumberOfTracksStage2_1() const { return m_uNumberOfTracksStage2_1; }
     UIDLandmark getNumberOfTracksStage3() const { return m_uNumberOfTracksStage3; }
     const std::vector<CLandmark*>& getLandmarksWINDOW() const { return m_vecLandmarksWINDOW; }
+    // the landmarks of the active detection points, in the order trackManual walks them
+    std::vector<const CLandmark*> getActiveLandmarks() const {
+        std::vector<const CLandmark*> v;
+        for (const CDetectionPoint& d : m_vecDetectionPointsActive) v.insert(v.end(), d.vecLandmarks->begin(), d.vecLandmarks->end());
+        return v;
+    }
+    size_t getNumberOfActiveLandmarks() const {
+        size_t n = 0;
+        for (const CDetectionPoint& d : m_vecDetectionPointsActive) n += d.vecLandmarks->size();
+        return n;
+    }
 
     // optimizeActiveLandmarks :265-277
     void optimizeActiveLandmarks(const UIDFrame& p_uFrame) const {

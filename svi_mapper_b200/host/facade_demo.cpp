@@ -118,7 +118,53 @@ static int maskMain(char** argv) {
     return 0;
 }
 
+// --sequence <left_calib> <right_calib> <n> <L.raw> <R.raw> <motions.txt> <max_corners> <out.txt>: n frames (concatenated W x H
+// planes) through CTrackerGT::process (track -> optimise -> re-detect), the per-frame relative motion LEFTLAST->LEFTNOW as
+// 12 numbers + the rotation norm per line.  Prints, per frame, the counters, every visible landmark's measurement and the
+// state of every active landmark after the frame -- compared line by line with the CPU restatement of the same loop.
+static int sequenceMain(char** argv) {
+    try {
+        CParameterBase::loadCameraLEFT(argv[2]);
+        CParameterBase::loadCameraRIGHT(argv[3]);
+        CParameterBase::constructCameraSTEREO(CPoint3D(-0.54, 0.0, 0.0));
+        const int W = (int)CParameterBase::pCameraLEFT->m_uWidthPixel, H = (int)CParameterBase::pCameraLEFT->m_uHeightPixel;
+        const int n = std::atoi(argv[4]);
+        const std::vector<uint8_t> L = readRaw(argv[5], (size_t)n * W * H), R = readRaw(argv[6], (size_t)n * W * H);
+        std::ifstream fm(argv[7]);
+        svi_params p;
+        svi_params_default(&p);
+        p.max_corners = std::atoi(argv[8]);
+        auto pGpu = std::make_shared<CGpuContext>(CParameterBase::pCameraSTEREO, &p);
+        CTrackerGT cTracker(CParameterBase::pCameraSTEREO, pGpu);
+        std::FILE* out = std::fopen(argv[9], "w");
+        for (int t = 0; t < n; ++t) {
+            Isometry3d M;
+            double dRotationNorm = 0.0;
+            for (int i = 0; i < 12; ++i) fm >> M.m[i];
+            fm >> dRotationNorm;
+            cTracker.process(ImageView(L.data() + (size_t)t * W * H, W, H), ImageView(R.data() + (size_t)t * W * H, W, H), M, dRotationNorm);
+            CFundamentalMatcher& m = cTracker.getMatcher();
+            std::fprintf(out, "F %d VISIBLE %lu ACTIVE %zu S1 %lu S2 %lu S3 %lu DETECTIONS %lu\n", t, (unsigned long)cTracker.getNumberOfVisibleLandmarksLAST(),
+                         m.getNumberOfActiveLandmarks(), (unsigned long)m.getNumberOfTracksStage1(), (unsigned long)m.getNumberOfTracksStage2_1(),
+                         (unsigned long)m.getNumberOfTracksStage3(), (unsigned long)cTracker.getNumberOfDetections());
+            for (const CMeasurementLandmark* q : m.getMeasurementsForVisibleLandmarks())
+                std::fprintf(out, "M %lu %.9g %.9g %.9g %.9g %.17g %.17g %.17g\n", (unsigned long)q->uID, q->ptUVLEFT.x, q->ptUVLEFT.y, q->ptUVRIGHT.x,
+                             q->ptUVRIGHT.y, q->vecPointXYZLEFT.x(), q->vecPointXYZLEFT.y(), q->vecPointXYZLEFT.z());
+            for (const CLandmark* q : m.getActiveLandmarks())
+                std::fprintf(out, "A %lu %.17g %.17g %.17g %d %d %u %u %u %zu\n", (unsigned long)q->uID, q->vecPointXYZOptimized.x(), q->vecPointXYZOptimized.y(),
+                             q->vecPointXYZOptimized.z(), (int)q->bIsOptimal, (int)q->bIsCurrentlyVisible, q->uOptimizationsSuccessful, q->uOptimizationsFailed,
+                             (unsigned)q->uFailedSubsequentTrackings, q->getNumberOfMeasurements());
+        }
+        std::fclose(out);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "facade_demo failed: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 10 && std::string(argv[1]) == "--sequence") return sequenceMain(argv);
     if (argc == 5 && std::string(argv[1]) == "--solver") return solverMain(argv);
     if (argc == 6 && std::string(argv[1]) == "--mask") return maskMain(argv);
     if (argc == 3 && std::string(argv[1]) == "--landmark") return landmarkMain(argv);

@@ -1028,3 +1028,62 @@ def test_multi_gpu_driver_equals_single_device(kitti1112_cams):
 def fe_one_frame(cams, L, R, M):
     with StereoFrontend(*cams, chunk_frames=8) as fe:
         return fe.stereo_frames(L, R, M)
+
+
+def test_cpp_tracker_sequence_matches_cpu_restatement(vi_cams, calib_dir, tmp_path):
+    """Sequence-level parity of the host orchestration (CTrackerGT::_trackLandmarks, src/core/CTrackerGT.cpp:137-380): the
+    C++ layer (facade_demo --sequence: CTrackerGT::process over the GPU front-end -- trackManual, CLandmark::addMeasurement /
+    optimize, retirement, masked re-detection) against oracle/tracker_np.py running the same loop over the CPU restatement,
+    frame by frame: counters, every visible landmark's id / measurement, and every active landmark's state (optimised
+    position, optimal / visible flags, optimisation and failure counters, number of measurements)."""
+    import pathlib
+    import subprocess
+    from oracle import c_oracle as co
+    from oracle import tracker_np as tn
+    from svi_mapper_b200.sequence import render_sequence
+    n, mc = 12, 150
+    L, R, T = render_sequence(vi_cams[0], vi_cams[1], n, 4100)
+    L.tofile(tmp_path / "L.raw")
+    R.tofile(tmp_path / "R.raw")
+    rel, rot = [], []
+    for t in range(n):
+        M = np.eye(4) if t == 0 else T[t] @ np.linalg.inv(T[t - 1])
+        rel.append(M)
+        rot.append(float(np.arccos(np.clip((np.trace(M[:3, :3]) - 1.0) / 2.0, -1.0, 1.0))))
+    with open(tmp_path / "motions.txt", "w") as f:
+        for M, a in zip(rel, rot):
+            f.write(" ".join(repr(float(v)) for v in M[:3].reshape(-1)) + " " + repr(a) + "\n")
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    out = tmp_path / "seq.txt"
+    r = subprocess.run([str(exe), "--sequence", str(calib_dir / "vi_sensor_left.txt"), str(calib_dir / "vi_sensor_right.txt"), str(n),
+                        str(tmp_path / "L.raw"), str(tmp_path / "R.raw"), str(tmp_path / "motions.txt"), str(mc), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    frames, cur = [], None
+    for line in out.read_text().splitlines():
+        w = line.split()
+        if w[0] == "F":
+            cur = dict(head=dict(zip(w[2::2], map(int, w[3::2]))), M=[], A=[])
+            frames.append(cur)
+        else:
+            cur[w[0]].append(w[1:])
+    assert len(frames) == n
+    trk = tn.TrackerGT(vi_cams[0], vi_cams[1], co.make_config(vi_cams[0], vi_cams[1], max_corners=mc), threads=co.host_threads())
+    optimised = retired = 0
+    for t in range(n):
+        before = {lm.uid for lm in trk.active()}
+        trk.process(L[t], R[t], rel[t], rot[t])
+        fr = frames[t]
+        act = trk.active()
+        assert fr["head"] == dict(VISIBLE=trk.visible_last, ACTIVE=len(act), S1=trk.tracks[0], S2=trk.tracks[1], S3=trk.tracks[2], DETECTIONS=trk.detections), (t, fr["head"])
+        assert [int(m[0]) for m in fr["M"]] == [lm.uid for lm in trk.visible], t
+        for m, lm in zip(fr["M"], trk.visible):
+            meas = lm.measurements[-1]
+            assert tuple(np.float32(v) for v in m[1:5]) == (meas[2][0], meas[2][1], meas[3][0], meas[3][1]), (t, lm.uid)
+            np.testing.assert_allclose([float(v) for v in m[5:8]], lm.last_xyz_left, rtol=1e-9, atol=0)
+        assert [int(a[0]) for a in fr["A"]] == [lm.uid for lm in act], t
+        for a, lm in zip(fr["A"], act):
+            assert [int(v) for v in a[4:10]] == [int(lm.optimal), int(lm.visible), lm.opt_success, lm.opt_failed, lm.failed, len(lm.measurements)], (t, lm.uid, a)
+            np.testing.assert_allclose([float(v) for v in a[1:4]], lm.xyz_opt, rtol=1e-6, atol=1e-9)
+        optimised += sum(lm.opt_success for lm in act if len(lm.measurements) == 6)
+        retired += len(before - {lm.uid for lm in act})
+    assert trk.detections >= 3 and optimised > 50 and sum(trk.tracks) > 100, (trk.detections, optimised, retired)
