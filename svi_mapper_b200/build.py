@@ -81,6 +81,19 @@ def build_host_demo(out: pathlib.Path | None = None, flags=("-O2", "-ffp-contrac
     return exe
 
 
+CHECKED_LIB = ROOT / "build" / "libsvi_gpu_checked.so"
+
+
+def build_checked(force: bool = False) -> pathlib.Path:
+    """The library with every run-time index asserted in range (-DSVI_BOUNDS_CHECK, see csrc/common.cuh); the parity tests
+    run against it once (tests/test_gpu_parity.py::test_bounds_checked_build) -- compute-sanitizer is closed on the GPU pool."""
+    newest = max(p.stat().st_mtime for p in sources())
+    if force or not CHECKED_LIB.exists() or CHECKED_LIB.stat().st_mtime < newest:
+        CHECKED_LIB.parent.mkdir(parents=True, exist_ok=True)
+        build_library(force=True, out=CHECKED_LIB, defines=["SVI_BOUNDS_CHECK"])
+    return CHECKED_LIB
+
+
 ALT_TABLES = {"alt_random": ROOT / "tests" / "golden" / "patterns" / "alt_random.txt",
               "alt_adversarial": ROOT / "tests" / "golden" / "patterns" / "alt_adversarial.txt"}
 ALT_DIR = ROOT / "build" / "alt"   # git-ignored, travels to the GPU box with the snapshot

@@ -269,6 +269,8 @@ __device__ __forceinline__ void search_run(const SearchPlan& p, PatchStage& ps, 
             patch_issue(ps, p.gy - kBriefReach, col_a, lane);
         }
         patch_wait(ps);
+        // the farthest word any test reads: row 48, word (48 >> 1) of a lane's pair -> woff + lane + 48 * PATCH_WORDS + 24
+        SVI_CHECK(3, woff >= 0 && woff + 31 + 2 * kBriefReach * PATCH_WORDS + kBriefReach < PATCH_COPY_WORDS);
         const uint32_t* Al = ps.words + woff + lane;
         const uint32_t* Bl = ps.words + PATCH_COPY_WORDS + woff + lane;
         uint32_t wlo[kDescWords], whi[kDescWords];
@@ -477,6 +479,7 @@ stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
             search_prefetch(plan_b, ps, lane);     // next window in flight under the epilogue below
         }
         if (r.status == SVI_OK) r.status = point_in_left(tc, x, y, r.u, xyz);
+        SVI_CHECK(3, slot < out.cap && slot < max_corners);
         const size_t o = (size_t)(out_frame0 + f) * out.cap + slot;
         store_desc(out.desc_l + o * 32, ref, lane);
         if (r.status == SVI_OK) store_desc(out.desc_r + o * 32, r.w, lane);
@@ -770,6 +773,7 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
         // over the warp (8 rounds of 2 gathers per lane, pattern offsets computed once) beats one corner per lane
         BriefOffsets bo;
         brief_offsets_init(bo, g.box_pitch, lane);
+        SVI_CHECK(3, nd <= max_corners);
         for (int k = 0; k < nd; ++k) {
             const ushort2 c = corners[k];
             const float px = (float)c.x + half, py = (float)c.y + half;

@@ -32,6 +32,20 @@ struct TriConst {
     float match_cutoff;
 };
 
+// Checked build (-DSVI_BOUNDS_CHECK, build/libsvi_gpu_checked.so): every index that is computed at run time and goes
+// into shared memory, a per-frame list or an output array is asserted in range; the first violation latches
+// tag * 100000 + line in g_svi_check and the next host call reports it.  compute-sanitizer is closed on the GPU pool
+// this library is developed on, so the parity tests are also run once against this build (tests: test_bounds_checked_build).
+#ifdef SVI_BOUNDS_CHECK
+__device__ int g_svi_check = 0;
+#define SVI_CHECK(tag, cond)                                                        \
+    do {                                                                            \
+        if (!(cond)) atomicCAS(&g_svi_check, 0, (tag) * 100000 + __LINE__);         \
+    } while (0)
+#else
+#define SVI_CHECK(tag, cond) ((void)0)
+#endif
+
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * n - 2 - i;

@@ -306,6 +306,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
         if (tid < HS_NSEG * COV_ROWS) {
             const int sgm = tid < HS_NSEG * 32 ? tid >> 5 : (tid - HS_NSEG * 32) / (COV_ROWS - 32);
             const int r = tid < HS_NSEG * 32 ? tid & 31 : 32 + (tid - HS_NSEG * 32) % (COV_ROWS - 32);
+            SVI_CHECK(1, r < COV_ROWS && sgm < HS_NSEG);
             const float* src = &sm.cov[p][r][sgm * HS_SEG];
             double v[HS_SEG + 6];
 #pragma unroll
@@ -361,6 +362,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
                 }
             }
             rv[k] = R;
+            SVI_CHECK(1, oy0 + k < HT_H && x < HT_W);
             Rs[oy0 + k][x] = R;
         }
     }
@@ -441,6 +443,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
                 float v = rv[0];
 #pragma unroll
                 for (int i = 1; i < 8; ++i) v = (k == i) ? rv[i] : v;
+                SVI_CHECK(1, base >= 0 && base < HT_MAX_KEYS);
                 s_keys[base++] = ((unsigned long long)float_to_ordered(v) << 32) | (yx0 + ((unsigned)k << 16));
             }
         }

@@ -179,7 +179,11 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         __syncthreads();
         for (int i = tid; i < n_raw; i += SEL_THREADS) {
             const unsigned long long k = gk[i];
-            if (live(k)) keys[atomicAdd(&s_fill, 1u)] = k;
+            if (live(k)) {
+                const uint32_t pos = atomicAdd(&s_fill, 1u);
+                SVI_CHECK(2, pos < (uint32_t)SEL_SMEM_KEYS);
+                keys[pos] = k;
+            }
         }
     } else {
         // global variant: sort the raw list in place with the dead keys zeroed (they sink to the end)
@@ -212,6 +216,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             __syncthreads();
             for (int i = tid; i < n_raw; i += SEL_THREADS) {
                 const unsigned long long k = gk[i];
+                SVI_CHECK(2, (uint32_t)(k >> kBucketShift) < (uint32_t)SEL_SMEM_CELLS);
                 if (live(k)) atomicAdd(&cursor[(uint32_t)(k >> kBucketShift)], 1u);
             }
             __syncthreads();
@@ -238,6 +243,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             if ((uint32_t)(k >> kBucketShift) < min_bucket || !live(k)) continue;
             int x, y;
             key_xy(k, x, y);
+            SVI_CHECK(2, (unsigned)(cell_of(y, sp) * sp.gw + cell_of(x, sp)) < (unsigned)ncells && ncells <= SEL_SMEM_CELLS);
             atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
         }
         __syncthreads();
@@ -262,6 +268,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             int x, y;
             key_xy(k, x, y);
             const uint32_t pos = atomicAdd(&cursor[cell_of(y, sp) * sp.gw + cell_of(x, sp)], 1u);
+            SVI_CHECK(2, pos < (uint32_t)n_act && n_act <= SEL_SMEM_KEYS);
             keys[pos] = k;
             state[pos] = 0;
         }
@@ -279,6 +286,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                 bool any_acc = false, any_und = false;
                 for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1) && !any_acc; ++yy) {
                     const int j1 = cell_start[yy * sp.gw + x_hi + 1];
+                    SVI_CHECK(2, yy * sp.gw + x_hi + 1 <= ncells && j1 <= n_act);
                     for (int j = cell_start[yy * sp.gw + x_lo]; j < j1; ++j) {
                         const unsigned long long kj = keys[j];
                         if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
@@ -386,7 +394,10 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         while (n_pad < n) n_pad <<= 1;
 #pragma unroll
         for (int k = 0; k < PER; ++k)
-            if (mine[k] != 0ull) keys[rank++] = mine[k];
+            if (mine[k] != 0ull) {
+                SVI_CHECK(2, rank < SEL_SMEM_KEYS);
+                keys[rank++] = mine[k];
+            }
         for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
         for (int i = tid; i < n; i += SEL_THREADS) state[i] = 1;
         __syncthreads();
@@ -415,6 +426,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             if ((int)acc_rank >= sp.max_corners) break;
             int x, y;
             key_xy(keys[i], x, y);
+            SVI_CHECK(2, (int)acc_rank < sp.max_corners && (int)kp_rank < sp.max_corners);
             det[acc_rank] = make_ushort2((unsigned short)x, (unsigned short)y);
             ++acc_rank;
             if (x >= kBriefBorder && x < sp.W - kBriefBorder && y >= kBriefBorder && y < sp.H - kBriefBorder) {

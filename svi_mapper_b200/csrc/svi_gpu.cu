@@ -268,6 +268,13 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
 }
 
 int check_overflow(svi_ctx* ctx) {
+#ifdef SVI_BOUNDS_CHECK
+    {
+        int line = 0;
+        CK(cudaMemcpyFromSymbol(&line, g_svi_check, sizeof(int)));
+        if (line) return fail(ctx, SVI_ERR_CUDA, "bounds check failed in a kernel: tag/line " + std::to_string(line));
+    }
+#endif
     int h = 0;
     CK(cudaMemcpy(&h, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
     if (h == 3) {

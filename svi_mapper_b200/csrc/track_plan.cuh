@@ -66,6 +66,7 @@ __global__ void stage2_plan_kernel(TrackPlanConst k, int plane, float tri_scale,
     it.search = __fmul_rn(tri_scale, lm.disparity[q]);
     it.size = size;
     const int slot = atomicAdd(n_items, 1);
+    SVI_CHECK(4, slot >= 0 && slot < q1 - q0);
     items[slot] = it;
     rois[slot] = RoiItem{plane, rx, ry, rw, rh};
 }
@@ -179,7 +180,11 @@ __global__ void stage3_plan_kernel(TrackPlanConst k, LandmarksDev lm, Stage3Extr
     uvr[0] = ex.uv_ref[2 * (size_t)q]; uvr[1] = ex.uv_ref[2 * (size_t)q + 1];
     pw[0] = lm.xyz_w[3 * q]; pw[1] = lm.xyz_w[3 * q + 1]; pw[2] = lm.xyz_w[3 * q + 2];
     const int st = epipolar_plan_dev(k, Td, uvr, pw, it);
-    if (st == SVI_OK) items[atomicAdd(n_items, 1)] = it;
+    if (st == SVI_OK) {
+        const int slot = atomicAdd(n_items, 1);
+        SVI_CHECK(4, slot >= 0 && slot < n);
+        items[slot] = it;
+    }
     else out.status[q] = (uint8_t)st;
 }
 
@@ -203,6 +208,7 @@ __global__ void mask_discs_kernel(uint8_t* __restrict__ mask, int W, int H, int 
     const int hw = row == 7 ? 7 : (row == 0 || row == 14) ? 0 : (row == 1 || row == 13) ? 3 : (row == 2 || row == 12) ? 4 : (row == 3 || row == 11) ? 5 : 6;
     const int xa = max(cx - hw, 0), xb = min(cx + hw, W - 1);
     uint8_t* r = mask + (size_t)y * pitch;
+    SVI_CHECK(4, xa >= 0 && xb < W && xb < pitch);
     for (int x = xa; x <= xb; ++x) r[x] = 0;
 }
 
