@@ -54,7 +54,10 @@ __device__ __forceinline__ void key_xy(unsigned long long k, int& x, int& y) {
     y = (int)((k >> 16) & 0xFFFFu);
 }
 
-// In-place bitonic sort, descending, of n_pad (power of two) keys by the whole CTA.
+// In-place bitonic sort, descending, of n_pad (power of two) keys by the whole CTA.  Thread t handles the pair
+// (i, i + j) with i = 2t - (t & (j - 1)): for j <= 32 the 32 pairs of a warp lie inside one aligned block of 64 keys that
+// no other warp touches, so those steps (six of every k-level, all of the levels k <= 64) only need __syncwarp();
+// the CTA-wide barrier is kept for the steps that exchange keys between warps.
 template <int T>
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n_pad, int tid) {
     for (int k = 2; k <= n_pad; k <<= 1) {
@@ -66,9 +69,11 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
                 bool desc = ((i & k) == 0);
                 if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
             }
-            __syncthreads();
+            if (j > 32) __syncthreads(); else __syncwarp();
         }
+        if (k >= 64) __syncthreads();   // the next level starts with j = k >= 64: keys cross warps again
     }
+    __syncthreads();
 }
 
 // Exclusive scan over the CTA of a packed pair of 32-bit counters; *total receives the CTA sum.
@@ -118,7 +123,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long wsum[SEL_THREADS / 32];
     __shared__ unsigned long long scan_total;
-    __shared__ uint32_t s_fill;
+    __shared__ uint32_t s_fill, s_min_bucket;
     const int f = blockIdx.x, tid = threadIdx.x;
     if (n_items && f >= *n_items) return;   // window mode with a device-side item count
     if (rois) {   // window mode: the bucket grid and the border filter follow the item's rectangle
@@ -139,11 +144,25 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     unsigned long long* gk = cand + (size_t)f * sp.raw_cap;
     const uint32_t thr_ord = frame_max ? float_to_ordered(gftt_threshold(frame_max[f], sp.quality)) : 0u;
     auto live = [thr_ord](unsigned long long k) { return (uint32_t)(k >> 32) > thr_ord; };
+    // The cell-sorted path walks the raw list four times (count, priority histogram, cell histogram, scatter): stage it
+    // once at the upper end of the shared key array -- every later pass then costs shared-memory, not L2, latency.
+    const bool staged_ok = kSmem && sp.filter && n_raw <= SEL_SMEM_KEYS;
+    const unsigned long long* raw = gk;
     int n;
     {
         int c = 0;
-        for (int i = tid; i < n_raw; i += SEL_THREADS) c += live(gk[i]) ? 1 : 0;
-        block_exclusive_scan<SEL_THREADS>((unsigned long long)c, wsum, &scan_total, tid);
+        if (staged_ok) {
+            unsigned long long* raw_s = reinterpret_cast<unsigned long long*>(sel_smem) + (SEL_SMEM_KEYS - n_raw);
+            for (int i = tid; i < n_raw; i += SEL_THREADS) {
+                const unsigned long long k = gk[i];
+                raw_s[i] = k;
+                c += live(k) ? 1 : 0;
+            }
+            raw = raw_s;
+        } else {
+            for (int i = tid; i < n_raw; i += SEL_THREADS) c += live(gk[i]) ? 1 : 0;
+        }
+        block_exclusive_scan<SEL_THREADS>((unsigned long long)c, wsum, &scan_total, tid);   // its barriers publish the staged list
         n = (int)scan_total;
     }
     if (defer && (n > SEL_SMEM_KEYS || sp.gw * sp.gh > SEL_SMEM_CELLS)) {   // CTA-uniform
@@ -170,33 +189,8 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
                            : g_head + (size_t)f * ncells;
     uint32_t* next = kSmem ? nullptr : g_next + (size_t)f * sp.cand_cap;
     const bool peel_first = kSmem && sp.filter;
-    if (peel_first) {
-        // keys are filled by the counting sort below
-    } else if (kSmem) {
-        // compact the live keys into shared memory (any order: they are sorted next)
-        if (tid == 0) s_fill = 0u;
-        for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
-        __syncthreads();
-        for (int i = tid; i < n_raw; i += SEL_THREADS) {
-            const unsigned long long k = gk[i];
-            if (live(k)) {
-                const uint32_t pos = atomicAdd(&s_fill, 1u);
-                SVI_CHECK(2, pos < (uint32_t)SEL_SMEM_KEYS);
-                keys[pos] = k;
-            }
-        }
-    } else {
-        // global variant: sort the raw list in place with the dead keys zeroed (they sink to the end)
-        n_pad = 1;
-        while (n_pad < n_raw) n_pad <<= 1;
-        for (int i = tid; i < n_pad; i += SEL_THREADS)
-            if (i >= n_raw || !live(keys[i])) keys[i] = 0ull;
-    }
-    __syncthreads();
-
-    // ---- sort everything up front only where the peeled set cannot be compacted in registers (global path) or
-    //      where nothing is peeled (no distance filter: every candidate is a corner)
-    if (!peel_first) bitonic_sort_desc<SEL_THREADS>(keys, n_pad, tid);
+    constexpr int kBucketShift = 64 - ilog2(SEL_SMEM_CELLS);   // top bits of the key: sign, exponent, leading mantissa bits
+    const int target = (int)min((long long)n, (long long)sp.max_corners * SEL_CUT_TENTHS / 10 + 256);
     if (peel_first) {
         // ---- counting sort of the candidates by grid cell, straight from the global list into `keys`
         uint16_t* cell_start = next16;            // ncells + 1 <= 8193 entries
@@ -206,16 +200,13 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         // head of the accepted sequence.  A 13-bit bucket of the key (sign, exponent, 4 mantissa bits of the response)
         // is monotone in priority; take the buckets that hold about 2.6 x max_corners candidates, and fall back to
         // the whole list in the rare case that they yield fewer than max_corners corners.
-        __shared__ uint32_t s_min_bucket;
-        constexpr int kBucketShift = 64 - ilog2(SEL_SMEM_CELLS);   // top bits of the key: sign, exponent, leading mantissa bits
-        const int target = (int)min((long long)n, (long long)sp.max_corners * SEL_CUT_TENTHS / 10 + 256);
         if (tid == 0) s_min_bucket = 0u;
         if (n > target) {
             constexpr int NB = SEL_SMEM_CELLS;   // one bucket per entry of the cursor area
             for (int b = tid; b < NB; b += SEL_THREADS) cursor[b] = 0u;
             __syncthreads();
             for (int i = tid; i < n_raw; i += SEL_THREADS) {
-                const unsigned long long k = gk[i];
+                const unsigned long long k = raw[i];
                 SVI_CHECK(2, (uint32_t)(k >> kBucketShift) < (uint32_t)SEL_SMEM_CELLS);
                 if (live(k)) atomicAdd(&cursor[(uint32_t)(k >> kBucketShift)], 1u);
             }
@@ -239,7 +230,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         for (int c = tid; c < ncells; c += SEL_THREADS) cursor[c] = 0u;
         __syncthreads();
         for (int i = tid; i < n_raw; i += SEL_THREADS) {
-            const unsigned long long k = gk[i];
+            const unsigned long long k = raw[i];
             if ((uint32_t)(k >> kBucketShift) < min_bucket || !live(k)) continue;
             int x, y;
             key_xy(k, x, y);
@@ -262,8 +253,10 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             if (tid == 0) cell_start[ncells] = (uint16_t)n_act;   // n_act <= 16384
         }
         __syncthreads();
+        // the scatter writes keys[0 .. n_act): it may read the staged list only while the two do not overlap
+        const unsigned long long* src = (raw != gk && n_act + n_raw <= SEL_SMEM_KEYS) ? raw : gk;
         for (int i = tid; i < n_raw; i += SEL_THREADS) {
-            const unsigned long long k = gk[i];
+            const unsigned long long k = src[i];
             if ((uint32_t)(k >> kBucketShift) < min_bucket || !live(k)) continue;
             int x, y;
             key_xy(k, x, y);
@@ -312,65 +305,129 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         block_exclusive_scan<SEL_THREADS>((unsigned long long)acc, wsum, &scan_total, tid);
         if ((int)scan_total >= sp.max_corners) break;   // enough corners from the cut list: exact
         if (tid == 0) s_min_bucket = 0u;
+        raw = gk;                                      // the staged copy may have been overwritten by the scatter
         __syncthreads();
         }
     }
 
-    // ---- (sorted path) grid cell lists, linked through `next`
+    // ---- (sorted path: FAST / no distance filter in shared memory, or the global variant for very large frames)
+    //      fill the key array with the live candidates, sort, cell lists linked through `next`, peel.
+    //      The global variant applies the same priority cut as the cell-sorted path (the cut list is compacted into the
+    //      free upper half of the frame's raw list, so a 3840x1080 frame sorts ~26 k keys instead of ~130 k), with the
+    //      same exact fallback to the whole list.
     if (!peel_first) {
-        for (int c = tid; c < ncells; c += SEL_THREADS) head[c] = SEL_NIL;
-        for (int i = tid; i < n; i += SEL_THREADS) state[i] = 0;
-        __syncthreads();
-    }
-    if (peel_first) {
-        // peeled above
-    } else if (sp.filter) {
-        for (int i = tid; i < n; i += SEL_THREADS) {
-            int x, y;
-            key_xy(keys[i], x, y);
-            int c = cell_of(y, sp) * sp.gw + cell_of(x, sp);
-            uint32_t prev = atomicExch(&head[c], (uint32_t)i);
-            if (kSmem) next16[i] = (uint16_t)(prev == SEL_NIL ? 0xFFFFu : prev);
-            else next[i] = prev;
-        }
-        __syncthreads();
-        // ---- peel to the fixed point
-        for (;;) {
-            int changed = 0;
-            for (int i = tid; i < n; i += SEL_THREADS) {
-                if (state[i] != 0) continue;
-                int x, y;
-                const unsigned long long ki = keys[i];
-                key_xy(ki, x, y);
-                const int cx = cell_of(x, sp), cy = cell_of(y, sp);
-                bool any_acc = false, any_und = false;
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1); ++yy)
-                    for (int xx = max(cx - 1, 0); xx <= min(cx + 1, sp.gw - 1); ++xx) {
-                        uint32_t j = head[yy * sp.gw + xx];
-                        while (j != SEL_NIL) {
-                            const unsigned long long kj = keys[j];
-                            if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
-                                int px, py;
-                                key_xy(kj, px, py);
-                                int dx = x - px, dy = y - py;
-                                if (dx * dx + dy * dy < sp.min_dist_sq_ceil) {
-                                    uint8_t s = state[j];
-                                    any_acc |= (s == 1);
-                                    any_und |= (s == 0);
-                                }
-                            }
-                            if (kSmem) { uint16_t nx = next16[j]; j = (nx == 0xFFFFu) ? SEL_NIL : nx; }
-                            else j = next[j];
-                        }
-                    }
-                if (any_acc) { state[i] = 2; changed = 1; }
-                else if (!any_und) { state[i] = 1; changed = 1; }
+        const bool can_cut = !kSmem && sp.filter && n_raw <= sp.raw_cap / 2 && n > target;
+        if (tid == 0) s_min_bucket = 0u;
+        if (can_cut) {   // histogram of the 13-bit priority buckets in (dynamic) shared memory
+            uint32_t* hist = reinterpret_cast<uint32_t*>(sel_smem);
+            constexpr int NB = SEL_SMEM_CELLS;
+            for (int b = tid; b < NB; b += SEL_THREADS) hist[b] = 0u;
+            __syncthreads();
+            for (int i = tid; i < n_raw; i += SEL_THREADS) {
+                const unsigned long long k = gk[i];
+                if (live(k)) atomicAdd(&hist[(uint32_t)(k >> kBucketShift)], 1u);
             }
-            if (!__syncthreads_or(changed)) break;
+            __syncthreads();
+            constexpr int BPT = NB / SEL_THREADS;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < BPT; ++k) sum += hist[NB - 1 - (tid * BPT + k)];
+            uint32_t above = (uint32_t)block_exclusive_scan<SEL_THREADS>((unsigned long long)sum, wsum, &scan_total, tid);
+#pragma unroll
+            for (int k = 0; k < BPT; ++k) {
+                const int b = NB - 1 - (tid * BPT + k);
+                const uint32_t c = hist[b];
+                if (above < (uint32_t)target && above + c >= (uint32_t)target) s_min_bucket = (uint32_t)b;
+                above += c;
+            }
         }
-    } else {
-        for (int i = tid; i < n; i += SEL_THREADS) state[i] = 1;
         __syncthreads();
+        const int n_live = n;
+        for (;;) {   // at most two attempts: cut list, then (rarely) the whole list
+            const uint32_t min_bucket = s_min_bucket;
+            if (kSmem || n_raw <= sp.raw_cap / 2) {
+                // compact the (cut) live keys -- into shared memory, or into the free upper half of the raw list
+                if (!kSmem) keys = gk + sp.raw_cap / 2;
+                if (tid == 0) s_fill = 0u;
+                __syncthreads();
+                for (int i = tid; i < n_raw; i += SEL_THREADS) {
+                    const unsigned long long k = gk[i];
+                    if (live(k) && (uint32_t)(k >> kBucketShift) >= min_bucket) {
+                        const uint32_t pos = atomicAdd(&s_fill, 1u);
+                        SVI_CHECK(2, kSmem ? pos < (uint32_t)SEL_SMEM_KEYS : pos < (uint32_t)(sp.raw_cap / 2));
+                        keys[pos] = k;
+                    }
+                }
+                __syncthreads();
+                n = (int)s_fill;
+                n_pad = 1;
+                while (n_pad < n) n_pad <<= 1;
+                for (int i = n + tid; i < n_pad; i += SEL_THREADS) keys[i] = 0ull;
+            } else {
+                // no room to compact: sort the raw list in place with the dead keys zeroed (they sink to the end)
+                n_pad = 1;
+                while (n_pad < n_raw) n_pad <<= 1;
+                for (int i = tid; i < n_pad; i += SEL_THREADS)
+                    if (i >= n_raw || !live(keys[i])) keys[i] = 0ull;
+                n = n_live;
+            }
+            __syncthreads();
+            bitonic_sort_desc<SEL_THREADS>(keys, n_pad, tid);
+            for (int c = tid; c < ncells; c += SEL_THREADS) head[c] = SEL_NIL;
+            for (int i = tid; i < n; i += SEL_THREADS) state[i] = sp.filter ? 0 : 1;
+            __syncthreads();
+            if (!sp.filter) break;   // every candidate is a corner
+            for (int i = tid; i < n; i += SEL_THREADS) {
+                int x, y;
+                key_xy(keys[i], x, y);
+                int c = cell_of(y, sp) * sp.gw + cell_of(x, sp);
+                uint32_t prev = atomicExch(&head[c], (uint32_t)i);
+                if (kSmem) next16[i] = (uint16_t)(prev == SEL_NIL ? 0xFFFFu : prev);
+                else next[i] = prev;
+            }
+            __syncthreads();
+            // ---- peel to the fixed point
+            for (;;) {
+                int changed = 0;
+                for (int i = tid; i < n; i += SEL_THREADS) {
+                    if (state[i] != 0) continue;
+                    int x, y;
+                    const unsigned long long ki = keys[i];
+                    key_xy(ki, x, y);
+                    const int cx = cell_of(x, sp), cy = cell_of(y, sp);
+                    bool any_acc = false, any_und = false;
+                    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1); ++yy)
+                        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, sp.gw - 1); ++xx) {
+                            uint32_t j = head[yy * sp.gw + xx];
+                            while (j != SEL_NIL) {
+                                const unsigned long long kj = keys[j];
+                                if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
+                                    int px, py;
+                                    key_xy(kj, px, py);
+                                    int dx = x - px, dy = y - py;
+                                    if (dx * dx + dy * dy < sp.min_dist_sq_ceil) {
+                                        uint8_t s = state[j];
+                                        any_acc |= (s == 1);
+                                        any_und |= (s == 0);
+                                    }
+                                }
+                                if (kSmem) { uint16_t nx = next16[j]; j = (nx == 0xFFFFu) ? SEL_NIL : nx; }
+                                else j = next[j];
+                            }
+                        }
+                    if (any_acc) { state[i] = 2; changed = 1; }
+                    else if (!any_und) { state[i] = 1; changed = 1; }
+                }
+                if (!__syncthreads_or(changed)) break;
+            }
+            if (min_bucket == 0u) break;   // the whole list was peeled
+            int acc = 0;
+            for (int i = tid; i < n; i += SEL_THREADS) acc += (state[i] == 1);
+            block_exclusive_scan<SEL_THREADS>((unsigned long long)acc, wsum, &scan_total, tid);
+            if ((int)scan_total >= sp.max_corners) break;   // enough corners from the cut list: exact
+            if (tid == 0) s_min_bucket = 0u;
+            __syncthreads();
+        }
     }
 
     if (peel_first) {

@@ -249,7 +249,7 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
         select_corners_kernel<true><<<nf, SEL_THREADS, 13 * SEL_SMEM_KEYS, s>>>(
             l.cand, l.cand_count, fmax, ctx->sel, nullptr, nullptr, nullptr, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     } else {
-        select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(
+        select_corners_kernel<false><<<nf, SEL_THREADS, 4 * SEL_SMEM_CELLS, s>>>(
             l.cand, l.cand_count, fmax, ctx->sel, l.g_head, l.g_next, l.g_state, l.det_xy, n_det, l.kp_xy, n_kp, ctx->d_overflow, nullptr);
     }
     mark(ctx, l);
@@ -1077,7 +1077,7 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
                                                                                   nullptr, l.det_xy, l.n_det, l.kp_xy, l.n_kp,
                                                                                   ctx->d_overflow, nullptr);
         else
-            select_corners_kernel<false><<<nf, SEL_THREADS, 0, s>>>(l.cand, l.cand_count, fmax, ctx->sel, l.g_head, l.g_next, l.g_state,
+            select_corners_kernel<false><<<nf, SEL_THREADS, 4 * SEL_SMEM_CELLS, s>>>(l.cand, l.cand_count, fmax, ctx->sel, l.g_head, l.g_next, l.g_state,
                                                                    l.det_xy, l.n_det, l.kp_xy, l.n_kp, ctx->d_overflow, nullptr);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_xy.data(), l.det_xy, sizeof(ushort2) * (size_t)nf * MC, cudaMemcpyDeviceToHost, s));
