@@ -113,6 +113,7 @@ struct svi_ctx {
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
     bool profiling = false;
+    bool batch_uploads = false;   // upload(): stage into the pinned mirror only (svi_track_landmarks sends one copy)
     bool serial = false;   // profiling mode 2: every chunk on lane 0, so that the stage events bracket ONE kernel each
     double stage_ms[kStages] = {0, 0, 0, 0};
     long stage_launches[kStages] = {0, 0, 0, 0};
@@ -327,7 +328,8 @@ int upload(svi_ctx* ctx, T** d, const T* h, size_t count, cudaStream_t s) {
     if (h && ctx->pin_arena) {
         unsigned char* mirror = ctx->pin_arena + (reinterpret_cast<unsigned char*>(*d) - ctx->arena);
         std::memcpy(mirror, h, count * sizeof(T));
-        CK(cudaMemcpyAsync(*d, mirror, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        // batch_uploads: the caller sends the whole staged range with ONE copy once every input is in the mirror
+        if (!ctx->batch_uploads) CK(cudaMemcpyAsync(*d, mirror, count * sizeof(T), cudaMemcpyHostToDevice, s));
     } else if (h) {
         CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
@@ -499,8 +501,11 @@ int ensure_track_scratch(svi_ctx* ctx) {
     if (r.items) return SVI_SUCCESS;
     const int items = std::min(std::max(ctx->p.max_queries, 64), kRoiBatch);
     const size_t MC = (size_t)ctx->p.max_corners;
-    CK(dmalloc(&r.max, (size_t)items));
-    CK(dmalloc(&r.cand_count, (size_t)items));
+    // [max | cand_count | defer | counters]: one block, so that a stage-2 side zeroes its bookkeeping with one memset
+    CK(dmalloc(&r.max, (size_t)items * 3 + 4));
+    r.cand_count = reinterpret_cast<int*>(r.max) + items;
+    r.defer = r.cand_count + items;
+    r.counters = r.defer + items;
     CK(dmalloc(&r.cand, (size_t)items * kRoiRawCap));
     CK(dmalloc(&r.det, (size_t)items * MC));
     CK(dmalloc(&r.kp, (size_t)items * MC));
@@ -508,8 +513,6 @@ int ensure_track_scratch(svi_ctx* ctx) {
     CK(dmalloc(&r.n_kp, (size_t)items));
     CK(dmalloc(&r.rois, (size_t)items));
     CK(dmalloc(&r.s2, (size_t)items));
-    CK(dmalloc(&r.defer, (size_t)items));
-    CK(dmalloc(&r.counters, 4));
     CK(dmalloc(&ctx->s3_items, (size_t)std::max(ctx->p.max_queries, 64)));
     r.items = items;
     return SVI_SUCCESS;
@@ -550,10 +553,7 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, int n, const do
     int* n_items = r.counters + (left ? 0 : 1);
     for (int q0 = 0; q0 < n; q0 += r.items) {
         const int nb = std::min(r.items, n - q0);
-        CK(cudaMemsetAsync(n_items, 0, sizeof(int), s));
-        CK(cudaMemsetAsync(r.max, 0, sizeof(uint32_t) * nb, s));
-        CK(cudaMemsetAsync(r.cand_count, 0, sizeof(int) * nb, s));
-        CK(cudaMemsetAsync(r.defer, 0, sizeof(int) * nb, s));
+        CK(cudaMemsetAsync(r.max, 0, sizeof(int) * ((size_t)r.items * 3 + 4), s));   // max, cand_count, defer, counters
         stage2_plan_kernel<<<(nb + 127) / 128, 128, 0, s>>>(k, left ? 0 : 1, (float)(1.0 + motion_scaling), ld, q0, q0 + nb, o, r.rois, r.s2, n_items);
         harris_box_kernel<<<harris_grid(max_w, max_h, nb), HT_THREADS, sizeof(HarrisSmem), s>>>(
             ctx->trk_img, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, r.max, r.cand,
@@ -681,8 +681,7 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->s3_items) cudaFree(ctx->s3_items);
     if (ctx->resp_one) cudaFree(ctx->resp_one);
     {
-        void* rp[] = {ctx->roi.max, ctx->roi.cand_count, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det,
-                      ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2, ctx->roi.defer, ctx->roi.counters};
+        void* rp[] = {ctx->roi.max, ctx->roi.cand, ctx->roi.det, ctx->roi.kp, ctx->roi.n_det, ctx->roi.n_kp, ctx->roi.rois, ctx->roi.s2};
         for (void* q : rp) if (q) cudaFree(q);
     }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
@@ -1245,7 +1244,11 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     if (rc != SVI_SUCCESS) return rc;
     rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s, 1);
     if (rc != SVI_SUCCESS) return rc;
+    // every input array goes through the pinned mirror of the arena and up in ONE copy; the outputs form one contiguous
+    // range behind them: one memset, one copy back
     double* d_xyzw; uint8_t* d_dl; uint8_t* d_dr; float* d_disp; float* d_size;
+    ctx->batch_uploads = ctx->pin_arena != nullptr;
+    struct Unbatch { svi_ctx* c; ~Unbatch() { c->batch_uploads = false; } } unbatch{ctx};
     UP(d_xyzw, lm->xyz_world, (size_t)n * 3);
     UP(d_dl, lm->last_desc_left, (size_t)n * 32);
     UP(d_dr, lm->last_desc_right, (size_t)n * 32);
@@ -1260,6 +1263,9 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         UP(d_orig, lm->desc_reference_left, (size_t)n * 32);
         ex.uv_ref = d_uvref; ex.T_det = d_tdet;
     }
+    if (ctx->batch_uploads) CK(cudaMemcpyAsync(ctx->arena, ctx->pin_arena, ctx->arena_used, cudaMemcpyHostToDevice, s));
+    ctx->batch_uploads = false;
+    const size_t out_begin = (ctx->arena_used + 255) & ~size_t(255);
     TrackOutDev o;
     UP(o.status, (const uint8_t*)nullptr, (size_t)n);
     UP(o.stage, (const uint8_t*)nullptr, (size_t)n);
@@ -1268,11 +1274,8 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     UP(o.xyz, (const double*)nullptr, (size_t)n * 3);
     UP(o.desc_l, (const uint8_t*)nullptr, (size_t)n * 32);
     UP(o.desc_r, (const uint8_t*)nullptr, (size_t)n * 32);
-    CK(cudaMemsetAsync(o.uv_l, 0, sizeof(float) * 2 * n, s));
-    CK(cudaMemsetAsync(o.uv_r, 0, sizeof(float) * 2 * n, s));
-    CK(cudaMemsetAsync(o.xyz, 0, sizeof(double) * 3 * n, s));
-    CK(cudaMemsetAsync(o.desc_l, 0, (size_t)32 * n, s));
-    CK(cudaMemsetAsync(o.desc_r, 0, (size_t)32 * n, s));
+    const size_t out_end = ctx->arena_used;
+    CK(cudaMemsetAsync(ctx->arena + out_begin, 0, out_end - out_begin, s));
     TrackConst k;
     for (int i = 0; i < 12; ++i) { k.T[i] = T_world_to_left[i]; k.PL[i] = ctx->cam_l.P[i]; k.PR[i] = ctx->cam_r.P[i]; }
     k.tri_scale = (float)(1.0 + motion_scaling);
@@ -1302,13 +1305,27 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         rc = track_stage3_all(ctx, l, g, n, T_world_to_left, motion_scaling, ld, ex, d_orig, o);
         if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
     }
-    int rd = download(ctx, out->status, o.status, (size_t)n, s);
-    if (rd == SVI_SUCCESS) rd = download(ctx, out->stage, o.stage, (size_t)n, s);
-    if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_left, o.uv_l, sizeof(float) * 2 * n, s);
-    if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_right, o.uv_r, sizeof(float) * 2 * n, s);
-    if (rd == SVI_SUCCESS) rd = download(ctx, out->xyz_left, o.xyz, sizeof(double) * 3 * n, s);
-    if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_left, o.desc_l, (size_t)32 * n, s);
-    if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_right, o.desc_r, (size_t)32 * n, s);
+    int rd = SVI_SUCCESS;
+    if (ctx->pin_arena) {   // one copy for the whole output range, scattered to the caller's arrays after the synchronisation
+        cudaError_t e = cudaMemcpyAsync(ctx->pin_arena + out_begin, ctx->arena + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rd = fail(ctx, SVI_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e));
+        auto mirror = [&](const void* d) { return ctx->pin_arena + (static_cast<const unsigned char*>(d) - ctx->arena); };
+        ctx->pending.push_back({out->status, mirror(o.status), (size_t)n});
+        ctx->pending.push_back({out->stage, mirror(o.stage), (size_t)n});
+        ctx->pending.push_back({out->uv_left, mirror(o.uv_l), sizeof(float) * 2 * n});
+        ctx->pending.push_back({out->uv_right, mirror(o.uv_r), sizeof(float) * 2 * n});
+        ctx->pending.push_back({out->xyz_left, mirror(o.xyz), sizeof(double) * 3 * n});
+        ctx->pending.push_back({out->desc_left, mirror(o.desc_l), (size_t)32 * n});
+        ctx->pending.push_back({out->desc_right, mirror(o.desc_r), (size_t)32 * n});
+    } else {
+        rd = download(ctx, out->status, o.status, (size_t)n, s);
+        if (rd == SVI_SUCCESS) rd = download(ctx, out->stage, o.stage, (size_t)n, s);
+        if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_left, o.uv_l, sizeof(float) * 2 * n, s);
+        if (rd == SVI_SUCCESS) rd = download(ctx, out->uv_right, o.uv_r, sizeof(float) * 2 * n, s);
+        if (rd == SVI_SUCCESS) rd = download(ctx, out->xyz_left, o.xyz, sizeof(double) * 3 * n, s);
+        if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_left, o.desc_l, (size_t)32 * n, s);
+        if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_right, o.desc_r, (size_t)32 * n, s);
+    }
     if (rd == SVI_SUCCESS) rd = flush_downloads(ctx, s);
     else cudaStreamSynchronize(s);
     if (rd != SVI_SUCCESS) return rd;
