@@ -494,6 +494,7 @@ def run_batch(args, rank, world, dev_index):
             "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": cfg["what"], "name": args.config, "frames_per_step_total": total_frames, "frames_this_rank": F,
                        "chunk_frames": chunk, "lanes": fcfg["n_lanes"], "device": dev_index, "cpu_affinity": args.numa,
+                       "brief_table": fe.brief_table,
                        "l2_policy": (f"inputs {2 * F * W * H / 1e9:.2f} GB per step and rank >> 126 MB L2 (no flush needed)" if 2 * F * W * H > 4e8 else
                                      "the pair fits the L2: value = back-to-back calls on resident inputs; e2e brings new bytes from the host every call"),
                        "keypoints_per_frame": total_kp / max(len(nk), 1), "matched_per_frame": total_ok / max(len(nk), 1),

@@ -106,6 +106,13 @@ enum { SVI_DETECTOR_GFTT_HARRIS = 0, SVI_DETECTOR_FAST_9_16 = 1 };
 int svi_params_default(svi_params* p);
 const char* svi_status_text(int status);
 
+/* Which BRIEF-32 pair table this build of the library carries (the 256 test pairs are compile-time constants of the
+ * match kernels): file name, its description line, number of distinct test points, FNV-1a hash of the offsets.
+ * The table shipped in this repository is a STAND-IN, not opencv_contrib's generated_32.i behind
+ * cv::xfeatures2d::BriefDescriptorExtractor::create(32) (src/core/CTriangulator.cpp:11): descriptors are bit-exact to
+ * the CPU restatement with the same table, not to the reference's.  Another table: python -m svi_mapper_b200.build --table. */
+const char* svi_brief_table_info(void);
+
 /* Replaces the CTriangulator / CFundamentalMatcher constructors' OpenCV object creation
  * (src/core/CTriangulator.cpp:8-21, src/core/CFundamentalMatcher.cpp:14-28). */
 int svi_create(const svi_camera* left, const svi_camera* right, const svi_params* params,

@@ -20,7 +20,7 @@ SVI_ERR_INVALID, SVI_ERR_CUDA, SVI_ERR_CAPACITY, SVI_ERR_NO_DEVICE, SVI_ERR_UNSU
  SVI_EPI_POOL_EMPTY, SVI_EPI_NO_MATCHES, SVI_EPI_DIST, SVI_EPI_ORIG_DIST, SVI_EPI_NO_TRANSLATION) = range(25)
 
 EXPORTS = (
-    "svi_params_default", "svi_status_text", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
+    "svi_params_default", "svi_status_text", "svi_brief_table_info", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
     "svi_stereo_frames", "svi_stereo_frames_device", "svi_check_overflow", "svi_mask_active_landmarks", "svi_stereo_frame_masked", "svi_harris_response", "svi_detect", "svi_describe",
     "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
     "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config",
@@ -94,6 +94,8 @@ def load(path=None):
     lib.svi_params_default.argtypes = [C.POINTER(Params)]
     lib.svi_status_text.argtypes = [ci]
     lib.svi_status_text.restype = C.c_char_p
+    lib.svi_brief_table_info.argtypes = []
+    lib.svi_brief_table_info.restype = C.c_char_p
     lib.svi_create.argtypes = [C.POINTER(Camera), C.POINTER(Camera), C.POINTER(Params), ci, C.POINTER(vp)]
     lib.svi_destroy.argtypes = [vp]
     lib.svi_destroy.restype = None

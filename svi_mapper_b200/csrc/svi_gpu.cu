@@ -651,6 +651,8 @@ const char* svi_status_text(int status) {
     }
 }
 
+const char* svi_brief_table_info(void) { return SVI_BRIEF_PATTERN_SOURCE; }
+
 int svi_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

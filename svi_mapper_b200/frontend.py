@@ -119,6 +119,11 @@ class StereoFrontend:
         if rc != _lib.SVI_SUCCESS:
             raise SviError(rc, self._lib.svi_last_error(self._ctx).decode())
 
+    @property
+    def brief_table(self) -> str:
+        """svi_brief_table_info: which pair table this library build carries (the shipped one is a stand-in)."""
+        return self._lib.svi_brief_table_info().decode()
+
     def config(self) -> dict:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self._lib.svi_config(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
