@@ -266,33 +266,87 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
             state[pos] = 0;
         }
         __syncthreads();
-        // ---- peel to the fixed point; neighbours = three contiguous key runs
-        for (;;) {
-            int changed = 0;
+        // ---- peel to the fixed point; neighbours = three contiguous key runs.
+        // A candidate's decision depends only on its BLOCKERS (higher-priority candidates closer than minDistance,
+        // rarely more than two): the first sweep scans the 3x3 cell neighbourhood once and remembers up to four of
+        // them (8 B per candidate in the free upper half of the key array); every later sweep only re-reads their
+        // states.  Candidates with more blockers (marker 0xFFFE) and lists too long for the cache rescan as before.
+        auto scan_neighbours = [&](int i, unsigned long long ki, bool& any_acc, bool& any_und) {
+            int x, y;
+            key_xy(ki, x, y);
+            const int cx = cell_of(x, sp), cy = cell_of(y, sp);
+            const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, sp.gw - 1);
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1) && !any_acc; ++yy) {
+                const int j1 = cell_start[yy * sp.gw + x_hi + 1];
+                SVI_CHECK(2, yy * sp.gw + x_hi + 1 <= ncells && j1 <= n_act);
+                for (int j = cell_start[yy * sp.gw + x_lo]; j < j1; ++j) {
+                    const unsigned long long kj = keys[j];
+                    if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
+                        int px, py;
+                        key_xy(kj, px, py);
+                        const int dx = x - px, dy = y - py;
+                        if (dx * dx + dy * dy < sp.min_dist_sq_ceil) {
+                            const uint8_t s = state[j];
+                            any_acc |= (s == 1);
+                            any_und |= (s == 0);
+                        }
+                    }
+                }
+            }
+        };
+        const bool cache_ok = n_act <= SEL_SMEM_KEYS / 2;
+        ushort4* blockers = reinterpret_cast<ushort4*>(keys + SEL_SMEM_KEYS / 2);
+        if (cache_ok) {
             for (int i = tid; i < n_act; i += SEL_THREADS) {
-                if (state[i] != 0) continue;
                 int x, y;
                 const unsigned long long ki = keys[i];
                 key_xy(ki, x, y);
                 const int cx = cell_of(x, sp), cy = cell_of(y, sp);
                 const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, sp.gw - 1);
-                bool any_acc = false, any_und = false;
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1) && !any_acc; ++yy) {
+                unsigned short b[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+                int nb = 0;
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, sp.gh - 1); ++yy) {
                     const int j1 = cell_start[yy * sp.gw + x_hi + 1];
                     SVI_CHECK(2, yy * sp.gw + x_hi + 1 <= ncells && j1 <= n_act);
                     for (int j = cell_start[yy * sp.gw + x_lo]; j < j1; ++j) {
                         const unsigned long long kj = keys[j];
-                        if (kj > ki) {   // higher priority: larger response, then larger address (keys are unique)
+                        if (kj > ki) {
                             int px, py;
                             key_xy(kj, px, py);
                             const int dx = x - px, dy = y - py;
                             if (dx * dx + dy * dy < sp.min_dist_sq_ceil) {
-                                const uint8_t s = state[j];
-                                any_acc |= (s == 1);
-                                any_und |= (s == 0);
+                                if (nb == 0) b[0] = (unsigned short)j;
+                                else if (nb == 1) b[1] = (unsigned short)j;
+                                else if (nb == 2) b[2] = (unsigned short)j;
+                                else if (nb == 3) b[3] = (unsigned short)j;
+                                ++nb;
                             }
                         }
                     }
+                }
+                if (nb > 4) b[0] = 0xFFFEu;
+                blockers[i] = make_ushort4(b[0], b[1], b[2], b[3]);
+                if (nb == 0) state[i] = 1;   // nothing of higher priority nearby: accepted at once
+            }
+            __syncthreads();
+        }
+        for (;;) {
+            int changed = 0;
+            for (int i = tid; i < n_act; i += SEL_THREADS) {
+                if (state[i] != 0) continue;
+                bool any_acc = false, any_und = false;
+                const ushort4 b = cache_ok ? blockers[i] : make_ushort4(0xFFFEu, 0, 0, 0);
+                if (b.x == 0xFFFEu) {
+                    scan_neighbours(i, keys[i], any_acc, any_und);
+                } else {
+                    const unsigned short bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (bb[q] != 0xFFFFu) {
+                            const uint8_t s = state[bb[q]];
+                            any_acc |= (s == 1);
+                            any_und |= (s == 0);
+                        }
                 }
                 if (any_acc) { state[i] = 2; changed = 1; }
                 else if (!any_und) { state[i] = 1; changed = 1; }
@@ -430,8 +484,61 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
         }
     }
 
-    if (peel_first) {
-        // ---- compact the accepted corners (each thread parks its <= 16 keys in registers), sort only those
+    if (peel_first && n_act <= SEL_SMEM_KEYS / 2) {
+        // ---- order the accepted corners by priority without a sorting network: counting sort by a monotone bucket of
+        // the key (sign, exponent, leading mantissa bits) into the free upper half of the key array, then every key
+        // finds its place inside its bucket by counting the bucket's greater keys (a bucket holds a handful of keys).
+        constexpr int NB2 = SEL_SMEM_CELLS < SEL_SMEM_KEYS / 2 ? SEL_SMEM_CELLS : SEL_SMEM_KEYS / 2;
+        constexpr int kShift2 = 64 - ilog2(NB2);
+        constexpr int BPT2 = NB2 / SEL_THREADS;
+        static_assert(NB2 % SEL_THREADS == 0 && NB2 * 4 <= 2 * SEL_SMEM_KEYS, "bucket tables fit the cursor / cell_start areas");
+        uint32_t* bcnt = head;                                    // counts, then fill cursors
+        uint32_t* bstart = reinterpret_cast<uint32_t*>(next16);   // the cell_start table is dead after the peeling
+        unsigned long long* tmp = keys + SEL_SMEM_KEYS / 2;       // so is the blocker cache
+        for (int b = tid; b < NB2; b += SEL_THREADS) bcnt[b] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n_act; i += SEL_THREADS)
+            if (state[i] == 1) atomicAdd(&bcnt[(uint32_t)(keys[i] >> kShift2)], 1u);
+        __syncthreads();
+        {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < BPT2; ++k) sum += bcnt[NB2 - 1 - (tid * BPT2 + k)];
+            uint32_t above = (uint32_t)block_exclusive_scan<SEL_THREADS>((unsigned long long)sum, wsum, &scan_total, tid);
+#pragma unroll
+            for (int k = 0; k < BPT2; ++k) {
+                const int b = NB2 - 1 - (tid * BPT2 + k);
+                const uint32_t c = bcnt[b];
+                bstart[b] = above;
+                bcnt[b] = 0u;
+                above += c;
+            }
+        }
+        n = (int)scan_total;
+        __syncthreads();
+        for (int i = tid; i < n_act; i += SEL_THREADS)
+            if (state[i] == 1) {
+                const unsigned long long k = keys[i];
+                const uint32_t b = (uint32_t)(k >> kShift2);
+                const uint32_t pos = bstart[b] + atomicAdd(&bcnt[b], 1u);
+                SVI_CHECK(2, pos < (uint32_t)n && n <= SEL_SMEM_KEYS / 2);
+                tmp[pos] = k;
+            }
+        __syncthreads();
+        for (int q = tid; q < n; q += SEL_THREADS) {
+            const unsigned long long k = tmp[q];
+            const uint32_t b = (uint32_t)(k >> kShift2);
+            const uint32_t s0 = bstart[b], s1 = s0 + bcnt[b];
+            uint32_t r = s0;
+            for (uint32_t j = s0; j < s1; ++j) r += tmp[j] > k ? 1u : 0u;
+            SVI_CHECK(2, r < (uint32_t)n);
+            keys[r] = k;
+            state[r] = 1;
+        }
+        __syncthreads();
+    } else if (peel_first) {
+        // ---- (lists longer than half the key array) compact the accepted corners (each thread parks its <= 16 keys in
+        //      registers), sort only those
         constexpr int PER = SEL_SMEM_KEYS / SEL_THREADS;
         unsigned long long mine[PER];
         int cnt = 0;
