@@ -185,6 +185,35 @@ __device__ __forceinline__ void brief_pair_all(const uint32_t* __restrict__ Al, 
     (brief_pair_word<J>(Al, Bl, wlo[J], whi[J]), ...);
 }
 
+// ------------------------------------------------------------------ one whole descriptor per LANE
+// For pools of unrelated points (the corners of a stage-2 window, the samples of a stage-3 line) every lane describes its
+// own point: the 512 box-sum gathers of a descriptor are issued 64 at a time (one 32-test word: offsets are compile-time
+// constants, dy * pitch + dx), so a round of 32 points costs eight memory round trips instead of hundreds.
+template <int T>
+__device__ __forceinline__ void brief_gather_pair(const uint16_t* __restrict__ c, int pitch, uint32_t& a, uint32_t& b) {
+    constexpr int y1 = kPat[T][0], x1 = kPat[T][1], y2 = kPat[T][2], x2 = kPat[T][3];
+    a = __ldg(c + y1 * pitch + x1);
+    b = __ldg(c + y2 * pitch + x2);
+}
+template <int J, int... I>
+__device__ __forceinline__ uint32_t brief_lane_word(const uint16_t* __restrict__ c, int pitch, std::integer_sequence<int, I...>) {
+    uint32_t a[32], b[32];
+    (brief_gather_pair<32 * J + I>(c, pitch, a[I], b[I]), ...);
+    uint32_t bits = 0u;
+    ((bits |= (a[I] < b[I] ? 1u : 0u) << (31 - I)), ...);
+    return bits;
+}
+template <int... J>
+__device__ __forceinline__ void brief_lane_words(const uint16_t* __restrict__ c, int pitch, uint32_t (&w)[kDescWords],
+                                                 std::integer_sequence<int, J...>) {
+    ((w[J] = brief_lane_word<J>(c, pitch, std::make_integer_sequence<int, 32>{})), ...);
+}
+// descriptor (word format of the kernels) of the point (cx, cy) of a box-sum plane, computed by the calling lane alone
+__device__ __forceinline__ void brief_at_point_lane(const uint16_t* __restrict__ box, int box_pitch, int cx, int cy,
+                                                    uint32_t (&w)[kDescWords]) {
+    brief_lane_words(box + cy * box_pitch + cx, box_pitch, w, std::make_integer_sequence<int, kDescWords>{});
+}
+
 struct SearchResult {
     int status, dist, idx;
     float u, v;
@@ -769,24 +798,24 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
     if (nd > 0) {
         status = SVI_TRK_NO_MATCHES;
         const ushort2* corners = det_xy + (size_t)i * max_corners;
-        // lanes = tests: a window holds a few dozen corners at most, so one corner at a time with the 256 tests spread
-        // over the warp (8 rounds of 2 gathers per lane, pattern offsets computed once) beats one corner per lane
-        BriefOffsets bo;
-        brief_offsets_init(bo, g.box_pitch, lane);
+        // lanes = corners: every lane describes its own corner (brief_at_point_lane), 32 corners per round
         SVI_CHECK(3, nd <= max_corners);
-        for (int k = 0; k < nd; ++k) {
-            const ushort2 c = corners[k];
-            const float px = (float)c.x + half, py = (float)c.y + half;
-            const int rx = cv_round_f(px), ry = cv_round_f(py), cx = brief_centre(px), cy = brief_centre(py);
-            const bool keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder &&
-                              cx >= kBriefBorder && cx < it.gw - kBriefBorder && cy >= kBriefBorder && cy < it.gh - kBriefBorder;
-            if (!keep) continue;   // warp-uniform
-            BriefGather gth;
-            brief_gather_issue(box_this, g.box_pitch, it.gx + cx, it.gy + cy, bo, gth);
-            uint32_t w[kDescWords];
-            brief_gather_finish(gth, w);
-            const uint32_t key = ((uint32_t)hamming_words(w, last_this) << 16) | (uint32_t)k;
-            best = min(best, key);   // smaller k wins ties: BFMatcher's first minimum in pool order
+        for (int k0 = 0; k0 < nd; k0 += 32) {
+            const int k = k0 + lane;
+            uint32_t key = 0xFFFFFFFFu;
+            if (k < nd) {
+                const ushort2 c = corners[k];
+                const float px = (float)c.x + half, py = (float)c.y + half;
+                const int rx = cv_round_f(px), ry = cv_round_f(py), cx = brief_centre(px), cy = brief_centre(py);
+                const bool keep = rx >= kBriefBorder && rx < it.gw - kBriefBorder && ry >= kBriefBorder && ry < it.gh - kBriefBorder &&
+                                  cx >= kBriefBorder && cx < it.gw - kBriefBorder && cy >= kBriefBorder && cy < it.gh - kBriefBorder;
+                if (keep) {
+                    uint32_t w[kDescWords];
+                    brief_at_point_lane(box_this, g.box_pitch, it.gx + cx, it.gy + cy, w);
+                    key = ((uint32_t)hamming_words(w, last_this) << 16) | (uint32_t)k;
+                }
+            }
+            best = min(best, warp_min_u32(key));   // smaller k wins ties: BFMatcher's first minimum in pool order
         }
     }
     SearchResult r;
@@ -906,13 +935,9 @@ track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
             }
             uint32_t dist = 0;
             if (keep) {
-#pragma unroll 4
-                for (int t = 0; t < SVI_BRIEF_NTESTS; ++t) {
-                    const char4 p = brief_pattern(t);
-                    const uint32_t s1 = __ldg(box_l + (sy + p.x) * g.box_pitch + sx + p.y);
-                    const uint32_t s2 = __ldg(box_l + (sy + p.z) * g.box_pitch + sx + p.w);
-                    dist += (s1 < s2 ? 1u : 0u) ^ ((last_l[t >> 5] >> (31 - (t & 31))) & 1u);
-                }
+                uint32_t w[kDescWords];
+                brief_at_point_lane(box_l, g.box_pitch, sx, sy, w);
+                dist = (uint32_t)hamming_words(w, last_l);
             }
             best = min(best, warp_min_u32(keep ? ((dist << 16) | (uint32_t)i) : 0xFFFFFFFFu));
         }
