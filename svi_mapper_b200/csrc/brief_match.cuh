@@ -11,10 +11,8 @@
 //
 // Work decomposition: one warp per query.  The candidates of a scan-line search are consecutive
 // pixels of one image row, so lane l evaluates candidates 2l and 2l+1 of a 64-candidate chunk
-// from 32-bit shared-memory loads: the u16 box sums of two neighbouring candidates are neighbours
-// in memory -- one aligned word for a test point in an even window column, the upper half of one
-// word and the lower half of the next (two loads that other test points share, one PRMT) for an odd
-// column.  The 256 test pairs are template constants
+// from ONE 32-bit shared-memory load per test point: the u16 box sums of two neighbouring
+// candidates are neighbours in memory.  The 256 test pairs are template constants
 // (brief_pattern_32.h), so every shared-memory offset is an instruction immediate.  Both
 // comparisons of a pair are one packed half-precision compare (values <= 20655 < 0x7C00 are
 // positive finite fp16 bit patterns, ordered like the integers): see lt_mask_u16x2.
@@ -42,11 +40,8 @@ constexpr int PATCH_WORDS = PATCH_W / 2;               // 60
 constexpr int PATCH_COPY_BYTES = PATCH_ROWS * PATCH_W * 2;          // 10976: one TMA box
 constexpr int PATCH_COPY_STRIDE = (PATCH_COPY_BYTES + 127) / 128 * 128; // TMA destinations are 128-B aligned
 constexpr int PATCH_COPY_WORDS = PATCH_COPY_STRIDE / 4;
-#ifndef MATCH_CTAS_PER_SM
-#define MATCH_CTAS_PER_SM 6
-#endif
-constexpr int MATCH_WARPS = 3;                                      // 6 CTAs/SM -> 18 warps, 207 KB of windows
-constexpr int MATCH_SMEM_PER_WARP = PATCH_COPY_STRIDE;              // one 49 x 120 window of u16 box sums
+constexpr int MATCH_WARPS = 3;                                      // 3 CTAs/SM -> 9 warps, 207 KB of windows
+constexpr int MATCH_SMEM_PER_WARP = 2 * PATCH_COPY_STRIDE;          // even- and odd-aligned copies
 constexpr int MATCH_SMEM = MATCH_WARPS * MATCH_SMEM_PER_WARP + MATCH_WARPS * 8;  // + one mbarrier per warp
 
 // ------------------------------------------------------------------ TMA / mbarrier (sm_90+ PTX)
@@ -78,26 +73,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-// Per-warp staging state: the shared copy of the box-sum window + the warp's mbarrier.
+// Per-warp staging state: two shared copies of the box-sum window + the warp's mbarrier.
 // TMA tile loads must start on a 16-byte boundary of the inner dimension (measured on B200: any
-// other start faults with "illegal instruction"), so a window starts at a multiple of 8 columns; the
-// remainder of the true start is an even word offset plus a parity that shifts the candidate slots.
+// other start faults with "illegal instruction"), so a window starts at a multiple of 8 columns and
+// the copy that is one element further right comes from the plane stored shifted by one element.
 struct PatchStage {
     const CUtensorMap* map;    // 2-D u16 tensor over S(y,x):   (W, frames*H), row pitch box_pitch
+    const CUtensorMap* map_s;  // same geometry over the shifted plane S(y,x+1)
     int row_base;              // first tensor row of this query's frame
-    uint32_t smem_a;          // shared address of the window
-    const uint32_t* words;    // generic pointer to the window
+    uint32_t smem_a;          // shared address of copy A (copy B follows at +PATCH_COPY_STRIDE)
+    const uint32_t* words;    // generic pointer to copy A
     uint32_t bar;             // shared address of the mbarrier
     uint32_t phase;           // parity of the next completion
 };
 
-// One elected lane arms the barrier and issues the box copy (col0 is a multiple of 8):
-// A[r][k] = S[row0+r][col0+k]; out-of-range elements are zero-filled.
+// One elected lane arms the barrier and issues both box copies (col0 is a multiple of 8):
+// A[r][k] = S[row0+r][col0+k], B[r][k] = S[row0+r][col0+1+k]; out-of-range elements are zero-filled.
 __device__ __forceinline__ void patch_issue(const PatchStage& ps, int row0, int col0, int lane) {
     if (lane == 0) {
-        fence_proxy_async();   // earlier generic-proxy reads of the buffer are ordered before the async writes
-        mbar_expect_tx(ps.bar, PATCH_COPY_BYTES);
+        fence_proxy_async();   // earlier generic-proxy reads of the buffers are ordered before the async writes
+        mbar_expect_tx(ps.bar, 2 * PATCH_COPY_BYTES);
         tma_load_2d(ps.smem_a, ps.map, col0, ps.row_base + row0, ps.bar);
+        tma_load_2d(ps.smem_a + PATCH_COPY_STRIDE, ps.map_s, col0, ps.row_base + row0, ps.bar);
     }
 }
 __device__ __forceinline__ void patch_wait(PatchStage& ps) {
@@ -141,13 +138,10 @@ __device__ __forceinline__ int hamming_words(const uint32_t (&a)[kDescWords], co
 }
 
 // ------------------------------------------------------------------ unrolled pair tests
-// A 32-bit LDS fetches the box sums of two adjacent window elements.  Lane l's candidates 2l, 2l+1 need, for a test
-// point in window column c, the elements 2l+c and 2l+c+1: the aligned word c/2 when c is even; for odd c the upper
-// half of word (c-1)/2 and the lower half of word (c+1)/2, joined by one PRMT -- the compiler loads every distinct
-// word once (458 words serve the 425 distinct points of the shipped table), so a single copy of the window is enough
-// and twice as many warps fit an SM.  Box sums are <= 81*255 = 20655 < 0x7C00, i.e. bit patterns of positive finite fp16
-// numbers, whose order equals the integer order (denormals included, no flush): one packed half-precision compare on the
-// FMA pipe tests both candidates and returns 0xFFFF per true half, so a test costs one compare and one LOP3 that keeps
+// One 32-bit LDS per test point fetches the box sums of two adjacent candidates.  Box sums are
+// <= 81*255 = 20655 < 0x7C00, i.e. bit patterns of positive finite fp16 numbers, whose order equals the
+// integer order (denormals included, no flush): one packed half-precision compare on the FMA pipe tests
+// both candidates and returns 0xFFFF per true half, so a test costs one compare and one LOP3 that keeps
 // the bit of this test in a 16-test accumulator (low half = even candidate, high half = odd candidate).
 __device__ __forceinline__ uint32_t lt_mask_u16x2(uint32_t a, uint32_t b) {
     uint32_t m;
@@ -155,40 +149,40 @@ __device__ __forceinline__ uint32_t lt_mask_u16x2(uint32_t a, uint32_t b) {
     return m;
 }
 
-template <int ROW, int COL>
-__device__ __forceinline__ uint32_t window_pair(const uint32_t* __restrict__ Al) {
-    constexpr int o = ROW * PATCH_WORDS + (COL >> 1);
-    if constexpr ((COL & 1) == 0) return Al[o];
-    else return __byte_perm(Al[o], Al[o + 1], 0x5432);
-}
-
 template <int T>
-__device__ __forceinline__ void brief_pair_test(const uint32_t* __restrict__ Al, uint32_t& acc) {
+__device__ __forceinline__ void brief_pair_test(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                                uint32_t& acc) {
+    constexpr int c1 = kPat[T][1] + kBriefReach, c2 = kPat[T][3] + kBriefReach;
+    constexpr int o1 = (kPat[T][0] + kBriefReach) * PATCH_WORDS + (c1 >> 1);
+    constexpr int o2 = (kPat[T][2] + kBriefReach) * PATCH_WORDS + (c2 >> 1);
     constexpr uint32_t bit = 0x00010001u << (15 - (T & 15));
-    const uint32_t a = window_pair<kPat[T][0] + kBriefReach, kPat[T][1] + kBriefReach>(Al);
-    const uint32_t b = window_pair<kPat[T][2] + kBriefReach, kPat[T][3] + kBriefReach>(Al);
+    const uint32_t a = (c1 & 1) ? Bl[o1] : Al[o1];
+    const uint32_t b = (c2 & 1) ? Bl[o2] : Al[o2];
     acc |= lt_mask_u16x2(a, b) & bit;
 }
 
 template <int G, int... I>
-__device__ __forceinline__ uint32_t brief_pair_group(const uint32_t* __restrict__ Al, std::integer_sequence<int, I...>) {
+__device__ __forceinline__ uint32_t brief_pair_group(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                                     std::integer_sequence<int, I...>) {
     uint32_t acc = 0u;
-    (brief_pair_test<G * 16 + I>(Al, acc), ...);
+    (brief_pair_test<G * 16 + I>(Al, Bl, acc), ...);
     return acc;
 }
 
 template <int J>
-__device__ __forceinline__ void brief_pair_word(const uint32_t* __restrict__ Al, uint32_t& wlo, uint32_t& whi) {
-    const uint32_t e = brief_pair_group<2 * J>(Al, std::make_integer_sequence<int, 16>{});      // tests 32J .. 32J+15
-    const uint32_t o = brief_pair_group<2 * J + 1>(Al, std::make_integer_sequence<int, 16>{});  // tests 32J+16 .. 32J+31
+__device__ __forceinline__ void brief_pair_word(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                                uint32_t& wlo, uint32_t& whi) {
+    const uint32_t e = brief_pair_group<2 * J>(Al, Bl, std::make_integer_sequence<int, 16>{});      // tests 32J .. 32J+15
+    const uint32_t o = brief_pair_group<2 * J + 1>(Al, Bl, std::make_integer_sequence<int, 16>{});  // tests 32J+16 .. 32J+31
     wlo = __byte_perm(o, e, 0x5410);   // (e.lo16 << 16) | o.lo16
     whi = __byte_perm(o, e, 0x7632);   // (e.hi16 << 16) | o.hi16
 }
 
 template <int... J>
-__device__ __forceinline__ void brief_pair_all(const uint32_t* __restrict__ Al, uint32_t (&wlo)[kDescWords],
-                                               uint32_t (&whi)[kDescWords], std::integer_sequence<int, J...>) {
-    (brief_pair_word<J>(Al, wlo[J], whi[J]), ...);
+__device__ __forceinline__ void brief_pair_all(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                               uint32_t (&wlo)[kDescWords], uint32_t (&whi)[kDescWords],
+                                               std::integer_sequence<int, J...>) {
+    (brief_pair_word<J>(Al, Bl, wlo[J], whi[J]), ...);
 }
 
 // ------------------------------------------------------------------ one whole descriptor per LANE
@@ -304,11 +298,12 @@ __device__ __forceinline__ void search_run(const SearchPlan& p, PatchStage& ps, 
             patch_issue(ps, p.gy - kBriefReach, col_a, lane);
         }
         patch_wait(ps);
-        // the farthest word any test reads: row 48, word 24 of a lane's pair -> woff + lane + 48 * PATCH_WORDS + 24
+        // the farthest word any test reads: row 48, word (48 >> 1) of a lane's pair -> woff + lane + 48 * PATCH_WORDS + 24
         SVI_CHECK(3, woff >= 0 && woff + 31 + 2 * kBriefReach * PATCH_WORDS + kBriefReach < PATCH_COPY_WORDS);
         const uint32_t* Al = ps.words + woff + lane;
+        const uint32_t* Bl = ps.words + PATCH_COPY_WORDS + woff + lane;
         uint32_t wlo[kDescWords], whi[kDescWords];
-        brief_pair_all(Al, wlo, whi, std::make_integer_sequence<int, kDescWords>{});
+        brief_pair_all(Al, Bl, wlo, whi, std::make_integer_sequence<int, kDescWords>{});
         const int l_lo = 2 * lane - par, l_hi = l_lo + 1;   // candidate index within this pass
         const int c_lo = cb + l_lo, c_hi = cb + l_hi;
         uint32_t k_lo = (l_lo >= 0 && l_lo < PATCH_CHUNK && c_lo < p.n_valid) ? (((uint32_t)hamming_words(wlo, ref) << 16) | (uint32_t)(c_lo & 0xFFFF)) : 0xFFFFFFFFu;
@@ -386,10 +381,11 @@ __device__ __forceinline__ void triangulate_left_dev(const FrameGeom& g, const T
 }
 
 // Carve the warp's staging buffers and barrier out of the CTA's dynamic shared memory.
-__device__ __forceinline__ void patch_stage_init(PatchStage& ps, unsigned char* smem, const CUtensorMap* map, int row_base,
-                                                 int warp, int lane) {
+__device__ __forceinline__ void patch_stage_init(PatchStage& ps, unsigned char* smem, const CUtensorMap* map,
+                                                 const CUtensorMap* map_s, int row_base, int warp, int lane) {
     unsigned char* mine = smem + (size_t)warp * MATCH_SMEM_PER_WARP;
     ps.map = map;
+    ps.map_s = map_s;
     ps.row_base = row_base;
     ps.smem_a = smem_u32(mine);
     ps.words = reinterpret_cast<const uint32_t*>(mine);
@@ -458,9 +454,9 @@ __device__ __forceinline__ void brief_gather_finish(const BriefGather& gth, uint
 //            is issued as soon as the last lane has finished reading the window
 // so every global round trip overlaps the ~1500 shared-memory/ALU instructions of stage C.
 constexpr int MATCH_KP_PER_WARP = 8;   // for full batches; small calls spread their key-points over more warps (latency)
-__global__ void __launch_bounds__(MATCH_WARPS * 32, MATCH_CTAS_PER_SM)
-stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r, FrameGeom g, TriConst tc,
-                    float size, float range,
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
+                    const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float size, float range,
                     const ushort2* __restrict__ kp_xy, const int* __restrict__ n_kp, int max_corners, StereoOutDev out,
                     int out_frame0, int kp_per_warp) {
     extern __shared__ __align__(128) unsigned char match_smem[];
@@ -470,7 +466,7 @@ stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
     if (slot0 >= n) return;
     const int slot_end = min(slot0 + kp_per_warp, n);
     PatchStage ps;
-    patch_stage_init(ps, match_smem, &map_r, f * g.H, warp, lane);
+    patch_stage_init(ps, match_smem, &map_r, &map_rs, f * g.H, warp, lane);
     const ushort2* kps = kp_xy + (size_t)f * max_corners;
     const uint16_t* bl = box_l + (size_t)f * g.H * g.box_pitch;
 
@@ -612,8 +608,8 @@ struct TriOutDev {
 
 // svi_triangulate_right / svi_triangulate_left: one warp per query against one image.
 template <bool kLeft>
-__global__ void __launch_bounds__(MATCH_WARPS * 32, MATCH_CTAS_PER_SM)
-triangulate_kernel(const __grid_constant__ CUtensorMap map, FrameGeom g,
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+triangulate_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_s, FrameGeom g,
                    TriConst tc, int n,
                    const float* __restrict__ search_range, const float* __restrict__ top_left,
                    const float* __restrict__ uv_ref, const uint8_t* __restrict__ desc_ref, float size, TriOutDev out) {
@@ -622,7 +618,7 @@ triangulate_kernel(const __grid_constant__ CUtensorMap map, FrameGeom g,
     const int q = blockIdx.x * MATCH_WARPS + warp;
     if (q >= n) return;
     PatchStage ps;
-    patch_stage_init(ps, match_smem, &map, 0, warp, lane);
+    patch_stage_init(ps, match_smem, &map, &map_s, 0, warp, lane);
     uint32_t ref[kDescWords];
     load_desc(desc_ref + (size_t)q * 32, ref);
     SearchResult r;
@@ -676,16 +672,17 @@ __device__ __forceinline__ void projection_rounded(const double* P, const double
     v = round_half_away((float)__ddiv_rn(h1, h2));
 }
 
-__global__ void __launch_bounds__(MATCH_WARPS * 32, MATCH_CTAS_PER_SM)
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
 track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restrict__ box_r,
-                    const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_r, FrameGeom g,
+                    const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_ls,
+                    const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_rs, FrameGeom g,
                     TriConst tc, TrackConst k, LandmarksDev lm, int n, TrackOutDev out) {
     extern __shared__ __align__(128) unsigned char match_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * MATCH_WARPS + warp;
     if (q >= n) return;
     PatchStage ps;
-    patch_stage_init(ps, match_smem, &map_r, 0, warp, lane);
+    patch_stage_init(ps, match_smem, &map_r, &map_rs, 0, warp, lane);
     const double wx = lm.xyz_w[3 * q], wy = lm.xyz_w[3 * q + 1], wz = lm.xyz_w[3 * q + 2];
     double p[3];
 #pragma unroll
@@ -718,7 +715,7 @@ track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restri
                 brief_at_point(box_l, g.box_pitch, (int)roi_x + brief_centre(half), (int)roi_y + brief_centre(half), lane, mine);
             status = roi_ok ? SVI_TRK_STAGE1_DIST : SVI_TRI_BAD_ROI;
             if (kp_ok && roi_ok && k.cutoff1 > (float)hamming_words(last_l, mine)) {
-                ps.map = &map_r;
+                ps.map = &map_r; ps.map_s = &map_rs;
                 triangulate_right_dev(g, tc, ps, fmaxf(0.f, roi_x - search), roi_y, size, roi_x + half, roi_y + half, mine,
                                       lane, r, xyz);
                 status = r.status;
@@ -737,7 +734,7 @@ track_stage1_kernel(const uint16_t* __restrict__ box_l, const uint16_t* __restri
                 brief_at_point(box_r, g.box_pitch, (int)roi_x + brief_centre(half), (int)roi_y + brief_centre(half), lane, mine);
             status = roi_ok ? SVI_TRK_STAGE1_DIST : SVI_TRI_BAD_ROI;
             if (kp_ok && roi_ok && k.cutoff1 > (float)hamming_words(last_r, mine)) {
-                ps.map = &map_l;
+                ps.map = &map_l; ps.map_s = &map_ls;
                 triangulate_left_dev(g, tc, ps, search, roi_x, roi_y, size, roi_x + half, mine, lane, r, xyz);
                 status = r.status;
                 if (status == SVI_OK) {
@@ -777,9 +774,9 @@ struct Stage2Item {
 // triangulation in the other image, depth window and the other-side descriptor check (:1586-1637).
 // One warp per item; lanes = corners for the K descriptors (box-sum gathers from global memory).
 template <bool kLeft>
-__global__ void __launch_bounds__(MATCH_WARPS * 32, MATCH_CTAS_PER_SM)
-track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant__ CUtensorMap map_other, FrameGeom g, TriConst tc,
-                    float cutoff2,
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant__ CUtensorMap map_other,
+                    const __grid_constant__ CUtensorMap map_other_s, FrameGeom g, TriConst tc, float cutoff2,
                     const Stage2Item* __restrict__ items, const int* __restrict__ n_items, const ushort2* __restrict__ det_xy,
                     const int* __restrict__ n_det, int max_corners, LandmarksDev lm, TrackOutDev out) {
     extern __shared__ __align__(128) unsigned char match_smem[];
@@ -789,7 +786,7 @@ track_stage2_kernel(const uint16_t* __restrict__ box_this, const __grid_constant
     const Stage2Item it = items[i];
     const int q = it.q;
     PatchStage ps;
-    patch_stage_init(ps, match_smem, &map_other, 0, warp, lane);
+    patch_stage_init(ps, match_smem, &map_other, &map_other_s, 0, warp, lane);
     const float half = 4.f * it.size;
     uint32_t last_this[kDescWords], last_other[kDescWords];
     load_desc((kLeft ? lm.desc_l : lm.desc_r) + (size_t)q * 32, last_this);
@@ -888,9 +885,9 @@ __device__ __forceinline__ void epipolar_sample(const Stage3Item& it, int i, dou
 
 // _getMatchSampleRecursiveU/V + _getMatch (:2142-2397) and _addMeasurementToLandmarkLEFT (:2399-2453):
 // the line geometry (coefficients, clipped range, sampling direction) comes from stage3_plan_kernel; one warp per item.
-__global__ void __launch_bounds__(MATCH_WARPS * 32, MATCH_CTAS_PER_SM)
-track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r, FrameGeom g, TriConst tc,
-                    float cutoff3, float cutoff_orig,
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3)
+track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
+                    const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float cutoff3, float cutoff_orig,
                     const Stage3Item* __restrict__ items, const int* __restrict__ n_items, const uint8_t* __restrict__ desc_orig,
                     LandmarksDev lm, TrackOutDev out) {
     extern __shared__ __align__(128) unsigned char match_smem[];
@@ -900,7 +897,7 @@ track_stage3_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
     const Stage3Item it = items[idx];
     const int q = it.q, n = it.count;
     PatchStage ps;
-    patch_stage_init(ps, match_smem, &map_r, 0, warp, lane);
+    patch_stage_init(ps, match_smem, &map_r, &map_rs, 0, warp, lane);
     uint32_t last_l[kDescWords], orig_l[kDescWords], mine[kDescWords];
     load_desc(lm.desc_l + (size_t)q * 32, last_l);
     load_desc(desc_orig + (size_t)q * 32, orig_l);

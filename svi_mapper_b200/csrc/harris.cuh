@@ -101,6 +101,9 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
 // 9x9 box sums (u16, max 81*255 = 20655) of the 64x32 tile from its u8 tile with 4-px halo.
 // S(y,x) = sum over [y-4,y+4]x[x-4,x+4]; equals the 4-corner integral-image expression of
 // OpenCV BRIEF's smoothedSum.  Values within 4 px of the image border are never sampled.
+// `box_shift` (optional) receives the same plane stored one element to the left,
+// box_shift[y][x] = S(y, x+1): TMA tile loads must start on a 16-byte boundary, so the match
+// kernels fetch their odd-aligned copy of a window from this plane at the same aligned address.
 __device__ __forceinline__ void box9_rows(const uint8_t (*tile)[U8_P], uint16_t (*h9)[H9_P]) {
     // horizontal 9-sums: one work item = 16 outputs of one tile row; its 24 source bytes arrive as six 32-bit loads
     // (one shared-memory wavefront each instead of one per byte), the 16 sums leave as eight packed stores
@@ -127,25 +130,37 @@ __device__ __forceinline__ void box9_rows(const uint8_t (*tile)[U8_P], uint16_t 
     }
 }
 // (a __syncthreads() separates the two halves)
-__device__ __forceinline__ void box9_cols(const uint16_t (*h9)[H9_P], uint16_t* __restrict__ box, int box_pitch, int W, int H,
-                                          int x0, int y0) {
+__device__ __forceinline__ void box9_cols(const uint16_t (*h9)[H9_P], uint16_t* __restrict__ box,
+                                          uint16_t* __restrict__ box_shift, int box_pitch, int W, int H, int x0, int y0) {
     // vertical 9-sums, two columns per thread as packed u16 pairs (sums <= 20655, so s + new - old never carries
-    // or borrows across the halves): one 32-bit store per row.  thread = (column pair, 8-row group)
+    // or borrows across the halves): one 32-bit store per plane and row.  thread = (column pair, 8-row group)
     if (threadIdx.x < (HT_W / 2) * (HT_H / 8)) {
         const int xp = (threadIdx.x % (HT_W / 2)) * 2, oy0 = (threadIdx.x / (HT_W / 2)) * 8;
         const int gx = x0 + xp, rows = min(8, H - (y0 + oy0));
         if (gx < W && rows > 0) {
             constexpr int HP = H9_P / 2;   // 33 words per row: conflict-free across the lanes of a warp
             const uint32_t* col = reinterpret_cast<const uint32_t*>(&h9[0][0]) + oy0 * HP + (xp >> 1);
-            uint32_t s0 = 0u;              // (S(xp), S(xp+1))
+            const bool pair2 = xp + 2 < HT_W;   // columns xp+2, xp+3 (for the shifted plane) are inside this tile
+            uint32_t s0 = 0u, s1 = 0u;          // (S(xp), S(xp+1)), (S(xp+2), S(xp+3))
 #pragma unroll
-            for (int i = 0; i < 9; ++i) s0 += col[i * HP];
+            for (int i = 0; i < 9; ++i) { s0 += col[i * HP]; s1 += col[i * HP + 1]; }
             uint16_t* brow = box + (size_t)(y0 + oy0) * box_pitch + gx;
+            uint16_t* srow = box_shift ? box_shift + (size_t)(y0 + oy0) * box_pitch + gx : nullptr;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (k < rows) {
-                    if (k > 0) s0 = s0 + col[(k + 8) * HP] - col[(k - 1) * HP];
+                    if (k > 0) {
+                        s0 = s0 + col[(k + 8) * HP] - col[(k - 1) * HP];
+                        s1 = s1 + col[(k + 8) * HP + 1] - col[(k - 1) * HP + 1];
+                    }
                     *reinterpret_cast<uint32_t*>(brow) = s0;
+                    if (srow) {
+                        // srow[j] = S(gx + j + 1)
+                        if (pair2) *reinterpret_cast<uint32_t*>(srow) = __byte_perm(s0, s1, 0x5432);
+                        else srow[0] = (uint16_t)(s0 >> 16);
+                        if (xp == 0 && gx > 0) srow[-1] = (uint16_t)s0;   // the previous tile's last element
+                        srow += box_pitch;
+                    }
                     brow += box_pitch;
                 }
             }
@@ -156,7 +171,7 @@ __device__ __forceinline__ void box9_cols(const uint16_t (*h9)[H9_P], uint16_t* 
 // K2: box-sum image of one plane per blockIdx.z (used for the RIGHT image, and for both images
 // on the per-query entry points).
 __global__ void __launch_bounds__(HT_THREADS)
-boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box) {
+boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restrict__ box, uint16_t* __restrict__ box_shift) {
     __shared__ __align__(16) uint8_t tile[U8_ROWS][U8_P];
     __shared__ __align__(16) uint16_t h9[U8_ROWS][H9_P];
     const int f = blockIdx.z, x0 = blockIdx.x * HT_W, y0 = blockIdx.y * HT_H;
@@ -165,7 +180,7 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
     const size_t fo = (size_t)f * g.H * g.box_pitch;
     box9_rows(tile, h9);
     __syncthreads();
-    box9_cols(h9, box + fo, g.box_pitch, g.W, g.H, x0, y0);
+    box9_cols(h9, box + fo, box_shift ? box_shift + fo : nullptr, g.box_pitch, g.W, g.H, x0, y0);
 }
 
 // K1: Harris response + per-frame masked maximum + 3x3 NMS candidates + LEFT box-sum image; one 64x32 response
@@ -188,7 +203,7 @@ boxsum9_kernel(const uint8_t* __restrict__ img, FrameGeom g, uint16_t* __restric
 __global__ void __launch_bounds__(HT_THREADS, HARRIS_CTAS_PER_SM)
 harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, FrameGeom g,
                   float f1, float f0, float kf, double quality, float* __restrict__ resp, uint16_t* __restrict__ box,
-                  uint32_t* __restrict__ frame_max,
+                  uint16_t* __restrict__ box_shift, uint32_t* __restrict__ frame_max,
                   unsigned long long* __restrict__ cand, int* __restrict__ cand_count, int cand_cap,
                   const RoiItem* __restrict__ rois, const int* __restrict__ n_rois, int out_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -447,7 +462,7 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
     }
     if (box) {
         const size_t fo = (size_t)f * H * g.box_pitch;
-        box9_cols(h9, box + fo, g.box_pitch, W, H, x0, y0);
+        box9_cols(h9, box + fo, box_shift ? box_shift + fo : nullptr, g.box_pitch, W, H, x0, y0);
     }
 }
 

@@ -41,6 +41,8 @@ struct Lane {
     cudaEvent_t done = nullptr;
     uint16_t* box_l = nullptr;   // S(y,x) of LEFT
     uint16_t* box_r = nullptr;   // S(y,x) of RIGHT
+    uint16_t* box_ls = nullptr;  // planes stored shifted by one element, S(y,x+1): the odd-aligned TMA copies
+    uint16_t* box_rs = nullptr;
     uint32_t* frame_max = nullptr;
     int* cand_count = nullptr;
     unsigned long long* cand = nullptr;
@@ -55,7 +57,7 @@ struct Lane {
     uint8_t* img_l = nullptr;
     uint8_t* img_r = nullptr;
     uint8_t* mask = nullptr;
-    CUtensorMap map_l{}, map_r{};  // TMA views of the two box-sum planes: (W, chunk*H) u16, row pitch box_pitch
+    CUtensorMap map_l{}, map_r{}, map_ls{}, map_rs{};  // TMA views of the four planes: (W, chunk*H) u16, row pitch box_pitch
     StereoOutDev out{};
     std::vector<cudaEvent_t> ev;  // stage boundary events (profiling)
     size_t ev_used = 0;
@@ -234,14 +236,14 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     if (fast) {
         fast_candidates_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, d_mask, g, ctx->p.fast_threshold, ctx->p.fast_nonmax, l.cand,
                                                             l.cand_count, ctx->raw_cap);
-        boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, g, l.box_l);
+        boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_left, g, l.box_l, nullptr);
     } else {
         harris_box_kernel<<<harris_grid(g.W, g.H, nf), HT_THREADS, sizeof(HarrisSmem), s>>>(
-            d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, l.box_l, l.frame_max, l.cand,
+            d_left, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, l.box_l, nullptr, l.frame_max, l.cand,
             l.cand_count, ctx->raw_cap, nullptr, nullptr, g.H);
     }
     mark(ctx, l);
-    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r);
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
     mark(ctx, l);
     const uint32_t* fmax = fast ? nullptr : l.frame_max;
     if (ctx->select_smem) {
@@ -258,7 +260,7 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     const int kp_per_warp = (int)std::max<long long>(1, std::min<long long>(MATCH_KP_PER_WARP, slots / (2LL * ctx->n_sm * 9)));
     const int kp_per_cta = MATCH_WARPS * kp_per_warp;
     const dim3 mgrid((ctx->p.max_corners + kp_per_cta - 1) / kp_per_cta, nf);
-    stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, g, ctx->tc, ctx->p.keypoint_size,
+    stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size,
                                                                     ctx->p.search_range_px, l.kp_xy, n_kp,
                                                                     ctx->p.max_corners, out, out_frame0, kp_per_warp);
     mark(ctx, l);
@@ -302,7 +304,8 @@ cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<vo
 
 // ---- per-query entry points: one image (or pair) staged in lane 0, queries in the arena ----
 namespace {
-int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, cudaStream_t s, int pin_plane = 0) {
+int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, uint16_t* d_box_shift,
+              cudaStream_t s, int pin_plane = 0) {
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
     if (ctx->pin && pin_plane >= 0 && (size_t)(pin_plane + 1) * plane <= ctx->pin_bytes) {
@@ -314,7 +317,7 @@ int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, ui
         CK(cudaMemcpy2DAsync(d_img, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
     }
     const dim3 tiles((g.W + HT_W - 1) / HT_W, (g.H + HT_H - 1) / HT_H, 1);
-    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_img, g, d_box);
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_img, g, d_box, d_box_shift);
     CK(cudaGetLastError());
     return SVI_SUCCESS;
 }
@@ -449,7 +452,7 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0; ctx->pending.clear();
-    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, s);
+    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     float* d_range = nullptr; float* d_tl; float* d_uv; uint8_t* d_desc;
     TriOutDev o;
@@ -469,9 +472,9 @@ int triangulate_common(svi_ctx* ctx, bool left_search, const uint8_t* img, size_
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
     const int blocks = (n + MATCH_WARPS - 1) / MATCH_WARPS;
     if (left_search)
-        triangulate_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.map_l, g, ctx->tc, n, d_range, d_tl, d_uv, d_desc, size, o);
+        triangulate_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.map_l, l.map_ls, g, ctx->tc, n, d_range, d_tl, d_uv, d_desc, size, o);
     else
-        triangulate_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.map_l, g, ctx->tc, n, nullptr, d_tl, d_uv, d_desc, size, o);
+        triangulate_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.map_l, l.map_ls, g, ctx->tc, n, nullptr, d_tl, d_uv, d_desc, size, o);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out->uv, o.uv, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out->xyz_left, o.xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
@@ -553,7 +556,7 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, int n, const do
         CK(cudaMemsetAsync(r.max, 0, sizeof(int) * ((size_t)r.items * 3 + 4), s));   // max, cand_count, defer, counters
         stage2_plan_kernel<<<(nb + 127) / 128, 128, 0, s>>>(k, left ? 0 : 1, (float)(1.0 + motion_scaling), ld, q0, q0 + nb, o, r.rois, r.s2, n_items);
         harris_box_kernel<<<harris_grid(max_w, max_h, nb), HT_THREADS, sizeof(HarrisSmem), s>>>(
-            ctx->trk_img, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, r.max, r.cand,
+            ctx->trk_img, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, r.max, r.cand,
             r.cand_count, kRoiRawCap, r.rois, n_items, 0);
         // thousands of small windows: seven small-configuration CTAs per SM; the rare window that does not fit is
         // deferred to the frame-size configuration (its CTAs return at once for every other window)
@@ -564,10 +567,10 @@ int track_stage2_side(svi_ctx* ctx, Lane& l, const FrameGeom& g, int n, const do
                                                                               r.n_det, r.kp, r.n_kp, ctx->d_overflow, r.rois, nullptr, r.defer, n_items);
         const int blocks = (nb + MATCH_WARPS - 1) / MATCH_WARPS;
         if (left)
-            track_stage2_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, g, ctx->tc, ctx->p.cutoff_stage2,
+            track_stage2_kernel<true><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage2,
                                                                                   r.s2, n_items, r.det, r.n_det, ctx->p.max_corners, ld, o);
         else
-            track_stage2_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_r, l.map_l, g, ctx->tc, ctx->p.cutoff_stage2,
+            track_stage2_kernel<false><<<blocks, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_r, l.map_l, l.map_ls, g, ctx->tc, ctx->p.cutoff_stage2,
                                                                                    r.s2, n_items, r.det, r.n_det, ctx->p.max_corners, ld, o);
         CK(cudaGetLastError());
     }
@@ -584,7 +587,7 @@ int track_stage3_all(svi_ctx* ctx, Lane& l, const FrameGeom& g, int n, const dou
     CK(cudaMemsetAsync(n_items, 0, sizeof(int), s));
     stage3_plan_kernel<<<(n + 127) / 128, 128, 0, s>>>(k, ld, ex, n, o, ctx->s3_items, n_items);
     track_stage3_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(
-        l.box_l, l.map_r, g, ctx->tc, ctx->p.cutoff_stage3, ctx->p.cutoff_original, ctx->s3_items, n_items, d_orig, ld, o);
+        l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.cutoff_stage3, ctx->p.cutoff_original, ctx->s3_items, n_items, d_orig, ld, o);
     CK(cudaGetLastError());
     return SVI_SUCCESS;
 }
@@ -664,7 +667,7 @@ void svi_destroy(svi_ctx* ctx) {
     for (int i = 0; i < kMaxLanes; ++i) {
         Lane& l = ctx->lanes[i];
         if (l.stream) cudaStreamSynchronize(l.stream);
-        void* ptrs[] = {l.box_l, l.box_r, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
+        void* ptrs[] = {l.box_l, l.box_r, l.box_ls, l.box_rs, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
                         l.g_head, l.g_next, l.g_state, l.img_l, l.img_r, l.mask, l.out.uv_l, l.out.uv_r, l.out.xyz,
                         l.out.desc_l, l.out.desc_r, l.out.dist, l.out.idx, l.out.status};
         for (void* p : ptrs) if (p) cudaFree(p);
@@ -821,9 +824,15 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         CK(dmalloc(&l.box_l, C * HH * ctx->box_pitch));
         CK(dmalloc(&l.box_r, C * HH * ctx->box_pitch));
+        CK(dmalloc(&l.box_ls, C * HH * ctx->box_pitch));
+        CK(dmalloc(&l.box_rs, C * HH * ctx->box_pitch));
+        CK(cudaMemset(l.box_ls, 0, sizeof(uint16_t) * C * HH * ctx->box_pitch));
+        CK(cudaMemset(l.box_rs, 0, sizeof(uint16_t) * C * HH * ctx->box_pitch));
         {
             std::string merr;
             if (!make_box_map(&l.map_l, l.box_l, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
+                !make_box_map(&l.map_ls, l.box_ls, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
+                !make_box_map(&l.map_rs, l.box_rs, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
                 !make_box_map(&l.map_r, l.box_r, ctx->W, (int)(C * HH), ctx->box_pitch, &merr)) {
                 svi_destroy(ctx);
                 return fail(nullptr, SVI_ERR_CUDA, merr);
@@ -1021,7 +1030,7 @@ int svi_harris_response(svi_ctx* ctx, const uint8_t* img, size_t pitch, float* r
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t), s));
     if (!ctx->resp_one) CK(dmalloc(&ctx->resp_one, (size_t)ctx->H * ctx->resp_pitch));
     harris_box_kernel<<<harris_grid(g.W, g.H, 1), HT_THREADS, sizeof(HarrisSmem), s>>>(
-        l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, ctx->resp_one, nullptr, l.frame_max, nullptr,
+        l.img_l, nullptr, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, ctx->resp_one, nullptr, nullptr, l.frame_max, nullptr,
         nullptr, 0, nullptr, nullptr, g.H);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(response, sizeof(float) * ctx->W, ctx->resp_one, sizeof(float) * ctx->resp_pitch, sizeof(float) * ctx->W,
@@ -1060,7 +1069,7 @@ int svi_detect(svi_ctx* ctx, const uint8_t* img, size_t pitch, size_t frame_stri
                                                                 l.cand_count, ctx->raw_cap);
         } else {
             harris_box_kernel<<<harris_grid(W, H, nf), HT_THREADS, sizeof(HarrisSmem), s>>>(
-                l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, l.frame_max, l.cand,
+                l.img_l, d_mask, g, ctx->f1, ctx->f0, ctx->kf, ctx->p.quality_level, nullptr, nullptr, nullptr, l.frame_max, l.cand,
                 l.cand_count, ctx->raw_cap, nullptr, nullptr, g.H);
         }
         const uint32_t* fmax = fast ? nullptr : l.frame_max;
@@ -1093,7 +1102,7 @@ int svi_describe(svi_ctx* ctx, const uint8_t* img, size_t pitch, const float* xy
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0; ctx->pending.clear();
-    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, s);
+    int rc = stage_box(ctx, img, pitch, l.img_l, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
     float* d_xy; uint8_t* d_desc; uint8_t* d_kept;
     UP(d_xy, xy, (size_t)n * 2);
@@ -1233,9 +1242,9 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     ctx->arena_used = 0; ctx->pending.clear();
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
     // both images as planes 0 / 1 of one buffer (the window-mode detector indexes them by plane)
-    rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, s);
+    rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
     if (rc != SVI_SUCCESS) return rc;
-    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, s, 1);
+    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s, 1);
     if (rc != SVI_SUCCESS) return rc;
     // every input array goes through the pinned mirror of the arena and up in ONE copy; the outputs form one contiguous
     // range behind them: one memset, one copy back
@@ -1280,7 +1289,7 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     // the device and plans its own work items there; the host only waits once, for the results.
     if (stage_mask & (SVI_STAGE_1 | SVI_STAGE_2)) {
         // ---- stage 1 LEFT / RIGHT for every landmark (or only its field-of-view gate when stage 2 runs alone)
-        track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_r, g,
+        track_stage1_kernel<<<(n + MATCH_WARPS - 1) / MATCH_WARPS, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.box_r, l.map_l, l.map_ls, l.map_r, l.map_rs, g,
                                                                                                       ctx->tc, k, ld, n, o);
         CK(cudaGetLastError());
     } else {
