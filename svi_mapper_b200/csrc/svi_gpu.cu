@@ -103,6 +103,13 @@ struct svi_ctx {
     // pinned bounce buffer of the small-call path (one or a few frames per call: the tracker's per-frame use)
     unsigned char* pin = nullptr;
     size_t pin_bytes = 0;
+    // ... and its device-side result block: every output array of up to kSmallFrames frames in ONE allocation, so that the
+    // results of a single-pair call come back with one copy
+    unsigned char* small_block = nullptr;
+    size_t small_bytes = 0;
+    StereoOutDev small_out{};
+    int* small_n_kp = nullptr;
+    int* small_n_det = nullptr;
     // pinned mirror of the per-query arena: uploads and result downloads of the per-query / tracking entry points bounce
     // through it, so that pageable caller buffers never turn a transfer into a blocking staged copy
     unsigned char* pin_arena = nullptr;
@@ -393,7 +400,7 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
         const int nf = n_frames;
         const size_t plane = dstride * nf;
         unsigned char* pin_in = ctx->pin;
-        unsigned char* pin_out = ctx->pin + 3 * (size_t)kSmallFrames * dstride;
+        unsigned char* pin_out = ctx->pin + ((3 * (size_t)kSmallFrames * dstride + 15) & ~size_t(15));
         const uint8_t* srcs[3] = {left, right, masks};
         uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
         for (int k = 0; k < 3; ++k) {
@@ -412,30 +419,25 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
             if (rc != SVI_SUCCESS) return rc;
             have_mask = true;
         }
-        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, l.out, 0, l.n_kp, l.n_det);
+        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, ctx->small_out, 0, ctx->small_n_kp, ctx->small_n_det);
         if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
-        struct Part { const void* dev; void* host; size_t elem; };   // elem = bytes per key-point slot
-        const Part parts[8] = {{l.out.uv_l, out->uv_left, 8}, {l.out.uv_r, out->uv_right, 8}, {l.out.xyz, out->xyz_left, 24},
-                               {l.out.desc_l, out->desc_left, 32}, {l.out.desc_r, out->desc_right, 32}, {l.out.dist, out->distance, 4},
-                               {l.out.idx, out->match_index, 4}, {l.out.status, out->status, 1}};
-        size_t off = 0;
-        for (const Part& q : parts) {
-            CK(cudaMemcpyAsync(pin_out + off, q.dev, (size_t)nf * MC * q.elem, cudaMemcpyDeviceToHost, s));
-            off += (size_t)kSmallFrames * MC * q.elem;
-        }
-        int* pin_cnt = reinterpret_cast<int*>(pin_out + off);
-        CK(cudaMemcpyAsync(pin_cnt, l.n_kp, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(pin_cnt + kSmallFrames, l.n_det, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+        // one copy brings the whole result block back; only the live slots are scattered to the caller's arrays
+        CK(cudaMemcpyAsync(pin_out, ctx->small_block, ctx->small_bytes, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        off = 0;
-        for (const Part& q : parts) {   // only the live slots reach the caller's arrays
+        const StereoOutDev& so = ctx->small_out;
+        auto host = [&](const void* d) { return pin_out + (static_cast<const unsigned char*>(d) - ctx->small_block); };
+        const int* pin_kp = reinterpret_cast<const int*>(host(ctx->small_n_kp));
+        const int* pin_det = reinterpret_cast<const int*>(host(ctx->small_n_det));
+        struct Part { const void* dev; void* host; size_t elem; };   // elem = bytes per key-point slot
+        const Part parts[8] = {{so.uv_l, out->uv_left, 8}, {so.uv_r, out->uv_right, 8}, {so.xyz, out->xyz_left, 24},
+                               {so.desc_l, out->desc_left, 32}, {so.desc_r, out->desc_right, 32}, {so.dist, out->distance, 4},
+                               {so.idx, out->match_index, 4}, {so.status, out->status, 1}};
+        for (const Part& q : parts)
             for (int f = 0; f < nf; ++f)
-                std::memcpy(static_cast<unsigned char*>(q.host) + (size_t)f * cap * q.elem, pin_out + off + (size_t)f * MC * q.elem,
-                            (size_t)std::min(std::max(pin_cnt[f], 0), MC) * q.elem);
-            off += (size_t)kSmallFrames * MC * q.elem;
-        }
-        std::memcpy(out->n_keypoints, pin_cnt, sizeof(int) * nf);
-        if (out->n_detected) std::memcpy(out->n_detected, pin_cnt + kSmallFrames, sizeof(int) * nf);
+                std::memcpy(static_cast<unsigned char*>(q.host) + (size_t)f * cap * q.elem, host(q.dev) + (size_t)f * MC * q.elem,
+                            (size_t)std::min(std::max(pin_kp[f], 0), MC) * q.elem);
+        std::memcpy(out->n_keypoints, pin_kp, sizeof(int) * nf);
+        if (out->n_detected) std::memcpy(out->n_detected, pin_det, sizeof(int) * nf);
         return check_overflow(ctx);
     }
 }
@@ -678,6 +680,7 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->small_block) cudaFree(ctx->small_block);
     if (ctx->pin_arena) cudaFreeHost(ctx->pin_arena);
     if (ctx->trk_img) cudaFree(ctx->trk_img);
     if (ctx->s3_items) cudaFree(ctx->s3_items);
@@ -871,9 +874,27 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), ctx->arena_bytes));
     if (ctx->arena_bytes <= (64u << 20)) CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->pin_arena), ctx->arena_bytes));
     // room for kSmallFrames frames: three image planes in, every output array out
-    ctx->pin_bytes = (size_t)kSmallFrames * (3 * HH * ctx->dev_pitch + (size_t)p.max_corners * kOutBytesPerSlot + 64);
+    ctx->pin_bytes = (size_t)kSmallFrames * (3 * HH * ctx->dev_pitch + (size_t)p.max_corners * kOutBytesPerSlot + 64) + 16;
     if (ctx->pin_bytes <= (64u << 20)) CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->pin), ctx->pin_bytes));
     else ctx->pin_bytes = 0;
+    {   // layout (descending alignment): xyz | uv_l | uv_r | dist | idx | n_kp | n_det | desc_l | desc_r | status
+        const size_t S = (size_t)kSmallFrames * MC;
+        ctx->small_bytes = S * kOutBytesPerSlot + 2 * sizeof(int) * kSmallFrames;
+        CK(cudaMalloc(reinterpret_cast<void**>(&ctx->small_block), ctx->small_bytes));
+        unsigned char* q = ctx->small_block;
+        StereoOutDev& o = ctx->small_out;
+        o.cap = p.max_corners;
+        o.xyz = reinterpret_cast<double*>(q); q += S * 24;
+        o.uv_l = reinterpret_cast<float*>(q); q += S * 8;
+        o.uv_r = reinterpret_cast<float*>(q); q += S * 8;
+        o.dist = reinterpret_cast<int*>(q); q += S * 4;
+        o.idx = reinterpret_cast<int*>(q); q += S * 4;
+        ctx->small_n_kp = reinterpret_cast<int*>(q); q += sizeof(int) * kSmallFrames;
+        ctx->small_n_det = reinterpret_cast<int*>(q); q += sizeof(int) * kSmallFrames;
+        o.desc_l = q; q += S * 32;
+        o.desc_r = q; q += S * 32;
+        o.status = q;
+    }
     *out = ctx;
     return SVI_SUCCESS;
 #undef CK
