@@ -525,6 +525,300 @@ stereo_match_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------ the same search, G warps per key-point
+// stereo_match_kernel runs 9 warps per SM (the windows fill the shared memory) and ncu shows those warps waiting on
+// their own LDS -> HSET2 -> LOP3 chains.  Here the G warps of a GROUP share one window and one mbarrier and each of them
+// evaluates kDescWords / G of the eight descriptor words (its share of the LDS / compares / popc); the partial Hamming
+// distances of the 64 candidate slots cross a 2 x G x 32-word exchange buffer once per pass, after which every warp of
+// the group holds the complete distances, finds the same arg-min and writes its own words of both descriptors.
+// Same shared memory per key-point, G times the warps per SM, the instruction count per key-point unchanged apart from
+// one named barrier per pass.
+template <int G>
+struct MatchSplit {
+    static constexpr int WORDS = kDescWords / G;                       // descriptor words per warp
+    static constexpr int THREADS = MATCH_WARPS * G * 32;               // MATCH_WARPS groups per CTA
+    static constexpr int BAR_OFF = MATCH_WARPS * MATCH_SMEM_PER_WARP;  // one mbarrier per group
+    static constexpr int XCH_OFF = BAR_OFF + 32;                       // exchange: [group][parity][warp of group][lane]
+    static constexpr int SMEM = XCH_OFF + MATCH_WARPS * 2 * G * 32 * 4;
+    static_assert(kDescWords % G == 0 && MATCH_WARPS * 8 <= 32, "group layout");
+};
+
+__device__ __forceinline__ void group_barrier(int grp, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(threads) : "memory");
+}
+
+template <int BASE, int N, int... J>
+__device__ __forceinline__ void brief_pair_range(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                                 uint32_t (&wlo)[N], uint32_t (&whi)[N], std::integer_sequence<int, J...>) {
+    (brief_pair_word<BASE + J>(Al, Bl, wlo[J], whi[J]), ...);
+}
+// words [sub * N, (sub + 1) * N) for a warp-uniform run-time `sub`: one unrolled body per value
+template <int G, int S = 0>
+__device__ __forceinline__ void brief_pair_sub(int sub, const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                               uint32_t (&wlo)[kDescWords / G], uint32_t (&whi)[kDescWords / G]) {
+    if constexpr (S < G) {
+        if (sub == S) brief_pair_range<S * (kDescWords / G)>(Al, Bl, wlo, whi, std::make_integer_sequence<int, kDescWords / G>{});
+        else brief_pair_sub<G, S + 1>(sub, Al, Bl, wlo, whi);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void store_desc_part(uint8_t* dst, const uint32_t (&w)[N], int first_word, int lane) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) if (lane == j) v = w[j];
+    if (lane < N) reinterpret_cast<uint32_t*>(dst)[first_word + lane] = desc_word_to_bytes(v);
+}
+
+template <int N>
+__device__ __forceinline__ void gather_part(const uint16_t* __restrict__ c, const int (&o1)[N], const int (&o2)[N],
+                                            uint16_t (&s1)[N], uint16_t (&s2)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) { s1[j] = __ldg(c + o1[j]); s2[j] = __ldg(c + o2[j]); }
+}
+
+template <int N>
+struct SplitResult {
+    int status, dist, idx;
+    float u, v;
+    uint32_t w[N];   // this warp's words of the best candidate's descriptor
+};
+
+template <int G>
+__device__ __forceinline__ void search_run_split(const SearchPlan& p, PatchStage& ps, const uint32_t (&ref)[kDescWords / G],
+                                                 float cutoff, int lane, int grp, int sub, uint32_t* __restrict__ xch,
+                                                 uint32_t& xpar, SplitResult<kDescWords / G>& out) {
+    constexpr int N = kDescWords / G;
+    out.dist = -1;
+    out.idx = -1;
+    out.status = p.status;
+    if (p.status != SVI_OK) return;
+    uint32_t best_key = 0xFFFFFFFFu;
+    for (int cb = 0; cb < p.n_valid; cb += PATCH_CHUNK) {
+        const int col = window_col(p, cb), col_a = window_col_aligned(col);
+        const int par = (col - col_a) & 1, woff = (col - col_a) >> 1;
+        patch_wait(ps);
+        SVI_CHECK(3, woff >= 0 && woff + 31 + 2 * kBriefReach * PATCH_WORDS + kBriefReach < PATCH_COPY_WORDS);
+        const uint32_t* Al = ps.words + woff + lane;
+        const uint32_t* Bl = ps.words + PATCH_COPY_WORDS + woff + lane;
+        uint32_t wlo[N], whi[N];
+        brief_pair_sub<G>(sub, Al, Bl, wlo, whi);
+        int d_lo = 0, d_hi = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { d_lo += __popc(wlo[j] ^ ref[j]); d_hi += __popc(whi[j] ^ ref[j]); }
+        uint32_t* x = xch + xpar * (G * 32);
+        xpar ^= 1u;
+        x[sub * 32 + lane] = (uint32_t)d_lo | ((uint32_t)d_hi << 16);
+        group_barrier(grp, G * 32);   // partial distances visible; every warp of the group is done with the window
+        const int cb_next = cb + PATCH_CHUNK;
+        if (sub == 0 && cb_next < p.n_valid)
+            patch_issue(ps, p.gy - kBriefReach, window_col_aligned(window_col(p, cb_next)), lane);
+        uint32_t dsum = 0;
+#pragma unroll
+        for (int s = 0; s < G; ++s) dsum += x[s * 32 + lane];   // two 16-bit sums, each <= 256
+        const int l_lo = 2 * lane - par, l_hi = l_lo + 1;
+        const int c_lo = cb + l_lo, c_hi = cb + l_hi;
+        const uint32_t k_lo = (l_lo >= 0 && l_lo < PATCH_CHUNK && c_lo < p.n_valid) ? (((dsum & 0xFFFFu) << 16) | (uint32_t)(c_lo & 0xFFFF)) : 0xFFFFFFFFu;
+        const uint32_t k_hi = (l_hi < PATCH_CHUNK && c_hi < p.n_valid) ? ((dsum & 0xFFFF0000u) | (uint32_t)(c_hi & 0xFFFF)) : 0xFFFFFFFFu;
+        const uint32_t k_mine = min(k_lo, k_hi);
+        const uint32_t k_min = warp_min_u32(k_mine);
+        if (k_min < best_key) {
+            best_key = k_min;
+            const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, k_mine == k_min)) - 1;
+            const bool hi = (k_hi == k_min) && (k_lo != k_min);
+#pragma unroll
+            for (int j = 0; j < N; ++j) out.w[j] = __shfl_sync(0xFFFFFFFFu, hi ? whi[j] : wlo[j], owner);
+        }
+    }
+    out.dist = (int)(best_key >> 16);
+    out.idx = (int)(best_key & 0xFFFFu);
+    if (!(cutoff > (float)out.dist)) { out.status = SVI_TRI_DISTANCE; return; }
+    const float px = (p.border + (float)(p.i_lo + out.idx)) + (float)p.first;
+    out.u = px + p.u_tl;
+    out.v = p.border + p.v_tl;
+    out.status = SVI_OK;
+}
+
+// ------------------------------------------------------------------ LEFT descriptors of a chunk, ahead of the matcher
+// In stereo_match_kernel the 512 box-sum gathers of a LEFT descriptor are 16 scattered LDG per lane: ncu counts 203
+// wavefronts of the L1 data pipe per key-point for them (every LDG touches ~27 sectors of ~27 lines), one third of what
+// the 256 tests of all 60 candidates cost, in a kernel whose binding unit is that pipe.  Here one TMA tile brings the
+// 49 x 56 patch around the key-point into shared memory (not an LSU wavefront), the same 16 reads per lane become
+// LDS.U16 with ordinary bank conflicts (~3 wavefronts each), and the matcher gets the descriptor as one 16-byte load.
+constexpr int DL_COLS = 2 * kBriefReach + 8;                       // 56: the patch start is rounded down to 8 elements
+constexpr int DL_BYTES = PATCH_ROWS * DL_COLS * 2;                 // 5488: one TMA box
+constexpr int DL_STRIDE = (DL_BYTES + 127) / 128 * 128;
+constexpr int DL_WARPS = 8;
+constexpr int DL_KP_PER_WARP = 8;
+constexpr int DL_SMEM = DL_WARPS * 2 * DL_STRIDE + DL_WARPS * 2 * 8;   // two patches and two mbarriers per warp
+
+__global__ void __launch_bounds__(DL_WARPS * 32)
+describe_left_kernel(const __grid_constant__ CUtensorMap map_l, FrameGeom g, const ushort2* __restrict__ kp_xy,
+                     const int* __restrict__ n_kp, int max_corners, uint8_t* __restrict__ desc_l, int cap, int out_frame0) {
+    extern __shared__ __align__(128) unsigned char dl_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.y, slot0 = (blockIdx.x * DL_WARPS + warp) * DL_KP_PER_WARP;
+    const int n = n_kp[f];
+    if (slot0 >= n) return;
+    const int slot_end = min(slot0 + DL_KP_PER_WARP, n);
+    unsigned char* mine = dl_smem + (size_t)warp * 2 * DL_STRIDE;
+    const uint32_t buf0 = smem_u32(mine), bar0 = smem_u32(dl_smem + (size_t)DL_WARPS * 2 * DL_STRIDE + warp * 16);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    int o1[kDescWords], o2[kDescWords];   // this lane's test points as element offsets inside a patch whose column 0 is x - 24
+#pragma unroll
+    for (int j = 0; j < kDescWords; ++j) {
+        const char4 pt = brief_pattern(32 * j + lane);
+        o1[j] = (pt.x + kBriefReach) * DL_COLS + pt.y + kBriefReach;
+        o2[j] = (pt.z + kBriefReach) * DL_COLS + pt.w + kBriefReach;
+    }
+    const ushort2* kps = kp_xy + (size_t)f * max_corners;
+    const int row_base = f * g.H;
+    auto issue = [&](ushort2 kp, int b) {
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar0 + 8 * b, DL_BYTES);
+            tma_load_2d(buf0 + b * DL_STRIDE, &map_l, ((kp.x - kBriefReach) >> 3) << 3, row_base + kp.y - kBriefReach, bar0 + 8 * b);
+        }
+    };
+    ushort2 kp = kps[slot0];
+    issue(kp, 0);
+    uint32_t phase = 0u;   // bit b = parity of the next completion of buffer b
+    for (int slot = slot0; slot < slot_end; ++slot) {
+        const int b = (slot - slot0) & 1;
+        ushort2 kp_next = kp;
+        if (slot + 1 < slot_end) {
+            kp_next = kps[slot + 1];
+            issue(kp_next, b ^ 1);   // that buffer was read two slots ago; the __syncwarp below ordered those reads
+        }
+        mbar_wait(bar0 + 8 * b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const uint16_t* patch = reinterpret_cast<const uint16_t*>(mine + b * DL_STRIDE) + ((kp.x - kBriefReach) & 7);
+        uint32_t w[kDescWords];
+#pragma unroll
+        for (int j = 0; j < kDescWords; ++j) w[j] = __brev(__ballot_sync(0xFFFFFFFFu, patch[o1[j]] < patch[o2[j]]));
+        SVI_CHECK(6, slot < cap && slot < max_corners);
+        store_desc(desc_l + ((size_t)(out_frame0 + f) * cap + slot) * 32, w, lane);
+        __syncwarp();
+        kp = kp_next;
+    }
+}
+
+// K5 with G warps per key-point: the software pipeline of stereo_match_kernel, per group.  PRE: the LEFT descriptors
+// are already in out.desc_l (describe_left_kernel) and arrive as one load per warp instead of 2 * WORDS gathers per lane.
+template <int G, bool PRE>
+__global__ void __launch_bounds__(MatchSplit<G>::THREADS, 3)
+stereo_match_split_kernel(const uint16_t* __restrict__ box_l, const __grid_constant__ CUtensorMap map_r,
+                          const __grid_constant__ CUtensorMap map_rs, FrameGeom g, TriConst tc, float size, float range,
+                          const ushort2* __restrict__ kp_xy, const int* __restrict__ n_kp, int max_corners, StereoOutDev out,
+                          int out_frame0, int kp_per_group) {
+    using MS = MatchSplit<G>;
+    constexpr int N = MS::WORDS;
+    extern __shared__ __align__(128) unsigned char match_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / G, sub = warp % G;
+    const int f = blockIdx.y, slot0 = (blockIdx.x * MATCH_WARPS + grp) * kp_per_group;
+    const int n = n_kp[f];
+    if (slot0 >= n) return;   // whole groups leave together
+    const int slot_end = min(slot0 + kp_per_group, n);
+    PatchStage ps;
+    {
+        unsigned char* mine = match_smem + (size_t)grp * MATCH_SMEM_PER_WARP;
+        ps.map = &map_r;
+        ps.map_s = &map_rs;
+        ps.row_base = f * g.H;
+        ps.smem_a = smem_u32(mine);
+        ps.words = reinterpret_cast<const uint32_t*>(mine);
+        ps.bar = smem_u32(match_smem + MS::BAR_OFF + grp * 8);
+        ps.phase = 0u;
+        if (sub == 0 && lane == 0) {
+            mbar_init(ps.bar, 1);
+            fence_barrier_init();
+        }
+        group_barrier(grp, G * 32);
+    }
+    uint32_t* xch = reinterpret_cast<uint32_t*>(match_smem + MS::XCH_OFF) + grp * (2 * G * 32);
+    uint32_t xpar = 0u;
+    const ushort2* kps = kp_xy + (size_t)f * max_corners;
+    const uint16_t* bl = box_l + (size_t)f * g.H * g.box_pitch;
+
+    int o1[N], o2[N];   // this lane's test pairs of this warp's words, as element offsets in a box-sum plane
+    if constexpr (!PRE) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const char4 pt = brief_pattern(32 * (sub * N + j) + lane);
+            o1[j] = pt.x * g.box_pitch + pt.y;
+            o2[j] = pt.z * g.box_pitch + pt.w;
+        }
+    }
+    uint16_t s1[N], s2[N];
+    uint32_t ref_raw[N];   // PRE: this warp's words of the stored descriptor (byte order of the output)
+    const uint32_t* dl = reinterpret_cast<const uint32_t*>(out.desc_l) + ((size_t)(out_frame0 + f) * out.cap) * kDescWords + sub * N;
+
+    ushort2 kp_b = kps[slot0];
+    ushort2 kp_a = (slot0 + 1 < slot_end) ? kps[slot0 + 1] : kp_b;
+    SearchPlan plan_b;
+    {
+        const float x = (float)kp_b.x, y = (float)kp_b.y;
+        plan_right(g, tc, fmaxf(0.f, (x - range) - 4.f * size), y - 4.f * size, size, x, lane, plan_b);
+        if (sub == 0) search_prefetch(plan_b, ps, lane);
+        if constexpr (PRE) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) ref_raw[j] = __ldg(dl + (size_t)slot0 * kDescWords + j);
+        } else {
+            gather_part<N>(bl + kp_b.y * g.box_pitch + kp_b.x, o1, o2, s1, s2);
+        }
+    }
+    for (int slot = slot0; slot < slot_end; ++slot) {
+        const ushort2 kp = kp_b;
+        const SearchPlan plan = plan_b;
+        uint32_t ref[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) ref[j] = PRE ? desc_word_to_bytes(ref_raw[j]) : __brev(__ballot_sync(0xFFFFFFFFu, s1[j] < s2[j]));
+        const bool has_next = slot + 1 < slot_end;
+        if (has_next) {
+            kp_b = kp_a;
+            const float xn = (float)kp_b.x, yn = (float)kp_b.y;
+            plan_right(g, tc, fmaxf(0.f, (xn - range) - 4.f * size), yn - 4.f * size, size, xn, lane, plan_b);
+            if constexpr (PRE) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) ref_raw[j] = __ldg(dl + (size_t)(slot + 1) * kDescWords + j);
+            } else {
+                gather_part<N>(bl + kp_b.y * g.box_pitch + kp_b.x, o1, o2, s1, s2);
+            }
+            if (slot + 2 < slot_end) kp_a = kps[slot + 2];
+        }
+        const float x = (float)kp.x, y = (float)kp.y;
+        SplitResult<N> r;
+        double xyz[3] = {0.0, 0.0, 0.0};
+        search_run_split<G>(plan, ps, ref, tc.match_cutoff, lane, grp, sub, xch, xpar, r);
+        if (has_next) {
+            // a search that ran at least one pass ended on a group barrier after the last window read; one that was
+            // never staged (status != OK) left the window untouched
+            if (sub == 0) search_prefetch(plan_b, ps, lane);
+        }
+        SVI_CHECK(3, slot < out.cap && slot < max_corners);
+        const size_t o = (size_t)(out_frame0 + f) * out.cap + slot;
+        if constexpr (!PRE) store_desc_part(out.desc_l + o * 32, ref, sub * N, lane);
+        if (r.status == SVI_OK) r.status = point_in_left(tc, x, y, r.u, xyz);   // every warp: the verdict gates its desc_r words
+        if (r.status == SVI_OK) store_desc_part(out.desc_r + o * 32, r.w, sub * N, lane);
+        if (sub == 0 && lane == 0) {
+            out.uv_l[o * 2] = x; out.uv_l[o * 2 + 1] = y;
+            out.status[o] = (uint8_t)r.status;
+            out.dist[o] = r.dist;
+            out.idx[o] = r.idx;
+            if (r.status == SVI_OK) {
+                out.uv_r[o * 2] = r.u; out.uv_r[o * 2 + 1] = r.v;
+                out.xyz[o * 3] = xyz[0]; out.xyz[o * 3 + 1] = xyz[1]; out.xyz[o * 3 + 2] = xyz[2];
+            }
+        }
+    }
+}
+
 // svi_describe: BRIEF-32 at n points of one image (full-image border filter).
 __global__ void describe_kernel(const uint16_t* __restrict__ box, FrameGeom g, const float* __restrict__ xy, int n,
                                 uint8_t* __restrict__ desc, uint8_t* __restrict__ kept) {

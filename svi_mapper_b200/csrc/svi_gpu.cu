@@ -58,6 +58,7 @@ struct Lane {
     uint8_t* img_r = nullptr;
     uint8_t* mask = nullptr;
     CUtensorMap map_l{}, map_r{}, map_ls{}, map_rs{};  // TMA views of the four planes: (W, chunk*H) u16, row pitch box_pitch
+    CUtensorMap map_l_patch{};                          // LEFT plane again, box = the 56 x 49 patch of one descriptor
     StereoOutDev out{};
     std::vector<cudaEvent_t> ev;  // stage boundary events (profiling)
     size_t ev_used = 0;
@@ -76,6 +77,8 @@ struct svi_ctx {
     int cand_cap = 0, raw_cap = 0;
     float* resp_one = nullptr;   // svi_harris_response only: one W x H plane
     bool select_smem = true;
+    int match_split = 0;     // warps per key-point in the scan-line matcher: 0 = chosen per launch; SVI_MATCH_SPLIT = 1 | 2 forces one
+    bool match_pre = true;   // LEFT descriptors by describe_left_kernel ahead of the matcher (SVI_MATCH_PRE = 0 | 1)
     SelectParams sel{};
     TriConst tc{};
     float f1 = 0, f0 = 0, kf = 0;
@@ -170,7 +173,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch, std::string* err) {
+bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch, std::string* err, int box_w = PATCH_W) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -184,7 +187,7 @@ bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)box_pitch * sizeof(uint16_t)};
-    const cuuint32_t box[2] = {(cuuint32_t)PATCH_W, (cuuint32_t)PATCH_ROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)PATCH_ROWS};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -267,9 +270,28 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     const int kp_per_warp = (int)std::max<long long>(1, std::min<long long>(MATCH_KP_PER_WARP, slots / (2LL * ctx->n_sm * 9)));
     const int kp_per_cta = MATCH_WARPS * kp_per_warp;
     const dim3 mgrid((ctx->p.max_corners + kp_per_cta - 1) / kp_per_cta, nf);
-    stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size,
-                                                                    ctx->p.search_range_px, l.kp_xy, n_kp,
-                                                                    ctx->p.max_corners, out, out_frame0, kp_per_warp);
+    // full batches: the LEFT descriptors first (one TMA patch per key-point), then the matcher with match_split warps per
+    // key-point; small calls keep the single fused kernel (one launch less on the latency path)
+    const bool pre = ctx->match_pre && kp_per_warp == MATCH_KP_PER_WARP;
+    // warps per key-point: measured -- two warps win whenever the LEFT gathers stay in the matcher
+    // (small calls) and on multi-pass searches (scan lines longer than one window), one warp wins on the batch path
+    const int split = ctx->match_split ? ctx->match_split : ((pre && ctx->p.search_range_px <= (float)PATCH_CHUNK) ? 1 : 2);
+    if (pre) {
+        const dim3 dgrid((ctx->p.max_corners + DL_WARPS * DL_KP_PER_WARP - 1) / (DL_WARPS * DL_KP_PER_WARP), nf);
+        describe_left_kernel<<<dgrid, DL_WARPS * 32, DL_SMEM, s>>>(l.map_l_patch, g, l.kp_xy, n_kp, ctx->p.max_corners, out.desc_l, out.cap,
+                                                                   out_frame0);
+    }
+#define SVI_MATCH_ARGS l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size, ctx->p.search_range_px, l.kp_xy, n_kp, \
+                       ctx->p.max_corners, out, out_frame0, kp_per_warp
+    if (pre && split == 1)
+        stereo_match_split_kernel<1, true><<<mgrid, MatchSplit<1>::THREADS, MatchSplit<1>::SMEM, s>>>(SVI_MATCH_ARGS);
+    else if (pre && split == 2)
+        stereo_match_split_kernel<2, true><<<mgrid, MatchSplit<2>::THREADS, MatchSplit<2>::SMEM, s>>>(SVI_MATCH_ARGS);
+    else if (split == 2)
+        stereo_match_split_kernel<2, false><<<mgrid, MatchSplit<2>::THREADS, MatchSplit<2>::SMEM, s>>>(SVI_MATCH_ARGS);
+    else
+        stereo_match_kernel<<<mgrid, MATCH_WARPS * 32, MATCH_SMEM, s>>>(SVI_MATCH_ARGS);
+#undef SVI_MATCH_ARGS
     mark(ctx, l);
     CK(cudaGetLastError());
     return SVI_SUCCESS;
@@ -746,6 +768,11 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     ctx->chunk = std::max(1, std::min(ctx->chunk, 4096));
     ctx->n_lanes = env_lanes ? std::max(1, std::min(std::atoi(env_lanes), kMaxLanes)) : 6;
     ctx->profiling = std::getenv("SVI_PROFILE") != nullptr;
+    if (const char* e = std::getenv("SVI_MATCH_SPLIT")) {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2) ctx->match_split = v;
+    }
+    if (const char* e = std::getenv("SVI_MATCH_PRE")) ctx->match_pre = std::atoi(e) != 0;
     int cap = 1024;
     while (cap < p.max_candidates) cap <<= 1;
     ctx->cand_cap = cap;
@@ -800,6 +827,10 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(cudaFuncSetAttribute(harris_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HarrisSmem)));
     CK(cudaFuncSetAttribute(select_corners_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * SEL_SMEM_KEYS));
     CK(cudaFuncSetAttribute(stereo_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
+    CK(cudaFuncSetAttribute(stereo_match_split_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSplit<1>::SMEM));
+    CK(cudaFuncSetAttribute(stereo_match_split_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSplit<2>::SMEM));
+    CK(cudaFuncSetAttribute(stereo_match_split_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSplit<2>::SMEM));
+    CK(cudaFuncSetAttribute(describe_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM));
     CK(cudaFuncSetAttribute(triangulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(triangulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(track_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
@@ -811,7 +842,9 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     {
         const void* kernels[] = {(const void*)harris_box_kernel, (const void*)boxsum9_kernel,
                                  (const void*)select_corners_kernel<true>, (const void*)select_corners_kernel<false>,
-                                 (const void*)stereo_match_kernel, (const void*)triangulate_kernel<true>,
+                                 (const void*)stereo_match_kernel, (const void*)stereo_match_split_kernel<1, true>,
+                                 (const void*)stereo_match_split_kernel<2, true>, (const void*)stereo_match_split_kernel<2, false>,
+                                 (const void*)describe_left_kernel, (const void*)triangulate_kernel<true>,
                                  (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
                                  (const void*)track_stage2_kernel<true>, (const void*)track_stage2_kernel<false>,
                                  (const void*)track_stage3_kernel, (const void*)fast_candidates_kernel,
@@ -836,7 +869,8 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
             if (!make_box_map(&l.map_l, l.box_l, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
                 !make_box_map(&l.map_ls, l.box_ls, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
                 !make_box_map(&l.map_rs, l.box_rs, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
-                !make_box_map(&l.map_r, l.box_r, ctx->W, (int)(C * HH), ctx->box_pitch, &merr)) {
+                !make_box_map(&l.map_r, l.box_r, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
+                !make_box_map(&l.map_l_patch, l.box_l, ctx->W, (int)(C * HH), ctx->box_pitch, &merr, DL_COLS)) {
                 svi_destroy(ctx);
                 return fail(nullptr, SVI_ERR_CUDA, merr);
             }

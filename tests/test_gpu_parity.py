@@ -791,6 +791,36 @@ def test_large_batch_against_c_oracle(kitti_cams):
     assert total > 150 * n
 
 
+@pytest.mark.parametrize("split,pre", [("1", "0"), ("2", "0"), ("1", "1"), ("2", "1")])
+def test_matcher_variants_agree_with_c_oracle(kitti_cams, monkeypatch, split, pre):
+    """The scan-line matcher exists in four shapes (one or two warps per key-point; LEFT descriptors gathered inside the
+    matcher or produced by describe_left_kernel ahead of it) and the library picks one per launch.  Each of them, forced
+    through the tuning knobs, equals the C restatement bit for bit on a batch large enough for the batch path (64 frames
+    x 2000 slots) and on a single pair (the small-call path)."""
+    from oracle import c_oracle as co
+    from svi_mapper_b200.synth import stereo_batch_torch
+    import torch
+    monkeypatch.setenv("SVI_MATCH_SPLIT", split)
+    monkeypatch.setenv("SVI_MATCH_PRE", pre)
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    n = 70   # one full chunk + a ragged one
+    dL, dR = stereo_batch_torch(n, W, H, seed=7100, device=torch.device("cuda", 0))
+    Ls, Rs = dL.cpu().numpy(), dR.cpu().numpy()
+    cfg = co.make_config(kitti_cams[0], kitti_cams[1], max_corners=2000)
+    ref = co.stereo_frames(cfg, Ls, Rs, n_threads=co.host_threads())
+    with StereoFrontend(*kitti_cams, max_corners=2000) as fe:
+        got = fe.stereo_frames(Ls, Rs)
+        one = fe.stereo_frames(Ls[3], Rs[3])
+    for f in list(range(n)) + [-1]:
+        r, g_ = co.frame(ref, 3 if f < 0 else f), (one.frame(0) if f < 0 else got.frame(f))
+        assert len(r["status"]) == len(g_["status"]) > 1000
+        for k in ("uv_l", "desc_l", "status", "dist", "idx"):
+            np.testing.assert_array_equal(g_[k], r[k], err_msg=f"frame {f} {k}")
+        ok = r["status"] == 0
+        for k in ("uv_r", "desc_r", "xyz"):
+            np.testing.assert_array_equal(g_[k][ok], r[k][ok], err_msg=f"frame {f} {k}")
+
+
 def test_candidate_overflow_is_reported_on_both_entry_points(kitti_cams):
     """A ctx sized too small for a frame's candidates never truncates silently: the host entry point returns
     SVI_ERR_CAPACITY, the device-resident one reports it through svi_check_overflow, and the condition is cleared."""
