@@ -85,6 +85,10 @@ struct svi_ctx {
     Lane lanes[kMaxLanes];
     int* d_overflow = nullptr;
     cudaEvent_t fork = nullptr;
+    // latency path (one pair per call): the RIGHT image travels and gets its box sums on a second stream while the
+    // detector runs on LEFT; `side_done` joins it back before the first kernel that needs both
+    cudaStream_t side = nullptr;
+    cudaEvent_t side_done = nullptr;
     // tracking: both images of the current pair as two planes of one buffer, and the scratch of the
     // window-mode detector of stage 2 (grown on demand)
     uint8_t* trk_img = nullptr;
@@ -236,7 +240,8 @@ void collect_timings(svi_ctx* c) {
 
 // The five kernels of the new-landmark path for `nf` frames on one lane.
 int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_right, const uint8_t* d_mask,
-                 const FrameGeom& g, int nf, const StereoOutDev& out, int out_frame0, int* n_kp, int* n_det) {
+                 const FrameGeom& g, int nf, const StereoOutDev& out, int out_frame0, int* n_kp, int* n_det,
+                 cudaStream_t side = nullptr) {
     cudaStream_t s = l.stream;
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
     CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
@@ -253,7 +258,13 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
             l.cand_count, ctx->raw_cap, nullptr, nullptr, g.H);
     }
     mark(ctx, l);
-    boxsum9_kernel<<<tiles, HT_THREADS, 0, s>>>(d_right, g, l.box_r, l.box_rs);
+    // `side` (latency path): the RIGHT plane was uploaded on that stream; its box sums run there, beside the detector
+    boxsum9_kernel<<<tiles, HT_THREADS, 0, side ? side : s>>>(d_right, g, l.box_r, l.box_rs);
+    if (side) {
+        CK(cudaEventRecord(ctx->side_done, side));
+        CK(cudaStreamWaitEvent(s, ctx->side_done, 0));   // the selection kernel below does not need it, the matcher does;
+                                                          // one wait here keeps the stage events of the profiler in order
+    }
     mark(ctx, l);
     const uint32_t* fmax = fast ? nullptr : l.frame_max;
     if (ctx->select_smem) {
@@ -333,11 +344,24 @@ cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<vo
 
 // ---- per-query entry points: one image (or pair) staged in lane 0, queries in the arena ----
 namespace {
+// Page-locked caller memory (cudaMallocHost, cudaHostRegister, a pinned torch tensor: a camera driver's DMA buffers) is
+// read by the copy engine directly; anything else goes through the library's pinned mirror, because a cudaMemcpyAsync
+// from pageable memory is a blocking staged copy.  (One driver query per image, ~1 us; the mirror memcpy of a
+// 1241 x 376 pair costs ~75 us of a 0.2 ms single-pair call.)
+bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int stage_box(svi_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* d_img, uint16_t* d_box, uint16_t* d_box_shift,
               cudaStream_t s, int pin_plane = 0) {
     const FrameGeom g = make_geom(ctx, ctx->dev_pitch, (size_t)ctx->H * ctx->dev_pitch);
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
-    if (ctx->pin && pin_plane >= 0 && (size_t)(pin_plane + 1) * plane <= ctx->pin_bytes) {
+    if (host_is_pinned(img)) {
+        if ((int)pitch == ctx->dev_pitch) CK(cudaMemcpyAsync(d_img, img, plane, cudaMemcpyHostToDevice, s));
+        else CK(cudaMemcpy2DAsync(d_img, ctx->dev_pitch, img, pitch, ctx->W, ctx->H, cudaMemcpyHostToDevice, s));
+    } else if (ctx->pin && pin_plane >= 0 && (size_t)(pin_plane + 1) * plane <= ctx->pin_bytes) {
         unsigned char* stage = ctx->pin + (size_t)pin_plane * plane;
         if ((int)pitch == ctx->dev_pitch) std::memcpy(stage, img, plane);
         else for (int y = 0; y < ctx->H; ++y) std::memcpy(stage + (size_t)y * ctx->dev_pitch, img + (size_t)y * pitch, ctx->W);
@@ -423,17 +447,35 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
         const size_t plane = dstride * nf;
         unsigned char* pin_in = ctx->pin;
         unsigned char* pin_out = ctx->pin + ((3 * (size_t)kSmallFrames * dstride + 15) & ~size_t(15));
-        const uint8_t* srcs[3] = {left, right, masks};
-        uint8_t* dsts[3] = {l.img_l, l.img_r, l.mask};
+        // upload order LEFT, mask, RIGHT: the detector starts as soon as LEFT (and the mask) is there; RIGHT goes up on the
+        // side stream and its box sums run beside the detector (not while profiling: stage events live on one stream)
+        cudaStream_t side = ctx->profiling ? nullptr : ctx->side;
+        if (side) {   // whatever is still queued on the lane (an un-synchronised device-resident batch) uses the same scratch
+            CK(cudaEventRecord(ctx->fork, s));
+            CK(cudaStreamWaitEvent(side, ctx->fork, 0));
+        }
+        const uint8_t* srcs[3] = {left, masks, right};
+        uint8_t* dsts[3] = {l.img_l, l.mask, l.img_r};
         for (int k = 0; k < 3; ++k) {
             if (!srcs[k]) continue;
+            cudaStream_t sk = (k == 2 && side) ? side : s;
+            if (host_is_pinned(srcs[k])) {   // the caller's buffer is page-locked: DMA straight from it
+                if ((int)pitch == ctx->dev_pitch && (nf == 1 || frame_stride == dstride)) {
+                    CK(cudaMemcpyAsync(dsts[k], srcs[k], plane, cudaMemcpyHostToDevice, sk));
+                } else {
+                    for (int f = 0; f < nf; ++f)
+                        CK(cudaMemcpy2DAsync(dsts[k] + f * dstride, ctx->dev_pitch, srcs[k] + (size_t)f * frame_stride, pitch, W, H,
+                                             cudaMemcpyHostToDevice, sk));
+                }
+                continue;
+            }
             unsigned char* stage = pin_in + k * (size_t)kSmallFrames * dstride;
             for (int f = 0; f < nf; ++f) {
                 const uint8_t* src = srcs[k] + (size_t)f * frame_stride;
                 if ((int)pitch == ctx->dev_pitch) std::memcpy(stage + f * dstride, src, dstride);
                 else for (int y = 0; y < H; ++y) std::memcpy(stage + f * dstride + (size_t)y * ctx->dev_pitch, src + (size_t)y * pitch, W);
             }
-            CK(cudaMemcpyAsync(dsts[k], stage, plane, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(dsts[k], stage, plane, cudaMemcpyHostToDevice, sk));
         }
         bool have_mask = masks != nullptr;
         if (centres) {
@@ -441,8 +483,8 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
             if (rc != SVI_SUCCESS) return rc;
             have_mask = true;
         }
-        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, ctx->small_out, 0, ctx->small_n_kp, ctx->small_n_det);
-        if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
+        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, ctx->small_out, 0, ctx->small_n_kp, ctx->small_n_det, side);
+        if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); if (side) cudaStreamSynchronize(side); return rc; }
         // one copy brings the whole result block back; only the live slots are scattered to the caller's arrays
         CK(cudaMemcpyAsync(pin_out, ctx->small_block, ctx->small_bytes, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -700,6 +742,8 @@ void svi_destroy(svi_ctx* ctx) {
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     if (ctx->d_overflow) cudaFree(ctx->d_overflow);
+    if (ctx->side_done) cudaEventDestroy(ctx->side_done);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->small_block) cudaFree(ctx->small_block);
@@ -903,6 +947,8 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(dmalloc(&ctx->d_overflow, 1));
     CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
     CK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming));
     CK(dmalloc(&ctx->trk_img, 2 * HH * ctx->dev_pitch));
     ctx->arena_bytes = (size_t)p.max_queries * 512 + (size_t)p.max_corners * 64 + 3 * HH * ctx->dev_pitch + (1 << 20);
     CK(cudaMalloc(reinterpret_cast<void**>(&ctx->arena), ctx->arena_bytes));
@@ -1297,10 +1343,14 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     ctx->arena_used = 0; ctx->pending.clear();
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
     // both images as planes 0 / 1 of one buffer (the window-mode detector indexes them by plane)
-    rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
-    if (rc != SVI_SUCCESS) return rc;
-    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, s, 1);
-    if (rc != SVI_SUCCESS) return rc;
+    // (RIGHT goes up and gets its box sums on the side stream, beside LEFT's)
+    CK(cudaEventRecord(ctx->fork, s));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->fork, 0));
+    rc = stage_box(ctx, img_right, pitch, ctx->trk_img + plane, l.box_r, l.box_rs, ctx->side, 1);
+    if (rc == SVI_SUCCESS) rc = stage_box(ctx, img_left, pitch, ctx->trk_img, l.box_l, l.box_ls, s);
+    if (cudaEventRecord(ctx->side_done, ctx->side) != cudaSuccess || cudaStreamWaitEvent(s, ctx->side_done, 0) != cudaSuccess)
+        rc = rc == SVI_SUCCESS ? fail(ctx, SVI_ERR_CUDA, "svi_track_landmarks: joining the side stream failed") : rc;
+    if (rc != SVI_SUCCESS) { cudaStreamSynchronize(ctx->side); cudaStreamSynchronize(s); return rc; }
     // every input array goes through the pinned mirror of the arena and up in ONE copy; the outputs form one contiguous
     // range behind them: one memset, one copy back
     double* d_xyzw; uint8_t* d_dl; uint8_t* d_dr; float* d_disp; float* d_size;

@@ -763,6 +763,64 @@ def test_small_call_path_matches_batch_path(kitti_cams):
             np.testing.assert_array_equal(arr[:n][sel], ref[key][sel])
 
 
+def test_pinned_caller_buffers_are_read_in_place(kitti_cams, vi_cams):
+    """Page-locked caller images (a camera driver's DMA buffers) skip the library's pinned mirror: the one-pair call, the
+    two-pair call with padded rows and the tracking call give byte-identical results from pinned and from pageable memory."""
+    import torch
+    W, H = kitti_cams[0].width, kitti_cams[0].height
+    pairs = [stereo_pair(W, H, 1200 + i) for i in range(2)]
+    Ls, Rs = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    pitch = W + 7
+    pad = torch.zeros((2, 2, H, pitch), dtype=torch.uint8).pin_memory()
+    pad[0, :, :, :W], pad[1, :, :, :W] = torch.from_numpy(Ls), torch.from_numpy(Rs)
+    pin = torch.stack([torch.from_numpy(Ls), torch.from_numpy(Rs)]).pin_memory()
+    with StereoFrontend(*kitti_cams) as fe:
+        ref = fe.stereo_frames(Ls, Rs)
+        got = fe.stereo_frames(pin[0].numpy(), pin[1].numpy())
+        one = fe.stereo_frames(pin[0, 1].numpy(), pin[1, 1].numpy())
+        def same(a, b):   # the RIGHT-side fields of a key-point without a match are unspecified
+            ok = b["status"] == 0
+            for key, v in b.items():
+                sel = ok if key in ("uv_r", "xyz", "desc_r") else slice(None)
+                np.testing.assert_array_equal(a[key][sel], v[sel], err_msg=key)
+        for k in range(2):
+            same(got.frame(k), ref.frame(k))
+        same(one.frame(0), ref.frame(1))
+        cap = fe.max_corners
+        o_ = dict(n_kp=np.zeros(2, np.int32), n_det=np.zeros(2, np.int32), uv_l=np.zeros((2, cap, 2), np.float32), uv_r=np.zeros((2, cap, 2), np.float32),
+                  xyz=np.zeros((2, cap, 3)), dl=np.zeros((2, cap, 32), np.uint8), dr=np.zeros((2, cap, 32), np.uint8), dist=np.zeros((2, cap), np.int32),
+                  idx=np.zeros((2, cap), np.int32), st=np.zeros((2, cap), np.uint8))
+        r = _lib.StereoResult(cap, *(a.ctypes.data for a in (o_["n_kp"], o_["n_det"], o_["uv_l"], o_["uv_r"], o_["xyz"], o_["dl"], o_["dr"],
+                                                              o_["dist"], o_["idx"], o_["st"])))
+        fe.stereo_frames_raw(pad[0].data_ptr(), pad[1].data_ptr(), pitch, pitch * H, 2, r)
+        for k in range(2):
+            f = ref.frame(k)
+            n = int(o_["n_kp"][k])
+            assert n == len(f["status"])
+            np.testing.assert_array_equal(o_["dl"][k, :n], f["desc_l"])
+            np.testing.assert_array_equal(o_["st"][k, :n], f["status"])
+            np.testing.assert_array_equal(o_["dist"][k, :n], f["dist"])
+    # tracking call: the same landmarks against pinned and pageable frames
+    Wv, Hv = vi_cams[0].width, vi_cams[0].height
+    L0, R0 = stereo_pair(Wv, Hv, 4100)
+    pv = torch.stack([torch.from_numpy(L0), torch.from_numpy(R0)]).pin_memory()
+    with StereoFrontend(*vi_cams) as fe:
+        f0 = fe.stereo_frames(L0, R0).frame(0)
+        ok = np.nonzero(f0["status"] == 0)[0][:400]
+        disp = (f0["uv_l"][ok, 0] - f0["uv_r"][ok, 0]).astype(np.float32)
+        L1, R1 = np.roll(L0, (1, 2), axis=(0, 1)), np.roll(R0, (1, 2), axis=(0, 1))   # stage 2 has work too
+        pv[0], pv[1] = torch.from_numpy(L1), torch.from_numpy(R1)
+        args = (np.eye(4), f0["xyz"][ok], f0["desc_l"][ok], f0["desc_r"][ok], disp, 7.0, 1.0)
+        a = fe.track_landmarks(L1, R1, *args)
+        b = fe.track_landmarks(pv[0].numpy(), pv[1].numpy(), *args)
+        hit = a["stage"] > 0
+        assert int(hit.sum()) > 100
+        np.testing.assert_array_equal(a["stage"], b["stage"])
+        np.testing.assert_array_equal(a["status"], b["status"])
+        for key in ("uv_l", "uv_r", "xyz", "desc_l", "desc_r"):
+            np.testing.assert_array_equal(a[key][hit], b[key][hit], err_msg=key)
+
+
 def test_large_batch_against_c_oracle(kitti_cams):
     """160 distinct pairs (more than two chunks on every lane pattern), maxCorners 2000: every frame of the batch path equals
     the C restatement of the reference run on all host threads -- key-points, descriptors, matches, statuses bit for bit."""
