@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -241,7 +242,7 @@ void collect_timings(svi_ctx* c) {
 // The five kernels of the new-landmark path for `nf` frames on one lane.
 int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_right, const uint8_t* d_mask,
                  const FrameGeom& g, int nf, const StereoOutDev& out, int out_frame0, int* n_kp, int* n_det,
-                 cudaStream_t side = nullptr) {
+                 cudaStream_t side = nullptr, const std::function<int(cudaStream_t)>* upload_right = nullptr) {
     cudaStream_t s = l.stream;
     CK(cudaMemsetAsync(l.frame_max, 0, sizeof(uint32_t) * nf, s));
     CK(cudaMemsetAsync(l.cand_count, 0, sizeof(int) * nf, s));
@@ -258,7 +259,12 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
             l.cand_count, ctx->raw_cap, nullptr, nullptr, g.H);
     }
     mark(ctx, l);
-    // `side` (latency path): the RIGHT plane was uploaded on that stream; its box sums run there, beside the detector
+    // `side` (latency path): the RIGHT plane goes up on that stream -- staged by the caller's hook only now, so that the
+    // host-side copy into the pinned mirror overlaps the detector -- and its box sums run there too
+    if (upload_right) {
+        const int rc = (*upload_right)(side ? side : s);
+        if (rc != SVI_SUCCESS) return rc;
+    }
     boxsum9_kernel<<<tiles, HT_THREADS, 0, side ? side : s>>>(d_right, g, l.box_r, l.box_rs);
     if (side) {
         CK(cudaEventRecord(ctx->side_done, side));
@@ -456,9 +462,8 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
         }
         const uint8_t* srcs[3] = {left, masks, right};
         uint8_t* dsts[3] = {l.img_l, l.mask, l.img_r};
-        for (int k = 0; k < 3; ++k) {
-            if (!srcs[k]) continue;
-            cudaStream_t sk = (k == 2 && side) ? side : s;
+        auto upload_plane = [&](int k, cudaStream_t sk) -> int {
+            if (!srcs[k]) return SVI_SUCCESS;
             if (host_is_pinned(srcs[k])) {   // the caller's buffer is page-locked: DMA straight from it
                 if ((int)pitch == ctx->dev_pitch && (nf == 1 || frame_stride == dstride)) {
                     CK(cudaMemcpyAsync(dsts[k], srcs[k], plane, cudaMemcpyHostToDevice, sk));
@@ -467,7 +472,7 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
                         CK(cudaMemcpy2DAsync(dsts[k] + f * dstride, ctx->dev_pitch, srcs[k] + (size_t)f * frame_stride, pitch, W, H,
                                              cudaMemcpyHostToDevice, sk));
                 }
-                continue;
+                return SVI_SUCCESS;
             }
             unsigned char* stage = pin_in + k * (size_t)kSmallFrames * dstride;
             for (int f = 0; f < nf; ++f) {
@@ -476,14 +481,21 @@ int small_call(svi_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t p
                 else for (int y = 0; y < H; ++y) std::memcpy(stage + f * dstride + (size_t)y * ctx->dev_pitch, src + (size_t)y * pitch, W);
             }
             CK(cudaMemcpyAsync(dsts[k], stage, plane, cudaMemcpyHostToDevice, sk));
+            return SVI_SUCCESS;
+        };
+        for (int k = 0; k < 2; ++k) {
+            const int rc = upload_plane(k, s);
+            if (rc != SVI_SUCCESS) return rc;
         }
+        const std::function<int(cudaStream_t)> upload_right = [&](cudaStream_t sk) { return upload_plane(2, sk); };
         bool have_mask = masks != nullptr;
         if (centres) {
             int rc = build_mask(ctx, l, centres, n_centres);
             if (rc != SVI_SUCCESS) return rc;
             have_mask = true;
         }
-        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, ctx->small_out, 0, ctx->small_n_kp, ctx->small_n_det, side);
+        int rc = run_pipeline(ctx, l, l.img_l, l.img_r, have_mask ? l.mask : nullptr, g, nf, ctx->small_out, 0, ctx->small_n_kp, ctx->small_n_det, side,
+                              &upload_right);
         if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); if (side) cudaStreamSynchronize(side); return rc; }
         // one copy brings the whole result block back; only the live slots are scattered to the caller's arrays
         CK(cudaMemcpyAsync(pin_out, ctx->small_block, ctx->small_bytes, cudaMemcpyDeviceToHost, s));

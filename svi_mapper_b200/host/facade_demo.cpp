@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "CGraphFile.h"
 #include "CKeyFrameCloud.h"
 #include "CTrackerGT.h"
 #include "CTrackerSV.h"
@@ -64,6 +65,52 @@ static int cloudMain(char** argv) {
             for (int k = 0; k < 12; ++k) std::printf(" %.17g", M.m[k]);
             std::printf("\n");
         }
+    } catch (const std::exception& e) {
+        std::printf("FAILED %s\n", e.what());
+    }
+    return 0;
+}
+
+// --graph <in.txt> <out.g2o>: the g2o graph file of a hand-off described by a plain text file (no GPU work):
+//   CAMERAS fxL fyL cxL cyL fxR fyR cxR cyR baseline | SHIFT x y z | LANDMARK id x y z |
+//   KEYFRAME id <16 numbers LEFTtoWORLD> ax ay az | MEASUREMENT id uL vL uR vR x y z (belongs to the last KEYFRAME)
+static int graphMain(char** argv) {
+    try {
+        std::ifstream ifIn(argv[2]);
+        if (!ifIn.is_open()) throw std::invalid_argument("invalid graph description");
+        CGraphCameras cCameras;
+        CPoint3D vecShift;
+        std::vector<CGraphKeyFrame> vecKeyFrames;
+        std::vector<CGraphLandmark> vecLandmarks;
+        std::string strTag;
+        while (ifIn >> strTag) {
+            if (strTag == "CAMERAS") {
+                for (double& d : cCameras.dLEFT) ifIn >> d;
+                for (double& d : cCameras.dRIGHT) ifIn >> d;
+                ifIn >> cCameras.dBaselineMeters;
+            } else if (strTag == "SHIFT") {
+                ifIn >> vecShift.v[0] >> vecShift.v[1] >> vecShift.v[2];
+            } else if (strTag == "LANDMARK") {
+                CGraphLandmark l;
+                ifIn >> l.uID >> l.vecPointXYZOptimized.v[0] >> l.vecPointXYZOptimized.v[1] >> l.vecPointXYZOptimized.v[2];
+                vecLandmarks.push_back(l);
+            } else if (strTag == "KEYFRAME") {
+                CGraphKeyFrame k;
+                ifIn >> k.uID;
+                for (double& d : k.matTransformationLEFTtoWORLD.m) ifIn >> d;
+                ifIn >> k.vecLinearAccelerationNormalized.v[0] >> k.vecLinearAccelerationNormalized.v[1] >> k.vecLinearAccelerationNormalized.v[2];
+                vecKeyFrames.push_back(k);
+            } else if (strTag == "MEASUREMENT" && !vecKeyFrames.empty()) {
+                CGraphMeasurement m;
+                ifIn >> m.uID >> m.ptUVLEFT.x >> m.ptUVLEFT.y >> m.ptUVRIGHT.x >> m.ptUVRIGHT.y >> m.vecPointXYZLEFT.v[0] >> m.vecPointXYZLEFT.v[1] >> m.vecPointXYZLEFT.v[2];
+                vecKeyFrames.back().vecMeasurements.push_back(m);
+            } else {
+                throw std::invalid_argument("unknown tag " + strTag);
+            }
+            if (!ifIn) throw std::invalid_argument("malformed graph description");
+        }
+        saveGraphToFile(argv[3], cCameras, vecKeyFrames, vecLandmarks, vecShift);
+        std::printf("GRAPH %zu keyframes %zu landmarks\n", vecKeyFrames.size(), vecLandmarks.size());
     } catch (const std::exception& e) {
         std::printf("FAILED %s\n", e.what());
     }
@@ -169,6 +216,7 @@ int main(int argc, char** argv) {
     if (argc == 6 && std::string(argv[1]) == "--mask") return maskMain(argv);
     if (argc == 3 && std::string(argv[1]) == "--landmark") return landmarkMain(argv);
     if (argc == 5 && std::string(argv[1]) == "--cloud") return cloudMain(argv);
+    if (argc == 4 && std::string(argv[1]) == "--graph") return graphMain(argv);
     if (argc < 10) { std::fprintf(stderr, "usage: see source\n"); return 2; }
     try {
         CParameterBase::loadCameraLEFT(argv[1]);

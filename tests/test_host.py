@@ -324,6 +324,96 @@ def test_cloud_and_kitti_pose_formats_roundtrip(tmp_path):
     assert r.stdout.startswith("FAILED truncated cloud file")
 
 
+def test_g2o_graph_file_cpp_matches_numpy(tmp_path, built_library):
+    """The g2o graph of a hand-off (Cg2oOptimizer.cpp:99-120, :982-1075, :1229-1270, :1383-1466): the C++ writer of the host
+    layer and the numpy twin produce the same file byte for byte; every edge type the reference selects appears (XYZ below
+    |p|^2 = 10, UV-depth below 50, UV-disparity beyond, nothing for an inconsistent landmark or a disparity <= 1 px), the
+    quaternion covers both branches of Eigen's conversion, and the file parses back to the numbers that went in."""
+    import pathlib
+    import subprocess
+    from svi_mapper_b200 import formats
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    rng = np.random.default_rng(5)
+    camL, camR, base = (450.5097158071153, 450.5097158071153, 375.9431800842285, 222.3379611968994), (450.5, 450.5, 375.9, 222.3), 0.11017
+    shift = (10.0, -2.5, 0.125)
+
+    def rot(ax, ang):
+        c, s_ = np.cos(ang), np.sin(ang)
+        R = {"x": [[1, 0, 0], [0, c, -s_], [0, s_, c]], "y": [[c, 0, s_], [0, 1, 0], [-s_, 0, c]], "z": [[c, -s_, 0], [s_, c, 0], [0, 0, 1]]}[ax]
+        return np.array(R, np.float64)
+    poses = []
+    for i, (ax, ang) in enumerate([("y", 0.0), ("y", 0.2), ("x", 3.0), ("z", 3.1), ("y", 2.9)]):   # trace > 0 and each largest-diagonal branch
+        T = np.eye(4)
+        T[:3, :3] = rot(ax, ang)
+        T[:3, 3] = [0.3 * i, -0.05 * i, 0.9 * i]
+        poses.append(T)
+    depths = [1.5, 2.5, 4.0, 6.5, 9.0, 30.0, 80.0, 99.0]
+    landmarks, keyframes = [], []
+    for k, z in enumerate(depths):
+        landmarks.append(dict(id=7 + 3 * k, xyz=poses[0][:3, :3] @ np.array([0.2 * k - 0.5, 0.1, z]) + poses[0][:3, 3]))
+    for n, T in enumerate(poses):
+        Ti = np.linalg.inv(T)
+        meas = []
+        for k, l in enumerate(landmarks):
+            p = Ti[:3, :3] @ l["xyz"] + Ti[:3, 3]
+            if k == 3 and n == 1:
+                p = p * 1.4                       # inconsistent with the estimate: no edge
+            uL = np.float32(camL[0] * p[0] / p[2] + camL[2])
+            d = np.float32(0.6) if (k == 7 and n == 0) else np.float32(camL[0] * base / abs(p[2]))   # sub-pixel disparity: no edge
+            meas.append(dict(id=l["id"], uv_l=(uL, np.float32(200.25)), uv_r=(np.float32(uL - d), np.float32(200.25)), xyz_left=p))
+        meas.append(dict(id=999, uv_l=(1.0, 2.0), uv_r=(0.0, 2.0), xyz_left=(0.0, 0.0, 1.0)))   # landmark not in the graph
+        keyframes.append(dict(id=2 * n, T_left_to_world=T, acceleration=rng.normal(size=3), measurements=meas))
+    desc, a, b = tmp_path / "graph.txt", tmp_path / "np.g2o", tmp_path / "cpp.g2o"
+    with open(desc, "w") as f:
+        f.write("CAMERAS " + " ".join(repr(float(v)) for v in camL + camR + (base,)) + "\n")
+        f.write("SHIFT " + " ".join(repr(float(v)) for v in shift) + "\n")
+        for l in landmarks:
+            f.write("LANDMARK %d " % l["id"] + " ".join(repr(float(v)) for v in l["xyz"]) + "\n")
+        for kf in keyframes:
+            f.write("KEYFRAME %d " % kf["id"] + " ".join(repr(float(v)) for v in np.concatenate([kf["T_left_to_world"].ravel(), kf["acceleration"]])) + "\n")
+            for m in kf["measurements"]:
+                f.write("MEASUREMENT %d " % m["id"] + " ".join(repr(float(v)) for v in (*m["uv_l"], *m["uv_r"], *m["xyz_left"])) + "\n")
+    formats.write_g2o(a, camL, camR, base, keyframes, landmarks, shift)
+    r = subprocess.run([str(exe), "--graph", str(desc), str(b)], capture_output=True, text=True)
+    assert r.stdout.startswith("GRAPH 5 keyframes 8 landmarks"), r.stdout + r.stderr
+    assert a.read_bytes() == b.read_bytes()
+    g = formats.read_g2o(a)
+    assert [v[0] for v in g["PARAMS_SE3OFFSET"]] == [0, 3] and [v[0] for v in g["PARAMS_CAMERAPARAMETERS"]] == [1, 2]
+    assert g["PARAMS_CAMERAPARAMETERS"][0][8:] == list(camL)
+    assert [v[0] for v in g["VERTEX_TRACKXYZ"]] == [l["id"] for l in landmarks]
+    assert [v[0] for v in g["VERTEX_SE3:QUAT"]] == [kf["id"] + 1000000 for kf in keyframes] and g["FIX"] == [[1000000]]
+    assert len(g["EDGE_SE3:QUAT"]) == 4 and len(g["EDGE_SE3_LINEAR_ACCELERATION"]) == 5
+    for v, T in zip(g["VERTEX_SE3:QUAT"], poses):   # quaternion back to the rotation that went in
+        x, y, z, w = v[4:8]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        np.testing.assert_allclose(R, T[:3, :3], atol=1e-12)
+        np.testing.assert_allclose(v[1:4], T[:3, 3] + np.array(shift), atol=0)
+    e = g["EDGE_SE3:QUAT"][0]
+    t2 = sum(c * c for c in e[2:5])
+    np.testing.assert_allclose([e[9], e[9 + 6 + 5 + 4]], [100000.0 / (1.0 + t2), 100000.0], rtol=1e-15)   # info(0,0), info(3,3)
+    n_xyz, n_dep, n_dis = len(g["EDGE_SE3_TRACKXYZ"]), len(g["EDGE_PROJECT_DEPTH"]), len(g["EDGE_PROJECT_DISPARITY"])
+    assert n_xyz > 0 and n_dep > 0 and n_dis > 0
+    want = [0, 0, 0]
+    for n, kf in enumerate(keyframes):
+        for k, m in enumerate(kf["measurements"][:-1]):
+            d2 = float(np.dot(m["xyz_left"], m["xyz_left"]))
+            if k == 3 and n == 1:
+                continue                                            # the inconsistent one
+            cls = 0 if d2 < 10 else 1 if d2 < 50 else 2 if d2 < 10000 else 3
+            disp = float(np.float32(m["uv_l"][0]) - np.float32(m["uv_r"][0]))
+            if cls < 3 and not (cls == 2 and not 1.0 < disp):        # far points: sub-pixel disparity, no edge
+                want[cls] += 1
+    assert [n_xyz, n_dep, n_dis] == want and sum(want) < 5 * 8 - 2
+    assert all(v[2] == 0 for v in g["EDGE_SE3_TRACKXYZ"]) and all(v[2] == 1 for v in g["EDGE_PROJECT_DEPTH"] + g["EDGE_PROJECT_DISPARITY"])
+    for v in g["EDGE_PROJECT_DISPARITY"]:
+        assert v[3 + 3] * 1000 == v[3 + 3 + 5] and 0 < v[5] < 0.2    # information (f, f, 1000 f), normalised disparity
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.g2o").write_text("VERTEX_XY 1 2 3\n")
+        formats.read_g2o(tmp_path / "bad.g2o")
+
+
 def test_synthetic_stream_is_partition_independent():
     """BASELINE configs[3] cuts ONE batch of frames over 2/4/8 GPUs: frame i of the synthetic stream must have the same content
     whatever contiguous range a rank generates (the stream is produced in seeded 64-frame blocks), so that the G-GPU job
