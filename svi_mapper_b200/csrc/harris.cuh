@@ -19,9 +19,18 @@
 
 namespace svi {
 
-constexpr int HT_W = 64, HT_H = 32, HT_THREADS = 256;
+// Tile width: 64 (CTAs of 256 threads, four per SM).  -DHARRIS_TILE_W=128 builds CTAs of 512 threads, two per SM: the
+// 6-px Sobel/box halo and the 2-px candidate overlap spread over twice the columns (1.35 instead of 1.43 pixels of work
+// per useful pixel, 10 instead of 21 tiles per 1241-px row) -- measured SLOWER (C2: harris_box 20.0 vs 17.7 ms per 64
+// launches, 97.3 k vs 103.9 k frames/s; C4 124.9 k vs 136.0 k): the kernel has seven barrier phases, and two big CTAs per
+// SM leave fewer independent CTAs to fill them than four small ones.  Kept as a build option, parity-tested at both widths.
+#ifndef HARRIS_TILE_W
+#define HARRIS_TILE_W 64
+#endif
+constexpr int HT_W = HARRIS_TILE_W, HT_H = 32, HT_THREADS = HT_W * 4;
+static_assert(HT_W == 64 || HT_W == 128, "tile width");
 #ifndef HARRIS_CTAS_PER_SM
-#define HARRIS_CTAS_PER_SM 4
+#define HARRIS_CTAS_PER_SM (HT_W == 64 ? 4 : 2)
 #endif
 constexpr int HT_SX = HT_W - 2, HT_SY = HT_H - 2;   // tile stride of the Harris kernel: candidates = tile interior
 constexpr int HT_MAX_KEYS = HT_SX * HT_SY;          // a plateau can make every interior pixel a local maximum
@@ -31,8 +40,8 @@ constexpr int H9_P = HT_W + 2;       // 33 words per row, same reason
 constexpr int U8_ROWS = HT_H + 8;
 constexpr int COV_W = HT_W + 6;      // covariance products: 3-px halo
 constexpr int COV_ROWS = HT_H + 6;
-constexpr int COV_P = 73;            // odd pitches: row-per-lane accesses are bank-conflict free
-constexpr int HS_P = 65;
+constexpr int COV_P = HT_W == 64 ? 73 : 139;   // odd pitches: row-per-lane accesses are bank-conflict free
+constexpr int HS_P = HT_W + 1;
 constexpr int COV_SEG_ROWS = 13;     // 38 rows = 3 segments for the sliding Sobel
 constexpr int HS_SEG = 11;           // horizontal box sums: 11 outputs per work item, 6 segments x 38 rows = 228 items
 constexpr int HS_NSEG = (HT_W + HS_SEG - 1) / HS_SEG;
@@ -63,7 +72,9 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
     constexpr int NW = HT_THREADS / 32, RPW = (U8_ROWS + NW - 1) / NW;   // rows per warp
     // all loads of the thread are issued before the first store: the global round trip is paid once.
     // 32-bit element offsets inside the frame; the three loads of a row share one address register.
-    uint8_t v[RPW][3];
+    constexpr int NG = (U8_W + 31) / 32;          // 32-byte column groups of a row; only the last one is partial
+    const bool last_ok = lane < U8_W - 32 * (NG - 1);
+    uint8_t v[RPW][NG];
     if (inside_x) {
         const uint8_t* col = img + gx0 + lane;
 #pragma unroll
@@ -71,19 +82,19 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
             const int ly = min(warp + k * NW, U8_ROWS - 1);
             const int ry = inside_y ? gy0 + ly : reflect101(gy0 + ly, H);
             const uint8_t* src = col + ry * pitch;
-            v[k][0] = __ldg(src);
-            v[k][1] = __ldg(src + 32);
-            v[k][2] = (lane < U8_W - 64) ? __ldg(src + 64) : (uint8_t)0;
+#pragma unroll
+            for (int c = 0; c < NG; ++c) v[k][c] = (c < NG - 1 || last_ok) ? __ldg(src + 32 * c) : (uint8_t)0;
         }
     } else {
-        const int c0 = reflect101(gx0 + lane, W), c1 = reflect101(gx0 + lane + 32, W), c2 = reflect101(gx0 + lane + 64, W);
+        int cx[NG];
+#pragma unroll
+        for (int c = 0; c < NG; ++c) cx[c] = reflect101(gx0 + lane + 32 * c, W);
 #pragma unroll
         for (int k = 0; k < RPW; ++k) {
             const int ly = min(warp + k * NW, U8_ROWS - 1);
             const uint8_t* row = img + reflect101(gy0 + ly, H) * pitch;
-            v[k][0] = __ldg(row + c0);
-            v[k][1] = __ldg(row + c1);
-            v[k][2] = (lane < U8_W - 64) ? __ldg(row + c2) : (uint8_t)0;
+#pragma unroll
+            for (int c = 0; c < NG; ++c) v[k][c] = (c < NG - 1 || last_ok) ? __ldg(row + cx[c]) : (uint8_t)0;
         }
     }
 #pragma unroll
@@ -91,9 +102,9 @@ __device__ __forceinline__ void load_tile_u8(uint8_t (*tile)[U8_P], const uint8_
         const int ly = warp + k * NW;
         if (ly < U8_ROWS) {
             uint8_t* dst = &tile[ly][lane];
-            dst[0] = v[k][0];
-            dst[32] = v[k][1];
-            if (lane < U8_W - 64) dst[64] = v[k][2];
+#pragma unroll
+            for (int c = 0; c < NG; ++c)
+                if (c < NG - 1 || last_ok) dst[32 * c] = v[k][c];
         }
     }
 }
@@ -283,9 +294,10 @@ harris_box_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ m
                     if (gy >= 0 && gy < H) fix(ly, c);
                 }
             }
-            const int c = tid & 127;           // outside rows, every column (corners included)
-            if (c < COV_W) {
-                for (int i = tid >> 7; i < ntr + nbr; i += HT_THREADS / 128) fix(i < ntr ? i : rb0 + (i - ntr), c);
+            // outside rows, every column (corners included)
+            for (int i = tid; i < (ntr + nbr) * COV_W; i += HT_THREADS) {
+                const int r = i / COV_W;
+                fix(r < ntr ? r : rb0 + (r - ntr), i - r * COV_W);
             }
             __syncthreads();
         }
