@@ -138,7 +138,7 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     // frame_max == nullptr (FAST mode): every key is a corner.
     int n_raw = cand_count[f];
     if (n_raw > sp.raw_cap) {
-        if (tid == 0) atomicExch(overflow, 1);
+        if (tid == 0) *reinterpret_cast<volatile int*>(overflow) = 1;   // mapped host memory: a plain store
         n_raw = sp.raw_cap;
     }
     unsigned long long* gk = cand + (size_t)f * sp.raw_cap;
@@ -171,10 +171,10 @@ select_corners_kernel(unsigned long long* __restrict__ cand, const int* __restri
     }
     if (n > sp.cand_cap || (kSmem && (n > SEL_SMEM_KEYS || sp.gw * sp.gh > SEL_SMEM_CELLS))) {
         // more candidates than the ctx was sized for: reported as SVI_ERR_CAPACITY by the host, never a silent cut
-        if (tid == 0) { atomicExch(overflow, n > sp.cand_cap ? 1 : 2); n_detected[f] = 0; n_keypoints[f] = 0; }
+        if (tid == 0) { *reinterpret_cast<volatile int*>(overflow) = n > sp.cand_cap ? 1 : 2; n_detected[f] = 0; n_keypoints[f] = 0; }
         return;
     }
-    if (sp.cap_is_error && n > sp.max_corners && tid == 0) atomicExch(overflow, 3);
+    if (sp.cap_is_error && n > sp.max_corners && tid == 0) *reinterpret_cast<volatile int*>(overflow) = 3;
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     int n_act = n;   // candidates that take part in the peeling (shared-memory path: the top-priority part)

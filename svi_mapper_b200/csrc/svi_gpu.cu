@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -79,12 +80,16 @@ struct svi_ctx {
     float* resp_one = nullptr;   // svi_harris_response only: one W x H plane
     bool select_smem = true;
     int match_split = 0;     // warps per key-point in the scan-line matcher: 0 = chosen per launch; SVI_MATCH_SPLIT = 1 | 2 forces one
+    bool trace = false;      // SVI_TRACE: host-side phase times of the tracking call on stderr (diagnostics)
     bool match_pre = true;   // LEFT descriptors by describe_left_kernel ahead of the matcher (SVI_MATCH_PRE = 0 | 1)
     SelectParams sel{};
     TriConst tc{};
     float f1 = 0, f0 = 0, kf = 0;
     Lane lanes[kMaxLanes];
-    int* d_overflow = nullptr;
+    // candidate-list overflow flag: one int of mapped page-locked host memory.  Kernels write it in place (only when a
+    // list overflows), the host reads it after the synchronisation it does anyway -- no copy, no extra round trip per call
+    int* d_overflow = nullptr;            // device view
+    volatile int* h_overflow = nullptr;   // host view
     cudaEvent_t fork = nullptr;
     // latency path (one pair per call): the RIGHT image travels and gets its box sums on a second stream while the
     // detector runs on LEFT; `side_done` joins it back before the first kernel that needs both
@@ -322,14 +327,12 @@ int check_overflow(svi_ctx* ctx) {
         if (line) return fail(ctx, SVI_ERR_CUDA, "bounds check failed in a kernel: tag/line " + std::to_string(line));
     }
 #endif
-    int h = 0;
-    CK(cudaMemcpy(&h, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    const int h = *ctx->h_overflow;   // every caller has synchronised the streams that could have written it
+    if (h) *ctx->h_overflow = 0;
     if (h == 3) {
-        CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
         return fail(ctx, SVI_ERR_CAPACITY, "FAST found more corners than svi_params.max_corners in a frame (cv::FAST returns all of them): raise max_corners");
     }
     if (h) {
-        CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
         return fail(ctx, SVI_ERR_CAPACITY,
                     "NMS candidate list overflow: raise svi_params.max_candidates (a frame produced more than " +
                         std::to_string(ctx->cand_cap) + " candidates)");
@@ -753,7 +756,7 @@ void svi_destroy(svi_ctx* ctx) {
         if (l.done) cudaEventDestroy(l.done);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
-    if (ctx->d_overflow) cudaFree(ctx->d_overflow);
+    if (ctx->h_overflow) cudaFreeHost(const_cast<int*>(ctx->h_overflow));
     if (ctx->side_done) cudaEventDestroy(ctx->side_done);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->arena) cudaFree(ctx->arena);
@@ -829,6 +832,7 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         if (v == 1 || v == 2) ctx->match_split = v;
     }
     if (const char* e = std::getenv("SVI_MATCH_PRE")) ctx->match_pre = std::atoi(e) != 0;
+    ctx->trace = std::getenv("SVI_TRACE") != nullptr;
     int cap = 1024;
     while (cap < p.max_candidates) cap <<= 1;
     ctx->cand_cap = cap;
@@ -956,8 +960,13 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         CK(dmalloc(&l.out.idx, C * MC));
         CK(dmalloc(&l.out.status, C * MC));
     }
-    CK(dmalloc(&ctx->d_overflow, 1));
-    CK(cudaMemset(ctx->d_overflow, 0, sizeof(int)));
+    {
+        int* h = nullptr;
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocMapped));
+        *h = 0;
+        ctx->h_overflow = h;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_overflow), h, 0));
+    }
     CK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming));
@@ -1353,6 +1362,10 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
     Lane& l = ctx->lanes[0];
     cudaStream_t s = l.stream;
     ctx->arena_used = 0; ctx->pending.clear();
+    using clk = std::chrono::steady_clock;
+    clk::time_point tp[6];
+    auto tick = [&](int i) { if (ctx->trace) tp[i] = clk::now(); };
+    tick(0);
     const size_t plane = (size_t)ctx->H * ctx->dev_pitch;
     // both images as planes 0 / 1 of one buffer (the window-mode detector indexes them by plane)
     // (RIGHT goes up and gets its box sums on the side stream, beside LEFT's)
@@ -1382,6 +1395,7 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         UP(d_orig, lm->desc_reference_left, (size_t)n * 32);
         ex.uv_ref = d_uvref; ex.T_det = d_tdet;
     }
+    tick(1);
     if (ctx->batch_uploads) CK(cudaMemcpyAsync(ctx->arena, ctx->pin_arena, ctx->arena_used, cudaMemcpyHostToDevice, s));
     ctx->batch_uploads = false;
     const size_t out_begin = (ctx->arena_used + 255) & ~size_t(255);
@@ -1424,6 +1438,7 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         rc = track_stage3_all(ctx, l, g, n, T_world_to_left, motion_scaling, ld, ex, d_orig, o);
         if (rc != SVI_SUCCESS) { cudaStreamSynchronize(s); return rc; }
     }
+    tick(2);
     int rd = SVI_SUCCESS;
     if (ctx->pin_arena) {   // one copy for the whole output range, scattered to the caller's arrays after the synchronisation
         cudaError_t e = cudaMemcpyAsync(ctx->pin_arena + out_begin, ctx->arena + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, s);
@@ -1445,10 +1460,20 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
         if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_left, o.desc_l, (size_t)32 * n, s);
         if (rd == SVI_SUCCESS) rd = download(ctx, out->desc_right, o.desc_r, (size_t)32 * n, s);
     }
+    if (ctx->trace) { cudaStreamSynchronize(s); tick(3); }
     if (rd == SVI_SUCCESS) rd = flush_downloads(ctx, s);
     else cudaStreamSynchronize(s);
+    tick(4);
     if (rd != SVI_SUCCESS) return rd;
-    return check_overflow(ctx);
+    rd = check_overflow(ctx);
+    tick(5);
+    if (ctx->trace) {
+        auto us = [&](int a, int b) { return std::chrono::duration<double, std::micro>(tp[b] - tp[a]).count(); };
+        std::fprintf(stderr, "svi_track_landmarks n=%d: stage images + mirror inputs %.0f us | enqueue cascade %.0f us | wait %.0f us | "
+                             "scatter outputs %.0f us | overflow check %.0f us | total %.0f us\n",
+                     n, us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5), us(0, 5));
+    }
+    return rd;
 }
 
 int svi_set_profiling(svi_ctx* ctx, int enable) {
