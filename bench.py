@@ -452,21 +452,30 @@ def run_batch(args, rank, world, dev_index):
     if rank == 0:
         chunk = fcfg["chunk_frames"]
         n_chunks = (F + chunk - 1) // chunk
-        launches = args.steps * n_chunks * 4   # harris_box, boxsum9, select_corners, stereo_match per chunk
+        # kernels per chunk: harris_box, boxsum9, select_corners, stereo_match + describe_left on the batch path (the
+        # library's stage list says whether that kernel ran)
+        per_chunk = sum(1 for v in stages.values() if v["launches"]) if stages else 4
+        launches = args.steps * n_chunks * per_chunk
         peak, peak_src = measured_hbm_peak()
         ncu = ncu_kernel_metrics() if args.config == "c2" else {}
         sm_clk = (clocks.get("sm_mhz") or 1965) * 1e6
         roofline = None
-        if stages and all(v["launches"] for v in stages.values()):
+        stages = {k: v for k, v in (stages or {}).items() if v["launches"]}
+        if stages:
             frames_per_launch = min(chunk, F)
             tot_ms = sum(v["total_ms"] for v in stages.values())
             kernels = {}
+            smem_peak = 148 * sm_clk   # one 128-byte wavefront of the L1 / shared data pipe per SM and clock
             for name, v in stages.items():
                 avg = v["total_ms"] / v["launches"]
                 rec = {"avg_launch_ms": avg, "share": v["total_ms"] / tot_ms, "hbm_gbs": frames_per_launch * frame_bytes / (avg * 1e-3) / 1e9}
                 rec["hbm_frac"] = rec["hbm_gbs"] / peak
                 if name in ncu:
                     rec["ncu"] = ncu[name]
+                    wf = ncu[name].get("shared_wavefronts")
+                    if wf and frames_per_launch == 64:   # the capture is a 64-frame launch of this configuration
+                        rec["smem_wavefronts_per_s"] = wf / (avg * 1e-3)
+                        rec["smem_frac"] = rec["smem_wavefronts_per_s"] / smem_peak
                 kernels[name] = rec
             dom = max(kernels, key=lambda k: kernels[k]["avg_launch_ms"])
             k = kernels[dom]
@@ -482,6 +491,10 @@ def run_batch(args, rank, world, dev_index):
                         "how": "one extra profiled step with all chunks on one stream: the library's CUDA events bracket exactly one kernel each",
                         "binding_unit": "shared-memory / L1 data pipe and instruction issue, not HBM (ncu: DRAM a few % of peak in every kernel; "
                                         "kernels[*].ncu, profiles/r2_*)",
+                        "smem": {"achieved": k.get("smem_wavefronts_per_s"), "peak": smem_peak, "unit": "wavefronts/s", "frac": k.get("smem_frac"),
+                                 "note": "LSU shared-memory wavefronts of one launch (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared, committed capture) over "
+                                         "the launch duration measured live, against 148 SMs x 1 wavefront per clock; TMA fills of the match windows "
+                                         "use the same banks and are not in this count"},
                         "kernels": kernels,
                         "popc": {"per_s": popc_rate, "peak_per_s": popc_peak, "frac": (popc_rate / popc_peak) if popc_rate else None,
                                  "note": "XOR+popc of the Hamming distances in stereo_match (8 words per candidate) vs 148 SM x 16 lanes x SM clock; "

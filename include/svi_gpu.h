@@ -290,7 +290,7 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
  * exclusive duration of one kernel (what the roofline record uses -- slower overall, not for timing
  * the step).  svi_set_profiling also clears the accumulators; svi_stage_timings waits for the ctx to
  * go idle and returns, per stage, the summed launch duration in ms and the number of launches
- * (arrays of length >= 4; returns the stage count). */
+ * (arrays of length >= 5; returns the stage count; "describe_left" has launches only on the batch path, where the LEFT descriptors are a kernel of their own ahead of the matcher). */
 int svi_set_profiling(svi_ctx* ctx, int enable);
 int svi_stage_timings(svi_ctx* ctx, const char** names, double* total_ms, int64_t* launches, int capacity);
 

@@ -32,8 +32,9 @@ namespace {
 constexpr int kMaxLanes = 8;
 constexpr int kSmallFrames = 2;          // calls of up to this many frames go through the pinned bounce buffer
 constexpr size_t kOutBytesPerSlot = 8 + 8 + 24 + 32 + 32 + 4 + 4 + 1;   // uv_l uv_r xyz desc_l desc_r dist idx status
-constexpr int kStages = 4;
-const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "select_corners", "stereo_match"};
+constexpr int kStages = 5;
+const char* const kStageNames[kStages] = {"harris_box", "boxsum_right", "select_corners", "describe_left", "stereo_match"};
+constexpr int kStageDescribe = 3;   // present only on the batch path (LEFT descriptors ahead of the matcher)
 constexpr int kRawFactor = 4;   // the Harris kernel's list (local maxima above the TILE threshold) vs max_candidates
 
 std::string g_create_error;
@@ -64,6 +65,7 @@ struct Lane {
     StereoOutDev out{};
     std::vector<cudaEvent_t> ev;  // stage boundary events (profiling)
     size_t ev_used = 0;
+    std::vector<uint8_t> ev_pre;  // per profiled chunk: did describe_left_kernel run between its two events?
 };
 
 }  // namespace
@@ -135,8 +137,8 @@ struct svi_ctx {
     bool profiling = false;
     bool batch_uploads = false;   // upload(): stage into the pinned mirror only (svi_track_landmarks sends one copy)
     bool serial = false;   // profiling mode 2: every chunk on lane 0, so that the stage events bracket ONE kernel each
-    double stage_ms[kStages] = {0, 0, 0, 0};
-    long stage_launches[kStages] = {0, 0, 0, 0};
+    double stage_ms[kStages] = {};
+    long stage_launches[kStages] = {};
     std::string err;
 };
 
@@ -231,8 +233,9 @@ void mark(svi_ctx* c, Lane& l) {
 void collect_timings(svi_ctx* c) {
     for (int li = 0; li < c->n_lanes; ++li) {
         Lane& l = c->lanes[li];
-        for (size_t i = 0; i + kStages < l.ev_used; i += kStages + 1) {
+        for (size_t i = 0, rec = 0; i + kStages < l.ev_used; i += kStages + 1, ++rec) {
             for (int s = 0; s < kStages; ++s) {
+                if (s == kStageDescribe && !(rec < l.ev_pre.size() && l.ev_pre[rec])) continue;   // no kernel in that bracket
                 float ms = 0.f;
                 if (cudaEventElapsedTime(&ms, l.ev[i + s], l.ev[i + s + 1]) == cudaSuccess) {
                     c->stage_ms[s] += ms;
@@ -241,6 +244,7 @@ void collect_timings(svi_ctx* c) {
             }
         }
         l.ev_used = 0;
+        l.ev_pre.clear();
     }
 }
 
@@ -303,6 +307,8 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
         describe_left_kernel<<<dgrid, DL_WARPS * 32, DL_SMEM, s>>>(l.map_l_patch, g, l.kp_xy, n_kp, ctx->p.max_corners, out.desc_l, out.cap,
                                                                    out_frame0);
     }
+    if (ctx->profiling) l.ev_pre.push_back(pre ? 1 : 0);
+    mark(ctx, l);
 #define SVI_MATCH_ARGS l.box_l, l.map_r, l.map_rs, g, ctx->tc, ctx->p.keypoint_size, ctx->p.search_range_px, l.kp_xy, n_kp, \
                        ctx->p.max_corners, out, out_frame0, kp_per_warp
     if (pre && split == 1)

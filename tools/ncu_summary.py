@@ -29,7 +29,8 @@ METRICS = {
     "launch__grid_size": "grid_size",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
 }
-SHORT = {"harris_box_kernel": "harris_box", "boxsum9_kernel": "boxsum_right", "select_corners_kernel": "select_corners", "stereo_match_kernel": "stereo_match"}
+SHORT = {"harris_box_kernel": "harris_box", "boxsum9_kernel": "boxsum_right", "select_corners_kernel": "select_corners", "describe_left_kernel": "describe_left",
+         "stereo_match_kernel": "stereo_match", "stereo_match_split_kernel": "stereo_match"}
 
 
 def main():
