@@ -336,6 +336,7 @@ def run_batch(args, rank, world, dev_index):
     F = f_hi - f_lo
     fe = StereoFrontend(cams[0], cams[1], device=dev_index, **frontend_kwargs(cfg))
     fcfg = fe.config()
+    kernels_per_chunk = fe.kernels_per_chunk(F)
     frame_bytes = 2 * W * H + BYTES_PER_KEYPOINT * cap   # every input byte once + 113 B per key-point slot
 
     # synthetic frames generated on the device; frame i has the same content whatever the partition
@@ -452,9 +453,9 @@ def run_batch(args, rank, world, dev_index):
     if rank == 0:
         chunk = fcfg["chunk_frames"]
         n_chunks = (F + chunk - 1) // chunk
-        # kernels per chunk: harris_box, boxsum9, select_corners, stereo_match + describe_left on the batch path (the
-        # library's stage list says whether that kernel ran)
-        per_chunk = sum(1 for v in stages.values() if v["launches"]) if stages else 4
+        # kernels per chunk, from the library: harris_box, boxsum9, select_corners, the matcher, + describe_left on the
+        # batch path, + bin_keypoints when the batch path bins the key-points (dense frames)
+        per_chunk = kernels_per_chunk
         launches = args.steps * n_chunks * per_chunk
         peak, peak_src = measured_hbm_peak()
         ncu = ncu_kernel_metrics() if args.config == "c2" else {}

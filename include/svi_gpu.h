@@ -316,6 +316,11 @@ int svi_multi_stereo_frames(svi_multi* m, const uint8_t* left, const uint8_t* ri
  * selection runs out of shared memory (1) or the global-memory variant for very large frames (0). */
 int svi_config(const svi_ctx* ctx, int32_t* chunk_frames, int32_t* n_lanes, int32_t* select_in_smem);
 
+/* Number of kernels the new-landmark path launches for one chunk of a call with n_frames frames: 4 (detector, RIGHT box
+ * sums, corner selection, matcher) on the small-call path, 5 when the LEFT descriptors are a kernel of their own (batch
+ * path), 6 when the batch path also sorts the key-points into image bins (dense frames).  For launch accounting. */
+int svi_kernels_per_chunk(const svi_ctx* ctx, int n_frames);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ EXPORTS = (
     "svi_params_default", "svi_status_text", "svi_brief_table_info", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
     "svi_stereo_frames", "svi_stereo_frames_device", "svi_check_overflow", "svi_mask_active_landmarks", "svi_stereo_frame_masked", "svi_harris_response", "svi_detect", "svi_describe",
     "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
-    "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config",
+    "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config", "svi_kernels_per_chunk",
     "svi_multi_create", "svi_multi_destroy", "svi_multi_last_error", "svi_multi_device_count", "svi_multi_frame_range",
     "svi_multi_stereo_frames",
 )
@@ -120,6 +120,7 @@ def load(path=None):
     lib.svi_set_profiling.argtypes = [vp, ci]
     lib.svi_stage_timings.argtypes = [vp, C.POINTER(C.c_char_p), f64p, C.POINTER(C.c_int64), ci]
     lib.svi_config.argtypes = [vp, i32p, i32p, i32p]
+    lib.svi_kernels_per_chunk.argtypes = [vp, ci]
     lib.svi_multi_create.argtypes = [C.POINTER(Camera), C.POINTER(Camera), C.POINTER(Params), i32p, ci, C.POINTER(vp)]
     lib.svi_multi_destroy.argtypes = [vp]
     lib.svi_multi_destroy.restype = None

@@ -149,40 +149,48 @@ __device__ __forceinline__ uint32_t lt_mask_u16x2(uint32_t a, uint32_t b) {
     return m;
 }
 
-template <int T>
+// PW = 32-bit words per row of the staged window (the per-warp window of the scan-line kernels, or the tile a CTA of the
+// binned matcher shares).
+template <int T, int PW = PATCH_WORDS>
 __device__ __forceinline__ void brief_pair_test(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
                                                 uint32_t& acc) {
     constexpr int c1 = kPat[T][1] + kBriefReach, c2 = kPat[T][3] + kBriefReach;
-    constexpr int o1 = (kPat[T][0] + kBriefReach) * PATCH_WORDS + (c1 >> 1);
-    constexpr int o2 = (kPat[T][2] + kBriefReach) * PATCH_WORDS + (c2 >> 1);
+    constexpr int o1 = (kPat[T][0] + kBriefReach) * PW + (c1 >> 1);
+    constexpr int o2 = (kPat[T][2] + kBriefReach) * PW + (c2 >> 1);
     constexpr uint32_t bit = 0x00010001u << (15 - (T & 15));
     const uint32_t a = (c1 & 1) ? Bl[o1] : Al[o1];
     const uint32_t b = (c2 & 1) ? Bl[o2] : Al[o2];
     acc |= lt_mask_u16x2(a, b) & bit;
 }
 
-template <int G, int... I>
+template <int G, int PW, int... I>
 __device__ __forceinline__ uint32_t brief_pair_group(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
                                                      std::integer_sequence<int, I...>) {
     uint32_t acc = 0u;
-    (brief_pair_test<G * 16 + I>(Al, Bl, acc), ...);
+    (brief_pair_test<G * 16 + I, PW>(Al, Bl, acc), ...);
     return acc;
 }
 
-template <int J>
+template <int J, int PW = PATCH_WORDS>
 __device__ __forceinline__ void brief_pair_word(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
                                                 uint32_t& wlo, uint32_t& whi) {
-    const uint32_t e = brief_pair_group<2 * J>(Al, Bl, std::make_integer_sequence<int, 16>{});      // tests 32J .. 32J+15
-    const uint32_t o = brief_pair_group<2 * J + 1>(Al, Bl, std::make_integer_sequence<int, 16>{});  // tests 32J+16 .. 32J+31
+    const uint32_t e = brief_pair_group<2 * J, PW>(Al, Bl, std::make_integer_sequence<int, 16>{});      // tests 32J .. 32J+15
+    const uint32_t o = brief_pair_group<2 * J + 1, PW>(Al, Bl, std::make_integer_sequence<int, 16>{});  // tests 32J+16 .. 32J+31
     wlo = __byte_perm(o, e, 0x5410);   // (e.lo16 << 16) | o.lo16
     whi = __byte_perm(o, e, 0x7632);   // (e.hi16 << 16) | o.hi16
 }
 
+template <int PW, int... J>
+__device__ __forceinline__ void brief_pair_all_pw(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
+                                                  uint32_t (&wlo)[kDescWords], uint32_t (&whi)[kDescWords],
+                                                  std::integer_sequence<int, J...>) {
+    (brief_pair_word<J, PW>(Al, Bl, wlo[J], whi[J]), ...);
+}
 template <int... J>
 __device__ __forceinline__ void brief_pair_all(const uint32_t* __restrict__ Al, const uint32_t* __restrict__ Bl,
                                                uint32_t (&wlo)[kDescWords], uint32_t (&whi)[kDescWords],
-                                               std::integer_sequence<int, J...>) {
-    (brief_pair_word<J>(Al, Bl, wlo[J], whi[J]), ...);
+                                               std::integer_sequence<int, J...> seq) {
+    brief_pair_all_pw<PATCH_WORDS>(Al, Bl, wlo, whi, seq);
 }
 
 // ------------------------------------------------------------------ one whole descriptor per LANE

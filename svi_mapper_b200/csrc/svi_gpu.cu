@@ -21,6 +21,7 @@
 
 #include "../../include/svi_gpu.h"
 #include "brief_match.cuh"
+#include "binned.cuh"
 #include "harris.cuh"
 #include "select.cuh"
 #include "track_plan.cuh"
@@ -62,6 +63,11 @@ struct Lane {
     uint8_t* mask = nullptr;
     CUtensorMap map_l{}, map_r{}, map_ls{}, map_rs{};  // TMA views of the four planes: (W, chunk*H) u16, row pitch box_pitch
     CUtensorMap map_l_patch{};                          // LEFT plane again, box = the 56 x 49 patch of one descriptor
+    // binned matcher (binned.cuh): key-points sorted by image bin, one tile of the planes per bin
+    int* bin_start = nullptr;          // [chunk][n_bins + 1]
+    uint32_t* bin_slot = nullptr;      // [chunk][max_corners]
+    ushort2* bin_kp = nullptr;         // [chunk][max_corners]
+    CUtensorMap map_l_bin{}, map_r_bin{}, map_rs_bin{};
     StereoOutDev out{};
     std::vector<cudaEvent_t> ev;  // stage boundary events (profiling)
     size_t ev_used = 0;
@@ -84,6 +90,8 @@ struct svi_ctx {
     int match_split = 0;     // warps per key-point in the scan-line matcher: 0 = chosen per launch; SVI_MATCH_SPLIT = 1 | 2 forces one
     bool trace = false;      // SVI_TRACE: host-side phase times of the tracking call on stderr (diagnostics)
     bool match_pre = true;   // LEFT descriptors by describe_left_kernel ahead of the matcher (SVI_MATCH_PRE = 0 | 1)
+    bool match_binned = true;  // batch path: key-points binned by position, one TMA tile per bin (SVI_MATCH_BINNED = 0 | 1 | 2: off, by density, forced)
+    int nbx = 0, n_bins = 0;
     SelectParams sel{};
     TriConst tc{};
     float f1 = 0, f0 = 0, kf = 0;
@@ -185,7 +193,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch, std::string* err, int box_w = PATCH_W) {
+bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch, std::string* err, int box_w = PATCH_W,
+                  int box_h = PATCH_ROWS) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -199,7 +208,7 @@ bool make_box_map(CUtensorMap* m, uint16_t* base, int W, int rows, int box_pitch
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)box_pitch * sizeof(uint16_t)};
-    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)PATCH_ROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -246,6 +255,34 @@ void collect_timings(svi_ctx* c) {
         l.ev_used = 0;
         l.ev_pre.clear();
     }
+}
+
+// Descriptor + match stages of the batch path, binned form (binned.cuh): sort the key-points into bins, LEFT descriptors
+// per bin, scan-line searches per bin.
+template <class G>
+int run_binned(svi_ctx* ctx, Lane& l, const FrameGeom& g, int nf, const StereoOutDev& out, int out_frame0, const int* n_kp) {
+    cudaStream_t s = l.stream;
+    const dim3 bgrid(ctx->n_bins, nf);
+    bin_keypoints_kernel<<<nf, BINK_THREADS, sizeof(uint32_t) * ctx->n_bins, s>>>(l.kp_xy, n_kp, ctx->p.max_corners, G::BIN_W, G::BIN_H, ctx->nbx,
+                                                                                 ctx->n_bins, l.bin_start, l.bin_slot, l.bin_kp);
+    describe_left_binned_kernel<G><<<bgrid, G::D_WARPS * 32, G::D_SMEM, s>>>(l.map_l_bin, g, l.bin_start, l.bin_slot, l.bin_kp, ctx->nbx, ctx->n_bins,
+                                                                            ctx->p.max_corners, out.desc_l, out.cap, out_frame0);
+    if (ctx->profiling) l.ev_pre.push_back(1);
+    mark(ctx, l);
+    stereo_match_binned_kernel<G><<<bgrid, G::M_WARPS * 32, G::M_SMEM, s>>>(l.map_r_bin, l.map_rs_bin, g, ctx->tc, ctx->p.keypoint_size,
+                                                                           ctx->p.search_range_px, l.bin_start, l.bin_slot, l.bin_kp, ctx->nbx,
+                                                                           ctx->n_bins, ctx->p.max_corners, out, out_frame0, ctx->d_overflow);
+    mark(ctx, l);
+    return SVI_SUCCESS;
+}
+
+template <class G>
+int setup_binned(svi_ctx* ctx, Lane& l, size_t rows, std::string* err) {
+    if (!make_box_map(&l.map_l_bin, l.box_l, ctx->W, (int)rows, ctx->box_pitch, err, G::D_COLS, G::ROWS) ||
+        !make_box_map(&l.map_r_bin, l.box_r, ctx->W, (int)rows, ctx->box_pitch, err, G::COLS, G::ROWS) ||
+        !make_box_map(&l.map_rs_bin, l.box_rs, ctx->W, (int)rows, ctx->box_pitch, err, G::COLS, G::ROWS))
+        return SVI_ERR_CUDA;
+    return SVI_SUCCESS;
 }
 
 // The five kernels of the new-landmark path for `nf` frames on one lane.
@@ -302,6 +339,13 @@ int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_
     // warps per key-point: measured -- two warps win whenever the LEFT gathers stay in the matcher
     // (small calls) and on multi-pass searches (scan lines longer than one window), one warp wins on the batch path
     const int split = ctx->match_split ? ctx->match_split : ((pre && ctx->p.search_range_px <= (float)PATCH_CHUNK) ? 1 : 2);
+    // batch path with the reference's geometry (scan line of one pass, whole-pixel ROI border): key-points binned by
+    // position, one shared tile per bin (binned.cuh)
+    if (pre && ctx->match_binned && l.bin_start) {
+        const int rc = run_binned<BinWide>(ctx, l, g, nf, out, out_frame0, n_kp);
+        CK(cudaGetLastError());
+        return rc;
+    }
     if (pre) {
         const dim3 dgrid((ctx->p.max_corners + DL_WARPS * DL_KP_PER_WARP - 1) / (DL_WARPS * DL_KP_PER_WARP), nf);
         describe_left_kernel<<<dgrid, DL_WARPS * 32, DL_SMEM, s>>>(l.map_l_patch, g, l.kp_xy, n_kp, ctx->p.max_corners, out.desc_l, out.cap,
@@ -335,6 +379,7 @@ int check_overflow(svi_ctx* ctx) {
 #endif
     const int h = *ctx->h_overflow;   // every caller has synchronised the streams that could have written it
     if (h) *ctx->h_overflow = 0;
+    if (h == 4) return fail(ctx, SVI_ERR_CUDA, "internal error: a search window left its tile in the binned matcher (SVI_MATCH_BINNED=0 selects the per-key-point kernels)");
     if (h == 3) {
         return fail(ctx, SVI_ERR_CAPACITY, "FAST found more corners than svi_params.max_corners in a frame (cv::FAST returns all of them): raise max_corners");
     }
@@ -756,7 +801,7 @@ void svi_destroy(svi_ctx* ctx) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         void* ptrs[] = {l.box_l, l.box_r, l.box_ls, l.box_rs, l.frame_max, l.cand_count, l.cand, l.det_xy, l.kp_xy, l.n_det, l.n_kp,
                         l.g_head, l.g_next, l.g_state, l.img_l, l.img_r, l.mask, l.out.uv_l, l.out.uv_r, l.out.xyz,
-                        l.out.desc_l, l.out.desc_r, l.out.dist, l.out.idx, l.out.status};
+                        l.out.desc_l, l.out.desc_r, l.out.dist, l.out.idx, l.out.status, l.bin_start, l.bin_slot, l.bin_kp};
         for (void* p : ptrs) if (p) cudaFree(p);
         for (cudaEvent_t e : l.ev) cudaEventDestroy(e);
         if (l.done) cudaEventDestroy(l.done);
@@ -838,6 +883,22 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
         if (v == 1 || v == 2) ctx->match_split = v;
     }
     if (const char* e = std::getenv("SVI_MATCH_PRE")) ctx->match_pre = std::atoi(e) != 0;
+    {   // The binned matcher's tile is laid out for scan lines of one pass (pool size ceil(range) + 1 <= 62 candidates) whose
+        // ROI border 4 * size is a whole number of pixels: the reference's 60 px / size 7.  It pays on dense frames only
+        // (measured, frames/s device-resident: C2, ~13 key-points per bin, 109.0 k vs 103.9 k for the per-key-point
+        // kernels; C4, ~7 per bin, 132.2 k vs 136.0 k): expected key-points per bin = ~0.8 of max_corners (BRIEF's border
+        // filter) spread over the image minus that border.  Anything else keeps the per-key-point kernels.
+        int mode = 1;
+        if (const char* e = std::getenv("SVI_MATCH_BINNED")) mode = std::atoi(e);
+        const float b4 = 4.f * p.keypoint_size;
+        const bool geom_ok = p.search_range_px > 0.f && std::ceil(p.search_range_px) + 1.f <= (float)BT_REACH && b4 == std::floor(b4) && b4 >= 1.f;
+        const double per_bin = 0.8 * p.max_corners * (double)(BinWide::BIN_W * BinWide::BIN_H) /
+                               std::max(1.0, (double)(ctx->W - 2 * kBriefBorder) * (double)(ctx->H - 2 * kBriefBorder));
+        ctx->match_binned = geom_ok && (mode == 2 || (mode == 1 && per_bin >= 10.0));
+        ctx->nbx = (ctx->W + BinWide::BIN_W - 1) / BinWide::BIN_W;
+        ctx->n_bins = ctx->nbx * ((ctx->H + BinWide::BIN_H - 1) / BinWide::BIN_H);
+        if (ctx->n_bins * (int)sizeof(uint32_t) > 40000) ctx->match_binned = false;   // the bin histogram must fit the default dynamic shared memory
+    }
     ctx->trace = std::getenv("SVI_TRACE") != nullptr;
     int cap = 1024;
     while (cap < p.max_candidates) cap <<= 1;
@@ -897,6 +958,8 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
     CK(cudaFuncSetAttribute(stereo_match_split_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSplit<2>::SMEM));
     CK(cudaFuncSetAttribute(stereo_match_split_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MatchSplit<2>::SMEM));
     CK(cudaFuncSetAttribute(describe_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM));
+    CK(cudaFuncSetAttribute(stereo_match_binned_kernel<BinWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, BinWide::M_SMEM));
+    CK(cudaFuncSetAttribute(describe_left_binned_kernel<BinWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, BinWide::D_SMEM));
     CK(cudaFuncSetAttribute(triangulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(triangulate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
     CK(cudaFuncSetAttribute(track_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATCH_SMEM));
@@ -910,7 +973,9 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
                                  (const void*)select_corners_kernel<true>, (const void*)select_corners_kernel<false>,
                                  (const void*)stereo_match_kernel, (const void*)stereo_match_split_kernel<1, true>,
                                  (const void*)stereo_match_split_kernel<2, true>, (const void*)stereo_match_split_kernel<2, false>,
-                                 (const void*)describe_left_kernel, (const void*)triangulate_kernel<true>,
+                                 (const void*)describe_left_kernel, (const void*)stereo_match_binned_kernel<BinWide>,
+                                 (const void*)describe_left_binned_kernel<BinWide>, (const void*)bin_keypoints_kernel,
+                                 (const void*)triangulate_kernel<true>,
                                  (const void*)triangulate_kernel<false>, (const void*)track_stage1_kernel,
                                  (const void*)track_stage2_kernel<true>, (const void*)track_stage2_kernel<false>,
                                  (const void*)track_stage3_kernel, (const void*)fast_candidates_kernel,
@@ -937,6 +1002,16 @@ int svi_create(const svi_camera* left, const svi_camera* right, const svi_params
                 !make_box_map(&l.map_rs, l.box_rs, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
                 !make_box_map(&l.map_r, l.box_r, ctx->W, (int)(C * HH), ctx->box_pitch, &merr) ||
                 !make_box_map(&l.map_l_patch, l.box_l, ctx->W, (int)(C * HH), ctx->box_pitch, &merr, DL_COLS)) {
+                svi_destroy(ctx);
+                return fail(nullptr, SVI_ERR_CUDA, merr);
+            }
+        }
+        if (ctx->match_binned) {
+            std::string merr;
+            CK(dmalloc(&l.bin_start, C * (size_t)(ctx->n_bins + 1)));
+            CK(dmalloc(&l.bin_slot, C * MC));
+            CK(dmalloc(&l.bin_kp, C * MC));
+            if (setup_binned<BinWide>(ctx, l, C * HH, &merr) != SVI_SUCCESS) {
                 svi_destroy(ctx);
                 return fail(nullptr, SVI_ERR_CUDA, merr);
             }
@@ -1599,6 +1674,14 @@ int svi_multi_stereo_frames(svi_multi* m, const uint8_t* left, const uint8_t* ri
             return rc[g];
         }
     return SVI_SUCCESS;
+}
+
+int svi_kernels_per_chunk(const svi_ctx* ctx, int n_frames) {
+    if (!ctx || n_frames <= 0) return SVI_ERR_INVALID;
+    const long long slots = (long long)std::min(n_frames, ctx->chunk) * ctx->p.max_corners;
+    const bool pre = ctx->match_pre && slots / (2LL * ctx->n_sm * 9) >= MATCH_KP_PER_WARP;
+    // detector, RIGHT box sums, corner selection, matcher (+ LEFT descriptors as a kernel of their own, + the bin sort)
+    return 4 + (pre ? 1 : 0) + (pre && ctx->match_binned ? 1 : 0);
 }
 
 int svi_config(const svi_ctx* ctx, int32_t* chunk_frames, int32_t* n_lanes, int32_t* select_in_smem) {

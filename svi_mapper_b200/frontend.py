@@ -129,6 +129,13 @@ class StereoFrontend:
         self._check(self._lib.svi_config(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
         return dict(chunk_frames=a.value, n_lanes=b.value, select_in_smem=bool(c.value))
 
+    def kernels_per_chunk(self, n_frames: int) -> int:
+        """svi_kernels_per_chunk: kernels launched per chunk of an n_frames call (launch accounting of bench.py)."""
+        n = self._lib.svi_kernels_per_chunk(self._ctx, int(n_frames))
+        if n < 0:
+            self._check(n)
+        return n
+
     def _images(self, img, name):
         a = np.asarray(img)
         if a.dtype != np.uint8:

@@ -849,17 +849,18 @@ def test_large_batch_against_c_oracle(kitti_cams):
     assert total > 150 * n
 
 
-@pytest.mark.parametrize("split,pre", [("1", "0"), ("2", "0"), ("1", "1"), ("2", "1")])
-def test_matcher_variants_agree_with_c_oracle(kitti_cams, monkeypatch, split, pre):
-    """The scan-line matcher exists in four shapes (one or two warps per key-point; LEFT descriptors gathered inside the
-    matcher or produced by describe_left_kernel ahead of it) and the library picks one per launch.  Each of them, forced
-    through the tuning knobs, equals the C restatement bit for bit on a batch large enough for the batch path (64 frames
-    x 2000 slots) and on a single pair (the small-call path)."""
+@pytest.mark.parametrize("split,pre,binned", [("1", "0", "0"), ("2", "0", "0"), ("1", "1", "0"), ("2", "1", "0"), ("1", "1", "2")])
+def test_matcher_variants_agree_with_c_oracle(kitti_cams, monkeypatch, split, pre, binned):
+    """The scan-line matcher exists in five shapes (one or two warps per key-point; LEFT descriptors gathered inside the
+    matcher or produced by describe_left_kernel ahead of it; key-points binned by position with one shared tile per bin)
+    and the library picks one per launch.  Each of them, forced through the tuning knobs, equals the C restatement bit for
+    bit on a batch large enough for the batch path (64 frames x 2000 slots) and on a single pair (the small-call path)."""
     from oracle import c_oracle as co
     from svi_mapper_b200.synth import stereo_batch_torch
     import torch
     monkeypatch.setenv("SVI_MATCH_SPLIT", split)
     monkeypatch.setenv("SVI_MATCH_PRE", pre)
+    monkeypatch.setenv("SVI_MATCH_BINNED", binned)
     W, H = kitti_cams[0].width, kitti_cams[0].height
     n = 70   # one full chunk + a ragged one
     dL, dR = stereo_batch_torch(n, W, H, seed=7100, device=torch.device("cuda", 0))
@@ -877,6 +878,41 @@ def test_matcher_variants_agree_with_c_oracle(kitti_cams, monkeypatch, split, pr
         ok = r["status"] == 0
         for k in ("uv_r", "desc_r", "xyz"):
             np.testing.assert_array_equal(g_[k][ok], r[k][ok], err_msg=f"frame {f} {k}")
+
+
+@pytest.mark.parametrize("cams_name,max_corners,search_range", [("vi_cams", 2000, 60.0), ("kitti1112_cams", 1000, 60.0),
+                                                                ("kitti_cams", 2000, 37.5), ("kitti_cams", 1500, 60.75), ("vi_cams", 1000, 61.5),
+                                                                ("kitti_cams", 1000, 60.0)])
+def test_binned_matcher_geometries(request, monkeypatch, cams_name, max_corners, search_range):
+    """The batch path sorts the key-points into image bins and matches each bin from one shared tile (binned.cuh).  Image
+    sizes that are no multiple of the bin size, sparse bins (maxCorners 1000), fractional and short search ranges and the
+    longest range the tile is laid out for -- and one past it (61.5: pool of 63, the library must fall back to the
+    per-key-point kernels) -- all equal the C restatement bit for bit.  (The library uses the binned form on dense frames
+    only; SVI_MATCH_BINNED=2 forces it wherever the geometry allows.)"""
+    monkeypatch.setenv("SVI_MATCH_BINNED", "2")
+    from oracle import c_oracle as co
+    from svi_mapper_b200.synth import stereo_batch_torch
+    import torch
+    cams = request.getfixturevalue(cams_name)
+    W, H = cams[0].width, cams[0].height
+    n = 40
+    dL, dR = stereo_batch_torch(n, W, H, seed=7300, device=torch.device("cuda", 0))
+    Ls, Rs = dL.cpu().numpy(), dR.cpu().numpy()
+    cfg = co.make_config(cams[0], cams[1], max_corners=max_corners, search_range=search_range)
+    ref = co.stereo_frames(cfg, Ls, Rs, n_threads=co.host_threads())
+    with StereoFrontend(*cams, max_corners=max_corners, search_range_px=search_range) as fe:
+        got = fe.stereo_frames(Ls, Rs)
+    n_ok = 0
+    for f in range(n):
+        r, g_ = co.frame(ref, f), got.frame(f)
+        assert len(r["status"]) == len(g_["status"]) > 300
+        for k in ("uv_l", "desc_l", "status", "dist", "idx"):
+            np.testing.assert_array_equal(g_[k], r[k], err_msg=f"frame {f} {k}")
+        ok = r["status"] == 0
+        n_ok += int(ok.sum())
+        for k in ("uv_r", "desc_r", "xyz"):
+            np.testing.assert_array_equal(g_[k][ok], r[k][ok], err_msg=f"frame {f} {k}")
+    assert n_ok > 100 * n
 
 
 def test_candidate_overflow_is_reported_on_both_entry_points(kitti_cams):
@@ -1182,7 +1218,7 @@ def test_bounds_checked_build():
     kernels carry their own assertions: in the -DSVI_BOUNDS_CHECK build every index that is computed at run time and goes into
     shared memory, a candidate / item list or an output array is checked, and a violation turns the next call into an error.
     The parity tests with the widest coverage of those indices run once against that build: whole frames incl. the window /
-    ROI detector, both selection variants (shared / global), the long scan lines, masks, the tracking cascade."""
+    ROI detector, both selection variants (shared / global), the long scan lines, masks, the tracking cascade, the binned matcher."""
     import os
     import pathlib
     import subprocess
@@ -1190,7 +1226,8 @@ def test_bounds_checked_build():
     from svi_mapper_b200 import build as bld
     lib = bld.build_checked()
     k = ("test_stereo_frame_parity or test_track_manual_stage2_window_search or test_stress_frame_global_select_and_long_scanlines "
-         "or test_stereo_batch_chunks_and_masks or test_track_manual_stage3_epipolar or test_edge_cases_empty_flat_masked_padded")
+         "or test_stereo_batch_chunks_and_masks or test_track_manual_stage3_epipolar or test_edge_cases_empty_flat_masked_padded "
+         "or test_binned_matcher_geometries")
     env = dict(os.environ, SVI_GPU_LIB=str(lib))
     r = subprocess.run([sys.executable, "-m", "pytest", str(pathlib.Path(__file__)), "-x", "-q", "-k", k], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

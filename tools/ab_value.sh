@@ -6,6 +6,6 @@ for i in $(seq $N); do
     SVI_GPU_LIB=$PWD/$L python bench.py --device-only --steps 5 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$L', round(d['value']), {k:round(v) for k,v in d['stage_ms'].items()})"
+print('$L', round(d['value']), {k:round(v,2) for k,v in d['stage_ms'].items()})"
   done
 done

@@ -19,10 +19,10 @@ if [ "${2:-}" != "quick" ]; then
 fi
 SMALL="python bench.py --frames 256 --steps 1 --warmup 3 --no-cpu-baseline"
 if $SMALL > $OUT/${TAG}_plain.log 2>&1; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'harris|boxsum|select|stereo_match|describe_left' -s 40 -c 80 \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'harris|boxsum|select|stereo_match|describe_left|bin_keypoints' -s 48 -c 96 \
       --csv --log-file $OUT/${TAG}_launches.csv $SMALL > $OUT/${TAG}_ncu_l.log 2>&1
   echo "ncu launches exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'harris|boxsum|select|stereo_match|describe_left' -s 40 -c 5 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'harris|boxsum|select|stereo_match|describe_left|bin_keypoints' -s 48 -c 6 \
       -o $OUT/${TAG}_prof -f $SMALL > $OUT/${TAG}_ncu_f.log 2>&1
   echo "ncu full exit $?"
 else

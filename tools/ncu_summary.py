@@ -30,7 +30,8 @@ METRICS = {
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
 }
 SHORT = {"harris_box_kernel": "harris_box", "boxsum9_kernel": "boxsum_right", "select_corners_kernel": "select_corners", "describe_left_kernel": "describe_left",
-         "stereo_match_kernel": "stereo_match", "stereo_match_split_kernel": "stereo_match"}
+         "stereo_match_kernel": "stereo_match", "stereo_match_split_kernel": "stereo_match",
+         "stereo_match_binned_kernel": "stereo_match", "describe_left_binned_kernel": "describe_left", "bin_keypoints_kernel": "bin_keypoints"}
 
 
 def main():
