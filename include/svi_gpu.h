@@ -283,6 +283,42 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
                         size_t pitch, const double* T_world_to_left, const svi_landmarks* lm, int n,
                         double motion_scaling, uint32_t stage_mask, svi_track_result* out);
 
+/* ---- landmark position refinement, batched.
+ * Replaces the loop of CFundamentalMatcher::optimizeActiveLandmarks (src/core/CFundamentalMatcher.cpp:265-277) over
+ * CLandmark::optimize (src/types/CLandmark.cpp:281-296) / _getOptimizedLandmarkSTEREOUV (:447-581): for each of n
+ * landmarks a robust Gauss-Newton refinement of its WORLD position on the stereo re-projection error of all its
+ * measurements (constants of CLandmark.h:90-98: at most 1000 iterations, convergence 1e-5 on the total squared error,
+ * kernel 10 px^2, inlier ratio > 0.5, optimal below 9 px^2 average).  Measurements of landmark i are the entries
+ * [first[i], first[i + 1]) of the measurement arrays; a measurement names the pose it was taken with by its row in the two
+ * projection tables (matProjectionWORLDtoLEFT / RIGHT of CMeasurementLandmark, Types.h:79-121: one row per frame, 3 x 4
+ * row-major).  Landmarks with <= 5 measurements are skipped as the reference does (bIsOptimal = true).
+ * One GPU thread per landmark, reference operation order, fp64 without contraction: the results equal the C++ host
+ * implementation of the same loop bit for bit. */
+enum svi_optimize_outcome {
+    SVI_OPT_SKIPPED = 0,        /* <= 5 measurements: position untouched, bIsOptimal = true */
+    SVI_OPT_CONVERGED = 1,      /* ++uOptimizationsSuccessful, position updated, not optimal (average error >= 9 px^2) */
+    SVI_OPT_OPTIMAL = 2,        /* ++uOptimizationsSuccessful, position updated, bIsOptimal = true */
+    SVI_OPT_REJECTED = 3,       /* converged with too few inliers: ++uOptimizationsFailed, position kept */
+    SVI_OPT_NOT_CONVERGED = 4   /* iteration cap reached: ++uOptimizationsFailed, position kept */
+};
+typedef struct svi_landmark_measurements {
+    const double* xyz_world_guess;      /* n x 3: vecPointXYZOptimized before the call */
+    const int32_t* first;               /* n + 1 */
+    const int32_t* pose_index;          /* m = first[n] */
+    const float* uv_left;               /* m x 2 */
+    const float* uv_right;              /* m x 2 */
+    const double* proj_world_to_left;   /* n_poses x 12 */
+    const double* proj_world_to_right;  /* n_poses x 12 */
+    int32_t n_poses;
+} svi_landmark_measurements;
+typedef struct svi_optimize_result {
+    double* xyz_world;                  /* n x 3: the refined position, or the guess where the outcome keeps it */
+    uint8_t* outcome;                   /* n: svi_optimize_outcome */
+    double* average_squared_error;      /* n: dCurrentAverageSquaredError of a converged landmark (0 otherwise) */
+    int32_t* iterations;                /* n, may be NULL */
+} svi_optimize_result;
+int svi_optimize_landmarks(svi_ctx* ctx, const svi_landmark_measurements* in, int n, svi_optimize_result* out);
+
 /* Stage profiling: when enabled, every kernel of the new-landmark path is bracketed by CUDA events
  * on the stream it is launched on (the events come from a pool filled here, none is created while
  * work is being timed).  enable = 1: the lanes keep overlapping, a bracket also contains other lanes'

@@ -23,7 +23,7 @@ EXPORTS = (
     "svi_params_default", "svi_status_text", "svi_brief_table_info", "svi_create", "svi_destroy", "svi_last_error", "svi_device_count",
     "svi_stereo_frames", "svi_stereo_frames_device", "svi_check_overflow", "svi_mask_active_landmarks", "svi_stereo_frame_masked", "svi_harris_response", "svi_detect", "svi_describe",
     "svi_match_hamming", "svi_match_epipolar", "svi_triangulate_right", "svi_triangulate_left", "svi_point_in_left",
-    "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config", "svi_kernels_per_chunk",
+    "svi_track_landmarks", "svi_track_landmarks_stages", "svi_set_profiling", "svi_stage_timings", "svi_config", "svi_kernels_per_chunk", "svi_optimize_landmarks",
     "svi_multi_create", "svi_multi_destroy", "svi_multi_last_error", "svi_multi_device_count", "svi_multi_frame_range",
     "svi_multi_stereo_frames",
 )
@@ -71,6 +71,17 @@ class TrackResult(C.Structure):
     _fields_ = [("status", C.c_void_p), ("stage", C.c_void_p), ("uv_left", C.c_void_p), ("uv_right", C.c_void_p),
                 ("xyz_left", C.c_void_p), ("desc_left", C.c_void_p), ("desc_right", C.c_void_p)]
 
+
+class LandmarkMeasurements(C.Structure):
+    _fields_ = [("xyz_world_guess", C.c_void_p), ("first", C.c_void_p), ("pose_index", C.c_void_p), ("uv_left", C.c_void_p),
+                ("uv_right", C.c_void_p), ("proj_world_to_left", C.c_void_p), ("proj_world_to_right", C.c_void_p), ("n_poses", C.c_int32)]
+
+
+class OptimizeResult(C.Structure):
+    _fields_ = [("xyz_world", C.c_void_p), ("outcome", C.c_void_p), ("average_squared_error", C.c_void_p), ("iterations", C.c_void_p)]
+
+
+(SVI_OPT_SKIPPED, SVI_OPT_CONVERGED, SVI_OPT_OPTIMAL, SVI_OPT_REJECTED, SVI_OPT_NOT_CONVERGED) = range(5)
 
 _lib = None
 _others: dict = {}
@@ -121,6 +132,7 @@ def load(path=None):
     lib.svi_stage_timings.argtypes = [vp, C.POINTER(C.c_char_p), f64p, C.POINTER(C.c_int64), ci]
     lib.svi_config.argtypes = [vp, i32p, i32p, i32p]
     lib.svi_kernels_per_chunk.argtypes = [vp, ci]
+    lib.svi_optimize_landmarks.argtypes = [vp, C.POINTER(LandmarkMeasurements), ci, C.POINTER(OptimizeResult)]
     lib.svi_multi_create.argtypes = [C.POINTER(Camera), C.POINTER(Camera), C.POINTER(Params), i32p, ci, C.POINTER(vp)]
     lib.svi_multi_destroy.argtypes = [vp]
     lib.svi_multi_destroy.restype = None

@@ -23,6 +23,7 @@
 #include "brief_match.cuh"
 #include "binned.cuh"
 #include "harris.cuh"
+#include "landmark_opt.cuh"
 #include "select.cuh"
 #include "track_plan.cuh"
 
@@ -139,6 +140,10 @@ struct svi_ctx {
     struct Pending { void* host; const unsigned char* pinned; size_t bytes; };
     std::vector<Pending> pending;
     int n_sm = 148;
+    // svi_optimize_landmarks: one device buffer + its pinned mirror (inputs, then outputs), grown on demand
+    unsigned char* opt_dev = nullptr;
+    unsigned char* opt_pin = nullptr;
+    size_t opt_bytes = 0;
     // per-query arena
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
@@ -811,6 +816,8 @@ void svi_destroy(svi_ctx* ctx) {
     if (ctx->side_done) cudaEventDestroy(ctx->side_done);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->opt_dev) cudaFree(ctx->opt_dev);
+    if (ctx->opt_pin) cudaFreeHost(ctx->opt_pin);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->small_block) cudaFree(ctx->small_block);
     if (ctx->pin_arena) cudaFreeHost(ctx->pin_arena);
@@ -1555,6 +1562,92 @@ int svi_track_landmarks_stages(svi_ctx* ctx, const uint8_t* img_left, const uint
                      n, us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5), us(0, 5));
     }
     return rd;
+}
+
+int svi_optimize_landmarks(svi_ctx* ctx, const svi_landmark_measurements* in, int n, svi_optimize_result* out) {
+    if (!ctx) return SVI_ERR_INVALID;
+    if (!in || !out || n < 0 || !out->xyz_world || !out->outcome || !out->average_squared_error)
+        return fail(ctx, SVI_ERR_INVALID, "svi_optimize_landmarks: bad argument");
+    if (n == 0) return SVI_SUCCESS;
+    if (!in->xyz_world_guess || !in->first || in->n_poses < 0) return fail(ctx, SVI_ERR_INVALID, "svi_optimize_landmarks: null array");
+    const int m = in->first[n];
+    if (in->first[0] != 0 || m < 0) return fail(ctx, SVI_ERR_INVALID, "svi_optimize_landmarks: first[] must start at 0 and end at the measurement count");
+    for (int i = 0; i < n; ++i)
+        if (in->first[i + 1] < in->first[i]) return fail(ctx, SVI_ERR_INVALID, "svi_optimize_landmarks: first[] must not decrease");
+    if (m > 0 && (!in->pose_index || !in->uv_left || !in->uv_right || !in->proj_world_to_left || !in->proj_world_to_right || in->n_poses == 0))
+        return fail(ctx, SVI_ERR_INVALID, "svi_optimize_landmarks: null measurement array");
+    for (int k = 0; k < m; ++k)
+        if (in->pose_index[k] < 0 || in->pose_index[k] >= in->n_poses) return fail(ctx, SVI_ERR_INVALID, "svi_optimize_landmarks: pose_index out of range");
+    CK(cudaSetDevice(ctx->device));
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t_begin = clk::now();
+    // layout: [xyz_guess | proj_left | proj_right | first | pose_index | uv_left | uv_right] -> [xyz | avg | iterations | outcome]
+    const size_t P = (size_t)in->n_poses;
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t o_guess = take(sizeof(double) * 3 * n), o_pl = take(sizeof(double) * 12 * P), o_pr = take(sizeof(double) * 12 * P);
+    const size_t o_first = take(sizeof(int) * ((size_t)n + 1)), o_pose = take(sizeof(int) * (size_t)m);
+    const size_t o_uvl = take(sizeof(float) * 2 * (size_t)m), o_uvr = take(sizeof(float) * 2 * (size_t)m);
+    const size_t in_bytes = off;
+    const size_t o_xyz = take(sizeof(double) * 3 * n), o_avg = take(sizeof(double) * n), o_it = take(sizeof(int) * (size_t)n), o_out = take((size_t)n);
+    const size_t total = off;
+    if (total > ctx->opt_bytes) {   // grows to twice the need: a tracker's measurement lists get longer frame by frame
+        if (ctx->opt_dev) cudaFree(ctx->opt_dev);
+        if (ctx->opt_pin) cudaFreeHost(ctx->opt_pin);
+        ctx->opt_dev = nullptr; ctx->opt_pin = nullptr; ctx->opt_bytes = 0;
+        const size_t want = std::max<size_t>(2 * total, 1u << 20);
+        CK(cudaMalloc(reinterpret_cast<void**>(&ctx->opt_dev), want));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->opt_pin), want));
+        ctx->opt_bytes = want;
+    }
+    unsigned char* hp = ctx->opt_pin;
+    std::memcpy(hp + o_guess, in->xyz_world_guess, sizeof(double) * 3 * n);
+    std::memcpy(hp + o_first, in->first, sizeof(int) * ((size_t)n + 1));
+    if (m > 0) {
+        std::memcpy(hp + o_pl, in->proj_world_to_left, sizeof(double) * 12 * P);
+        std::memcpy(hp + o_pr, in->proj_world_to_right, sizeof(double) * 12 * P);
+        std::memcpy(hp + o_pose, in->pose_index, sizeof(int) * (size_t)m);
+        std::memcpy(hp + o_uvl, in->uv_left, sizeof(float) * 2 * (size_t)m);
+        std::memcpy(hp + o_uvr, in->uv_right, sizeof(float) * 2 * (size_t)m);
+    }
+    cudaStream_t s = ctx->lanes[0].stream;
+    const clk::time_point t_staged = clk::now();
+    CK(cudaMemcpyAsync(ctx->opt_dev, hp, in_bytes, cudaMemcpyHostToDevice, s));
+    unsigned char* d = ctx->opt_dev;
+    LandmarkOptIn li{reinterpret_cast<const double*>(d + o_guess), reinterpret_cast<const int*>(d + o_first), reinterpret_cast<const int*>(d + o_pose),
+                     reinterpret_cast<const float*>(d + o_uvl), reinterpret_cast<const float*>(d + o_uvr), reinterpret_cast<const double*>(d + o_pl),
+                     reinterpret_cast<const double*>(d + o_pr), in->n_poses};
+    LandmarkOptOut lo{reinterpret_cast<double*>(d + o_xyz), d + o_out, reinterpret_cast<double*>(d + o_avg), reinterpret_cast<int*>(d + o_it)};
+    optimize_landmarks_kernel<<<(n + kOptWarps - 1) / kOptWarps, kOptWarps * 32, 0, s>>>(li, n, lo);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hp + o_xyz, d + o_xyz, total - o_xyz, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::memcpy(out->xyz_world, hp + o_xyz, sizeof(double) * 3 * n);
+    std::memcpy(out->average_squared_error, hp + o_avg, sizeof(double) * n);
+    std::memcpy(out->outcome, hp + o_out, (size_t)n);
+    if (out->iterations) std::memcpy(out->iterations, hp + o_it, sizeof(int) * (size_t)n);
+    if (const char* dump = std::getenv("SVI_OPT_DUMP")) {   // diagnostics: the landmark with the most iterations, in facade_demo --landmark format
+        const int* it = reinterpret_cast<const int*>(hp + o_it);
+        int worst = 0;
+        for (int i = 1; i < n; ++i) if (it[i] > it[worst]) worst = i;
+        if (std::FILE* f = std::fopen(dump, "w")) {
+            std::fprintf(f, "%.17g %.17g %.17g\n", in->xyz_world_guess[3 * worst], in->xyz_world_guess[3 * worst + 1], in->xyz_world_guess[3 * worst + 2]);
+            for (int k = in->first[worst]; k < in->first[worst + 1]; ++k) {
+                for (int q = 0; q < 12; ++q) std::fprintf(f, "%.17g ", in->proj_world_to_left[12 * (size_t)in->pose_index[k] + q]);
+                for (int q = 0; q < 12; ++q) std::fprintf(f, "%.17g ", in->proj_world_to_right[12 * (size_t)in->pose_index[k] + q]);
+                std::fprintf(f, "%.9g %.9g %.9g %.9g\n", in->uv_left[2 * k], in->uv_left[2 * k + 1], in->uv_right[2 * k], in->uv_right[2 * k + 1]);
+            }
+            std::fprintf(f, "# iterations %d outcome %d\n", it[worst], (int)hp[o_out + worst]);
+            std::fclose(f);
+        }
+    }
+    if (ctx->trace) {
+        const clk::time_point t_end = clk::now();
+        auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        std::fprintf(stderr, "svi_optimize_landmarks n=%d m=%d poses=%d: check + stage inputs %.0f us | copy up, kernel, copy back %.0f us | total %.0f us\n",
+                     n, m, in->n_poses, us(t_begin, t_staged), us(t_staged, t_end), us(t_begin, t_end));
+    }
+    return check_overflow(ctx);
 }
 
 int svi_set_profiling(svi_ctx* ctx, int enable) {

@@ -348,6 +348,27 @@ class StereoFrontend:
                                                              float(motion_scaling), int(stages), C.byref(r)))
         return out
 
+    def optimize_landmarks(self, xyz_world_guess, first, pose_index, uv_left, uv_right, proj_world_to_left, proj_world_to_right) -> dict:
+        """svi_optimize_landmarks: CLandmark::optimize for n landmarks in one call.  Measurements of landmark i are the entries
+        [first[i], first[i + 1]) of pose_index / uv_left / uv_right; pose_index selects a row of the two (n_poses, 3, 4) tables."""
+        xg = np.ascontiguousarray(np.asarray(xyz_world_guess, np.float64).reshape(-1, 3))
+        n = len(xg)
+        fi = np.ascontiguousarray(np.asarray(first, np.int32).reshape(n + 1))
+        m = int(fi[-1]) if n else 0
+        pi = np.ascontiguousarray(np.asarray(pose_index, np.int32).reshape(m))
+        ul = np.ascontiguousarray(np.asarray(uv_left, np.float32).reshape(m, 2))
+        ur = np.ascontiguousarray(np.asarray(uv_right, np.float32).reshape(m, 2))
+        pl = np.ascontiguousarray(np.asarray(proj_world_to_left, np.float64).reshape(-1, 12))
+        pr = np.ascontiguousarray(np.asarray(proj_world_to_right, np.float64).reshape(-1, 12))
+        if len(pl) != len(pr):
+            raise ValueError("projection tables differ in length")
+        out = dict(xyz=np.zeros((n, 3), np.float64), outcome=np.zeros(n, np.uint8), average_squared_error=np.zeros(n, np.float64),
+                   iterations=np.zeros(n, np.int32))
+        a = _lib.LandmarkMeasurements(_ptr(xg), _ptr(fi), _ptr(pi), _ptr(ul), _ptr(ur), _ptr(pl), _ptr(pr), len(pl))
+        r = _lib.OptimizeResult(_ptr(out["xyz"]), _ptr(out["outcome"]), _ptr(out["average_squared_error"]), _ptr(out["iterations"]))
+        self._check(self._lib.svi_optimize_landmarks(self._ctx, C.byref(a), n, C.byref(r)))
+        return out
+
     # -- profiling
     def set_profiling(self, enable):
         """0 / False: off; 1 / True: stage events with overlapping lanes; 2: one lane, exclusive per-kernel durations."""

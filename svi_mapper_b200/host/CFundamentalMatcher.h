@@ -9,6 +9,8 @@
 #define SVI_HOST_CFUNDAMENTALMATCHER_H
 
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 #include "CSolverStereoPosit.h"
 #include "CTriangulator.h"
@@ -61,7 +63,7 @@ public:
     static constexpr size_t uMinimumMeasurementsForOptimization = 5;
 
     // src/types/CLandmark.cpp:80-279 without the per-bit statistics (loop-closure data, out of scope)
-    void addMeasurement(const UIDFrame&, const Point2f& p_ptUVLEFT, const Point2f& p_ptUVRIGHT, const CDescriptor& p_matDescriptorLEFT,
+    void addMeasurement(const UIDFrame& p_uFrame, const Point2f& p_ptUVLEFT, const Point2f& p_ptUVRIGHT, const CDescriptor& p_matDescriptorLEFT,
                         const CDescriptor& p_matDescriptorRIGHT, const CPoint3DCAMERA& p_vecXYZLEFT, const Isometry3d& p_matTransformationLEFTtoWORLD,
                         const Isometry3d& p_matTransformationWORLDtoLEFT, const MatrixProjection& p_matProjectionWORLDtoLEFT,
                         const MatrixProjection& p_matProjectionWORLDtoRIGHT) {
@@ -72,6 +74,7 @@ public:
         m_vecMeasurements.push_back(new CMeasurementLandmark(uID, p_ptUVLEFT, p_ptUVRIGHT, p_vecXYZLEFT, vecXYZWORLD,
                                                              vecPointXYZOptimized, p_matTransformationWORLDtoLEFT, p_matProjectionWORLDtoLEFT,
                                                              p_matProjectionWORLDtoRIGHT, uOptimizationsSuccessful));
+        m_vecMeasurementFrames.push_back(p_uFrame);   // every measurement of a frame carries the same projection pair
     }
     const Point2f getLastDetectionLEFT() const { return m_vecMeasurements.back()->ptUVLEFT; }
     const Point2f getLastDetectionRIGHT() const { return m_vecMeasurements.back()->ptUVRIGHT; }
@@ -86,6 +89,47 @@ public:
         bIsOptimal = false;
         if (uMinimumMeasurementsForOptimization < m_vecMeasurements.size()) vecPointXYZOptimized = _getOptimizedLandmarkSTEREOUV(p_uFrame, vecPointXYZOptimized);
         else bIsOptimal = true;
+    }
+
+    // ---- the batched form of optimize (svi_optimize_landmarks: one GPU thread per landmark, same arithmetic).
+    // Table of the projection pairs of the frames the packed measurements were taken in: one row per frame id.
+    struct CPoseTable {
+        std::vector<double> vecProjectionsLEFT, vecProjectionsRIGHT;   // rows of 12
+        std::vector<int32_t> vecRowOfFrame;                            // frame id -> row, -1 = not seen yet
+        void clear() { vecProjectionsLEFT.clear(); vecProjectionsRIGHT.clear(); vecRowOfFrame.clear(); }
+        int32_t getRow(const UIDFrame p_uFrame, const CMeasurementLandmark* p_pMeasurement) {
+            if (vecRowOfFrame.size() <= p_uFrame) vecRowOfFrame.resize(p_uFrame + 1, -1);
+            int32_t& iRow = vecRowOfFrame[p_uFrame];
+            if (0 > iRow) {
+                iRow = (int32_t)(vecProjectionsLEFT.size() / 12);
+                vecProjectionsLEFT.insert(vecProjectionsLEFT.end(), p_pMeasurement->matProjectionWORLDtoLEFT.m, p_pMeasurement->matProjectionWORLDtoLEFT.m + 12);
+                vecProjectionsRIGHT.insert(vecProjectionsRIGHT.end(), p_pMeasurement->matProjectionWORLDtoRIGHT.m, p_pMeasurement->matProjectionWORLDtoRIGHT.m + 12);
+            }
+            return iRow;
+        }
+    };
+    // appends this landmark's measurements (pose row, uv LEFT, uv RIGHT) to the packed arrays of a batch
+    void packMeasurements(CPoseTable& p_cPoses, std::vector<int32_t>& p_vecPoseIndex, std::vector<float>& p_vecUVLEFT, std::vector<float>& p_vecUVRIGHT) const {
+        for (size_t u = 0; u < m_vecMeasurements.size(); ++u) {
+            const CMeasurementLandmark* pMeasurement = m_vecMeasurements[u];
+            p_vecPoseIndex.push_back(p_cPoses.getRow(m_vecMeasurementFrames[u], pMeasurement));
+            p_vecUVLEFT.push_back(pMeasurement->ptUVLEFT.x); p_vecUVLEFT.push_back(pMeasurement->ptUVLEFT.y);
+            p_vecUVRIGHT.push_back(pMeasurement->ptUVRIGHT.x); p_vecUVRIGHT.push_back(pMeasurement->ptUVRIGHT.y);
+        }
+    }
+    // the state changes of optimize / _getOptimizedLandmarkSTEREOUV for an outcome computed by the library
+    void applyOptimization(const uint8_t p_uOutcome, const double* p_pXYZ, const double p_dAverageSquaredError) {
+        bIsOptimal = false;
+        switch (p_uOutcome) {
+            case SVI_OPT_SKIPPED: bIsOptimal = true; break;
+            case SVI_OPT_OPTIMAL: bIsOptimal = true;   // fall through
+            case SVI_OPT_CONVERGED:
+                ++uOptimizationsSuccessful;
+                dCurrentAverageSquaredError = p_dAverageSquaredError;
+                vecPointXYZOptimized = CPoint3DWORLD(p_pXYZ[0], p_pXYZ[1], p_pXYZ[2]);
+                break;
+            default: ++uOptimizationsFailed; break;   // SVI_OPT_REJECTED, SVI_OPT_NOT_CONVERGED: position kept
+        }
     }
 
 private:
@@ -174,6 +218,7 @@ private:
     }
 
     std::vector<CMeasurementLandmark*> m_vecMeasurements;
+    std::vector<UIDFrame> m_vecMeasurementFrames;
 };
 
 class CFundamentalMatcher {
@@ -210,10 +255,36 @@ public:
         return n;
     }
 
-    // optimizeActiveLandmarks :265-277
-    void optimizeActiveLandmarks(const UIDFrame& p_uFrame) const {
+    // optimizeActiveLandmarks :265-277: CLandmark::optimize for every active landmark -- ONE library call (one GPU thread per
+    // landmark, the arithmetic of CLandmark::_getOptimizedLandmarkSTEREOUV in the same order) instead of the per-landmark
+    // CPU loop, which is the largest item of the host's frame time (SVI_HOST_OPTIMIZE=cpu keeps that loop: the checker of
+    // the parity test)
+    void optimizeActiveLandmarks(const UIDFrame& p_uFrame) {
+        static const bool bCPU = [] { const char* e = std::getenv("SVI_HOST_OPTIMIZE"); return e && std::string(e) == "cpu"; }();
+        if (bCPU) {
+            for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
+                for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) pLandmark->optimize(p_uFrame);
+            return;
+        }
+        m_vecOptLandmarks.clear(); m_vecOptGuess.clear(); m_vecOptFirst.clear(); m_vecOptPoseIndex.clear(); m_vecOptUVLEFT.clear(); m_vecOptUVRIGHT.clear();
+        m_cOptPoses.clear();
+        m_vecOptFirst.push_back(0);
         for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
-            for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) pLandmark->optimize(p_uFrame);
+            for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
+                m_vecOptLandmarks.push_back(pLandmark);
+                for (int k = 0; k < 3; ++k) m_vecOptGuess.push_back(pLandmark->vecPointXYZOptimized.v[k]);
+                pLandmark->packMeasurements(m_cOptPoses, m_vecOptPoseIndex, m_vecOptUVLEFT, m_vecOptUVRIGHT);
+                m_vecOptFirst.push_back((int32_t)m_vecOptPoseIndex.size());
+            }
+        const int n = (int)m_vecOptLandmarks.size();
+        if (0 == n) return;
+        m_vecOptXYZ.resize(3 * (size_t)n); m_vecOptOutcome.resize(n); m_vecOptError.resize(n);
+        svi_landmark_measurements cIn{m_vecOptGuess.data(), m_vecOptFirst.data(), m_vecOptPoseIndex.data(), m_vecOptUVLEFT.data(), m_vecOptUVRIGHT.data(),
+                                      m_cOptPoses.vecProjectionsLEFT.data(), m_cOptPoses.vecProjectionsRIGHT.data(),
+                                      (int32_t)(m_cOptPoses.vecProjectionsLEFT.size() / 12)};
+        svi_optimize_result cOut{m_vecOptXYZ.data(), m_vecOptOutcome.data(), m_vecOptError.data(), nullptr};
+        m_pGpu->check(svi_optimize_landmarks(m_pGpu->ctx, &cIn, n, &cOut));
+        for (int i = 0; i < n; ++i) m_vecOptLandmarks[i]->applyOptimization(m_vecOptOutcome[i], &m_vecOptXYZ[3 * (size_t)i], m_vecOptError[i]);
     }
 
     // :244-254
@@ -539,6 +610,13 @@ private:
     UIDLandmark m_uAvailableLandmarkID = 0, m_uNumberOfTracksStage1 = 0, m_uNumberOfTracksStage2_1 = 0, m_uNumberOfTracksStage2_2 = 0, m_uNumberOfTracksStage3 = 0;
     CSolverStereoPosit m_cSolverSterePosit;
     std::vector<CSolverStereoPosit::CMatch> m_vecMeasurementsStereoPositLAST;
+    // packed arrays of optimizeActiveLandmarks (kept between frames: no allocation once they have grown)
+    std::vector<CLandmark*> m_vecOptLandmarks;
+    std::vector<double> m_vecOptGuess, m_vecOptXYZ, m_vecOptError;
+    std::vector<int32_t> m_vecOptFirst, m_vecOptPoseIndex;
+    std::vector<float> m_vecOptUVLEFT, m_vecOptUVRIGHT;
+    std::vector<uint8_t> m_vecOptOutcome;
+    CLandmark::CPoseTable m_cOptPoses;
 };
 
 #if defined(__GNUC__) && !defined(__clang__)

@@ -6,6 +6,8 @@
 #ifndef SVI_HOST_CTRACKERGT_H
 #define SVI_HOST_CTRACKERGT_H
 
+#include <chrono>
+
 #include "CFundamentalMatcher.h"
 
 // Pinned arithmetic: every product and sum below rounds on its own, in the written order (the GPU kernels and the CPU
@@ -33,11 +35,14 @@ public:
         const Isometry3d matTransformationLEFTtoWORLD(inverseIsometry(matTransformationWORLDtoLEFT));
         // :157 motion scaling (capped)
         const double dMotionScaling = std::min(1.0 + (10.0 * p_dRotationNorm + 0.5 * dTranslationNorm), 5.0);
+        const auto tStart = std::chrono::steady_clock::now();
         m_cMatcher.resetVisibilityActiveLandmarks();                                                               // :160
         m_cMatcher.trackManual(m_uFrameCount, p_matImageLEFT, p_matImageRIGHT, matTransformationWORLDtoLEFT, matTransformationLEFTtoWORLD,
                                dMotionScaling);                                                                    // :167-174
         m_uNumberofVisibleLandmarksLAST = m_cMatcher.getNumberOfVisibleLandmarks();                                // :176-193
+        const auto tTracked = std::chrono::steady_clock::now();
         m_cMatcher.optimizeActiveLandmarks(m_uFrameCount);                                                         // :197
+        const auto tOptimized = std::chrono::steady_clock::now();
         if (m_uVisibleLandmarksMinimum > m_uNumberofVisibleLandmarksLAST || m_uMaximumNumberOfFramesWithoutDetection < m_uNumberOfFramesWithoutDetection) {
             m_uNumberofVisibleLandmarksLAST = m_cMatcher.addNewLandmarks(p_matImageLEFT, p_matImageRIGHT, matTransformationWORLDtoLEFT,
                                                                          matTransformationLEFTtoWORLD, m_uFrameCount);   // :305-315
@@ -46,9 +51,17 @@ public:
         } else {
             ++m_uNumberOfFramesWithoutDetection;
         }
+        // the reference keeps such timers too (m_dDurationTotalSeconds* printed by tracker_gt.cpp:291-296)
+        const auto tEnd = std::chrono::steady_clock::now();
+        m_dDurationTrackingSeconds += std::chrono::duration<double>(tTracked - tStart).count();
+        m_dDurationOptimizationSeconds += std::chrono::duration<double>(tOptimized - tTracked).count();
+        m_dDurationDetectionSeconds += std::chrono::duration<double>(tEnd - tOptimized).count();
         m_matTransformationWORLDtoLEFTLAST = matTransformationWORLDtoLEFT;
         ++m_uFrameCount;
     }
+    double getDurationTrackingSeconds() const { return m_dDurationTrackingSeconds; }
+    double getDurationOptimizationSeconds() const { return m_dDurationOptimizationSeconds; }
+    double getDurationDetectionSeconds() const { return m_dDurationDetectionSeconds; }
 
     CFundamentalMatcher& getMatcher() { return m_cMatcher; }
     const Isometry3d getTransformationLEFTtoWORLD() const { return inverseIsometry(m_matTransformationWORLDtoLEFTLAST); }
@@ -64,6 +77,7 @@ private:
     const uint64_t m_uVisibleLandmarksMinimum = 100;            // CTrackerGT.cpp:29
     const uint8_t m_uMaximumNumberOfFramesWithoutDetection = 2; // CTrackerGT.h:56
     uint8_t m_uNumberOfFramesWithoutDetection = 0;
+    double m_dDurationTrackingSeconds = 0.0, m_dDurationOptimizationSeconds = 0.0, m_dDurationDetectionSeconds = 0.0;
 };
 
 #if defined(__GNUC__) && !defined(__clang__)

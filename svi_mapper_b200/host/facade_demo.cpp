@@ -8,6 +8,8 @@
 //        facade_demo --landmark <measurements.txt>
 // CLandmark::optimize alone (no GPU work): first line "x y z" = first triangulation in the camera frame of measurement 0,
 // then per line 16 numbers of LEFTtoWORLD... see landmarkMain; prints "x y z optimal successful failed".
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -169,6 +171,8 @@ static int maskMain(char** argv) {
 // planes) through CTrackerGT::process (track -> optimise -> re-detect), the per-frame relative motion LEFTLAST->LEFTNOW as
 // 12 numbers + the rotation norm per line.  Prints, per frame, the counters, every visible landmark's measurement and the
 // state of every active landmark after the frame -- compared line by line with the CPU restatement of the same loop.
+// With SVI_DEMO_TIMING set the per-frame dump is skipped and ONE line goes to stdout instead: the wall time of every
+// process() call (frames after the first three), split into trackManual / landmark optimisation / re-detection.
 static int sequenceMain(char** argv) {
     try {
         CParameterBase::loadCameraLEFT(argv[2]);
@@ -183,13 +187,29 @@ static int sequenceMain(char** argv) {
         p.max_corners = std::atoi(argv[8]);
         auto pGpu = std::make_shared<CGpuContext>(CParameterBase::pCameraSTEREO, &p);
         CTrackerGT cTracker(CParameterBase::pCameraSTEREO, pGpu);
-        std::FILE* out = std::fopen(argv[9], "w");
+        const bool bTiming = std::getenv("SVI_DEMO_TIMING") != nullptr;
+        std::FILE* out = bTiming ? nullptr : std::fopen(argv[9], "w");
+        std::vector<double> vecFrameMilliseconds;
+        double dWarmTracking = 0.0, dWarmOptimization = 0.0, dWarmDetection = 0.0;
+        size_t uLandmarksTracked = 0;
         for (int t = 0; t < n; ++t) {
             Isometry3d M;
             double dRotationNorm = 0.0;
             for (int i = 0; i < 12; ++i) fm >> M.m[i];
             fm >> dRotationNorm;
+            if (t == 3) {
+                dWarmTracking = cTracker.getDurationTrackingSeconds();
+                dWarmOptimization = cTracker.getDurationOptimizationSeconds();
+                dWarmDetection = cTracker.getDurationDetectionSeconds();
+            }
+            const size_t uActiveBefore = cTracker.getMatcher().getNumberOfActiveLandmarks();
+            const auto t0 = std::chrono::steady_clock::now();
             cTracker.process(ImageView(L.data() + (size_t)t * W * H, W, H), ImageView(R.data() + (size_t)t * W * H, W, H), M, dRotationNorm);
+            if (t >= 3) {
+                vecFrameMilliseconds.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                uLandmarksTracked += uActiveBefore;
+            }
+            if (bTiming) continue;
             CFundamentalMatcher& m = cTracker.getMatcher();
             std::fprintf(out, "F %d VISIBLE %lu ACTIVE %zu S1 %lu S2 %lu S3 %lu DETECTIONS %lu\n", t, (unsigned long)cTracker.getNumberOfVisibleLandmarksLAST(),
                          m.getNumberOfActiveLandmarks(), (unsigned long)m.getNumberOfTracksStage1(), (unsigned long)m.getNumberOfTracksStage2_1(),
@@ -202,7 +222,18 @@ static int sequenceMain(char** argv) {
                              q->vecPointXYZOptimized.z(), (int)q->bIsOptimal, (int)q->bIsCurrentlyVisible, q->uOptimizationsSuccessful, q->uOptimizationsFailed,
                              (unsigned)q->uFailedSubsequentTrackings, q->getNumberOfMeasurements());
         }
-        std::fclose(out);
+        if (out) std::fclose(out);
+        if (bTiming && !vecFrameMilliseconds.empty()) {
+            double dTotal = 0.0;
+            for (const double d : vecFrameMilliseconds) dTotal += d;
+            std::vector<double> vecSorted(vecFrameMilliseconds);
+            std::sort(vecSorted.begin(), vecSorted.end());
+            std::printf("{\"frames\": %zu, \"total_ms\": %.4f, \"median_ms\": %.4f, \"track_manual_ms\": %.4f, \"optimize_ms\": %.4f, "
+                        "\"add_new_landmarks_ms\": %.4f, \"landmarks_tracked\": %zu, \"detections\": %lu}\n",
+                        vecFrameMilliseconds.size(), dTotal, vecSorted[vecSorted.size() / 2],
+                        1e3 * (cTracker.getDurationTrackingSeconds() - dWarmTracking), 1e3 * (cTracker.getDurationOptimizationSeconds() - dWarmOptimization),
+                        1e3 * (cTracker.getDurationDetectionSeconds() - dWarmDetection), uLandmarksTracked, (unsigned long)cTracker.getNumberOfDetections());
+        }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "facade_demo failed: %s\n", e.what());
         return 1;
