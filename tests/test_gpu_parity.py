@@ -1316,7 +1316,7 @@ def test_bounds_checked_build():
     lib = bld.build_checked()
     k = ("test_stereo_frame_parity or test_track_manual_stage2_window_search or test_stress_frame_global_select_and_long_scanlines "
          "or test_stereo_batch_chunks_and_masks or test_track_manual_stage3_epipolar or test_edge_cases_empty_flat_masked_padded "
-         "or test_binned_matcher_geometries")
+         "or test_binned_matcher_geometries or test_optimize_landmarks_batch_matches_oracle_and_cpp")
     env = dict(os.environ, SVI_GPU_LIB=str(lib))
     r = subprocess.run([sys.executable, "-m", "pytest", str(pathlib.Path(__file__)), "-x", "-q", "-k", k], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
