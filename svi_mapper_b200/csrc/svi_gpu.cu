@@ -3,8 +3,9 @@
 //
 // Execution model.  A batch of independent stereo pairs is cut into chunks of `chunk_frames`
 // frames; chunk c runs on lane c % n_lanes.  A lane is one CUDA stream plus the scratch of one
-// chunk (box-sum planes of both images, candidate lists, corner lists); different lanes overlap
+// chunk (box-sum planes of both images, candidate lists, corner lists, bin lists); different lanes overlap
 // each other's copies, wide kernels (Harris, match) and the one-CTA-per-frame selection kernel.
+// Per-query entry points (triangulate, describe, track, landmark refinement) run on lane 0's stream.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -290,7 +291,8 @@ int setup_binned(svi_ctx* ctx, Lane& l, size_t rows, std::string* err) {
     return SVI_SUCCESS;
 }
 
-// The five kernels of the new-landmark path for `nf` frames on one lane.
+// The kernels of the new-landmark path for `nf` frames on one lane: detector, RIGHT box sums, corner selection, then the
+// descriptor / match stages in the form that fits the call (svi_kernels_per_chunk: 4 to 6 launches).
 int run_pipeline(svi_ctx* ctx, Lane& l, const uint8_t* d_left, const uint8_t* d_right, const uint8_t* d_mask,
                  const FrameGeom& g, int nf, const StereoOutDev& out, int out_frame0, int* n_kp, int* n_det,
                  cudaStream_t side = nullptr, const std::function<int(cudaStream_t)>* upload_right = nullptr) {
