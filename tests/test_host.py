@@ -103,6 +103,30 @@ def test_create_without_gpu_fails_loudly(kitti_cams):
         StereoFrontend(*kitti_cams)
 
 
+def test_entry_points_reject_a_null_context(built_library):
+    """Every compute entry point checks its context before touching the device: a NULL ctx is SVI_ERR_INVALID (-1), not a
+    crash -- this is what a host gets when svi_create failed (e.g. on a machine without a GPU) and it calls on anyway."""
+    import ctypes as C
+    from svi_mapper_b200 import _lib
+    lib = _lib.load()
+    lm, tr = _lib.Landmarks(), _lib.TrackResult()
+    meas, opt = _lib.LandmarkMeasurements(), _lib.OptimizeResult()
+    res = _lib.StereoResult()
+    calls = [
+        lambda: lib.svi_stereo_frames(None, None, None, 0, 0, 1, None, C.byref(res)),
+        lambda: lib.svi_stereo_frames_device(None, None, None, 0, 0, 1, None, C.byref(res), None),
+        lambda: lib.svi_check_overflow(None),
+        lambda: lib.svi_track_landmarks(None, None, None, 0, None, C.byref(lm), 1, 1.0, C.byref(tr)),
+        lambda: lib.svi_optimize_landmarks(None, C.byref(meas), 1, C.byref(opt)),
+        lambda: lib.svi_kernels_per_chunk(None, 64),
+        lambda: lib.svi_set_profiling(None, 1),
+        lambda: lib.svi_point_in_left(None, 1, None, None, None, None),
+    ]
+    for call in calls:
+        assert call() == _lib.SVI_ERR_INVALID
+    lib.svi_destroy(None)   # a no-op
+
+
 def test_product_code_never_imports_the_oracle():
     for p in (ROOT / "svi_mapper_b200").rglob("*.py"):
         txt = p.read_text()
