@@ -29,7 +29,8 @@ namespace svi {
 // The matcher's time barely moves with the tile traffic; it follows the number of resident warps (9 per SM for the
 // per-key-point kernels, 15-16 here at 127 registers) and the balance inside a CTA (key-points per bin over warps per CTA).
 // Sparse frames (maxCorners 1000 at KITTI size: ~7 key-points per 128 x 24 bin, ~3.5 per 64 x 24 bin) are faster with the
-// per-key-point kernels (C4: 136.0 k vs 132.2 k / 129.5 k), so svi_create selects this path by expected density.
+// per-key-point kernels (C4: 136.0 k vs 132.2 k / 129.5 k; 128 x 48 bins with 7 warps x 2 CTAs: 132.4 k), so svi_create
+// selects this path by expected density.
 template <int BW, int BH, int NW, int NCTA, int DW>
 struct BinGeom {
     static constexpr int BIN_W = BW, BIN_H = BH;
