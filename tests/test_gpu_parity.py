@@ -1279,6 +1279,38 @@ def test_optimize_landmarks_batch_matches_oracle_and_cpp(vi_cams, calib_dir, tmp
         np.testing.assert_allclose(got["xyz"][i], ref["xyz"], rtol=0, atol=1e-7, err_msg=str(i))
     assert {0, 2, 3} <= seen                            # skipped, optimal and rejected all occur
 
+    # extreme magnitudes: far points, a guess a million times too far, and the run-away landmark captured from
+    # the C3 sequence (position 1e83 m, exhausts the 1000 iterations) -- bit for bit against the host's IEEE arithmetic
+    exe = pathlib.Path(__file__).resolve().parents[1] / "svi_mapper_b200" / "host" / "facade_demo"
+    golden = pathlib.Path(__file__).resolve().parent / "golden" / "landmark_runaway.txt"
+    cases = []
+    rows = [ln for ln in golden.read_text().splitlines() if ln and not ln.startswith("#")]
+    cases.append((np.array([float(v) for v in rows[0].split()]),
+                  [(np.array(v[:12]), np.array(v[12:24]), np.float32(v[24:26]), np.float32(v[26:28])) for v in ([float(t) for t in r.split()] for r in rows[1:])]))
+    for z, scale in ((1e3, 1.3), (1e5, 0.7), (1e8, 2.0), (1e12, 1.1), (40.0, 1e6)):
+        truth = np.array([0.3 * z, -0.1 * z, z])
+        ms = []
+        for k in range(9):
+            a, b = PL[3 * k] @ np.append(truth, 1), PR[3 * k] @ np.append(truth, 1)
+            l = np.float32([a[0] / a[2], a[1] / a[2]]) + np.float32(rng.normal(0, 0.3, 2))
+            ms.append((PL[3 * k], PR[3 * k], l, np.float32([b[0] / b[2], l[1]]) + np.float32([rng.normal(0, 0.3), 0])))
+        cases.append((truth * scale, ms))
+    with StereoFrontend(*vi_cams) as fe:
+        for ci, (x0, ms) in enumerate(cases):
+            g1 = fe.optimize_landmarks(x0[None], [0, len(ms)], np.arange(len(ms)), np.array([m[2] for m in ms]), np.array([m[3] for m in ms]),
+                                       np.stack([np.asarray(m[0]).reshape(12) for m in ms]), np.stack([np.asarray(m[1]).reshape(12) for m in ms]))
+            f = tmp_path / f"lm_{ci}.txt"
+            f.write_text("\n".join([" ".join(repr(float(v)) for v in x0)] +
+                                    [" ".join(repr(float(v)) for v in list(np.asarray(m[0]).ravel()) + list(np.asarray(m[1]).ravel()) + [m[2][0], m[2][1], m[3][0], m[3][1]]) for m in ms]) + "\n")
+            r = subprocess.run([str(exe), "--landmark", str(f)], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            v = r.stdout.split()
+            oc = int(g1["outcome"][0])
+            assert (int(v[3]), int(v[4]), int(v[5])) == (int(oc == 2), int(oc in (1, 2)), int(oc in (3, 4))), (ci, oc, v)
+            assert [repr(float(t)) for t in g1["xyz"][0]] == [repr(float(t)) for t in v[:3]], (ci, g1["xyz"][0], v[:3])
+        assert int(fe.optimize_landmarks(cases[0][0][None], [0, len(cases[0][1])], np.arange(len(cases[0][1])), np.array([m[2] for m in cases[0][1]]),
+                                         np.array([m[3] for m in cases[0][1]]), np.stack([m[0] for m in cases[0][1]]), np.stack([m[1] for m in cases[0][1]]))["iterations"][0]) == 1000
+
     # the C++ tracker over a rendered sequence: library call vs the host's own CPU loop
     nf, mc = 14, 200
     L, R, T = render_sequence(vi_cams[0], vi_cams[1], nf, 4200)
