@@ -575,7 +575,8 @@ def cpp_tracker_timing(cfg, L, R, T):
     best["landmarks_per_s"] = best["landmarks_tracked"] / (best["total_ms"] * 1e-3)
     best["note"] = ("facade_demo --sequence (C++): wall time of CTrackerGT::process per frame after three warm-up frames, pageable images; "
                     "optimize_ms is optimizeActiveLandmarks = one svi_optimize_landmarks call per frame (CLandmark::optimize for every active landmark, "
-                    "one warp each; 629 ms for the same 57 frames with the host's per-landmark CPU loop, SVI_HOST_OPTIMIZE=cpu)")
+                    "one warp each; a failed optimisation whose inputs did not change is repeated, not recomputed); 629 ms for the same 57 "
+                    "frames with the host's per-landmark CPU loop (SVI_HOST_OPTIMIZE=cpu)")
     return best
 
 

@@ -120,6 +120,7 @@ public:
     // the state changes of optimize / _getOptimizedLandmarkSTEREOUV for an outcome computed by the library
     void applyOptimization(const uint8_t p_uOutcome, const double* p_pXYZ, const double p_dAverageSquaredError) {
         bIsOptimal = false;
+        m_bLastOptimizationFailed = false;
         switch (p_uOutcome) {
             case SVI_OPT_SKIPPED: bIsOptimal = true; break;
             case SVI_OPT_OPTIMAL: bIsOptimal = true;   // fall through
@@ -128,9 +129,24 @@ public:
                 dCurrentAverageSquaredError = p_dAverageSquaredError;
                 vecPointXYZOptimized = CPoint3DWORLD(p_pXYZ[0], p_pXYZ[1], p_pXYZ[2]);
                 break;
-            default: ++uOptimizationsFailed; break;   // SVI_OPT_REJECTED, SVI_OPT_NOT_CONVERGED: position kept
+            default:   // SVI_OPT_REJECTED, SVI_OPT_NOT_CONVERGED: position kept
+                ++uOptimizationsFailed;
+                m_bLastOptimizationFailed = true;
+                m_uMeasurementsAtFailedOptimization = m_vecMeasurements.size();
+                m_vecGuessAtFailedOptimization = vecPointXYZOptimized;
+                break;
         }
     }
+    // A failed optimisation leaves the landmark as it was, and trackManual never tracks it again (:1375-1384: no new
+    // measurements), yet optimizeActiveLandmarks visits it in every later frame: the same measurements from the same guess
+    // through a deterministic iteration -- the same failure, typically after all 1000 iterations.  When nothing the
+    // optimisation reads has changed since it last failed, its outcome is repeated instead of recomputed.
+    bool isRepeatOfFailedOptimization() const {
+        return m_bLastOptimizationFailed && m_uMeasurementsAtFailedOptimization == m_vecMeasurements.size() &&
+               m_vecGuessAtFailedOptimization.v[0] == vecPointXYZOptimized.v[0] && m_vecGuessAtFailedOptimization.v[1] == vecPointXYZOptimized.v[1] &&
+               m_vecGuessAtFailedOptimization.v[2] == vecPointXYZOptimized.v[2];
+    }
+    void repeatFailedOptimization() { bIsOptimal = false; ++uOptimizationsFailed; }
 
 private:
     // _getOptimizedLandmarkSTEREOUV :447-581: Gauss-Newton on the stereo reprojection error over all measurements, robust
@@ -219,6 +235,9 @@ private:
 
     std::vector<CMeasurementLandmark*> m_vecMeasurements;
     std::vector<UIDFrame> m_vecMeasurementFrames;
+    bool m_bLastOptimizationFailed = false;
+    size_t m_uMeasurementsAtFailedOptimization = 0;
+    CPoint3DWORLD m_vecGuessAtFailedOptimization;
 };
 
 class CFundamentalMatcher {
@@ -271,6 +290,7 @@ public:
         m_vecOptFirst.push_back(0);
         for (const CDetectionPoint& cDetectionPoint : m_vecDetectionPointsActive)
             for (CLandmark* pLandmark : *cDetectionPoint.vecLandmarks) {
+                if (pLandmark->isRepeatOfFailedOptimization()) { pLandmark->repeatFailedOptimization(); continue; }
                 m_vecOptLandmarks.push_back(pLandmark);
                 for (int k = 0; k < 3; ++k) m_vecOptGuess.push_back(pLandmark->vecPointXYZOptimized.v[k]);
                 pLandmark->packMeasurements(m_cOptPoses, m_vecOptPoseIndex, m_vecOptUVLEFT, m_vecOptUVRIGHT);
