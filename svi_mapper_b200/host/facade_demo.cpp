@@ -138,6 +138,30 @@ static int landmarkMain(char** argv) {
     }
     if (!pLandmark) return 2;
     pLandmark->optimize(0);
+    if (std::getenv("SVI_DEMO_REPEAT")) {
+        // host bookkeeping of the batched refinement, without the GPU: feed the CPU verdict through applyOptimization the way
+        // optimizeActiveLandmarks does, and check when a failed optimisation may be repeated instead of recomputed
+        const bool bFailed = 0 < pLandmark->uOptimizationsFailed;
+        const uint8_t uOutcome = bFailed ? (uint8_t)SVI_OPT_NOT_CONVERGED : (pLandmark->bIsOptimal ? (0 < pLandmark->uOptimizationsSuccessful ? (uint8_t)SVI_OPT_OPTIMAL : (uint8_t)SVI_OPT_SKIPPED) : (uint8_t)SVI_OPT_CONVERGED);
+        const double arrXYZ[3] = {pLandmark->vecPointXYZOptimized.x(), pLandmark->vecPointXYZOptimized.y(), pLandmark->vecPointXYZOptimized.z()};
+        const uint32_t uFailedBefore = pLandmark->uOptimizationsFailed;
+        if (bFailed) --pLandmark->uOptimizationsFailed; else if (0 < pLandmark->uOptimizationsSuccessful) --pLandmark->uOptimizationsSuccessful;
+        pLandmark->applyOptimization(uOutcome, arrXYZ, pLandmark->dCurrentAverageSquaredError);
+        const bool bRepeatAfterVerdict = pLandmark->isRepeatOfFailedOptimization();
+        bool bCountersAgree = pLandmark->uOptimizationsFailed == uFailedBefore;
+        if (bRepeatAfterVerdict) {
+            pLandmark->repeatFailedOptimization();
+            const uint32_t uAfterRepeat = pLandmark->uOptimizationsFailed;
+            --pLandmark->uOptimizationsFailed;
+            pLandmark->optimize(1);   // what the reference does in the next frame: the same failure again
+            bCountersAgree = bCountersAgree && uAfterRepeat == pLandmark->uOptimizationsFailed && !pLandmark->bIsOptimal;
+        }
+        pLandmark->addMeasurement(1, Point2f(uL, vL), Point2f(uR, vR), CDescriptor(), CDescriptor(), CPoint3D(x, y, z), matIdentity, matIdentity, PL, PR);
+        std::printf("REPEAT failed=%d repeat_after_verdict=%d counters_agree=%d repeat_after_new_measurement=%d\n", (int)bFailed, (int)bRepeatAfterVerdict,
+                    (int)bCountersAgree, (int)pLandmark->isRepeatOfFailedOptimization());
+        delete pLandmark;
+        return 0;
+    }
     std::printf("%.17g %.17g %.17g %d %u %u\n", pLandmark->vecPointXYZOptimized.x(), pLandmark->vecPointXYZOptimized.y(), pLandmark->vecPointXYZOptimized.z(),
                 (int)pLandmark->bIsOptimal, pLandmark->uOptimizationsSuccessful, pLandmark->uOptimizationsFailed);
     delete pLandmark;

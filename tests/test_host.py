@@ -307,6 +307,38 @@ def test_landmark_optimize_cpp_matches_oracle(calib_dir, tmp_path):
 
 
 
+def test_failed_landmark_optimisation_is_repeated_only_while_nothing_changed(calib_dir, tmp_path):
+    """Host bookkeeping of the batched refinement (CFundamentalMatcher::optimizeActiveLandmarks over svi_optimize_landmarks): a
+    landmark whose optimisation failed is not sent to the GPU again while its measurements and position are unchanged -- the
+    iteration is deterministic, so the failure is repeated.  Checked without a GPU on the run-away landmark captured from the
+    C3 sequence (fails after all 1000 iterations: repeat allowed, counters equal the CPU loop's, a new measurement ends it) and
+    on a landmark that converges (never repeated)."""
+    import os
+    exe = ROOT / "svi_mapper_b200" / "host" / "facade_demo"
+    env = dict(os.environ, SVI_DEMO_REPEAT="1")
+    bad = tmp_path / "bad.txt"
+    bad.write_text("\n".join(ln for ln in (ROOT / "tests" / "golden" / "landmark_runaway.txt").read_text().splitlines() if not ln.startswith("#")) + "\n")
+    r = subprocess.run([str(exe), "--landmark", str(bad)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "REPEAT failed=1 repeat_after_verdict=1 counters_agree=1 repeat_after_new_measurement=0"
+    from svi_mapper_b200 import load_camera
+    cl, cr = load_camera(calib_dir / "vi_sensor_left.txt"), load_camera(calib_dir / "vi_sensor_right.txt")
+    P_l, P_r = np.asarray(cl.P).reshape(3, 4), np.asarray(cr.P).reshape(3, 4)
+    truth = np.array([0.4, -0.2, 6.0])
+    rows = [" ".join(repr(float(v)) for v in truth + [0.1, -0.05, 0.5])]
+    for k in range(8):
+        T = np.eye(4)
+        T[:3, 3] = [0.03 * k, -0.01 * k, 0.02 * k]
+        a, b = (P_l @ T) @ np.append(truth, 1), (P_r @ T) @ np.append(truth, 1)
+        rows.append(" ".join(repr(float(v)) for v in list((P_l @ T).ravel()) + list((P_r @ T).ravel()) +
+                             [np.float32(a[0] / a[2]), np.float32(a[1] / a[2]), np.float32(b[0] / b[2]), np.float32(a[1] / a[2])]))
+    good = tmp_path / "good.txt"
+    good.write_text("\n".join(rows) + "\n")
+    r = subprocess.run([str(exe), "--landmark", str(good)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "REPEAT failed=0 repeat_after_verdict=0 counters_agree=1 repeat_after_new_measurement=0"
+
+
 def test_cloud_and_kitti_pose_formats_roundtrip(tmp_path):
     """Key-frame .cloud files (src/types/CKeyFrame.cpp:138-270) and KITTI pose lines (tracker_gt.cpp:208-229): the
     numpy writer, the C++ reader/writer of the host layer and the numpy reader agree byte for byte; truncated files
