@@ -91,6 +91,7 @@ def load(native=False):
     lib.svo_harris_response_roi.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, C.c_double, vp]
     lib.svo_gftt_roi.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, C.c_double, C.c_double, vp, ci]
     lib.svo_track_params_default.argtypes = [C.POINTER(TrackParams)]
+    lib.svo_optimize_landmark.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.svo_track_landmarks.argtypes = [C.POINTER(Config), C.POINTER(TrackParams), vp, vp, ci, vp, C.POINTER(Landmarks), ci, C.c_double,
                                         C.c_uint, C.POINTER(TrackResult), ci]
     _libs[key] = lib
@@ -217,3 +218,22 @@ def host_threads() -> int:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def optimize_landmark(xyz_guess, measurements, native=False) -> dict:
+    """svo_optimize_landmark: CLandmark::optimize for one landmark; measurements = list of (P_world_to_left 3x4,
+    P_world_to_right 3x4, uv_left, uv_right) like oracle.frontend_np.optimize_landmark.  Returns dict(xyz, outcome,
+    average_squared_error, iterations) with outcome 0 skipped / 1 converged / 2 optimal / 3 rejected / 4 not converged."""
+    m = len(measurements)
+    g = np.ascontiguousarray(np.asarray(xyz_guess, np.float64).reshape(3))
+    pl = np.ascontiguousarray(np.stack([np.asarray(q[0], np.float64).reshape(12) for q in measurements])) if m else np.zeros((0, 12))
+    pr = np.ascontiguousarray(np.stack([np.asarray(q[1], np.float64).reshape(12) for q in measurements])) if m else np.zeros((0, 12))
+    ul = np.ascontiguousarray(np.stack([np.asarray(q[2], np.float32).reshape(2) for q in measurements])) if m else np.zeros((0, 2), np.float32)
+    ur = np.ascontiguousarray(np.stack([np.asarray(q[3], np.float32).reshape(2) for q in measurements])) if m else np.zeros((0, 2), np.float32)
+    xyz = np.zeros(3, np.float64)
+    outcome, iters = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    avg = np.zeros(1, np.float64)
+    rc = load(native).svo_optimize_landmark(g.ctypes.data, m, pl.ctypes.data, pr.ctypes.data, ul.ctypes.data, ur.ctypes.data, xyz.ctypes.data,
+                                            outcome.ctypes.data, avg.ctypes.data, iters.ctypes.data)
+    assert rc == 0
+    return dict(xyz=xyz, outcome=int(outcome[0]), average_squared_error=float(avg[0]), iterations=int(iters[0]))

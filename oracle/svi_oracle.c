@@ -12,6 +12,8 @@
  *       one BRIEF::compute on the 57-row ROI (its own integral image), one BFMatcher::match,
  *       cut-off, getPointInLEFT :326-356
  *   CTriangulator::getPointTriangulatedInLEFT (7 args)    src/core/CTriangulator.cpp:255-324
+ *   CLandmark::optimize / _getOptimizedLandmarkSTEREOUV    src/types/CLandmark.cpp:281-296, :447-581 -> svo_optimize_landmark
+ *   (CFundamentalMatcher::trackManual stages 1-3           src/core/CFundamentalMatcher.cpp:1334-2027 -> svo_track_landmarks)
  * OpenCV arithmetic (not in the reference tree, un-versioned "trunk") is restated from its
  * published algorithms in the operation order validated against cv2 4.13 with optimisations off
  * (SURVEY.md Appendix A); tests/test_oracle.py pins this file against cv2 and against the numpy
@@ -948,5 +950,103 @@ int svo_track_landmarks(const svo_config* c, const svo_track_params* tp, const u
     for (int i = 1; i < n_threads; ++i) pthread_join(th[i], NULL);
     free(th);
     pthread_mutex_destroy(&j.mu);
+    return 0;
+}
+
+/* ---- CLandmark::optimize / _getOptimizedLandmarkSTEREOUV (src/types/CLandmark.cpp:281-296, :447-581): robust Gauss-Newton
+ * refinement of one landmark's WORLD position on the stereo re-projection error of its measurements; constants of
+ * CLandmark.h:90-98.  Written from the reference's loop: per measurement the two projections, the error, the Jacobian of the
+ * homogeneous division times the projection, the weight, the accumulation of H and b; then
+ * H.block<4,3>(0,0).householderQr().solve(-b) restated as three Householder reflections and a back substitution (Eigen's
+ * result up to rounding), the convergence test on the total squared error and the inlier / average-error verdicts.
+ * m measurements: proj_left / proj_right m x 12 (row-major 3 x 4), uv_left / uv_right m x 2.
+ * outcome: 0 skipped (m <= 5: position kept, optimal), 1 converged, 2 converged and optimal, 3 rejected (inlier ratio),
+ * 4 not converged in 1000 iterations.  xyz_out = refined position for 1 / 2, the guess otherwise. */
+static void svo_ls_4x3(double H[4][4], const double b[4], double x[3]) {
+    double A[4][3], y[4];
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 3; ++j) A[i][j] = H[i][j]; y[i] = -b[i]; }
+    for (int c = 0; c < 3; ++c) {
+        double norm = 0.0;
+        for (int r = c; r < 4; ++r) norm += A[r][c] * A[r][c];
+        norm = sqrt(norm);
+        if (norm == 0.0) continue;
+        const double alpha = A[c][c] > 0.0 ? -norm : norm;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        v[c] = A[c][c] - alpha;
+        for (int r = c + 1; r < 4; ++r) v[r] = A[r][c];
+        double vv = 0.0;
+        for (int r = c; r < 4; ++r) vv += v[r] * v[r];
+        if (vv == 0.0) continue;
+        for (int j = c; j < 3; ++j) {
+            double d = 0.0;
+            for (int r = c; r < 4; ++r) d += v[r] * A[r][j];
+            for (int r = c; r < 4; ++r) A[r][j] -= 2.0 * d / vv * v[r];
+        }
+        double d = 0.0;
+        for (int r = c; r < 4; ++r) d += v[r] * y[r];
+        for (int r = c; r < 4; ++r) y[r] -= 2.0 * d / vv * v[r];
+    }
+    for (int r = 2; r >= 0; --r) {
+        double s = y[r];
+        for (int j = r + 1; j < 3; ++j) s -= A[r][j] * x[j];
+        x[r] = A[r][r] != 0.0 ? s / A[r][r] : 0.0;
+    }
+}
+
+int svo_optimize_landmark(const double* xyz_guess, int m, const double* proj_left, const double* proj_right, const float* uv_left,
+                          const float* uv_right, double* xyz_out, int32_t* outcome, double* average_squared_error, int32_t* iterations) {
+    const double kernel = 10.0, delta = 1e-5, min_ratio = 0.5, max_avg = 9.0;
+    xyz_out[0] = xyz_guess[0]; xyz_out[1] = xyz_guess[1]; xyz_out[2] = xyz_guess[2];
+    *average_squared_error = 0.0;
+    *iterations = 0;
+    if (!(5 < m)) { *outcome = 0; return 0; }
+    double X[4] = {xyz_guess[0], xyz_guess[1], xyz_guess[2], 1.0};
+    double prev = 0.0;
+    for (int it = 0; it < 1000; ++it) {
+        double H[4][4] = {{0}}, b[4] = {0, 0, 0, 0}, total = 0.0;
+        int inliers = 0;
+        for (int k = 0; k < m; ++k) {
+            const double* P[2] = {proj_left + 12 * (size_t)k, proj_right + 12 * (size_t)k};
+            const float* uv[2] = {uv_left + 2 * (size_t)k, uv_right + 2 * (size_t)k};
+            double J[4][4], e[4];
+            for (int s = 0; s < 2; ++s) {
+                const double* p = P[s];
+                double a[3];
+                for (int r = 0; r < 3; ++r) a[r] = p[4 * r] * X[0] + p[4 * r + 1] * X[1] + p[4 * r + 2] * X[2] + p[4 * r + 3] * X[3];
+                const double c = a[2];
+                e[2 * s] = a[0] / c - uv[s][0];
+                e[2 * s + 1] = a[1] / c - uv[s][1];
+                for (int q = 0; q < 4; ++q) {
+                    J[2 * s][q] = p[q] / c - a[0] / (c * c) * p[8 + q];
+                    J[2 * s + 1][q] = p[4 + q] / c - a[1] / (c * c) * p[8 + q];
+                }
+            }
+            const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
+            double w = 1.0;
+            if (kernel < e2) w = kernel / e2; else ++inliers;
+            total += w * e2;
+            for (int r = 0; r < 4; ++r) {
+                for (int q = 0; q < 4; ++q) H[r][q] += w * (J[0][r] * J[0][q] + J[1][r] * J[1][q] + J[2][r] * J[2][q] + J[3][r] * J[3][q]);
+                b[r] += w * (J[0][r] * e[0] + J[1][r] * e[1] + J[2][r] * e[2] + J[3][r] * e[3]);
+            }
+        }
+        double dx[3];
+        svo_ls_4x3(H, b, dx);
+        X[0] += dx[0]; X[1] += dx[1]; X[2] += dx[2];
+        *iterations = it + 1;
+        if (delta > fabs(prev - total)) {
+            const double avg = total / (double)m;
+            if (min_ratio < (double)inliers / (double)m) {
+                xyz_out[0] = X[0]; xyz_out[1] = X[1]; xyz_out[2] = X[2];
+                *average_squared_error = avg;
+                *outcome = max_avg > avg ? 2 : 1;
+            } else {
+                *outcome = 3;
+            }
+            return 0;
+        }
+        prev = total;
+    }
+    *outcome = 4;
     return 0;
 }
